@@ -1,0 +1,72 @@
+"""ctypes binding of libffr_sm100.so (include/ffr_sm100.h). There is no fallback: if the library is missing or a
+call fails, a RuntimeError is raised."""
+import ctypes
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libffr_sm100.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "ffr_sm100.h")
+
+_lib = None
+
+_p = ctypes.c_void_p
+_i = ctypes.c_int
+_u32 = ctypes.c_uint32
+_i64 = ctypes.c_int64
+
+_SIGNATURES = {
+    "ffr_version": (_i, []),
+    "ffr_last_error": (ctypes.c_char_p, []),
+    "ffr_conv_gemm": (_i, [_p, _i64, _i, _i, _p, _i, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _u32, _p, _p, _p, _i, _i,
+                           _p, _p, _p, _i, _p, _i, _p]),
+    "ffr_conv3x3_bnpre_prelu_fwd": (_i, [_p, _i, _i, _i, _p, _i, _p, _p, _p, _i, _p]),
+    "ffr_conv3x3_bn_pool_fwd": (_i, [_p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p]),
+    "ffr_conv1x1_bn_fwd": (_i, [_p, _i, _i, _i, _p, _i, _p, _p, _p]),
+    "ffr_subsample2": (_i, [_p, _p, _i, _i, _i, _p]),
+    "ffr_stem_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _p]),
+    "ffr_se_residual_fwd": (_i, [_p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _p]),
+    "ffr_export_nchw_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
+    "ffr_head_fwd": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "ffr_debug_rowshift_probe": (_i, [_p, _p, _p, _i, _i, _p]),
+}
+
+
+def declared_symbols():
+    """Names of every function include/ffr_sm100.h declares (used by the CPU-side export test)."""
+    with open(HEADER_PATH) as f:
+        text = f.read()
+    return sorted(set(re.findall(r"FFR_API\s+[\w\s\*]+?\b(ffr_\w+)\s*\(", text)))
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libffr_sm100.so not built (%s missing): run `python -c 'import __graft_entry__ as g; g.build()'`; "
+            "there is no CPU / PyTorch fallback for this path" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name in declared_symbols():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        if name in _SIGNATURES:
+            fn.restype, fn.argtypes = _SIGNATURES[name]
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().ffr_last_error()
+        raise RuntimeError("libffr_sm100 %s failed (rc=%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,192 @@
+// extern "C" entry points declared in include/ffr_sm100.h.
+#include "../../include/ffr_sm100.h"
+
+#include <cstring>
+
+#include "conv_gemm.cuh"
+#include "host.h"
+
+namespace ffr {
+int conv_gemm_launch(const void* a, long long a_rows, int a_cols, int a_ld, const void* wp, int Cin, ConvGemmParams p,
+                     int num_splits, cudaStream_t stream);
+int stem_launch(const float* x, const float* w, const float* b, const float* a, void* out, int n_img, int S,
+                cudaStream_t stream);
+int se_residual_launch(const void* u, const float* pool, const float* w1, const float* w2, const void* sc,
+                       int shortcut_mode, void* y, int n_img, int S, int C, cudaStream_t stream);
+int subsample2_launch(const void* x, void* out, int n_img, int So, int C, cudaStream_t stream);
+int export_nchw_launch(const void* h, const float* scale, const float* shift, float* y, int n_img, int S, int C,
+                       cudaStream_t stream);
+int bias_l2norm_launch(const float* acc, const float* bias, float* f, int rows, int D, cudaStream_t stream);
+}  // namespace ffr
+
+using namespace ffr;
+
+static inline cudaStream_t S_(ffr_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// 3x3 taps on a flat grid with row pitch G: tap (r,s) reads row m + (r-1)*G + (s-1).
+static void taps_3x3_flat(ConvGemmParams& p, int G) {
+    p.ntaps = 9;
+    for (int r = 0; r < 3; ++r)
+        for (int s = 0; s < 3; ++s) {
+            p.tap_row_shift[r * 3 + s] = (r - 1) * G + (s - 1);
+            p.tap_ch_off[r * 3 + s] = 0;
+        }
+}
+
+// 3x3 stride-2 taps on the space-to-depth grid (pitch G = So+1, 4*C channels): input pixel 2*ho + r - 1 lives in
+// block ho + dh with parity ph where r=0 -> (dh=-1, ph=1), r=1 -> (0,0), r=2 -> (0,1).
+static void taps_3x3_s2d(ConvGemmParams& p, int G, int C) {
+    p.ntaps = 9;
+    for (int r = 0; r < 3; ++r)
+        for (int s = 0; s < 3; ++s) {
+            const int dh = (r == 0) ? -1 : 0, ph = (r == 1) ? 0 : 1;
+            const int dw = (s == 0) ? -1 : 0, pw = (s == 1) ? 0 : 1;
+            p.tap_row_shift[r * 3 + s] = dh * G + dw;
+            p.tap_ch_off[r * 3 + s] = (ph * 2 + pw) * C;
+        }
+}
+
+extern "C" {
+
+FFR_API int ffr_version(void) { return 100; }
+
+FFR_API const char* ffr_last_error(void) { return last_error_buf(); }
+
+FFR_API int ffr_conv_gemm(const void* a, int64_t a_rows, int a_cols, int a_ld, const void* wp, int Cin, int Cout, int ntaps,
+                  const int* tap_row_shift, const int* tap_ch_off, int M, int rows_per_img, int Wp, int S, int h0,
+                  int n_img, uint32_t flags, const float* bias, const float* slope, void* out, int ldo, int s2d_So,
+                  float* pool, float* out_f32, const void* res, int ldres, float* stats, int num_splits,
+                  ffr_stream_t stream) {
+    FFR_CHECK_ARG(a && wp, "ffr_conv_gemm: null operand");
+    FFR_CHECK_ARG(ntaps >= 1 && ntaps <= 9, "ffr_conv_gemm: ntaps=%d", ntaps);
+    ConvGemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = M;
+    p.Cout = Cout;
+    p.ntaps = ntaps;
+    for (int t = 0; t < ntaps; ++t) {
+        p.tap_row_shift[t] = tap_row_shift ? tap_row_shift[t] : 0;
+        p.tap_ch_off[t] = tap_ch_off ? tap_ch_off[t] : 0;
+    }
+    p.rows_per_img = rows_per_img; p.Wp = Wp; p.S = S; p.h0 = h0; p.n_img = n_img;
+    p.flags = flags;
+    p.bias = bias; p.slope = slope;
+    p.out = reinterpret_cast<__nv_bfloat16*>(out); p.ldo = ldo; p.s2d_So = s2d_So;
+    p.pool = pool; p.out_f32 = out_f32;
+    p.res = reinterpret_cast<const __nv_bfloat16*>(res); p.ldres = ldres;
+    p.stats = stats;
+    if (flags & (EPI_BIAS | EPI_BORDER_BIAS)) FFR_CHECK_ARG(bias, "ffr_conv_gemm: bias flag without bias");
+    if (flags & EPI_PRELU) FFR_CHECK_ARG(slope, "ffr_conv_gemm: PReLU flag without slopes");
+    if (flags & EPI_POOL) FFR_CHECK_ARG(pool, "ffr_conv_gemm: pool flag without buffer");
+    if (flags & (EPI_OUT_F32_ATOMIC | EPI_OUT_F32)) FFR_CHECK_ARG(out_f32, "ffr_conv_gemm: fp32 output missing");
+    if (flags & EPI_RESIDUAL) FFR_CHECK_ARG(res, "ffr_conv_gemm: residual missing");
+    if (flags & EPI_STATS) FFR_CHECK_ARG(stats, "ffr_conv_gemm: stats buffer missing");
+    return conv_gemm_launch(a, a_rows, a_cols, a_ld, wp, Cin, p, num_splits, S_(stream));
+}
+
+FFR_API int ffr_conv3x3_bnpre_prelu_fwd(const void* x, int n_img, int S, int Cin, const void* wp, int Cout,
+                                const float* bias9, const float* slope, void* out, int out_s2d, ffr_stream_t stream) {
+    FFR_CHECK_ARG(x && wp && bias9 && slope && out, "ffr_conv3x3_bnpre_prelu_fwd: null pointer");
+    FFR_CHECK_ARG(!out_s2d || S % 2 == 0, "ffr_conv3x3_bnpre_prelu_fwd: s2d output needs even S (got %d)", S);
+    const int G = S + 1;
+    ConvGemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = n_img * G * G;
+    p.Cout = Cout;
+    taps_3x3_flat(p, G);
+    p.rows_per_img = G * G; p.Wp = G; p.S = S; p.h0 = 0; p.n_img = n_img;
+    p.flags = EPI_GEOM | EPI_BORDER_BIAS | EPI_PRELU | (out_s2d ? EPI_OUT_S2D : 0u);
+    p.bias = bias9; p.slope = slope;
+    p.out = reinterpret_cast<__nv_bfloat16*>(out);
+    p.ldo = out_s2d ? 4 * Cout : Cout;
+    p.s2d_So = S / 2;
+    return conv_gemm_launch(x, (long long)p.M, Cin, Cin, wp, Cin, p, 1, S_(stream));
+}
+
+FFR_API int ffr_conv3x3_bn_pool_fwd(const void* x, int n_img, int S, int C, int stride, const void* wp, int Cout,
+                            const float* bias, void* out, float* pool, ffr_stream_t stream) {
+    FFR_CHECK_ARG(x && wp && bias && out, "ffr_conv3x3_bn_pool_fwd: null pointer");
+    FFR_CHECK_ARG(stride == 1 || (stride == 2 && S % 2 == 0), "ffr_conv3x3_bn_pool_fwd: stride=%d S=%d", stride, S);
+    const int So = S / stride, G = So + 1;
+    ConvGemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = n_img * G * G;
+    p.Cout = Cout;
+    if (stride == 1) taps_3x3_flat(p, G); else taps_3x3_s2d(p, G, C);
+    p.rows_per_img = G * G; p.Wp = G; p.S = So; p.h0 = 0; p.n_img = n_img;
+    p.flags = EPI_GEOM | EPI_BIAS | (pool ? EPI_POOL : 0u);
+    p.bias = bias;
+    p.out = reinterpret_cast<__nv_bfloat16*>(out);
+    p.ldo = Cout;
+    p.pool = pool;
+    if (pool) FFR_CUDA(cudaMemsetAsync(pool, 0, sizeof(float) * (size_t)n_img * Cout, S_(stream)));
+    const int a_cols = (stride == 1) ? C : 4 * C;
+    return conv_gemm_launch(x, (long long)p.M, a_cols, a_cols, wp, C, p, 1, S_(stream));
+}
+
+FFR_API int ffr_conv1x1_bn_fwd(const void* xs, int n_img, int S, int Cin, const void* wp, int Cout, const float* bias,
+                       void* out, ffr_stream_t stream) {
+    FFR_CHECK_ARG(xs && wp && bias && out, "ffr_conv1x1_bn_fwd: null pointer");
+    const int G = S + 1;
+    ConvGemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = n_img * G * G;
+    p.Cout = Cout;
+    p.ntaps = 1;
+    p.rows_per_img = G * G; p.Wp = G; p.S = S; p.h0 = 0; p.n_img = n_img;
+    p.flags = EPI_GEOM | EPI_BIAS;
+    p.bias = bias;
+    p.out = reinterpret_cast<__nv_bfloat16*>(out);
+    p.ldo = Cout;
+    return conv_gemm_launch(xs, (long long)p.M, Cin, Cin, wp, Cin, p, 1, S_(stream));
+}
+
+FFR_API int ffr_subsample2(const void* x, void* out, int n_img, int So, int C, ffr_stream_t stream) {
+    FFR_CHECK_ARG(x && out && C % 8 == 0, "ffr_subsample2: bad arguments");
+    return subsample2_launch(x, out, n_img, So, C, S_(stream));
+}
+
+FFR_API int ffr_stem_fwd(const float* x, const float* w, const float* b, const float* a, void* out, int n_img, int S,
+                 ffr_stream_t stream) {
+    FFR_CHECK_ARG(x && w && b && a && out, "ffr_stem_fwd: null pointer");
+    return stem_launch(x, w, b, a, out, n_img, S, S_(stream));
+}
+
+FFR_API int ffr_se_residual_fwd(const void* u, const float* pool, const float* w1, const float* w2, const void* shortcut,
+                        int shortcut_mode, void* y, int n_img, int S, int C, ffr_stream_t stream) {
+    FFR_CHECK_ARG(u && pool && w1 && w2 && shortcut && y, "ffr_se_residual_fwd: null pointer");
+    return se_residual_launch(u, pool, w1, w2, shortcut, shortcut_mode, y, n_img, S, C, S_(stream));
+}
+
+FFR_API int ffr_export_nchw_fwd(const void* h, const float* scale, const float* shift, float* y, int n_img, int S, int C,
+                        ffr_stream_t stream) {
+    FFR_CHECK_ARG(h && scale && shift && y, "ffr_export_nchw_fwd: null pointer");
+    return export_nchw_launch(h, scale, shift, y, n_img, S, C, S_(stream));
+}
+
+FFR_API int ffr_head_fwd(const void* h, int n_img, int S, int C, const void* wp, const float* bias, float* acc, float* f,
+                 ffr_stream_t stream) {
+    FFR_CHECK_ARG(h && wp && bias && acc && f, "ffr_head_fwd: null pointer");
+    const int D = 512;
+    const int K = (S + 1) * (S + 1) * C;       // one image's flat rows, viewed as a single GEMM row
+    FFR_CHECK_ARG(K % 64 == 0, "ffr_head_fwd: K=%d", K);
+    FFR_CUDA(cudaMemsetAsync(acc, 0, sizeof(float) * (size_t)n_img * D, S_(stream)));
+    ConvGemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = n_img;
+    p.Cout = D;
+    p.ntaps = 1;
+    p.flags = EPI_OUT_F32_ATOMIC;
+    p.out_f32 = acc;
+    // enough splits to put ~one wave of CTAs on the machine
+    const int tiles = ((n_img + 127) / 128) * (D / 256);
+    int splits = (num_sms() + tiles - 1) / tiles;
+    const int kb = K / 64;
+    if (splits > kb / 4) splits = kb / 4;
+    if (splits < 1) splits = 1;
+    int rc = conv_gemm_launch(h, n_img, K, K, wp, K, p, splits, S_(stream));
+    if (rc) return rc;
+    return bias_l2norm_launch(acc, bias, f, n_img, D, S_(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,400 @@
+#include "conv_gemm.cuh"
+#include "host.h"
+#include "ptx.cuh"
+
+namespace ffr {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;                       // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int NUM_THREADS = 256;                  // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 epilogue
+constexpr int EPI_THREADS = 128;
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int TMEM_COLS = 2 * BN;      // double-buffered fp32 accumulator, 128 lanes x BN columns each
+    static constexpr int PARAM_FLOATS = 10 * BN;  // 9 border-class biases (or 1) + PReLU slopes
+    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 256 /*barriers*/ + PARAM_FLOATS * 4;
+};
+
+__device__ __forceinline__ float sigmoidf_fast(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+// Column sums across the 32 lanes of a warp for 32 per-lane values: after the call lane L holds, in x[0],
+// sum over lanes of (their) x[L]. 31 shuffles (butterfly transpose-reduce).
+__device__ __forceinline__ float warp_colsum32(float (&x)[32], int lane) {
+#pragma unroll
+    for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const float send = up ? x[i] : x[i + n];
+            const float keep = up ? x[i + n] : x[i];
+            x[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return x[0];
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const ConvGemmParams p) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = bars;                   // [STAGES]  TMA -> MMA
+    uint64_t* empty_bar = bars + STAGES;         // [STAGES]  MMA -> TMA
+    uint64_t* tfull_bar = bars + 2 * STAGES;     // [2]       MMA -> epilogue
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2;// [2]       epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    float* sparam = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], EPI_THREADS);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_work = p.num_m_tiles * p.num_n_tiles * p.num_splits;
+    const int kb_total = p.ntaps * p.kb_per_tap;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+                const int split = work % p.num_splits;
+                const int t = work / p.num_splits;
+                const int n_tile = t % p.num_n_tiles;
+                const int m_tile = t / p.num_n_tiles;
+                const int m0 = m_tile * BLOCK_M;
+                const int n0 = n_tile * BN;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(kb0 + p.kb_per_split, kb_total);
+                int tap = kb0 / p.kb_per_tap;
+                int c = kb0 - tap * p.kb_per_tap;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], p.tap_ch_off[tap] + c * BLOCK_K,
+                                m0 + p.tap_row_shift[tap]);
+                    tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, n0);
+                    if (++c == p.kb_per_tap) { c = 0; ++tap; }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++it) {
+                const int split = work % p.num_splits;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(kb0 + p.kb_per_split, kb_total);
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
+                    const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 16; ++k) {
+                        umma_bf16(d_tmem, umma_smem_desc_sw128(a_addr + k * 32), umma_smem_desc_sw128(b_addr + k * 32),
+                                  idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);        // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== Epilogue: TMEM -> registers -> fused ops -> global =====================
+        const int ew = warp - 4;                     // TMEM lane quadrant == warp % 4
+        const int row_in_tile = ew * 32 + lane;
+        const int etid = threadIdx.x - 128;
+        const uint32_t flags = p.flags;
+        const bool border = (flags & EPI_BORDER_BIAS) != 0;
+        const int nbias = border ? 9 : 1;
+        int loaded_n_tile = -1;
+        int it = 0;
+        for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++it) {
+            const int t = work / p.num_splits;
+            const int n_tile = t % p.num_n_tiles;
+            const int m_tile = t / p.num_n_tiles;
+            const int m0 = m_tile * BLOCK_M;
+            const int n0 = n_tile * BN;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+
+            if (n_tile != loaded_n_tile) {           // stage per-channel epilogue parameters in smem
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (flags & (EPI_BIAS | EPI_BORDER_BIAS))
+                    for (int i = etid; i < nbias * BN; i += EPI_THREADS)
+                        sparam[i] = p.bias[(i / BN) * p.Cout + n0 + (i % BN)];
+                if (flags & EPI_PRELU)
+                    for (int i = etid; i < BN; i += EPI_THREADS) sparam[9 * BN + i] = p.slope[n0 + i];
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                loaded_n_tile = n_tile;
+            }
+
+            const int m = m0 + row_in_tile;
+            int n_img = 0, h = 0, w = 0;
+            bool valid = m < p.M;
+            int cls = 0;
+            if (flags & EPI_GEOM) {
+                n_img = m / p.rows_per_img;
+                const int rem = m - n_img * p.rows_per_img;
+                h = rem / p.Wp;
+                w = rem - h * p.Wp;
+                h -= p.h0;
+                w -= p.h0;
+                valid = valid && h >= 0 && h < p.S && w >= 0 && w < p.S;
+                if (border) {
+                    const int ch = (h == 0) ? 0 : ((h == p.S - 1) ? 2 : 1);
+                    const int cw = (w == 0) ? 0 : ((w == p.S - 1) ? 2 : 1);
+                    cls = ch * 3 + cw;
+                }
+            }
+            const float* sbias = sparam + cls * BN;
+            const float* sslope = sparam + 9 * BN;
+
+            // output addressing
+            __nv_bfloat16* orow = nullptr;
+            bool do_store = false;
+            if (p.out != nullptr) {
+                if (flags & EPI_OUT_S2D) {
+                    const int g = p.s2d_So + 1;
+                    const long long r = (long long)n_img * g * g + (h >> 1) * g + (w >> 1);
+                    orow = p.out + r * p.ldo + ((h & 1) * 2 + (w & 1)) * p.Cout + n0;
+                    do_store = valid;
+                } else {
+                    orow = p.out + (long long)m * p.ldo + n0;
+                    do_store = (m < p.M) && (valid || !(flags & EPI_OUT_REFLECT));
+                }
+            }
+            // reflection-halo mirrors (7x7 map stored with a 1-pixel halo, Wp == 9): interior index 1 mirrors to
+            // halo index -1 and S-2 mirrors to S
+            int mir_h = 0, mir_w = 0;
+            if (flags & EPI_OUT_REFLECT) {
+                mir_h = (h == 1) ? -2 : ((h == p.S - 2) ? 2 : 0);
+                mir_w = (w == 1) ? -2 : ((w == p.S - 2) ? 2 : 0);
+            }
+            const int n_lo = __shfl_sync(0xffffffffu, n_img, 0);
+            const int n_hi = __shfl_sync(0xffffffffu, n_img, 31);
+
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(ew * 32) << 16);
+
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_row + c0, v);
+                tmem_ld_wait();
+                float x[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+                if (flags & (EPI_BIAS | EPI_BORDER_BIAS)) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] += sbias[c0 + j];
+                }
+                if (flags & EPI_PRELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = x[j] > 0.f ? x[j] : x[j] * sslope[c0 + j];
+                }
+                if (flags & EPI_RESIDUAL) {
+                    if (valid) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(p.res + (long long)m * p.ldres + n0 + c0);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint4 r = __ldg(rp + q);
+                            x[q * 8 + 0] += bf16lo(r.x); x[q * 8 + 1] += bf16hi(r.x);
+                            x[q * 8 + 2] += bf16lo(r.y); x[q * 8 + 3] += bf16hi(r.y);
+                            x[q * 8 + 4] += bf16lo(r.z); x[q * 8 + 5] += bf16hi(r.z);
+                            x[q * 8 + 6] += bf16lo(r.w); x[q * 8 + 7] += bf16hi(r.w);
+                        }
+                    }
+                }
+                if (flags & EPI_SIGMOID) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = sigmoidf_fast(x[j]);
+                }
+                if (!valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = 0.f;
+                }
+                if (flags & EPI_OUT_F32_ATOMIC) {
+                    if (valid) {
+                        float* o = p.out_f32 + (long long)m * p.Cout + n0 + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) atomicAdd(o + j, x[j]);
+                    }
+                }
+                if (flags & EPI_OUT_F32) {
+                    if (m < p.M) {
+                        float4* o = reinterpret_cast<float4*>(p.out_f32 + (long long)m * p.Cout + n0 + c0);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) o[q] = make_float4(x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
+                    }
+                }
+                if (do_store) {
+                    uint4 pk[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        pk[q].x = pack_bf16x2(x[q * 8 + 0], x[q * 8 + 1]);
+                        pk[q].y = pack_bf16x2(x[q * 8 + 2], x[q * 8 + 3]);
+                        pk[q].z = pack_bf16x2(x[q * 8 + 4], x[q * 8 + 5]);
+                        pk[q].w = pack_bf16x2(x[q * 8 + 6], x[q * 8 + 7]);
+                    }
+                    uint4* o = reinterpret_cast<uint4*>(orow + c0);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) o[q] = pk[q];
+                    if (flags & EPI_OUT_REFLECT) {
+                        if (mir_h) {
+                            uint4* o2 = reinterpret_cast<uint4*>(orow + (long long)mir_h * p.Wp * p.ldo + c0);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) o2[q] = pk[q];
+                        }
+                        if (mir_w) {
+                            uint4* o2 = reinterpret_cast<uint4*>(orow + (long long)mir_w * p.ldo + c0);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) o2[q] = pk[q];
+                        }
+                        if (mir_h && mir_w) {
+                            uint4* o2 = reinterpret_cast<uint4*>(orow + ((long long)mir_h * p.Wp + mir_w) * p.ldo + c0);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) o2[q] = pk[q];
+                        }
+                    }
+                }
+                if (flags & EPI_STATS) {   // x is already zero on invalid rows
+                    float sq[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sq[j] = x[j] * x[j];
+                    float xs[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) xs[j] = x[j];
+                    const float s1 = warp_colsum32(xs, lane);
+                    const float s2 = warp_colsum32(sq, lane);
+                    atomicAdd(p.stats + n0 + c0 + lane, s1);
+                    atomicAdd(p.stats + p.Cout + n0 + c0 + lane, s2);
+                }
+                if (flags & EPI_POOL) {    // x is already zero on invalid rows
+                    if (n_lo == n_hi) {
+                        const float s = warp_colsum32(x, lane);
+                        if (n_lo < p.n_img) atomicAdd(p.pool + (long long)n_lo * p.Cout + n0 + c0 + lane, s);
+                    } else {               // the warp's 32 rows straddle two images
+                        float xb[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            xb[j] = (n_img == n_lo) ? 0.f : x[j];
+                            x[j] = (n_img == n_lo) ? x[j] : 0.f;
+                        }
+                        const float sa = warp_colsum32(x, lane);
+                        const float sb = warp_colsum32(xb, lane);
+                        if (n_lo < p.n_img) atomicAdd(p.pool + (long long)n_lo * p.Cout + n0 + c0 + lane, sa);
+                        if (n_hi < p.n_img) atomicAdd(p.pool + (long long)n_hi * p.Cout + n0 + c0 + lane, sb);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    }
+}
+
+template <int BN>
+static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int grid,
+                      cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FFR_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    conv_gemm_kernel<BN><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+    return launch_status("conv_gemm_kernel");
+}
+
+// Host entry used by every C-ABI wrapper. `a`: activation matrix [a_rows, a_ld]; `wp`: packed weights
+// [Cout, ntaps*Cin]. Fills the tiling fields of `p` (M, Cout, ntaps, kb_per_tap, taps, geometry and epilogue
+// fields must be set by the caller).
+int conv_gemm_launch(const void* a, long long a_rows, int a_cols, int a_ld, const void* wp, int Cin, ConvGemmParams p,
+                     int num_splits, cudaStream_t stream) {
+    FFR_CHECK_ARG(Cin % BLOCK_K == 0, "conv_gemm: Cin=%d not a multiple of 64", Cin);
+    FFR_CHECK_ARG(p.Cout % 64 == 0, "conv_gemm: Cout=%d not a multiple of 64", p.Cout);
+    FFR_CHECK_ARG(p.ntaps >= 1 && p.ntaps <= 9, "conv_gemm: ntaps=%d", p.ntaps);
+    const int BN = (p.Cout % 256 == 0) ? 256 : ((p.Cout % 128 == 0) ? 128 : 64);
+    p.kb_per_tap = Cin / BLOCK_K;
+    const int kb_total = p.ntaps * p.kb_per_tap;
+    if (num_splits < 1) num_splits = 1;
+    p.kb_per_split = (kb_total + num_splits - 1) / num_splits;
+    p.num_splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
+    p.num_m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+    p.num_n_tiles = p.Cout / BN;
+    FFR_CHECK_ARG(p.num_splits == 1 || (p.flags & EPI_OUT_F32_ATOMIC), "conv_gemm: split-K needs the atomic epilogue");
+    if (p.flags & (EPI_POOL | EPI_OUT_S2D | EPI_BORDER_BIAS | EPI_OUT_REFLECT))
+        FFR_CHECK_ARG(p.flags & EPI_GEOM, "conv_gemm: epilogue needs row geometry");
+    if (p.flags & EPI_GEOM) FFR_CHECK_ARG(p.rows_per_img >= 32 && p.Wp > 0, "conv_gemm: bad geometry");
+
+    CUtensorMap tmA, tmB;
+    int rc = make_tmap_2d_bf16(&tmA, a, (uint64_t)a_rows, (uint64_t)a_cols, (uint64_t)a_ld, BLOCK_M);
+    if (rc) return rc;
+    rc = make_tmap_2d_bf16(&tmB, wp, (uint64_t)p.Cout, (uint64_t)p.ntaps * Cin, (uint64_t)p.ntaps * Cin, BN);
+    if (rc) return rc;
+
+    const long long num_work = (long long)p.num_m_tiles * p.num_n_tiles * p.num_splits;
+    const int grid = (int)((num_work < num_sms()) ? num_work : num_sms());
+    if (grid == 0) return 0;
+    switch (BN) {
+        case 256: return launch_cfg<256>(tmA, tmB, p, grid, stream);
+        case 128: return launch_cfg<128>(tmA, tmB, p, grid, stream);
+        default:  return launch_cfg<64>(tmA, tmB, p, grid, stream);
+    }
+}
+
+}  // namespace ffr

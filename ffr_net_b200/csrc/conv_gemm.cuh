@@ -1,0 +1,59 @@
+// Shifted-row implicit-GEMM on tcgen05 (sm_100a).
+//
+//   D[m, co] = sum_{tap} sum_{c < Cin}  A[m + row_shift[tap], ch_off[tap] + c] * Wp[co, tap*Cin + c]
+//
+// A is a row-major bf16 matrix whose rows are pixels of a "halo-shared flat NHWC" activation:
+// a 3x3 convolution tap is then nothing but a row offset, so every A tile is a plain 2-D TMA box and the
+// zero padding comes from rows that are stored as zeros (or from TMA out-of-bounds fill at the tensor ends).
+// Wp is the packed K-major weight matrix [Cout, ntaps*Cin]. Accumulators live in TMEM (double buffered, so the
+// epilogue of tile i overlaps the MMAs of tile i+1); one thread issues tcgen05.mma, one thread issues TMA, four
+// warps run the fused epilogue straight out of TMEM.
+#pragma once
+#include <cstdint>
+#include <cuda_bf16.h>
+
+namespace ffr {
+
+enum EpiFlags : uint32_t {
+    EPI_BIAS        = 1u << 0,   // + bias[co]
+    EPI_BORDER_BIAS = 1u << 1,   // + bias9[border_class(h,w)][co]  (pre-conv BatchNorm shift under zero padding)
+    EPI_PRELU       = 1u << 2,   // x > 0 ? x : slope[co] * x
+    EPI_GEOM        = 1u << 3,   // rows carry (n,h,w); pad rows (h==S or w==S) are invalid
+    EPI_POOL        = 1u << 4,   // atomically accumulate per-(image, co) sums of valid rows (SE squeeze)
+    EPI_OUT_S2D     = 1u << 5,   // scatter valid rows into the space-to-depth layout of the next stride-2 conv
+    EPI_OUT_F32_ATOMIC = 1u << 6,// split-K: atomicAdd fp32 partial sums into out_f32[m, co]
+    EPI_SIGMOID     = 1u << 7,   // 1 / (1 + exp(-x)) after everything else
+    EPI_OUT_REFLECT = 1u << 8,   // write valid rows of a 9x9-haloed 7x7 map and mirror them into the reflection halo
+    EPI_RESIDUAL    = 1u << 9,   // + res[m, co] (bf16, same row grid) after PReLU
+    EPI_STATS       = 1u << 10,  // atomically accumulate per-co sum and sum of squares of valid rows (batch-stat BN)
+    EPI_OUT_F32     = 1u << 11,  // plain fp32 store to out_f32[m, co] (no atomics)
+};
+
+struct ConvGemmParams {
+    // GEMM shape
+    int M;              // rows of the output grid
+    int Cout;           // total output channels (multiple of the N tile)
+    int num_m_tiles, num_n_tiles, num_splits;
+    int ntaps;          // 1..9
+    int kb_per_tap;     // Cin / 64
+    int kb_per_split;   // k-blocks per split (ntaps * kb_per_tap when num_splits == 1)
+    int tap_row_shift[9];
+    int tap_ch_off[9];
+    // row geometry (EPI_GEOM): row m = n * rows_per_img + h * Wp + w ; valid iff h0 <= h < h0+S and w0 <= w < w0+S
+    int rows_per_img, Wp, S, h0;
+    int n_img;
+    // epilogue
+    uint32_t flags;
+    const float* bias;     // [Cout] or [9][Cout]
+    const float* slope;    // [Cout]
+    __nv_bfloat16* out;    // bf16 output, row pitch ldo elements
+    int ldo;
+    int s2d_So;            // EPI_OUT_S2D: output grid is (So+1)x(So+1) rows per image, 4*Cout channels
+    float* pool;           // [n_img, Cout]
+    float* out_f32;        // [M, Cout]
+    const __nv_bfloat16* res;  // residual, row pitch ldres
+    int ldres;
+    float* stats;          // [2, Cout] : sum, sum of squares
+};
+
+}  // namespace ffr

@@ -1,0 +1,40 @@
+// Host-side helpers shared by the C-ABI entry points: error reporting and TMA tensor-map encoding.
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace ffr {
+
+// Thread-local message behind ffr_last_error().
+char* last_error_buf();
+int set_error(int code, const char* fmt, ...);
+
+#define FFR_CHECK_ARG(cond, ...)                            \
+    do {                                                    \
+        if (!(cond)) return ::ffr::set_error(-1, __VA_ARGS__); \
+    } while (0)
+
+#define FFR_CUDA(expr)                                                                               \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return ::ffr::set_error(static_cast<int>(_e), "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+inline int launch_status(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(static_cast<int>(e), "%s launch failed: %s", what, cudaGetErrorString(e));
+    return 0;
+}
+
+// 2-D bf16 row-major matrix [rows, cols] with row pitch `ld` elements; box = [box_rows, 64 cols]
+// (64 bf16 = 128 B = one SWIZZLE_128B row). Out-of-bounds elements read as zero.
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                      uint32_t box_rows, uint32_t box_cols = 64);
+
+int num_sms();
+
+}  // namespace ffr

@@ -1,0 +1,79 @@
+// Hardware-semantics probe (debug entry point, not on the product path):
+// does a SWIZZLE_128B K-major UMMA descriptor whose start address is offset by a whole number of 128-byte rows
+// (not a multiple of the 1024-byte swizzle atom) read rows [r0, r0+128) of a TMA-written tile?
+// variant 0: base_offset field = 0; variant 1: base_offset = (start_address >> 7) & 7.
+// The answer decides how the sliding-window convolution kernel addresses its taps.
+#include "../../include/ffr_sm100.h"
+#include "host.h"
+#include "ptx.cuh"
+
+namespace ffr {
+
+__global__ void __launch_bounds__(128, 1)
+rowshift_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* out,
+                      int row_off, int variant) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;                 // 256 rows x 128 B
+    uint8_t* sB = smem + 256 * 128;     // 64 rows x 128 B
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 256 * 128 + 64 * 128);
+    uint64_t* mma_bar = bar + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_init(mma_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc<64>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(bar, 256 * 128 + 64 * 128);
+        tma_load_2d(sA, &tmA, bar, 0, 0);
+        tma_load_2d(sB, &tmB, bar, 0, 0);
+        mbar_wait(bar, 0);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(sA) + row_off * 128;
+        const uint32_t b_addr = smem_u32(sB);
+        const uint32_t bo = variant ? ((a_addr >> 7) & 7u) : 0u;
+        constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+        for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base, umma_smem_desc_sw128(a_addr + k * 32, bo), umma_smem_desc_sw128(b_addr + k * 32),
+                      idesc, k > 0);
+        umma_commit(mma_bar);
+    }
+    __syncwarp();
+    mbar_wait(mma_bar, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + c0 + (static_cast<uint32_t>(warp * 32) << 16), v);
+        tmem_ld_wait();
+        for (int j = 0; j < 32; ++j) out[(warp * 32 + lane) * 64 + c0 + j] = __uint_as_float(v[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc<64>(tmem_base);
+    }
+}
+
+}  // namespace ffr
+
+extern "C" FFR_API int ffr_debug_rowshift_probe(const void* a, const void* w, float* out, int row_off, int variant,
+                                                ffr_stream_t stream) {
+    using namespace ffr;
+    CUtensorMap tmA, tmB;
+    int rc = make_tmap_2d_bf16(&tmA, a, 256, 64, 64, 256);
+    if (rc) return rc;
+    rc = make_tmap_2d_bf16(&tmB, w, 64, 64, 64, 64);
+    if (rc) return rc;
+    const int smem = 1024 + 256 * 128 + 64 * 128 + 64;
+    FFR_CUDA(cudaFuncSetAttribute(rowshift_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    rowshift_probe_kernel<<<1, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tmA, tmB, out, row_off, variant);
+    return launch_status("rowshift_probe_kernel");
+}

@@ -1,0 +1,113 @@
+/*
+ * libffr_sm100 — C ABI of the B200-native (sm_100a) FFR-Net hot path.
+ *
+ * The reference (haoosz/FFR-Net) has no FFI: its operator surface is the PyTorch nn.Module layer
+ * (pretrain/model_ir_se50.py, models/recnet.py, lfw/lfw_eval.py). Each entry point below replaces the library
+ * kernels one reference call site dispatches to; the citation names that call site. The Python modules in
+ * ffr_net_b200/ (same class names, constructor arguments and state_dict keys as the reference) bind these
+ * functions with ctypes — see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (16-byte aligned); the library never allocates or frees
+ *     device memory and never synchronises: work is enqueued on `stream`;
+ *   - return 0 on success, <0 for an argument/shape/driver-lookup error, >0 for a cudaError_t;
+ *     ffr_last_error() returns a thread-local message for the last non-zero return;
+ *   - activations are bf16 in the "halo-shared flat NHWC" layout: an SxS map of C channels is a row-major matrix
+ *     with n_img*(S+1)^2 rows of C elements, pixel (n,h,w) in row n*(S+1)^2 + h*(S+1) + w, rows with h==S or w==S
+ *     being zero padding shared by neighbouring rows/images (DESIGN.md "Data layout");
+ *   - packed conv weights are bf16 [Cout][ntaps*Cin], k = (r*3+s)*Cin + ci (BatchNorm scales folded in on the host).
+ */
+#ifndef FFR_SM100_H_
+#define FFR_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* ffr_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define FFR_API __attribute__((visibility("default")))
+#else
+#define FFR_API
+#endif
+
+/* Epilogue flags of the implicit-GEMM kernel (values mirror ffr::EpiFlags). */
+#define FFR_EPI_BIAS           (1u << 0)
+#define FFR_EPI_BORDER_BIAS    (1u << 1)
+#define FFR_EPI_PRELU          (1u << 2)
+#define FFR_EPI_GEOM           (1u << 3)
+#define FFR_EPI_POOL           (1u << 4)
+#define FFR_EPI_OUT_S2D        (1u << 5)
+#define FFR_EPI_OUT_F32_ATOMIC (1u << 6)
+#define FFR_EPI_SIGMOID        (1u << 7)
+#define FFR_EPI_OUT_REFLECT    (1u << 8)
+#define FFR_EPI_RESIDUAL       (1u << 9)
+#define FFR_EPI_STATS          (1u << 10)
+#define FFR_EPI_OUT_F32        (1u << 11)
+
+FFR_API int ffr_version(void);
+FFR_API const char* ffr_last_error(void);
+
+/* Generic shifted-row implicit GEMM on tcgen05/TMEM/TMA (ffr_net_b200/csrc/conv_gemm.cu):
+ *   D[m,co] = sum_t sum_c A[m + tap_row_shift[t], tap_ch_off[t] + c] * Wp[co, t*Cin + c], then the fused epilogue.
+ * Replaces every nn.Conv2d / nn.Linear GEMM of the path (model_ir_se50.py:63-69,118,124; recnet.py:65,373-385). */
+FFR_API int ffr_conv_gemm(const void* a, int64_t a_rows, int a_cols, int a_ld, const void* wp, int Cin, int Cout, int ntaps,
+                  const int* tap_row_shift, const int* tap_ch_off, int M, int rows_per_img, int Wp, int S, int h0,
+                  int n_img, uint32_t flags, const float* bias, const float* slope, void* out, int ldo, int s2d_So,
+                  float* pool, float* out_f32, const void* res, int ldres, float* stats, int num_splits,
+                  ffr_stream_t stream);
+
+/* Conv2d(Cin,Cout,3,stride 1,pad 1) on a flat SxS map (model_ir_se50.py:67 with the BatchNorm of :66 folded:
+ * scale into wp, shift into the 9-class border bias table `bias9` [9][Cout]) + PReLU (:68).
+ * out_s2d != 0 writes the space-to-depth layout consumed by ffr_conv3x3_s2_fwd. */
+FFR_API int ffr_conv3x3_bnpre_prelu_fwd(const void* x, int n_img, int S, int Cin, const void* wp, int Cout,
+                                const float* bias9, const float* slope, void* out, int out_s2d, ffr_stream_t stream);
+
+/* Conv2d(C,Cout,3,stride,pad 1) + BatchNorm (model_ir_se50.py:69-70; scale folded into wp, shift = bias) and the
+ * SE squeeze: per-(image,channel) sums of the result are atomically added into pool[n_img][Cout] (:31, zero it first).
+ * stride 1: x is flat SxS. stride 2: x is the space-to-depth map written by ffr_conv3x3_bnpre_prelu_fwd
+ * (rows of the (S/2+1)^2 grid, 4*C channels); S is the INPUT size. Output is flat (S/stride)x(S/stride). */
+FFR_API int ffr_conv3x3_bn_pool_fwd(const void* x, int n_img, int S, int C, int stride, const void* wp, int Cout,
+                            const float* bias, void* out, float* pool, ffr_stream_t stream);
+
+/* Conv2d(Cin,Cout,1,stride 2)+BatchNorm shortcut (model_ir_se50.py:62-64) on an already subsampled flat map. */
+FFR_API int ffr_conv1x1_bn_fwd(const void* xs, int n_img, int S, int Cin, const void* wp, int Cout, const float* bias,
+                       void* out, ffr_stream_t stream);
+
+/* out(n,h,w) = x(n,2h,2w) on flat maps; So = output size (MaxPool2d(1,2) / stride of the 1x1 conv, :60,63). */
+FFR_API int ffr_subsample2(const void* x, void* out, int n_img, int So, int C, ffr_stream_t stream);
+
+/* input_layer: Conv2d(3,64,3,1,1)+BatchNorm+PReLU on fp32 NCHW images (model_ir_se50.py:118-120).
+ * w [27][64] fp32 (k = ci*9+r*3+s, BN scale folded), b [64] BN shift, a [64] PReLU slopes; out flat bf16 SxS x 64. */
+FFR_API int ffr_stem_fwd(const float* x, const float* w, const float* b, const float* a, void* out, int n_img, int S,
+                 ffr_stream_t stream);
+
+/* SEModule gate + residual add (model_ir_se50.py:29-36,73-76): y = u*sigmoid(W2 relu(W1 mean(u))) + shortcut.
+ * pool = per-(image,channel) sums of u; shortcut_mode 0: same-grid x, 1: x on the 2Sx2S grid (MaxPool2d(1,2)),
+ * 2: same-grid conv shortcut. w1 [C/16][C], w2 [C][C/16] fp32. */
+FFR_API int ffr_se_residual_fwd(const void* u, const float* pool, const float* w1, const float* w2, const void* shortcut,
+                        int shortcut_mode, void* y, int n_img, int S, int C, ffr_stream_t stream);
+
+/* y = bn(h) exported as fp32 NCHW (model_ir_se50.py:126,139). */
+FFR_API int ffr_export_nchw_fwd(const void* h, const float* scale, const float* shift, float* y, int n_img, int S, int C,
+                        ffr_stream_t stream);
+
+/* output_layer (BatchNorm2d -> Dropout(eval) -> Flatten -> Linear(25088,512) -> BatchNorm1d) + l2_norm
+ * (model_ir_se50.py:121-125,13-16,141). wp: folded bf16 weights [512][(S+1)^2*C] over the flat rows of one image
+ * (zero columns at pad pixels), bias [512] folded; acc [n_img][512] fp32 scratch; f [n_img][512] fp32. */
+FFR_API int ffr_head_fwd(const void* h, int n_img, int S, int C, const void* wp, const float* bias, float* acc, float* f,
+                 ffr_stream_t stream);
+
+/* Debug: hardware-semantics probe for row-offset UMMA descriptors (csrc/probe.cu); not on the product path.
+ * a [256][64] bf16, w [64][64] bf16, out [128][64] fp32 = a[row_off : row_off+128] @ w^T. */
+FFR_API int ffr_debug_rowshift_probe(const void* a, const void* w, float* out, int row_off, int variant,
+                                     ffr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFR_SM100_H_ */

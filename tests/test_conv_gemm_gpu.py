@@ -1,0 +1,174 @@
+"""GPU parity of the tcgen05 implicit-GEMM kernel (through the C ABI) against torch fp32 on bf16-rounded operands.
+
+Integer-exact checks where the arithmetic allows (small-integer operands make fp32 accumulation exact), tolerance
+2e-3 relative otherwise (fp32 accumulation-order differences on bf16 operands; stated per test)."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from ffr_net_b200 import _lib, layout
+import emulate
+
+pytestmark = pytest.mark.gpu
+
+P = _lib.ptr
+EPI = dict(BIAS=1, BORDER=2, PRELU=4, GEOM=8, POOL=16, S2D=32, F32ATOMIC=64, SIGMOID=128, REFLECT=256, RESIDUAL=512,
+           STATS=1024, F32=2048)
+
+
+def _stream():
+    return _lib.stream_ptr()
+
+
+def _gemm(lib, a, wp, cin, cout, taps, M, flags=0, bias=None, slope=None, out=None, ldo=0, geom=(64, 1, 1, 0, 1),
+          s2d_so=0, pool=None, out_f32=None, res=None, ldres=0, stats=None, splits=1):
+    shifts = (ctypes.c_int * 9)(*([t[0] for t in taps] + [0] * (9 - len(taps))))
+    choffs = (ctypes.c_int * 9)(*([t[1] for t in taps] + [0] * (9 - len(taps))))
+    rpi, wp_, s, h0, nimg = geom
+    rc = lib.ffr_conv_gemm(P(a), a.shape[0], a.shape[1], a.stride(0), P(wp), cin, cout, len(taps), shifts, choffs, M,
+                           rpi, wp_, s, h0, nimg, flags, P(bias), P(slope), P(out), ldo, s2d_so, P(pool), P(out_f32),
+                           P(res), ldres, P(stats), splits, _stream())
+    _lib.check(rc, "ffr_conv_gemm")
+
+
+@pytest.mark.parametrize("cout", [64, 128, 256, 512])
+@pytest.mark.parametrize("M,K", [(128, 64), (300, 192), (1000, 576)])
+def test_plain_gemm_exact(lib, cout, M, K):
+    """Small-integer operands: every product and partial sum is exactly representable -> bit-exact vs torch."""
+    g = torch.Generator(device="cuda").manual_seed(M + K + cout)
+    a = torch.randint(-3, 4, (M, K), generator=g, device="cuda").to(torch.bfloat16)
+    w = torch.randint(-2, 3, (cout, K), generator=g, device="cuda").to(torch.bfloat16)
+    out = torch.full((M, cout), 7.0, dtype=torch.bfloat16, device="cuda")
+    _gemm(lib, a, w, K, cout, [(0, 0)], M, out=out, ldo=cout)
+    torch.cuda.synchronize()
+    ref = (a.float() @ w.float().t())
+    assert torch.equal(out.float(), ref.to(torch.bfloat16).float())
+
+
+def test_gemm_f32_out_and_bias(lib):
+    M, K, cout = 515, 256, 128
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.randn(M, K, generator=g, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(cout, K, generator=g, device="cuda") * 0.1).to(torch.bfloat16)
+    bias = torch.randn(cout, generator=g, device="cuda")
+    out = torch.zeros(M, cout, dtype=torch.float32, device="cuda")
+    _gemm(lib, a, w, K, cout, [(0, 0)], M, flags=EPI["BIAS"] | EPI["F32"], bias=bias, out_f32=out)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + bias
+    assert (out - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("splits", [2, 5, 16])
+def test_splitk_atomic(lib, splits):
+    M, K, cout = 200, 2048, 512
+    g = torch.Generator(device="cuda").manual_seed(2)
+    a = torch.randint(-2, 3, (M, K), generator=g, device="cuda").to(torch.bfloat16)
+    w = torch.randint(-2, 3, (cout, K), generator=g, device="cuda").to(torch.bfloat16)
+    out = torch.zeros(M, cout, dtype=torch.float32, device="cuda")
+    _gemm(lib, a, w, K, cout, [(0, 0)], M, flags=EPI["F32ATOMIC"], out_f32=out, splits=splits)
+    torch.cuda.synchronize()
+    assert torch.equal(out, a.float() @ w.float().t())   # integer-valued: exact in any order
+
+
+@pytest.mark.parametrize("n,S,cin,cout", [(3, 14, 64, 64), (2, 7, 128, 256), (5, 28, 64, 128), (2, 14, 256, 512)])
+def test_conv3x3_bnpre_prelu(lib, n, S, cin, cout):
+    """conv(pad0(BN(x))) + PReLU through ffr_conv3x3_bnpre_prelu_fwd vs F.conv2d on the same bf16-rounded operands.
+    Tolerance 2e-3 of max|ref| (fp32 accumulation order) + bf16 output rounding (2^-8 relative)."""
+    from ffr_net_b200 import packing
+    g = torch.Generator(device="cuda").manual_seed(n * S + cin)
+    x = torch.randn(n, cin, S, S, generator=g, device="cuda")
+    w = torch.randn(cout, cin, 3, 3, generator=g, device="cuda") / (3 * cin ** 0.5)
+    s0 = torch.empty(cin, device="cuda").uniform_(0.8, 1.2, generator=g)
+    b0 = torch.empty(cin, device="cuda").uniform_(-0.3, 0.3, generator=g)
+    slope = torch.empty(cout, device="cuda").uniform_(0.1, 0.4, generator=g)
+    wp = packing.pack_conv(w, in_scale=s0)
+    bias9 = packing.border_bias_table(w, b0)
+    xf = layout.to_flat(x)
+    out = torch.full((xf.shape[0], cout), 3.0, dtype=torch.bfloat16, device="cuda")
+    rc = lib.ffr_conv3x3_bnpre_prelu_fwd(P(xf), n, S, cin, P(wp), cout, P(bias9), P(slope), P(out), 0, _stream())
+    _lib.check(rc)
+    torch.cuda.synchronize()
+    # reference on the operands the kernel sees: bf16 x, bf16 folded weights; the shift part in fp32
+    xb = layout.from_flat(xf, n, S, cin)
+    wb = wp.float().reshape(cout, 3, 3, cin).permute(0, 3, 1, 2)
+    shift_map = b0.view(1, -1, 1, 1).expand(n, cin, S, S)
+    ref = F.conv2d(xb, wb, padding=1) + F.conv2d(shift_map, w, padding=1)
+    ref = torch.where(ref > 0, ref, ref * slope.view(1, -1, 1, 1))
+    got = layout.from_flat(out, n, S, cout)
+    tol = 2e-3 * ref.abs().max().item() + 2 ** -8 * ref.abs().max().item()
+    assert (got - ref).abs().max().item() <= tol
+    assert layout.flat_pad_rows(out, n, S, cout).abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("n,S,c,cout,stride", [(3, 14, 64, 64, 1), (2, 14, 128, 128, 2), (4, 28, 64, 64, 2),
+                                                (2, 7, 512, 512, 1)])
+def test_conv3x3_bn_pool(lib, n, S, c, cout, stride):
+    from ffr_net_b200 import packing
+    g = torch.Generator(device="cuda").manual_seed(S + c + stride)
+    x = torch.randn(n, c, S, S, generator=g, device="cuda")
+    w = torch.randn(cout, c, 3, 3, generator=g, device="cuda") / (3 * c ** 0.5)
+    s1 = torch.empty(cout, device="cuda").uniform_(0.8, 1.2, generator=g)
+    b1 = torch.empty(cout, device="cuda").uniform_(-0.3, 0.3, generator=g)
+    wp = packing.pack_conv(w, out_scale=s1)
+    xin = layout.to_flat(x) if stride == 1 else layout.to_s2d(x)
+    so = S // stride
+    rows = n * (so + 1) * (so + 1)
+    out = torch.full((rows, cout), 3.0, dtype=torch.bfloat16, device="cuda")
+    pool = torch.full((n, cout), 5.0, dtype=torch.float32, device="cuda")
+    rc = lib.ffr_conv3x3_bn_pool_fwd(P(xin), n, S, c, stride, P(wp), cout, P(b1), P(out), P(pool), _stream())
+    _lib.check(rc)
+    torch.cuda.synchronize()
+    xb = x.to(torch.bfloat16).float()
+    wb = wp.float().reshape(cout, 3, 3, c).permute(0, 3, 1, 2)
+    ref = F.conv2d(xb, wb, stride=stride, padding=1) + b1.view(1, -1, 1, 1)
+    got = layout.from_flat(out, n, so, cout)
+    scale = ref.abs().max().item()
+    assert (got - ref).abs().max().item() <= (2e-3 + 2 ** -8) * scale
+    assert layout.flat_pad_rows(out, n, so, cout).abs().max().item() == 0.0
+    ref_pool = ref.sum(dim=(2, 3))
+    assert (pool - ref_pool).abs().max().item() <= 2e-3 * scale * so * so ** 0.5 + 1e-3
+
+
+def test_conv3x3_s2d_output_roundtrip(lib):
+    """conv1 writing the space-to-depth layout, then the stride-2 conv reading it == conv -> prelu -> stride-2 conv."""
+    from ffr_net_b200 import packing
+    n, S, cin, c = 2, 28, 64, 128
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(n, cin, S, S, generator=g, device="cuda")
+    w1 = torch.randn(c, cin, 3, 3, generator=g, device="cuda") / (3 * cin ** 0.5)
+    w2 = torch.randn(c, c, 3, 3, generator=g, device="cuda") / (3 * c ** 0.5)
+    slope = torch.empty(c, device="cuda").uniform_(0.1, 0.4, generator=g)
+    zeros9 = torch.zeros(9, c, device="cuda")
+    zb = torch.zeros(c, device="cuda")
+    wp1, wp2 = packing.pack_conv(w1), packing.pack_conv(w2)
+    so = S // 2
+    t = torch.zeros(n * (so + 1) ** 2, 4 * c, dtype=torch.bfloat16, device="cuda")
+    out = torch.empty(n * (so + 1) ** 2, c, dtype=torch.bfloat16, device="cuda")
+    xf = layout.to_flat(x)
+    _lib.check(lib.ffr_conv3x3_bnpre_prelu_fwd(P(xf), n, S, cin, P(wp1), c, P(zeros9), P(slope), P(t), 1, _stream()))
+    _lib.check(lib.ffr_conv3x3_bn_pool_fwd(P(t), n, S, c, 2, P(wp2), c, P(zb), P(out), None, _stream()))
+    torch.cuda.synchronize()
+    xb = x.to(torch.bfloat16).float()
+    r1 = F.conv2d(xb, wp1.float().reshape(c, 3, 3, cin).permute(0, 3, 1, 2), padding=1)
+    r1 = torch.where(r1 > 0, r1, r1 * slope.view(1, -1, 1, 1)).to(torch.bfloat16).float()
+    assert (layout.from_s2d(t, n, S, c) - r1).abs().max().item() <= 2 ** -7 * r1.abs().max().item()
+    t_exact = layout.from_s2d(t, n, S, c)
+    r2 = F.conv2d(t_exact, wp2.float().reshape(c, 3, 3, c).permute(0, 3, 1, 2), stride=2, padding=1)
+    got = layout.from_flat(out, n, so, c)
+    assert (got - r2).abs().max().item() <= (2e-3 + 2 ** -8) * r2.abs().max().item()
+
+
+def test_emulation_matches_kernel(lib):
+    """The torch emulation used by the CPU tests is the same function as the kernel (ties CPU tests to the device)."""
+    n, S, cin, cout = 2, 14, 64, 64
+    G = S + 1
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randint(-2, 3, (n * G * G, cin), generator=g, device="cuda").to(torch.bfloat16)
+    w = torch.randint(-2, 3, (cout, 9 * cin), generator=g, device="cuda").to(torch.bfloat16)
+    out = torch.zeros(n * G * G, cout, dtype=torch.float32, device="cuda")
+    taps = emulate.taps_3x3_flat(G)
+    _gemm(lib, a, w, cin, cout, taps, n * G * G, flags=EPI["F32"], out_f32=out)
+    torch.cuda.synchronize()
+    assert torch.equal(out, emulate.conv_gemm(a, w, cin, taps))

@@ -1,0 +1,34 @@
+"""Hardware-semantics probe: row-offset UMMA descriptors on a SWIZZLE_128B tile (csrc/probe.cu).
+Records which descriptor variant addresses rows [r0, r0+128) correctly; the sliding-window conv kernel relies on it."""
+import json
+import os
+
+import pytest
+import torch
+
+from ffr_net_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def test_rowshift_descriptor_semantics(lib):
+    g = torch.Generator(device="cuda").manual_seed(0)
+    a = torch.randint(-4, 5, (256, 64), generator=g, device="cuda").to(torch.bfloat16)
+    w = torch.randint(-2, 3, (64, 64), generator=g, device="cuda").to(torch.bfloat16)
+    result = {}
+    for variant in (0, 1):
+        ok = []
+        for r0 in (0, 1, 3, 7, 8, 15, 16, 17, 29, 64, 100, 128):
+            out = torch.zeros(128, 64, dtype=torch.float32, device="cuda")
+            _lib.check(lib.ffr_debug_rowshift_probe(_lib.ptr(a), _lib.ptr(w), _lib.ptr(out), r0, variant,
+                                                    _lib.stream_ptr()))
+            torch.cuda.synchronize()
+            ref = a[r0:r0 + 128].float() @ w.float().t()
+            ok.append(bool(torch.equal(out, ref)))
+        result["variant%d" % variant] = ok
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/probe_rowshift.json", "w") as f:
+        json.dump(result, f)
+    print("rowshift probe:", result)
+    assert result["variant0"][0] and result["variant1"][0], "aligned descriptor must work in both variants"
+    assert all(result["variant0"]) or all(result["variant1"]), result
