@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Benchmark of the FFR-Net hot path on B200 (contract: one JSON line on stdout from rank 0).
+
+  python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path (libffr_sm100.so)
+  python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU (oracle port)
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # one process per GPU, weak scaling
+
+Workload (BASELINE.json configs[1] / metric): IR-SE50 [+ RecBlock] embedding extraction, batch 512 per GPU,
+synthetic 112x112 faces, random-init weights. A "step" is one forward pass over one batch.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GFLOP_BACKBONE = 12.5934          # per image, 2*MAC, SURVEY.md §A.1
+GFLOP_RECNET = 2.549              # per sample (2.493 conv/linear + 0.056 bmm), SURVEY.md §A.2
+BATCH = 512
+METRIC = "IR-SE50+RecBlock embeddings/s (bs512)"
+UNIT = "img/s"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p, "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def _cpu_forward_factory(with_recnet):
+    import torch
+    from oracle import backbone as ob
+    sd = ob.synth_backbone_state_dict(0)
+    rsd = None
+    if with_recnet:
+        from oracle import recnet as orr
+        rsd = orr.synth_recnet_state_dict(0)
+
+    def fwd(x):
+        with torch.no_grad():
+            y, f = ob.backbone_forward(sd, x)
+            if rsd is not None:
+                from oracle import recnet as orr
+                v, _ = orr.recnet_forward(rsd, y)
+                return v
+            return f
+    return fwd, ob
+
+
+def cpu_baseline(with_recnet, budget_s=12.0, batch=8):
+    """Reference algorithm (oracle port, fp32 PyTorch CPU ops) on the host cores, bounded sample of the workload."""
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    fwd, ob = _cpu_forward_factory(with_recnet)
+    x = ob.synth_faces(batch, 0)
+    fwd(x)
+    times = []
+    t_end = time.perf_counter() + budget_s
+    while time.perf_counter() < t_end or len(times) < 3:
+        t0 = time.perf_counter()
+        fwd(x)
+        times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return {"value": batch / med, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d forward passes of batch %d (same network, fp32 torch CPU ops, median)" % (len(times), batch)}
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm on the host CPU (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    with_recnet = _have_recnet()
+    fwd, ob = _cpu_forward_factory(with_recnet)
+    batch = 8
+    x = ob.synth_faces(batch, 0)
+    for _ in range(max(1, min(args.warmup, 3))):
+        fwd(x)
+    steps = min(args.steps, 40)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fwd(x)
+    dt = time.perf_counter() - t0
+    value = batch * steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": _config(with_recnet, cpu_sample="each step = one batch-%d forward (bounded sample of the bs512 workload)" % batch),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": "%d steps of batch %d" % (steps, batch)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def _have_recnet():
+    try:
+        from ffr_net_b200 import recnet  # noqa: F401
+        return hasattr(recnet, "RecNet") and getattr(recnet, "READY", False)
+    except Exception:
+        return False
+
+
+def _config(with_recnet, cpu_sample=None):
+    c = {"workload": ("IR-SE50 frozen-backbone embedding extraction + RecNet (RecBlock) rectification"
+                      if with_recnet else "IR-SE50 frozen-backbone embedding extraction (BASELINE configs[1])")
+         + ", batch 512 per GPU, 3x112x112 synthetic faces, random-init weights",
+         "batch_per_gpu": BATCH, "input": "fp32 NCHW (512,3,112,112)", "parallelism": "replicas (batch-sharded, no collective)",
+         "l2": "activation working set (>2 GB per step) and 77 MB input exceed the 126 MB L2; no explicit flush"}
+    if cpu_sample:
+        c["cpu_sample"] = cpu_sample
+    return c
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from oracle import backbone as ob          # synthetic weights/input generator (not on the timed path)
+    from ffr_net_b200 import _lib
+    from ffr_net_b200.backbone import Backbone
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    with_recnet = _have_recnet()
+    enc = Backbone(50, 0.6, "ir_se")
+    enc.load_state_dict(ob.synth_backbone_state_dict(0))
+    enc = enc.to(dev).eval()
+    rec = None
+    if with_recnet:
+        from oracle import recnet as orr
+        from ffr_net_b200.recnet import RecNet
+        rec = RecNet()
+        rec.load_state_dict(orr.synth_recnet_state_dict(0))
+        rec = rec.to(dev).eval()
+
+    base = ob.synth_faces(64, seed=rank)
+    x_host = base.repeat(BATCH // 64, 1, 1, 1).contiguous().pin_memory()
+    x_dev = x_host.to(dev)
+
+    def step(x):
+        with torch.no_grad():
+            if rec is None:
+                _, f = enc(x)
+                return f
+            return rec.embed_from_images(enc, x)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    # ---- device-resident throughput ----
+    for _ in range(args.warmup):
+        step(x_dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.ffr_launch_count()
+    ms = timed(lambda: step(x_dev), args.steps)
+    launches = lib.ffr_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * BATCH * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the module API with host buffers ----
+    out_host = torch.empty(BATCH, 512, dtype=torch.float32).pin_memory()
+    x_stage = torch.empty_like(x_dev)
+
+    def e2e_step():
+        x_stage.copy_(x_host, non_blocking=True)
+        f = step(x_stage)
+        out_host.copy_(f, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_value = world * BATCH * args.steps / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel (256->256 @14x14 implicit GEMM), timed inside a real step ----
+    roof = None
+    cpu = None
+    if rank == 0:
+        peaks, peak_src = _peaks()
+        enc._profile = []
+        e_first = torch.cuda.Event(enable_timing=True)
+        e_first.record()
+        step(x_dev)
+        torch.cuda.synchronize()
+        prev, durs, total = e_first, [], 0.0
+        for what, ev in enc._profile:
+            dt = prev.elapsed_time(ev)
+            total += dt
+            if what.startswith("conv") and "256>256@14s1" in what:
+                durs.append(dt)
+            prev = ev
+        enc._profile = None
+        if durs:
+            flop = 2.0 * BATCH * 196 * 256 * 2304
+            avg_ms = sum(durs) / len(durs)
+            achieved = flop / (avg_ms * 1e-3) / 1e12
+            peak = peaks.get("bf16_tflops_sustained", 1400.0)
+            roof = {"bound": "tensor", "kernel": "conv_gemm_kernel<256> (3x3 256->256 @14x14, %d launches/step)" % len(durs),
+                    "achieved": achieved, "peak": peak, "peak_source": peak_src + " (sustained: timed inside the step)",
+                    "unit": "TFLOP/s", "frac": achieved / peak, "avg_launch_ms": avg_ms,
+                    "share_of_step": sum(durs) / total if total > 0 else None,
+                    "traffic": _ncu_traffic()}
+        if world == 1:
+            cpu = cpu_baseline(with_recnet)
+
+    if rank == 0:
+        gflop = GFLOP_BACKBONE + (GFLOP_RECNET if with_recnet else 0.0)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": _config(with_recnet),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
+                    "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "tflops_whole_step": value * gflop / 1e3,
+            "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture, if present."""
+    path = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -18,6 +18,7 @@ _i64 = ctypes.c_int64
 _SIGNATURES = {
     "ffr_version": (_i, []),
     "ffr_last_error": (ctypes.c_char_p, []),
+    "ffr_launch_count": (ctypes.c_longlong, []),
     "ffr_conv_gemm": (_i, [_p, _i64, _i, _i, _p, _i, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _u32, _p, _p, _p, _i, _i,
                            _p, _p, _p, _i, _p, _i, _p]),
     "ffr_conv3x3_bnpre_prelu_fwd": (_i, [_p, _i, _i, _i, _p, _i, _p, _p, _p, _i, _p]),
@@ -28,6 +29,7 @@ _SIGNATURES = {
     "ffr_se_residual_fwd": (_i, [_p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _p]),
     "ffr_export_nchw_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "ffr_head_fwd": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "ffr_debug_set_window": (_i, [_i]),
     "ffr_debug_rowshift_probe": (_i, [_p, _p, _p, _i, _i, _p]),
 }
 

@@ -209,13 +209,13 @@ class Backbone(nn.Module):
             if u.stride == 2:
                 t = ws.s2d[i]
                 L.check(lib.ffr_conv3x3_bnpre_prelu_fwd(P(cur), n, S, u.cin, P(u.w1), u.depth, P(u.bias9), P(u.slope),
-                                                        P(t), 1, st), "conv1")
+                                                        P(t), 1, st), "conv1 %d>%d@%ds1" % (u.cin, u.depth, S))
             else:
                 t = ws.t
                 L.check(lib.ffr_conv3x3_bnpre_prelu_fwd(P(cur), n, S, u.cin, P(u.w1), u.depth, P(u.bias9), P(u.slope),
-                                                        P(t), 0, st), "conv1")
+                                                        P(t), 0, st), "conv1 %d>%d@%ds1" % (u.cin, u.depth, S))
             L.check(lib.ffr_conv3x3_bn_pool_fwd(P(t), n, S, u.depth, u.stride, P(u.w2), u.depth, P(u.b2), P(ws.u),
-                                                P(ws.pool), st), "conv2")
+                                                P(ws.pool), st), "conv2 %d>%d@%ds%d" % (u.depth, u.depth, S, u.stride))
             if u.cin == u.depth:
                 sc, mode = cur, (1 if u.stride == 2 else 0)
             else:

@@ -17,6 +17,7 @@ int subsample2_launch(const void* x, void* out, int n_img, int So, int C, cudaSt
 int export_nchw_launch(const void* h, const float* scale, const float* shift, float* y, int n_img, int S, int C,
                        cudaStream_t stream);
 int bias_l2norm_launch(const float* acc, const float* bias, float* f, int rows, int D, cudaStream_t stream);
+void set_use_window(bool on);
 }  // namespace ffr
 
 using namespace ffr;
@@ -51,6 +52,10 @@ extern "C" {
 FFR_API int ffr_version(void) { return 100; }
 
 FFR_API const char* ffr_last_error(void) { return last_error_buf(); }
+
+FFR_API long long ffr_launch_count(void) { return launch_count(); }
+
+FFR_API int ffr_debug_set_window(int enable) { set_use_window(enable != 0); return 0; }
 
 FFR_API int ffr_conv_gemm(const void* a, int64_t a_rows, int a_cols, int a_ld, const void* wp, int Cin, int Cout, int ntaps,
                   const int* tap_row_shift, const int* tap_ch_off, int M, int rows_per_img, int Wp, int S, int h0,

@@ -38,6 +38,205 @@ __device__ __forceinline__ float warp_colsum32(float (&x)[32], int lane) {
     return x[0];
 }
 
+// ===================== Epilogue: TMEM -> registers -> fused ops -> global =====================
+// Runs on warps 4..7 (128 threads, thread i <-> TMEM lane i <-> tile row i).
+template <int BN>
+__device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uint32_t tmem_base, uint64_t* tfull_bar,
+                                              uint64_t* tempty_bar, float* sparam, const int warp, const int lane) {
+    const int num_work = p.num_m_tiles * p.num_n_tiles * p.num_splits;
+    const int ew = warp - 4;                     // TMEM lane quadrant == warp % 4
+    const int row_in_tile = ew * 32 + lane;
+    const int etid = threadIdx.x - 128;
+    const uint32_t flags = p.flags;
+    const bool border = (flags & EPI_BORDER_BIAS) != 0;
+    const int nbias = border ? 9 : 1;
+    int loaded_n_tile = -1;
+    int it = 0;
+    for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++it) {
+        const int t = work / p.num_splits;
+        const int n_tile = t % p.num_n_tiles;
+        const int m_tile = t / p.num_n_tiles;
+        const int m0 = m_tile * BLOCK_M;
+        const int n0 = n_tile * BN;
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+
+        if (n_tile != loaded_n_tile) {           // stage per-channel epilogue parameters in smem
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (flags & (EPI_BIAS | EPI_BORDER_BIAS))
+                for (int i = etid; i < nbias * BN; i += EPI_THREADS)
+                    sparam[i] = p.bias[(i / BN) * p.Cout + n0 + (i % BN)];
+            if (flags & EPI_PRELU)
+                for (int i = etid; i < BN; i += EPI_THREADS) sparam[9 * BN + i] = p.slope[n0 + i];
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            loaded_n_tile = n_tile;
+        }
+
+        const int m = m0 + row_in_tile;
+        int n_img = 0, h = 0, w = 0, r_local = 0;
+        bool valid = m < p.M;
+        int cls = 0;
+        if (flags & EPI_GEOM) {
+            n_img = m / p.rows_per_img;
+            r_local = m - n_img * p.rows_per_img;
+            h = r_local / p.Wp;
+            w = r_local - h * p.Wp;
+            h -= p.h0;
+            w -= p.h0;
+            if (!(flags & EPI_SCATTER)) valid = valid && h >= 0 && h < p.S && w >= 0 && w < p.S;
+            if (border) {
+                const int ch = (h == 0) ? 0 : ((h == p.S - 1) ? 2 : 1);
+                const int cw = (w == 0) ? 0 : ((w == p.S - 1) ? 2 : 1);
+                cls = ch * 3 + cw;
+            }
+        }
+        const float* sbias = sparam + cls * BN;
+        const float* sslope = sparam + 9 * BN;
+
+        // output addressing
+        __nv_bfloat16* orow = nullptr;
+        bool do_store = false;
+        __nv_bfloat16* sdst[8];
+        if (flags & EPI_SCATTER) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                sdst[k] = nullptr;
+                if (k < p.scatter_n && m < p.M) {
+                    const int2 e = __ldg(p.scatter + r_local * p.scatter_n + k);
+                    if (e.x >= 0)
+                        sdst[k] = p.out + ((long long)n_img * p.out_rows_per_img + e.x) * p.ldo + e.y + n0;
+                }
+            }
+            valid = valid && sdst[0] != nullptr;
+        } else if (p.out != nullptr) {
+            if (flags & EPI_OUT_S2D) {
+                const int g = p.s2d_So + 1;
+                const long long r = (long long)n_img * g * g + (h >> 1) * g + (w >> 1);
+                orow = p.out + r * p.ldo + ((h & 1) * 2 + (w & 1)) * p.Cout + n0;
+                do_store = valid;
+            } else {
+                orow = p.out + (long long)m * p.ldo + n0;
+                do_store = (m < p.M);
+            }
+        }
+        const int n_lo = __shfl_sync(0xffffffffu, n_img, 0);
+        const int n_hi = __shfl_sync(0xffffffffu, n_img, 31);
+
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(ew * 32) << 16);
+
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_row + c0, v);
+            tmem_ld_wait();
+            float x[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+            if (flags & (EPI_BIAS | EPI_BORDER_BIAS)) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] += sbias[c0 + j];
+            }
+            if (flags & EPI_PRELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = x[j] > 0.f ? x[j] : x[j] * sslope[c0 + j];
+            }
+            if (flags & EPI_RESIDUAL) {
+                if (valid) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(p.res + (long long)m * p.ldres + n0 + c0);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint4 r = __ldg(rp + q);
+                        x[q * 8 + 0] += bf16lo(r.x); x[q * 8 + 1] += bf16hi(r.x);
+                        x[q * 8 + 2] += bf16lo(r.y); x[q * 8 + 3] += bf16hi(r.y);
+                        x[q * 8 + 4] += bf16lo(r.z); x[q * 8 + 5] += bf16hi(r.z);
+                        x[q * 8 + 6] += bf16lo(r.w); x[q * 8 + 7] += bf16hi(r.w);
+                    }
+                }
+            }
+            if (flags & EPI_SIGMOID) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = sigmoidf_fast(x[j]);
+            }
+            if (!valid) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = 0.f;
+            }
+            if (flags & EPI_OUT_F32_ATOMIC) {
+                if (valid) {
+                    float* o = p.out_f32 + (long long)m * p.Cout + n0 + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) atomicAdd(o + j, x[j]);
+                }
+            }
+            if (flags & EPI_OUT_F32) {
+                if (m < p.M) {
+                    float4* o = reinterpret_cast<float4*>(p.out_f32 + (long long)m * p.Cout + n0 + c0);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) o[q] = make_float4(x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
+                }
+            }
+            if (do_store || (flags & EPI_SCATTER)) {
+                uint4 pk[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    pk[q].x = pack_bf16x2(x[q * 8 + 0], x[q * 8 + 1]);
+                    pk[q].y = pack_bf16x2(x[q * 8 + 2], x[q * 8 + 3]);
+                    pk[q].z = pack_bf16x2(x[q * 8 + 4], x[q * 8 + 5]);
+                    pk[q].w = pack_bf16x2(x[q * 8 + 6], x[q * 8 + 7]);
+                }
+                if (do_store) {
+                    uint4* o = reinterpret_cast<uint4*>(orow + c0);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) o[q] = pk[q];
+                }
+                if (flags & EPI_SCATTER) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if (sdst[k] != nullptr) {
+                            uint4* o = reinterpret_cast<uint4*>(sdst[k] + c0);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) o[q] = pk[q];
+                        }
+                    }
+                }
+            }
+            if (flags & EPI_STATS) {   // x is already zero on invalid rows
+                float sq[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sq[j] = x[j] * x[j];
+                float xs[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) xs[j] = x[j];
+                const float s1 = warp_colsum32(xs, lane);
+                const float s2 = warp_colsum32(sq, lane);
+                atomicAdd(p.stats + n0 + c0 + lane, s1);
+                atomicAdd(p.stats + p.Cout + n0 + c0 + lane, s2);
+            }
+            if (flags & EPI_POOL) {    // x is already zero on invalid rows
+                if (n_lo == n_hi) {
+                    const float s = warp_colsum32(x, lane);
+                    if (n_lo < p.n_img) atomicAdd(p.pool + (long long)n_lo * p.Cout + n0 + c0 + lane, s);
+                } else {               // the warp's 32 rows straddle two images
+                    float xb[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        xb[j] = (n_img == n_lo) ? 0.f : x[j];
+                        x[j] = (n_img == n_lo) ? x[j] : 0.f;
+                    }
+                    const float sa = warp_colsum32(x, lane);
+                    const float sb = warp_colsum32(xb, lane);
+                    if (n_lo < p.n_img) atomicAdd(p.pool + (long long)n_lo * p.Cout + n0 + c0 + lane, sa);
+                    if (n_hi < p.n_img) atomicAdd(p.pool + (long long)n_hi * p.Cout + n0 + c0 + lane, sb);
+                }
+            }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[acc]);
+    }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -105,7 +304,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                     tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], p.tap_ch_off[tap] + c * BLOCK_K,
                                 m0 + p.tap_row_shift[tap]);
-                    tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, n0);
+                    tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K,
+                                n0 + m_tile * p.b_rows_per_mtile);
                     if (++c == p.kb_per_tap) { c = 0; ++tap; }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -144,198 +344,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else if (warp >= 4) {
-        // ===================== Epilogue: TMEM -> registers -> fused ops -> global =====================
-        const int ew = warp - 4;                     // TMEM lane quadrant == warp % 4
-        const int row_in_tile = ew * 32 + lane;
-        const int etid = threadIdx.x - 128;
-        const uint32_t flags = p.flags;
-        const bool border = (flags & EPI_BORDER_BIAS) != 0;
-        const int nbias = border ? 9 : 1;
-        int loaded_n_tile = -1;
-        int it = 0;
-        for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++it) {
-            const int t = work / p.num_splits;
-            const int n_tile = t % p.num_n_tiles;
-            const int m_tile = t / p.num_n_tiles;
-            const int m0 = m_tile * BLOCK_M;
-            const int n0 = n_tile * BN;
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
-
-            if (n_tile != loaded_n_tile) {           // stage per-channel epilogue parameters in smem
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (flags & (EPI_BIAS | EPI_BORDER_BIAS))
-                    for (int i = etid; i < nbias * BN; i += EPI_THREADS)
-                        sparam[i] = p.bias[(i / BN) * p.Cout + n0 + (i % BN)];
-                if (flags & EPI_PRELU)
-                    for (int i = etid; i < BN; i += EPI_THREADS) sparam[9 * BN + i] = p.slope[n0 + i];
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                loaded_n_tile = n_tile;
-            }
-
-            const int m = m0 + row_in_tile;
-            int n_img = 0, h = 0, w = 0;
-            bool valid = m < p.M;
-            int cls = 0;
-            if (flags & EPI_GEOM) {
-                n_img = m / p.rows_per_img;
-                const int rem = m - n_img * p.rows_per_img;
-                h = rem / p.Wp;
-                w = rem - h * p.Wp;
-                h -= p.h0;
-                w -= p.h0;
-                valid = valid && h >= 0 && h < p.S && w >= 0 && w < p.S;
-                if (border) {
-                    const int ch = (h == 0) ? 0 : ((h == p.S - 1) ? 2 : 1);
-                    const int cw = (w == 0) ? 0 : ((w == p.S - 1) ? 2 : 1);
-                    cls = ch * 3 + cw;
-                }
-            }
-            const float* sbias = sparam + cls * BN;
-            const float* sslope = sparam + 9 * BN;
-
-            // output addressing
-            __nv_bfloat16* orow = nullptr;
-            bool do_store = false;
-            if (p.out != nullptr) {
-                if (flags & EPI_OUT_S2D) {
-                    const int g = p.s2d_So + 1;
-                    const long long r = (long long)n_img * g * g + (h >> 1) * g + (w >> 1);
-                    orow = p.out + r * p.ldo + ((h & 1) * 2 + (w & 1)) * p.Cout + n0;
-                    do_store = valid;
-                } else {
-                    orow = p.out + (long long)m * p.ldo + n0;
-                    do_store = (m < p.M) && (valid || !(flags & EPI_OUT_REFLECT));
-                }
-            }
-            // reflection-halo mirrors (7x7 map stored with a 1-pixel halo, Wp == 9): interior index 1 mirrors to
-            // halo index -1 and S-2 mirrors to S
-            int mir_h = 0, mir_w = 0;
-            if (flags & EPI_OUT_REFLECT) {
-                mir_h = (h == 1) ? -2 : ((h == p.S - 2) ? 2 : 0);
-                mir_w = (w == 1) ? -2 : ((w == p.S - 2) ? 2 : 0);
-            }
-            const int n_lo = __shfl_sync(0xffffffffu, n_img, 0);
-            const int n_hi = __shfl_sync(0xffffffffu, n_img, 31);
-
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after();
-            const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(ew * 32) << 16);
-
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32(t_row + c0, v);
-                tmem_ld_wait();
-                float x[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-                if (flags & (EPI_BIAS | EPI_BORDER_BIAS)) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] += sbias[c0 + j];
-                }
-                if (flags & EPI_PRELU) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] = x[j] > 0.f ? x[j] : x[j] * sslope[c0 + j];
-                }
-                if (flags & EPI_RESIDUAL) {
-                    if (valid) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(p.res + (long long)m * p.ldres + n0 + c0);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const uint4 r = __ldg(rp + q);
-                            x[q * 8 + 0] += bf16lo(r.x); x[q * 8 + 1] += bf16hi(r.x);
-                            x[q * 8 + 2] += bf16lo(r.y); x[q * 8 + 3] += bf16hi(r.y);
-                            x[q * 8 + 4] += bf16lo(r.z); x[q * 8 + 5] += bf16hi(r.z);
-                            x[q * 8 + 6] += bf16lo(r.w); x[q * 8 + 7] += bf16hi(r.w);
-                        }
-                    }
-                }
-                if (flags & EPI_SIGMOID) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] = sigmoidf_fast(x[j]);
-                }
-                if (!valid) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] = 0.f;
-                }
-                if (flags & EPI_OUT_F32_ATOMIC) {
-                    if (valid) {
-                        float* o = p.out_f32 + (long long)m * p.Cout + n0 + c0;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) atomicAdd(o + j, x[j]);
-                    }
-                }
-                if (flags & EPI_OUT_F32) {
-                    if (m < p.M) {
-                        float4* o = reinterpret_cast<float4*>(p.out_f32 + (long long)m * p.Cout + n0 + c0);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) o[q] = make_float4(x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
-                    }
-                }
-                if (do_store) {
-                    uint4 pk[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        pk[q].x = pack_bf16x2(x[q * 8 + 0], x[q * 8 + 1]);
-                        pk[q].y = pack_bf16x2(x[q * 8 + 2], x[q * 8 + 3]);
-                        pk[q].z = pack_bf16x2(x[q * 8 + 4], x[q * 8 + 5]);
-                        pk[q].w = pack_bf16x2(x[q * 8 + 6], x[q * 8 + 7]);
-                    }
-                    uint4* o = reinterpret_cast<uint4*>(orow + c0);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) o[q] = pk[q];
-                    if (flags & EPI_OUT_REFLECT) {
-                        if (mir_h) {
-                            uint4* o2 = reinterpret_cast<uint4*>(orow + (long long)mir_h * p.Wp * p.ldo + c0);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) o2[q] = pk[q];
-                        }
-                        if (mir_w) {
-                            uint4* o2 = reinterpret_cast<uint4*>(orow + (long long)mir_w * p.ldo + c0);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) o2[q] = pk[q];
-                        }
-                        if (mir_h && mir_w) {
-                            uint4* o2 = reinterpret_cast<uint4*>(orow + ((long long)mir_h * p.Wp + mir_w) * p.ldo + c0);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) o2[q] = pk[q];
-                        }
-                    }
-                }
-                if (flags & EPI_STATS) {   // x is already zero on invalid rows
-                    float sq[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) sq[j] = x[j] * x[j];
-                    float xs[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) xs[j] = x[j];
-                    const float s1 = warp_colsum32(xs, lane);
-                    const float s2 = warp_colsum32(sq, lane);
-                    atomicAdd(p.stats + n0 + c0 + lane, s1);
-                    atomicAdd(p.stats + p.Cout + n0 + c0 + lane, s2);
-                }
-                if (flags & EPI_POOL) {    // x is already zero on invalid rows
-                    if (n_lo == n_hi) {
-                        const float s = warp_colsum32(x, lane);
-                        if (n_lo < p.n_img) atomicAdd(p.pool + (long long)n_lo * p.Cout + n0 + c0 + lane, s);
-                    } else {               // the warp's 32 rows straddle two images
-                        float xb[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            xb[j] = (n_img == n_lo) ? 0.f : x[j];
-                            x[j] = (n_img == n_lo) ? x[j] : 0.f;
-                        }
-                        const float sa = warp_colsum32(x, lane);
-                        const float sb = warp_colsum32(xb, lane);
-                        if (n_lo < p.n_img) atomicAdd(p.pool + (long long)n_lo * p.Cout + n0 + c0 + lane, sa);
-                        if (n_hi < p.n_img) atomicAdd(p.pool + (long long)n_hi * p.Cout + n0 + c0 + lane, sb);
-                    }
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(&tempty_bar[acc]);
-        }
+        epilogue_loop<BN>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane);
     }
 
     tc_fence_before();
@@ -344,6 +353,167 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
     }
+}
+
+
+// ----------------------------------------------------------------------------------------------------------
+// Sliding-window variant for 3x3 / stride-1 convolutions on a flat map of row pitch G.
+// For one 128-row tile and one 64-channel chunk all nine taps read rows inside the window
+// [m0 - G - 1, m0 + 128 + G + 1): it is loaded ONCE by TMA (instead of nine shifted 128-row tiles) and tap (r,s)
+// is just an operand descriptor that starts r*G + s rows (128 B each) into the window. SWIZZLE_128B is a function of
+// the absolute shared-memory address, so a row-offset start address needs no base_offset (profiles/r01_probe_*).
+// Weights stream through their own ring, one [BN x 64] tile per (chunk, tap).
+// ----------------------------------------------------------------------------------------------------------
+constexpr int WIN_MAX_A_STAGES = 4;
+constexpr int WIN_MAX_B_STAGES = 8;
+
+struct WinCfg {
+    int G;            // row pitch of the flat map
+    int box_rows;     // rows per TMA box (multiple of 8, <= 256)
+    int nbox;         // 1 or 2 boxes per window
+    int a_stages, b_stages;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const ConvGemmParams p, const WinCfg wc) {
+    constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int win_bytes = wc.box_rows * wc.nbox * 128;            // multiple of 1024
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + wc.a_stages * win_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + wc.b_stages * B_STAGE_BYTES);
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = bars + WIN_MAX_A_STAGES;
+    uint64_t* b_full = bars + 2 * WIN_MAX_A_STAGES;
+    uint64_t* b_empty = b_full + WIN_MAX_B_STAGES;
+    uint64_t* tfull_bar = b_empty + WIN_MAX_B_STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* sparam = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < wc.a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < wc.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], EPI_THREADS); }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc<2 * BN>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_work = p.num_m_tiles * p.num_n_tiles;
+    const int chunks = p.kb_per_tap;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+                const int n_tile = work % p.num_n_tiles;
+                const int m_tile = work / p.num_n_tiles;
+                const int row0 = m_tile * BLOCK_M - wc.G - 1;
+                const int n0 = n_tile * BN;
+                for (int c = 0; c < chunks; ++c) {
+                    mbar_wait(&a_empty[sa], pa ^ 1);
+                    mbar_arrive_expect_tx(&a_full[sa], win_bytes);
+                    uint8_t* dst = sA + sa * win_bytes;
+                    tma_load_2d(dst, &tmA, &a_full[sa], c * BLOCK_K, row0);
+                    if (wc.nbox == 2)
+                        tma_load_2d(dst + wc.box_rows * 128, &tmA, &a_full[sa], c * BLOCK_K, row0 + wc.box_rows);
+                    if (++sa == wc.a_stages) { sa = 0; pa ^= 1; }
+                    for (int t = 0; t < 9; ++t) {
+                        mbar_wait(&b_empty[sb], pb ^ 1);
+                        mbar_arrive_expect_tx(&b_full[sb], B_STAGE_BYTES);
+                        tma_load_2d(sB + sb * B_STAGE_BYTES, &tmB, &b_full[sb], (t * chunks + c) * BLOCK_K, n0);
+                        if (++sb == wc.b_stages) { sb = 0; pb ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN);
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            int it = 0;
+            for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int c = 0; c < chunks; ++c) {
+                    mbar_wait(&a_full[sa], pa);
+                    tc_fence_after();
+                    const uint32_t win = smem_u32(sA + sa * win_bytes);
+#pragma unroll 1
+                    for (int t = 0; t < 9; ++t) {
+                        mbar_wait(&b_full[sb], pb);
+                        tc_fence_after();
+                        const int r = t / 3, sx = t - 3 * r;
+                        const uint32_t a_addr = win + static_cast<uint32_t>(r * wc.G + sx) * 128u;
+                        const uint32_t b_addr = smem_u32(sB + sb * B_STAGE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / 16; ++k)
+                            umma_bf16(d_tmem, umma_smem_desc_sw128(a_addr + k * 32),
+                                      umma_smem_desc_sw128(b_addr + k * 32), idesc, (c > 0 || t > 0 || k > 0) ? 1u : 0u);
+                        umma_commit(&b_empty[sb]);
+                        if (++sb == wc.b_stages) { sb = 0; pb ^= 1; }
+                    }
+                    umma_commit(&a_empty[sa]);
+                    if (++sa == wc.a_stages) { sa = 0; pa ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);
+            }
+        }
+    } else if (warp >= 4) {
+        epilogue_loop<BN>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<2 * BN>(tmem_base);
+    }
+}
+
+template <int BN>
+static int launch_win(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, const WinCfg& wc,
+                      int smem_bytes, int grid, cudaStream_t stream) {
+    static int attr_bytes = 0;
+    if (attr_bytes < smem_bytes) {
+        FFR_CUDA(cudaFuncSetAttribute(conv_win_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        attr_bytes = 232448;
+    }
+    conv_win_kernel<BN><<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, p, wc);
+    return launch_status("conv_win_kernel");
+}
+
+static bool g_use_window = true;
+void set_use_window(bool on) { g_use_window = on; }
+
+// Is this launch a plain 3x3/stride-1 flat convolution (taps (r-1)*G + (s-1), no channel offsets)?
+static bool window_eligible(const ConvGemmParams& p, int* G_out) {
+    if (!g_use_window || p.ntaps != 9 || p.num_splits != 1 || p.b_rows_per_mtile != 0) return false;
+    const int G = p.tap_row_shift[7] - p.tap_row_shift[4];
+    if (G < 4) return false;
+    for (int r = 0; r < 3; ++r)
+        for (int s = 0; s < 3; ++s)
+            if (p.tap_row_shift[r * 3 + s] != (r - 1) * G + (s - 1) || p.tap_ch_off[r * 3 + s] != 0) return false;
+    *G_out = G;
+    return true;
 }
 
 template <int BN>
@@ -377,19 +547,51 @@ int conv_gemm_launch(const void* a, long long a_rows, int a_cols, int a_ld, cons
     p.num_m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
     p.num_n_tiles = p.Cout / BN;
     FFR_CHECK_ARG(p.num_splits == 1 || (p.flags & EPI_OUT_F32_ATOMIC), "conv_gemm: split-K needs the atomic epilogue");
-    if (p.flags & (EPI_POOL | EPI_OUT_S2D | EPI_BORDER_BIAS | EPI_OUT_REFLECT))
+    if (p.flags & EPI_SCATTER)
+        FFR_CHECK_ARG(p.scatter && p.scatter_n >= 1 && p.scatter_n <= 8 && p.out && p.out_rows_per_img > 0,
+                      "conv_gemm: bad scatter table");
+    if (p.flags & (EPI_POOL | EPI_OUT_S2D | EPI_BORDER_BIAS | EPI_SCATTER))
         FFR_CHECK_ARG(p.flags & EPI_GEOM, "conv_gemm: epilogue needs row geometry");
     if (p.flags & EPI_GEOM) FFR_CHECK_ARG(p.rows_per_img >= 32 && p.Wp > 0, "conv_gemm: bad geometry");
-
-    CUtensorMap tmA, tmB;
-    int rc = make_tmap_2d_bf16(&tmA, a, (uint64_t)a_rows, (uint64_t)a_cols, (uint64_t)a_ld, BLOCK_M);
-    if (rc) return rc;
-    rc = make_tmap_2d_bf16(&tmB, wp, (uint64_t)p.Cout, (uint64_t)p.ntaps * Cin, (uint64_t)p.ntaps * Cin, BN);
-    if (rc) return rc;
 
     const long long num_work = (long long)p.num_m_tiles * p.num_n_tiles * p.num_splits;
     const int grid = (int)((num_work < num_sms()) ? num_work : num_sms());
     if (grid == 0) return 0;
+
+    CUtensorMap tmA, tmB;
+    int rc = make_tmap_2d_bf16(&tmB, wp, (uint64_t)p.Cout, (uint64_t)p.ntaps * Cin, (uint64_t)p.ntaps * Cin, BN);
+    if (rc) return rc;
+
+    int G = 0;
+    if (window_eligible(p, &G)) {
+        WinCfg wc;
+        wc.G = G;
+        const int need = BLOCK_M + 2 * G + 2;
+        if (need <= 256) { wc.nbox = 1; wc.box_rows = (need + 7) & ~7; }
+        else             { wc.nbox = 2; wc.box_rows = (((need + 1) / 2) + 7) & ~7; }
+        const int win_bytes = wc.box_rows * wc.nbox * 128;
+        const int b_stage = BN * BLOCK_K * 2;
+        const int fixed = 1024 + 512 + 10 * BN * 4;
+        const int budget = 225 * 1024 - fixed;
+        // weights ring: up to ~96 KB; windows get the rest (at least 2 stages)
+        wc.b_stages = (96 * 1024) / b_stage;
+        if (wc.b_stages > WIN_MAX_B_STAGES) wc.b_stages = WIN_MAX_B_STAGES;
+        if (wc.b_stages < 2) wc.b_stages = 2;
+        wc.a_stages = (budget - wc.b_stages * b_stage) / win_bytes;
+        if (wc.a_stages > WIN_MAX_A_STAGES) wc.a_stages = WIN_MAX_A_STAGES;
+        if (wc.a_stages >= 2 && wc.box_rows <= 256) {
+            rc = make_tmap_2d_bf16(&tmA, a, (uint64_t)a_rows, (uint64_t)a_cols, (uint64_t)a_ld, wc.box_rows);
+            if (rc) return rc;
+            const int smem_bytes = fixed + wc.a_stages * win_bytes + wc.b_stages * b_stage;
+            switch (BN) {
+                case 256: return launch_win<256>(tmA, tmB, p, wc, smem_bytes, grid, stream);
+                case 128: return launch_win<128>(tmA, tmB, p, wc, smem_bytes, grid, stream);
+                default:  return launch_win<64>(tmA, tmB, p, wc, smem_bytes, grid, stream);
+            }
+        }
+    }
+    rc = make_tmap_2d_bf16(&tmA, a, (uint64_t)a_rows, (uint64_t)a_cols, (uint64_t)a_ld, BLOCK_M);
+    if (rc) return rc;
     switch (BN) {
         case 256: return launch_cfg<256>(tmA, tmB, p, grid, stream);
         case 128: return launch_cfg<128>(tmA, tmB, p, grid, stream);

@@ -23,7 +23,9 @@ enum EpiFlags : uint32_t {
     EPI_OUT_S2D     = 1u << 5,   // scatter valid rows into the space-to-depth layout of the next stride-2 conv
     EPI_OUT_F32_ATOMIC = 1u << 6,// split-K: atomicAdd fp32 partial sums into out_f32[m, co]
     EPI_SIGMOID     = 1u << 7,   // 1 / (1 + exp(-x)) after everything else
-    EPI_OUT_REFLECT = 1u << 8,   // write valid rows of a 9x9-haloed 7x7 map and mirror them into the reflection halo
+    EPI_SCATTER     = 1u << 8,   // bf16 rows go to up to scatter_n (row, channel-offset) destinations per image-local
+                                 // row, looked up in a table (reflection-halo mirrors, W-flip, concatenation slots);
+                                 // a row whose first entry is negative is invalid
     EPI_RESIDUAL    = 1u << 9,   // + res[m, co] (bf16, same row grid) after PReLU
     EPI_STATS       = 1u << 10,  // atomically accumulate per-co sum and sum of squares of valid rows (batch-stat BN)
     EPI_OUT_F32     = 1u << 11,  // plain fp32 store to out_f32[m, co] (no atomics)
@@ -54,6 +56,10 @@ struct ConvGemmParams {
     const __nv_bfloat16* res;  // residual, row pitch ldres
     int ldres;
     float* stats;          // [2, Cout] : sum, sum of squares
+    const int2* scatter;   // [rows_per_img][scatter_n] : (destination row within the image, channel offset) or (-1, *)
+    int scatter_n;         // 1..8
+    int out_rows_per_img;  // rows per image of the destination matrix
+    int b_rows_per_mtile;  // batched B: weight-matrix row offset added per M tile (0 = shared weights)
 };
 
 }  // namespace ffr

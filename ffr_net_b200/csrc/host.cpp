@@ -1,5 +1,6 @@
 #include "host.h"
 
+#include <atomic>
 #include <cstring>
 #include <mutex>
 
@@ -58,6 +59,17 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
                          box_cols);
     return 0;
 }
+
+static std::atomic<long long> g_launches{0};
+
+int launch_status(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(static_cast<int>(e), "%s launch failed: %s", what, cudaGetErrorString(e));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int num_sms() {
     static int n = 0;

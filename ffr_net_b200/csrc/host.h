@@ -24,11 +24,9 @@ int set_error(int code, const char* fmt, ...);
             return ::ffr::set_error(static_cast<int>(_e), "%s failed: %s", #expr, cudaGetErrorString(_e)); \
     } while (0)
 
-inline int launch_status(const char* what) {
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return set_error(static_cast<int>(e), "%s launch failed: %s", what, cudaGetErrorString(e));
-    return 0;
-}
+// Called after every kernel launch: checks the launch and counts it (ffr_launch_count()).
+int launch_status(const char* what);
+long long launch_count();
 
 // 2-D bf16 row-major matrix [rows, cols] with row pitch `ld` elements; box = [box_rows, 64 cols]
 // (64 bf16 = 128 B = one SWIZZLE_128B row). Out-of-bounds elements read as zero.

@@ -51,6 +51,8 @@ typedef void* ffr_stream_t; /* cudaStream_t */
 
 FFR_API int ffr_version(void);
 FFR_API const char* ffr_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py reports it as gpu_launches). */
+FFR_API long long ffr_launch_count(void);
 
 /* Generic shifted-row implicit GEMM on tcgen05/TMEM/TMA (ffr_net_b200/csrc/conv_gemm.cu):
  *   D[m,co] = sum_t sum_c A[m + tap_row_shift[t], tap_ch_off[t] + c] * Wp[co, t*Cin + c], then the fused epilogue.
@@ -101,6 +103,10 @@ FFR_API int ffr_export_nchw_fwd(const void* h, const float* scale, const float* 
  * (zero columns at pad pixels), bias [512] folded; acc [n_img][512] fp32 scratch; f [n_img][512] fp32. */
 FFR_API int ffr_head_fwd(const void* h, int n_img, int S, int C, const void* wp, const float* bias, float* acc, float* f,
                  ffr_stream_t stream);
+
+/* Debug/tuning: 1 (default) lets 3x3 stride-1 convolutions use the sliding-window kernel, 0 forces the
+ * tile-per-tap kernel (the two must agree; tests run both). */
+FFR_API int ffr_debug_set_window(int enable);
 
 /* Debug: hardware-semantics probe for row-offset UMMA descriptors (csrc/probe.cu); not on the product path.
  * a [256][64] bf16, w [64][64] bf16, out [128][64] fp32 = a[row_off : row_off+128] @ w^T. */

@@ -65,7 +65,7 @@ def backbone_forward(pk_units, stem, head, bn, x):
     n = x.shape[0]
     S = x.shape[2]
     w = stem_w.t().reshape(64, 3, 3, 3)
-    h = F.conv2d(x, w, padding=1) + stem_b.view(1, -1, 1, 1)
+    h = F.conv2d(bf16(x).float(), bf16(w).float(), padding=1) + stem_b.view(1, -1, 1, 1)
     h = torch.where(h > 0, h, h * stem_a.view(1, -1, 1, 1))
     cur = layout.to_flat(h)
     for u in pk_units:

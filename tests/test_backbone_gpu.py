@@ -83,3 +83,24 @@ def test_backbone_rejects_training_and_cpu(models):
             m(torch.zeros(1, 3, 112, 112, device="cuda"))
     finally:
         m.eval()
+
+
+@pytest.mark.parametrize("n,S", [(2, 112), (3, 14)])
+def test_stem_kernel(lib, n, S):
+    """ffr_stem_fwd (warp-MMA im2col) vs F.conv2d on bf16-rounded operands; tolerance = bf16 output rounding."""
+    from ffr_net_b200 import _lib, layout
+    g = torch.Generator().manual_seed(S)
+    x = torch.randn(n, 3, S, S, generator=g).clamp_(-1, 1).cuda()
+    w = (torch.randn(64, 3, 3, 3, generator=g) * 0.2).cuda()
+    b = torch.randn(64, generator=g).cuda() * 0.1
+    a = torch.empty(64).uniform_(0.1, 0.4, generator=g).cuda()
+    wk = w.reshape(64, 27).t().contiguous()
+    out = torch.full((n * (S + 1) * (S + 1), 64), 9.0, dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.ffr_stem_fwd(_lib.ptr(x), _lib.ptr(wk), _lib.ptr(b), _lib.ptr(a), _lib.ptr(out), n, S,
+                                _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), padding=1) + b.view(1, -1, 1, 1)
+    ref = torch.where(ref > 0, ref, ref * a.view(1, -1, 1, 1))
+    got = layout.from_flat(out, n, S, 64)
+    assert (got - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+    assert layout.flat_pad_rows(out, n, S, 64).abs().max().item() == 0.0

@@ -14,12 +14,20 @@ import emulate
 pytestmark = pytest.mark.gpu
 
 P = _lib.ptr
-EPI = dict(BIAS=1, BORDER=2, PRELU=4, GEOM=8, POOL=16, S2D=32, F32ATOMIC=64, SIGMOID=128, REFLECT=256, RESIDUAL=512,
+EPI = dict(BIAS=1, BORDER=2, PRELU=4, GEOM=8, POOL=16, S2D=32, F32ATOMIC=64, SIGMOID=128, SCATTER=256, RESIDUAL=512,
            STATS=1024, F32=2048)
 
 
 def _stream():
     return _lib.stream_ptr()
+
+
+@pytest.fixture(params=["window", "tiles"], autouse=True)
+def conv_variant(request, lib):
+    """Every test runs with the sliding-window kernel enabled and with the tile-per-tap kernel forced."""
+    lib.ffr_debug_set_window(1 if request.param == "window" else 0)
+    yield request.param
+    lib.ffr_debug_set_window(1)
 
 
 def _gemm(lib, a, wp, cin, cout, taps, M, flags=0, bias=None, slope=None, out=None, ldo=0, geom=(64, 1, 1, 0, 1),
@@ -72,7 +80,8 @@ def test_splitk_atomic(lib, splits):
     assert torch.equal(out, a.float() @ w.float().t())   # integer-valued: exact in any order
 
 
-@pytest.mark.parametrize("n,S,cin,cout", [(3, 14, 64, 64), (2, 7, 128, 256), (5, 28, 64, 128), (2, 14, 256, 512)])
+@pytest.mark.parametrize("n,S,cin,cout", [(3, 14, 64, 64), (2, 7, 128, 256), (5, 28, 64, 128), (2, 14, 256, 512),
+                                            (2, 112, 64, 64), (3, 56, 64, 128)])
 def test_conv3x3_bnpre_prelu(lib, n, S, cin, cout):
     """conv(pad0(BN(x))) + PReLU through ffr_conv3x3_bnpre_prelu_fwd vs F.conv2d on the same bf16-rounded operands.
     Tolerance 2e-3 of max|ref| (fp32 accumulation order) + bf16 output rounding (2^-8 relative)."""
