@@ -7,5 +7,6 @@ Drop-in module surface of the reference (haoosz/FFR-Net):
 Everything below these modules runs in libffr_sm100.so (hand-written CUDA, C ABI in include/ffr_sm100.h).
 """
 from .backbone import Backbone, ir_se_50_512, l2_norm  # noqa: F401
+from .recnet import RecNet, selfSimilarity, cosine_sim, init_weights  # noqa: F401
 
-__all__ = ["Backbone", "ir_se_50_512", "l2_norm"]
+__all__ = ["Backbone", "ir_se_50_512", "l2_norm", "RecNet", "selfSimilarity", "cosine_sim", "init_weights"]

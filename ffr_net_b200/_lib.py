@@ -20,7 +20,12 @@ _SIGNATURES = {
     "ffr_last_error": (ctypes.c_char_p, []),
     "ffr_launch_count": (ctypes.c_longlong, []),
     "ffr_conv_gemm": (_i, [_p, _i64, _i, _i, _p, _i, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _u32, _p, _p, _p, _i, _i,
-                           _p, _p, _p, _i, _p, _i, _p]),
+                           _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _p]),
+    "ffr_recnet_prep": (_i, [_p, _i] + [_p] * 15 + [_p]),
+    "ffr_recnet_convlayer_fwd": (_i, [_p, _i, _i, _p, _i, _p, _p, _p, _i, _i, _p, _i, _p, _i, _i, _p, _p, _p]),
+    "ffr_feat_space": (_i, [_p, _p, _p, _p, _i, _p]),
+    "ffr_rows_to_nchw": (_i, [_p, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "ffr_scale_f32": (_i, [_p, _p, _i64, ctypes.c_float, _p]),
     "ffr_conv3x3_bnpre_prelu_fwd": (_i, [_p, _i, _i, _i, _p, _i, _p, _p, _p, _i, _p]),
     "ffr_conv3x3_bn_pool_fwd": (_i, [_p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p]),
     "ffr_conv1x1_bn_fwd": (_i, [_p, _i, _i, _i, _p, _i, _p, _p, _p]),

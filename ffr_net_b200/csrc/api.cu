@@ -18,6 +18,16 @@ int export_nchw_launch(const void* h, const float* scale, const float* shift, fl
                        cudaStream_t stream);
 int bias_l2norm_launch(const float* acc, const float* bias, float* f, int rows, int D, cudaStream_t stream);
 void set_use_window(bool on);
+struct PrepParams {
+    const float* x; const float* w0aT; const float* w0bT; const float* b0; const float* slope1; const float* A1;
+    const float* c1; const float* slope4; const float* A2; const float* c2; const float* slope7;
+    __nv_bfloat16* s0; __nv_bfloat16* cm; __nv_bfloat16* xt; __nv_bfloat16* h5; float* ss_space;
+};
+int recnet_prep_launch(const PrepParams& p, int n, cudaStream_t stream);
+int feat_space_launch(const float* x, const float* mspace, void* cm, float* out_nchw, int n, cudaStream_t stream);
+int rows_to_nchw_launch(const void* rows, int is_f32, int ld, int ch0, const float* scale, const float* shift, float* y,
+                        int n, int S, int G, int off, int rows_per_img, int C, cudaStream_t stream);
+int scale_f32_launch(const float* in, float* out, long long count, float scale, cudaStream_t stream);
 }  // namespace ffr
 
 using namespace ffr;
@@ -61,7 +71,7 @@ FFR_API int ffr_conv_gemm(const void* a, int64_t a_rows, int a_cols, int a_ld, c
                   const int* tap_row_shift, const int* tap_ch_off, int M, int rows_per_img, int Wp, int S, int h0,
                   int n_img, uint32_t flags, const float* bias, const float* slope, void* out, int ldo, int s2d_So,
                   float* pool, float* out_f32, const void* res, int ldres, float* stats, int num_splits,
-                  ffr_stream_t stream) {
+                  const int* scatter, int scatter_n, int out_rows_per_img, int b_rows_per_mtile, ffr_stream_t stream) {
     FFR_CHECK_ARG(a && wp, "ffr_conv_gemm: null operand");
     FFR_CHECK_ARG(ntaps >= 1 && ntaps <= 9, "ffr_conv_gemm: ntaps=%d", ntaps);
     ConvGemmParams p;
@@ -80,6 +90,8 @@ FFR_API int ffr_conv_gemm(const void* a, int64_t a_rows, int a_cols, int a_ld, c
     p.pool = pool; p.out_f32 = out_f32;
     p.res = reinterpret_cast<const __nv_bfloat16*>(res); p.ldres = ldres;
     p.stats = stats;
+    p.scatter = reinterpret_cast<const int2*>(scatter); p.scatter_n = scatter_n; p.out_rows_per_img = out_rows_per_img;
+    p.b_rows_per_mtile = b_rows_per_mtile;
     if (flags & (EPI_BIAS | EPI_BORDER_BIAS)) FFR_CHECK_ARG(bias, "ffr_conv_gemm: bias flag without bias");
     if (flags & EPI_PRELU) FFR_CHECK_ARG(slope, "ffr_conv_gemm: PReLU flag without slopes");
     if (flags & EPI_POOL) FFR_CHECK_ARG(pool, "ffr_conv_gemm: pool flag without buffer");
@@ -192,6 +204,59 @@ FFR_API int ffr_head_fwd(const void* h, int n_img, int S, int C, const void* wp,
     int rc = conv_gemm_launch(h, n_img, K, K, wp, K, p, splits, S_(stream));
     if (rc) return rc;
     return bias_l2norm_launch(acc, bias, f, n_img, D, S_(stream));
+}
+
+FFR_API int ffr_recnet_prep(const float* x, int n, const float* w0aT, const float* w0bT, const float* b0,
+                            const float* slope1, const float* A1, const float* c1, const float* slope4,
+                            const float* A2, const float* c2, const float* slope7, void* s0, void* cm, void* xt,
+                            void* h5, float* ss_space, ffr_stream_t stream) {
+    FFR_CHECK_ARG(x && w0aT && w0bT && b0 && slope1 && A1 && c1 && slope4 && A2 && c2 && slope7 && s0 && cm && xt && h5,
+                  "ffr_recnet_prep: null pointer");
+    PrepParams p{x, w0aT, w0bT, b0, slope1, A1, c1, slope4, A2, c2, slope7,
+                 reinterpret_cast<__nv_bfloat16*>(s0), reinterpret_cast<__nv_bfloat16*>(cm),
+                 reinterpret_cast<__nv_bfloat16*>(xt), reinterpret_cast<__nv_bfloat16*>(h5), ss_space};
+    return recnet_prep_launch(p, n, S_(stream));
+}
+
+FFR_API int ffr_recnet_convlayer_fwd(const void* x, int n, int Cin, const void* wp, int Cout, const float* bias,
+                                     const float* slope, const void* res, int ldres, int sigmoid, void* out, int ldo,
+                                     const int* scatter, int scatter_n, int out_rows_per_img, float* out_f32,
+                                     float* pool, ffr_stream_t stream) {
+    FFR_CHECK_ARG(x && wp && bias, "ffr_recnet_convlayer_fwd: null pointer");
+    FFR_CHECK_ARG(out || out_f32, "ffr_recnet_convlayer_fwd: no output");
+    ConvGemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = n * 81;
+    p.Cout = Cout;
+    taps_3x3_flat(p, 9);
+    p.rows_per_img = 81; p.Wp = 9; p.S = 7; p.h0 = 1; p.n_img = n;
+    p.flags = EPI_GEOM | EPI_BIAS | (slope ? EPI_PRELU : 0u) | (res ? EPI_RESIDUAL : 0u) |
+              (sigmoid ? EPI_SIGMOID : 0u) | (out ? EPI_SCATTER : 0u) | (out_f32 ? EPI_OUT_F32 : 0u) |
+              (pool ? EPI_POOL : 0u);
+    p.bias = bias; p.slope = slope;
+    p.res = reinterpret_cast<const __nv_bfloat16*>(res); p.ldres = ldres;
+    p.out = reinterpret_cast<__nv_bfloat16*>(out); p.ldo = ldo;
+    p.scatter = reinterpret_cast<const int2*>(scatter); p.scatter_n = scatter_n; p.out_rows_per_img = out_rows_per_img;
+    p.out_f32 = out_f32;
+    p.pool = pool;
+    if (pool) FFR_CUDA(cudaMemsetAsync(pool, 0, sizeof(float) * (size_t)n * Cout, S_(stream)));
+    return conv_gemm_launch(x, (long long)p.M, Cin, Cin, wp, Cin, p, 1, S_(stream));
+}
+
+FFR_API int ffr_feat_space(const float* x, const float* mspace, void* cm, float* out_nchw, int n, ffr_stream_t stream) {
+    FFR_CHECK_ARG(x && mspace && cm, "ffr_feat_space: null pointer");
+    return feat_space_launch(x, mspace, cm, out_nchw, n, S_(stream));
+}
+
+FFR_API int ffr_rows_to_nchw(const void* rows, int is_f32, int ld, int ch0, const float* scale, const float* shift,
+                             float* y, int n, int S, int G, int off, int rows_per_img, int C, ffr_stream_t stream) {
+    FFR_CHECK_ARG(rows && y, "ffr_rows_to_nchw: null pointer");
+    return rows_to_nchw_launch(rows, is_f32, ld, ch0, scale, shift, y, n, S, G, off, rows_per_img, C, S_(stream));
+}
+
+FFR_API int ffr_scale_f32(const float* in, float* out, int64_t count, float scale, ffr_stream_t stream) {
+    FFR_CHECK_ARG(in && out, "ffr_scale_f32: null pointer");
+    return scale_f32_launch(in, out, count, scale, S_(stream));
 }
 
 }  // extern "C"

@@ -7,8 +7,8 @@ namespace ffr {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                       // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int NUM_THREADS = 256;                  // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 epilogue
-constexpr int EPI_THREADS = 128;
+constexpr int NUM_THREADS = 384;                  // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-11 epilogue
+constexpr int EPI_THREADS = 256;                  // two warps per TMEM lane quadrant, each owning half of the columns
 
 template <int BN>
 struct GemmCfg {
@@ -38,18 +38,31 @@ __device__ __forceinline__ float warp_colsum32(float (&x)[32], int lane) {
     return x[0];
 }
 
+// q = m / d, r = m % d for 0 <= m < 2^24 via a float reciprocal and one correction step (exact in that range).
+__device__ __forceinline__ void fast_divmod(int m, int d, float inv_d, int& q, int& r) {
+    q = __float2int_rz(__int2float_rz(m) * inv_d);
+    r = m - q * d;
+    if (r >= d) { ++q; r -= d; }
+    if (r < 0) { --q; r += d; }
+}
+
 // ===================== Epilogue: TMEM -> registers -> fused ops -> global =====================
-// Runs on warps 4..7 (128 threads, thread i <-> TMEM lane i <-> tile row i).
+// Runs on warps 4..11 (256 threads). Warp w reads TMEM lanes 32*(w%4).. (tile rows) and the column half (w-4)/4.
 template <int BN>
 __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uint32_t tmem_base, uint64_t* tfull_bar,
                                               uint64_t* tempty_bar, float* sparam, const int warp, const int lane) {
+    constexpr int HALF = BN / 2;                 // columns per epilogue warp
     const int num_work = p.num_m_tiles * p.num_n_tiles * p.num_splits;
-    const int ew = warp - 4;                     // TMEM lane quadrant == warp % 4
-    const int row_in_tile = ew * 32 + lane;
+    const int quad = warp & 3;                   // TMEM lane quadrant == warp % 4
+    const int chalf = (warp - 4) >> 2;           // which half of the accumulator columns
+    const int row_in_tile = quad * 32 + lane;
     const int etid = threadIdx.x - 128;
     const uint32_t flags = p.flags;
     const bool border = (flags & EPI_BORDER_BIAS) != 0;
     const int nbias = border ? 9 : 1;
+    const bool small_m = p.M < (1 << 24);
+    const float inv_rpi = 1.0f / (float)max(p.rows_per_img, 1);
+    const float inv_wp = 1.0f / (float)max(p.Wp, 1);
     int loaded_n_tile = -1;
     int it = 0;
     for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++it) {
@@ -62,13 +75,13 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
         const uint32_t acc_phase = (it >> 1) & 1;
 
         if (n_tile != loaded_n_tile) {           // stage per-channel epilogue parameters in smem
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             if (flags & (EPI_BIAS | EPI_BORDER_BIAS))
                 for (int i = etid; i < nbias * BN; i += EPI_THREADS)
                     sparam[i] = p.bias[(i / BN) * p.Cout + n0 + (i % BN)];
             if (flags & EPI_PRELU)
                 for (int i = etid; i < BN; i += EPI_THREADS) sparam[9 * BN + i] = p.slope[n0 + i];
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             loaded_n_tile = n_tile;
         }
 
@@ -77,10 +90,15 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
         bool valid = m < p.M;
         int cls = 0;
         if (flags & EPI_GEOM) {
-            n_img = m / p.rows_per_img;
-            r_local = m - n_img * p.rows_per_img;
-            h = r_local / p.Wp;
-            w = r_local - h * p.Wp;
+            if (small_m) {
+                fast_divmod(m, p.rows_per_img, inv_rpi, n_img, r_local);
+                fast_divmod(r_local, p.Wp, inv_wp, h, w);
+            } else {
+                n_img = m / p.rows_per_img;
+                r_local = m - n_img * p.rows_per_img;
+                h = r_local / p.Wp;
+                w = r_local - h * p.Wp;
+            }
             h -= p.h0;
             w -= p.h0;
             if (!(flags & EPI_SCATTER)) valid = valid && h >= 0 && h < p.S && w >= 0 && w < p.S;
@@ -90,8 +108,9 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
                 cls = ch * 3 + cw;
             }
         }
-        const float* sbias = sparam + cls * BN;
-        const float* sslope = sparam + 9 * BN;
+        const float4* sbias4 = reinterpret_cast<const float4*>(sparam + cls * BN + chalf * HALF);
+        const float4* sslope4 = reinterpret_cast<const float4*>(sparam + 9 * BN + chalf * HALF);
+        const int nc0 = n0 + chalf * HALF;       // first global output channel of this warp
 
         // output addressing
         __nv_bfloat16* orow = nullptr;
@@ -104,7 +123,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
                 if (k < p.scatter_n && m < p.M) {
                     const int2 e = __ldg(p.scatter + r_local * p.scatter_n + k);
                     if (e.x >= 0)
-                        sdst[k] = p.out + ((long long)n_img * p.out_rows_per_img + e.x) * p.ldo + e.y + n0;
+                        sdst[k] = p.out + ((long long)n_img * p.out_rows_per_img + e.x) * p.ldo + e.y + nc0;
                 }
             }
             valid = valid && sdst[0] != nullptr;
@@ -112,10 +131,10 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
             if (flags & EPI_OUT_S2D) {
                 const int g = p.s2d_So + 1;
                 const long long r = (long long)n_img * g * g + (h >> 1) * g + (w >> 1);
-                orow = p.out + r * p.ldo + ((h & 1) * 2 + (w & 1)) * p.Cout + n0;
+                orow = p.out + r * p.ldo + ((h & 1) * 2 + (w & 1)) * p.Cout + nc0;
                 do_store = valid;
             } else {
-                orow = p.out + (long long)m * p.ldo + n0;
+                orow = p.out + (long long)m * p.ldo + nc0;
                 do_store = (m < p.M);
             }
         }
@@ -124,27 +143,38 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
 
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
-        const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(ew * 32) << 16);
+        const uint32_t t_row = tmem_base + acc * BN + chalf * HALF + (static_cast<uint32_t>(quad * 32) << 16);
 
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld_32x32(t_row + c0, v);
+        uint32_t vbuf[2][32];
+        tmem_ld_32x32(t_row, vbuf[0]);
+#pragma unroll
+        for (int ci = 0; ci < HALF / 32; ++ci) {
+            const int c0 = ci * 32;
             tmem_ld_wait();
+            if (ci + 1 < HALF / 32) tmem_ld_32x32(t_row + c0 + 32, vbuf[(ci + 1) & 1]);   // prefetch next chunk
             float x[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(vbuf[ci & 1][j]);
             if (flags & (EPI_BIAS | EPI_BORDER_BIAS)) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] += sbias[c0 + j];
+                for (int q = 0; q < 8; ++q) {
+                    const float4 b4 = sbias4[ci * 8 + q];
+                    x[q * 4 + 0] += b4.x; x[q * 4 + 1] += b4.y; x[q * 4 + 2] += b4.z; x[q * 4 + 3] += b4.w;
+                }
             }
             if (flags & EPI_PRELU) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] = x[j] > 0.f ? x[j] : x[j] * sslope[c0 + j];
+                for (int q = 0; q < 8; ++q) {
+                    const float4 s4 = sslope4[ci * 8 + q];
+                    x[q * 4 + 0] = fmaxf(x[q * 4 + 0], 0.f) + s4.x * fminf(x[q * 4 + 0], 0.f);
+                    x[q * 4 + 1] = fmaxf(x[q * 4 + 1], 0.f) + s4.y * fminf(x[q * 4 + 1], 0.f);
+                    x[q * 4 + 2] = fmaxf(x[q * 4 + 2], 0.f) + s4.z * fminf(x[q * 4 + 2], 0.f);
+                    x[q * 4 + 3] = fmaxf(x[q * 4 + 3], 0.f) + s4.w * fminf(x[q * 4 + 3], 0.f);
+                }
             }
             if (flags & EPI_RESIDUAL) {
                 if (valid) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(p.res + (long long)m * p.ldres + n0 + c0);
+                    const uint4* rp = reinterpret_cast<const uint4*>(p.res + (long long)m * p.ldres + nc0 + c0);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const uint4 r = __ldg(rp + q);
@@ -165,14 +195,14 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
             }
             if (flags & EPI_OUT_F32_ATOMIC) {
                 if (valid) {
-                    float* o = p.out_f32 + (long long)m * p.Cout + n0 + c0;
+                    float* o = p.out_f32 + (long long)m * p.Cout + nc0 + c0;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) atomicAdd(o + j, x[j]);
                 }
             }
             if (flags & EPI_OUT_F32) {
                 if (m < p.M) {
-                    float4* o = reinterpret_cast<float4*>(p.out_f32 + (long long)m * p.Cout + n0 + c0);
+                    float4* o = reinterpret_cast<float4*>(p.out_f32 + (long long)m * p.Cout + nc0 + c0);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) o[q] = make_float4(x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
                 }
@@ -203,21 +233,18 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
                 }
             }
             if (flags & EPI_STATS) {   // x is already zero on invalid rows
-                float sq[32];
+                float sq[32], xs[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) sq[j] = x[j] * x[j];
-                float xs[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) xs[j] = x[j];
+                for (int j = 0; j < 32; ++j) { sq[j] = x[j] * x[j]; xs[j] = x[j]; }
                 const float s1 = warp_colsum32(xs, lane);
                 const float s2 = warp_colsum32(sq, lane);
-                atomicAdd(p.stats + n0 + c0 + lane, s1);
-                atomicAdd(p.stats + p.Cout + n0 + c0 + lane, s2);
+                atomicAdd(p.stats + nc0 + c0 + lane, s1);
+                atomicAdd(p.stats + p.Cout + nc0 + c0 + lane, s2);
             }
             if (flags & EPI_POOL) {    // x is already zero on invalid rows
                 if (n_lo == n_hi) {
                     const float s = warp_colsum32(x, lane);
-                    if (n_lo < p.n_img) atomicAdd(p.pool + (long long)n_lo * p.Cout + n0 + c0 + lane, s);
+                    if (n_lo < p.n_img) atomicAdd(p.pool + (long long)n_lo * p.Cout + nc0 + c0 + lane, s);
                 } else {               // the warp's 32 rows straddle two images
                     float xb[32];
 #pragma unroll
@@ -227,8 +254,8 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
                     }
                     const float sa = warp_colsum32(x, lane);
                     const float sb = warp_colsum32(xb, lane);
-                    if (n_lo < p.n_img) atomicAdd(p.pool + (long long)n_lo * p.Cout + n0 + c0 + lane, sa);
-                    if (n_hi < p.n_img) atomicAdd(p.pool + (long long)n_hi * p.Cout + n0 + c0 + lane, sb);
+                    if (n_lo < p.n_img) atomicAdd(p.pool + (long long)n_lo * p.Cout + nc0 + c0 + lane, sa);
+                    if (n_hi < p.n_img) atomicAdd(p.pool + (long long)n_hi * p.Cout + nc0 + c0 + lane, sb);
                 }
             }
         }
@@ -559,7 +586,8 @@ int conv_gemm_launch(const void* a, long long a_rows, int a_cols, int a_ld, cons
     if (grid == 0) return 0;
 
     CUtensorMap tmA, tmB;
-    int rc = make_tmap_2d_bf16(&tmB, wp, (uint64_t)p.Cout, (uint64_t)p.ntaps * Cin, (uint64_t)p.ntaps * Cin, BN);
+    const uint64_t b_rows = (uint64_t)p.Cout + (uint64_t)(p.num_m_tiles - 1) * (uint64_t)p.b_rows_per_mtile;
+    int rc = make_tmap_2d_bf16(&tmB, wp, b_rows, (uint64_t)p.ntaps * Cin, (uint64_t)p.ntaps * Cin, BN);
     if (rc) return rc;
 
     int G = 0;

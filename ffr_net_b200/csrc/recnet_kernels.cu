@@ -1,0 +1,286 @@
+// RecNet (feature rectification, models/recnet.py) — the kernels that are not implicit GEMMs.
+//
+// Layouts (DESIGN.md "RecNet"):
+//   H9  : a 7x7 map with its 1-pixel REFLECTION halo materialised, bf16 [n*81][C]; pixel (h,w) at row (h+1)*9+(w+1).
+//         A 3x3 "ReflectionPad2d(1) + Conv2d(pad 0)" (recnet.py:64-65,78-82) is then a shifted-row GEMM with G = 9;
+//         producers write every valid pixel to its own row and to the (up to 3) halo rows that mirror it.
+//   XT  : X^T per sample, bf16 [n*128][512] (rows hw < 49 valid) — the A operand of feat_channel = M_channel @ X.
+//   H5  : input of the last Conv4Channel linear, bf16 [n*512][64] (32 valid columns).
+#include "host.h"
+#include "ptx.cuh"
+
+namespace ffr {
+
+__device__ __forceinline__ float warp_sum_r(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ int reflect_src(int p) {  // padded index 0..8 -> source index 0..6 (ReflectionPad2d(1))
+    return p == 0 ? 1 : (p == 8 ? 5 : p - 1);
+}
+
+struct PrepParams {
+    const float* x;        // [n][512][49] fp32 (NCHW feature map from the backbone)
+    const float* w0aT;     // [49][32]   Conv4Channel.0.weight[:, :49]^T
+    const float* w0bT;     // [512][32]  Conv4Channel.0.weight[:, 49:]^T
+    const float* b0;       // [32]
+    const float* slope1;   // [512] PReLU over the 512 rows (recnet.py:374; nn.PReLU(512) acts on dim 1)
+    const float* A1;       // [32][32]   Conv4Channel.3.weight @ Conv4Channel.2.weight
+    const float* c1;       // [32]       Conv4Channel.3.weight @ Conv4Channel.2.bias + Conv4Channel.3.bias
+    const float* slope4;   // [512]
+    const float* A2;       // [32][32]   Conv4Channel.6.weight @ Conv4Channel.5.weight
+    const float* c2;       // [32]
+    const float* slope7;   // [512]
+    __nv_bfloat16* s0;     // H9 [n*81][576]: X | ss_space | 0        (input of Conv4Space.0, recnet.py:401)
+    __nv_bfloat16* cm;     // H9 [n*81][1536]: slot [1024,1536) <- X  (input of Conv4Merge.0, recnet.py:420)
+    __nv_bfloat16* xt;     // XT [n*128][512]
+    __nv_bfloat16* h5;     // H5 [n*512][64]
+    float* ss_space;       // optional fp32 [n][49][49]   (selfSimilarity outputs for callers that want them)
+};
+
+// One CTA per sample: self-similarity (recnet.py:220-236), layout fan-out of X, and the thin part of the channel
+// rectifier Conv4Channel (recnet.py:372-385) up to the input of its last Linear.
+//   ss_space[i][j]  = <x[:,i], x[:,j]> / (max(|x[:,i]|,eps) max(|x[:,j]|,eps))
+//   ss_channel      = Xh Xh^T with Xh = row-normalised X is never materialised: Linear(561->32) applied to
+//                     cat(X, ss_channel) equals X W0a^T + Xh (Xh^T W0b^T) + b0 (associativity), a 49x32 intermediate.
+//   Linear(32->512) followed by Linear(512->32) has no non-linearity in between and is applied as the folded 32x32 map.
+__global__ void __launch_bounds__(512, 1) recnet_prep_kernel(const PrepParams p) {
+    extern __shared__ float sm[];
+    float* xs = sm;                      // [512][49]
+    float* inv_c = xs + 512 * 49;        // [512]
+    float* inv_s = inv_c + 512;          // [64]
+    float* Gs = inv_s + 64;              // [49][49]
+    float* T = Gs + 49 * 49 + 3;         // [49][32]
+    float* W0a = T + 49 * 32;            // [49][32]
+    float* A1s = W0a + 49 * 32;          // [32][32]
+    float* A2s = A1s + 1024;             // [32][32]
+    float* misc = A2s + 1024;            // b0, c1, c2 [3][32]
+    const int n = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* x = p.x + (long long)n * 512 * 49;
+
+    for (int i = tid; i < 512 * 49; i += 512) xs[i] = x[i];
+    for (int i = tid; i < 49 * 32; i += 512) W0a[i] = p.w0aT[i];
+    for (int i = tid; i < 1024; i += 512) { A1s[i] = p.A1[i]; A2s[i] = p.A2[i]; }
+    if (tid < 32) { misc[tid] = p.b0[tid]; misc[32 + tid] = p.c1[tid]; misc[64 + tid] = p.c2[tid]; }
+    __syncthreads();
+
+    {   // row norms over HW (F.normalize(dim=2) of (N,C,HW), eps 1e-12)
+        float ss = 0.f;
+        for (int hw = 0; hw < 49; ++hw) { const float v = xs[tid * 49 + hw]; ss = fmaf(v, v, ss); }
+        inv_c[tid] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    }
+    for (int hw = warp; hw < 49; hw += 16) {   // column norms over C
+        float ss = 0.f;
+        for (int c = lane; c < 512; c += 32) { const float v = xs[c * 49 + hw]; ss = fmaf(v, v, ss); }
+        ss = warp_sum_r(ss);
+        if (lane == 0) inv_s[hw] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    }
+    __syncthreads();
+
+    // spatial self-similarity Gram (49x49 over C)
+    for (int o = tid; o < 49 * 49; o += 512) {
+        const int i = o / 49, j = o - i * 49;
+        float a = 0.f;
+#pragma unroll 8
+        for (int c = 0; c < 512; ++c) a = fmaf(xs[c * 49 + i], xs[c * 49 + j], a);
+        Gs[o] = a * inv_s[i] * inv_s[j];
+    }
+    // T[hw][j] = sum_c Xh[c][hw] * W0b[j][c]
+    for (int o = tid; o < 49 * 32; o += 512) {
+        const int hw = o >> 5, j = o & 31;
+        float a = 0.f;
+#pragma unroll 4
+        for (int c = 0; c < 512; ++c) a = fmaf(xs[c * 49 + hw] * inv_c[c], __ldg(p.w0bT + c * 32 + j), a);
+        T[o] = a;
+    }
+    __syncthreads();
+
+    // ---- layout fan-out of X (bf16) ----
+    {
+        const int c2 = (tid & 255) * 2;            // channel pair
+        const int half = tid >> 8;                 // two row streams
+        for (int hw = half; hw < 49; hw += 2) {
+            const uint32_t v = pack_bf16x2(xs[c2 * 49 + hw], xs[(c2 + 1) * 49 + hw]);
+            *reinterpret_cast<uint32_t*>(p.xt + ((long long)n * 128 + hw) * 512 + c2) = v;
+        }
+        for (int pos = half; pos < 81; pos += 2) {
+            const int hp = pos / 9, wp = pos - hp * 9;
+            const int hw = reflect_src(hp) * 7 + reflect_src(wp);
+            const uint32_t v = pack_bf16x2(xs[c2 * 49 + hw], xs[(c2 + 1) * 49 + hw]);
+            *reinterpret_cast<uint32_t*>(p.s0 + ((long long)n * 81 + pos) * 576 + c2) = v;
+            *reinterpret_cast<uint32_t*>(p.cm + ((long long)n * 81 + pos) * 1536 + 1024 + c2) = v;
+        }
+    }
+    // ss_space as 49 extra channels of the Conv4Space input: channel i at pixel j holds Gram[i][j]
+    for (int o = tid; o < 81 * 49; o += 512) {
+        const int pos = o / 49, i = o - pos * 49;
+        const int hp = pos / 9, wp = pos - hp * 9;
+        const int j = reflect_src(hp) * 7 + reflect_src(wp);
+        p.s0[((long long)n * 81 + pos) * 576 + 512 + i] = __float2bfloat16(Gs[i * 49 + j]);
+    }
+    if (p.ss_space)
+        for (int o = tid; o < 49 * 49; o += 512) p.ss_space[(long long)n * 2401 + o] = Gs[o];
+
+    // ---- thin channel-rectifier chain, one thread per channel row ----
+    {
+        const int c = tid;
+        float h[32], g[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { h[j] = misc[j]; g[j] = 0.f; }
+        for (int hw = 0; hw < 49; ++hw) {
+            const float xv = xs[c * 49 + hw];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                h[j] = fmaf(xv, W0a[hw * 32 + j], h[j]);
+                g[j] = fmaf(xv, T[hw * 32 + j], g[j]);
+            }
+        }
+        const float ic = inv_c[c];
+        const float s1 = p.slope1[c], s4 = p.slope4[c], s7 = p.slope7[c];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float v = fmaf(ic, g[j], h[j]);
+            h[j] = v > 0.f ? v : v * s1;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float a = misc[32 + j];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a = fmaf(A1s[j * 32 + i], h[i], a);
+            g[j] = a > 0.f ? a : a * s4;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float a = misc[64 + j];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a = fmaf(A2s[j * 32 + i], g[i], a);
+            h[j] = a > 0.f ? a : a * s7;
+        }
+        uint4* o = reinterpret_cast<uint4*>(p.h5 + ((long long)n * 512 + c) * 64);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            o[q] = make_uint4(pack_bf16x2(h[q * 8 + 0], h[q * 8 + 1]), pack_bf16x2(h[q * 8 + 2], h[q * 8 + 3]),
+                              pack_bf16x2(h[q * 8 + 4], h[q * 8 + 5]), pack_bf16x2(h[q * 8 + 6], h[q * 8 + 7]));
+#pragma unroll
+        for (int q = 4; q < 8; ++q) o[q] = make_uint4(0, 0, 0, 0);
+    }
+}
+
+int recnet_prep_launch(const PrepParams& p, int n, cudaStream_t stream) {
+    const int smem = (512 * 49 + 512 + 64 + 49 * 49 + 3 + 49 * 32 * 2 + 2048 + 96) * (int)sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        FFR_CUDA(cudaFuncSetAttribute(recnet_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    recnet_prep_kernel<<<n, 512, smem, stream>>>(p);
+    return launch_status("recnet_prep_kernel");
+}
+
+// ----------------------------------------------------------------------------------------------
+// feat_space = X (512x49) @ M_space (49x49)  (recnet.py:409), written as bf16 into slot [0,512) of the Conv4Merge
+// input (H9 with mirrors) and optionally as fp32 NCHW. mspace: fp32 rows of the H9 grid, [n*81][64]; row = pixel j,
+// column = channel i holds M_space[n, i, j] (the conv output is NHWC; recnet.py:405 views it as (N, HW, HW)).
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) feat_space_kernel(const float* __restrict__ x, const float* __restrict__ mspace,
+                                                         __nv_bfloat16* __restrict__ cm, float* __restrict__ out_nchw) {
+    __shared__ float Ms[49 * 49];     // Ms[i*49 + j] = M_space[n,i,j]
+    const int n = blockIdx.x, tid = threadIdx.x;
+    for (int o = tid; o < 49 * 49; o += 256) {
+        const int j = o / 49, i = o - j * 49;
+        const int pos = (j / 7 + 1) * 9 + (j % 7 + 1);
+        Ms[i * 49 + j] = mspace[((long long)n * 81 + pos) * 64 + i];
+    }
+    __syncthreads();
+    const int c2 = tid * 2;
+    float xa[49], xb[49];
+    const float* xr = x + ((long long)n * 512 + c2) * 49;
+#pragma unroll
+    for (int i = 0; i < 49; ++i) { xa[i] = __ldg(xr + i); xb[i] = __ldg(xr + 49 + i); }
+    for (int j = 0; j < 49; ++j) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int i = 0; i < 49; ++i) {
+            const float m = Ms[i * 49 + j];
+            a = fmaf(xa[i], m, a);
+            b = fmaf(xb[i], m, b);
+        }
+        if (out_nchw) {
+            out_nchw[((long long)n * 512 + c2) * 49 + j] = a;
+            out_nchw[((long long)n * 512 + c2 + 1) * 49 + j] = b;
+        }
+        const uint32_t v = pack_bf16x2(a, b);
+        const int h = j / 7, w = j - h * 7;
+        const int mh = (h == 1) ? -2 : ((h == 5) ? 2 : 0);
+        const int mw = (w == 1) ? -2 : ((w == 5) ? 2 : 0);
+        const long long base = (long long)n * 81 + (h + 1) * 9 + (w + 1);
+        *reinterpret_cast<uint32_t*>(cm + base * 1536 + c2) = v;
+        if (mh) *reinterpret_cast<uint32_t*>(cm + (base + mh * 9) * 1536 + c2) = v;
+        if (mw) *reinterpret_cast<uint32_t*>(cm + (base + mw) * 1536 + c2) = v;
+        if (mh && mw) *reinterpret_cast<uint32_t*>(cm + (base + mh * 9 + mw) * 1536 + c2) = v;
+    }
+}
+
+int feat_space_launch(const float* x, const float* mspace, void* cm, float* out_nchw, int n, cudaStream_t stream) {
+    feat_space_kernel<<<n, 256, 0, stream>>>(x, mspace, reinterpret_cast<__nv_bfloat16*>(cm), out_nchw);
+    return launch_status("feat_space_kernel");
+}
+
+// ----------------------------------------------------------------------------------------------
+// Rows of a haloed/flat grid -> fp32 NCHW (S x S valid pixels at row (h+off)*G + (w+off)), from bf16 or fp32 rows,
+// optional per-channel affine. grid = (C/64, n).
+// ----------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) rows_to_nchw_kernel(const T* __restrict__ rows, int ld, int ch0,
+                                                           const float* __restrict__ scale,
+                                                           const float* __restrict__ shift, float* __restrict__ y,
+                                                           int S, int G, int off, int rows_per_img, int C) {
+    extern __shared__ float tile[];  // [S*S][65]
+    const int n = blockIdx.y, c0 = blockIdx.x * 64;
+    const int P = S * S;
+    for (int i = threadIdx.x; i < P * 64; i += blockDim.x) {
+        const int c = i & 63, pix = i >> 6;
+        const int ph = pix / S, pw = pix - ph * S;
+        const long long row = (long long)n * rows_per_img + (ph + off) * G + (pw + off);
+        float v = static_cast<float>(rows[row * ld + ch0 + c0 + c]);
+        if (scale) v = v * scale[c0 + c] + shift[c0 + c];
+        tile[pix * 65 + c] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < P * 64; i += blockDim.x) {
+        const int pix = i % P, c = i / P;
+        y[((long long)n * C + c0 + c) * P + pix] = tile[pix * 65 + c];
+    }
+}
+
+int rows_to_nchw_launch(const void* rows, int is_f32, int ld, int ch0, const float* scale, const float* shift, float* y,
+                        int n, int S, int G, int off, int rows_per_img, int C, cudaStream_t stream) {
+    FFR_CHECK_ARG(C % 64 == 0, "rows_to_nchw: C=%d", C);
+    dim3 grid(C / 64, n);
+    const size_t smem = (size_t)S * S * 65 * sizeof(float);
+    FFR_CHECK_ARG(smem <= 48 * 1024, "rows_to_nchw: map %dx%d too large", S, S);
+    if (is_f32)
+        rows_to_nchw_kernel<float><<<grid, 256, smem, stream>>>(reinterpret_cast<const float*>(rows), ld, ch0, scale,
+                                                                shift, y, S, G, off, rows_per_img, C);
+    else
+        rows_to_nchw_kernel<__nv_bfloat16><<<grid, 256, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(rows),
+                                                                        ld, ch0, scale, shift, y, S, G, off,
+                                                                        rows_per_img, C);
+    return launch_status("rows_to_nchw_kernel");
+}
+
+// out[i] = in[i] * scale   (AvgPool2d(7) finish: pooled sums -> means, recnet.py:423)
+__global__ void scale_f32_kernel(const float* __restrict__ in, float* __restrict__ out, long long count, float scale) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = in[i] * scale;
+}
+
+int scale_f32_launch(const float* in, float* out, long long count, float scale, cudaStream_t stream) {
+    scale_f32_kernel<<<(int)((count + 255) / 256), 256, 0, stream>>>(in, out, count, scale);
+    return launch_status("scale_f32_kernel");
+}
+
+}  // namespace ffr

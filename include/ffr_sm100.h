@@ -61,7 +61,10 @@ FFR_API int ffr_conv_gemm(const void* a, int64_t a_rows, int a_cols, int a_ld, c
                   const int* tap_row_shift, const int* tap_ch_off, int M, int rows_per_img, int Wp, int S, int h0,
                   int n_img, uint32_t flags, const float* bias, const float* slope, void* out, int ldo, int s2d_So,
                   float* pool, float* out_f32, const void* res, int ldres, float* stats, int num_splits,
-                  ffr_stream_t stream);
+                  const int* scatter, int scatter_n, int out_rows_per_img, int b_rows_per_mtile, ffr_stream_t stream);
+/*   scatter: device table [rows_per_img][scatter_n][2] of (destination row within the image, channel offset), -1 = none
+ *   (FFR_EPI_SCATTER); b_rows_per_mtile != 0 makes the weight operand batched: M tile i reads weight rows starting at
+ *   i*b_rows_per_mtile (per-sample matrices such as M_channel). */
 
 /* Conv2d(Cin,Cout,3,stride 1,pad 1) on a flat SxS map (model_ir_se50.py:67 with the BatchNorm of :66 folded:
  * scale into wp, shift into the 9-class border bias table `bias9` [9][Cout]) + PReLU (:68).
@@ -103,6 +106,37 @@ FFR_API int ffr_export_nchw_fwd(const void* h, const float* scale, const float* 
  * (zero columns at pad pixels), bias [512] folded; acc [n_img][512] fp32 scratch; f [n_img][512] fp32. */
 FFR_API int ffr_head_fwd(const void* h, int n_img, int S, int C, const void* wp, const float* bias, float* acc, float* f,
                  ffr_stream_t stream);
+
+/* ---- RecNet (models/recnet.py) ------------------------------------------------------------------------------
+ * H9 layout: a 7x7 map with its reflection halo materialised, bf16 [n*81][C], pixel (h,w) at row (h+1)*9+(w+1). */
+
+/* selfSimilarity (recnet.py:220-236), the cat() fan-out of X (:401-402,420) and the thin part of Conv4Channel
+ * (:372-384, up to the input of its last Linear) for one batch. x fp32 NCHW (n,512,7,7).
+ * Outputs: s0 H9 [n*81][576] (X | ss_space | zero pad), cm H9 [n*81][1536] slot [1024,1536) <- X,
+ * xt [n*128][512] (X^T, 49 valid rows), h5 [n*512][64] (32 valid columns), ss_space optional fp32 [n][49][49]. */
+FFR_API int ffr_recnet_prep(const float* x, int n, const float* w0aT, const float* w0bT, const float* b0,
+                            const float* slope1, const float* A1, const float* c1, const float* slope4,
+                            const float* A2, const float* c2, const float* slope7, void* s0, void* cm, void* xt,
+                            void* h5, float* ss_space, ffr_stream_t stream);
+
+/* ConvLayer.forward in eval mode (recnet.py:78-85): ReflectionPad2d(1) -> Conv2d 3x3 -> BatchNorm (folded: scale in
+ * wp, shift = bias) -> PReLU, optionally + residual (ResidualBlock, :213-218) and sigmoid (:370), on H9 rows.
+ * bf16 result rows are scattered through `scatter` (self + reflection mirrors, concat slot, W-flip); out_f32
+ * (optional) receives plain fp32 rows [n*81][Cout]; pool (optional) per-(sample,channel) sums of valid rows. */
+FFR_API int ffr_recnet_convlayer_fwd(const void* x, int n, int Cin, const void* wp, int Cout, const float* bias,
+                                     const float* slope, const void* res, int ldres, int sigmoid, void* out, int ldo,
+                                     const int* scatter, int scatter_n, int out_rows_per_img, float* out_f32,
+                                     float* pool, ffr_stream_t stream);
+
+/* feat_space = X @ M_space (recnet.py:409) -> slot [0,512) of cm (H9 + mirrors); optional fp32 NCHW copy. */
+FFR_API int ffr_feat_space(const float* x, const float* mspace, void* cm, float* out_nchw, int n, ffr_stream_t stream);
+
+/* Rows of a haloed/flat grid -> fp32 NCHW (S x S valid pixels at row (h+off)*G + (w+off)), optional affine. */
+FFR_API int ffr_rows_to_nchw(const void* rows, int is_f32, int ld, int ch0, const float* scale, const float* shift,
+                             float* y, int n, int S, int G, int off, int rows_per_img, int C, ffr_stream_t stream);
+
+/* out = in * scale (AvgPool2d(7) finish, recnet.py:423). */
+FFR_API int ffr_scale_f32(const float* in, float* out, int64_t count, float scale, ffr_stream_t stream);
 
 /* Debug/tuning: 1 (default) lets 3x3 stride-1 convolutions use the sliding-window kernel, 0 forces the
  * tile-per-tap kernel (the two must agree; tests run both). */

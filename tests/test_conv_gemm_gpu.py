@@ -31,13 +31,14 @@ def conv_variant(request, lib):
 
 
 def _gemm(lib, a, wp, cin, cout, taps, M, flags=0, bias=None, slope=None, out=None, ldo=0, geom=(64, 1, 1, 0, 1),
-          s2d_so=0, pool=None, out_f32=None, res=None, ldres=0, stats=None, splits=1):
+          s2d_so=0, pool=None, out_f32=None, res=None, ldres=0, stats=None, splits=1, scatter=None, scatter_n=0,
+          out_rpi=0, b_rows_per_mtile=0):
     shifts = (ctypes.c_int * 9)(*([t[0] for t in taps] + [0] * (9 - len(taps))))
     choffs = (ctypes.c_int * 9)(*([t[1] for t in taps] + [0] * (9 - len(taps))))
     rpi, wp_, s, h0, nimg = geom
     rc = lib.ffr_conv_gemm(P(a), a.shape[0], a.shape[1], a.stride(0), P(wp), cin, cout, len(taps), shifts, choffs, M,
                            rpi, wp_, s, h0, nimg, flags, P(bias), P(slope), P(out), ldo, s2d_so, P(pool), P(out_f32),
-                           P(res), ldres, P(stats), splits, _stream())
+                           P(res), ldres, P(stats), splits, P(scatter), scatter_n, out_rpi, b_rows_per_mtile, _stream())
     _lib.check(rc, "ffr_conv_gemm")
 
 

@@ -1,0 +1,88 @@
+"""GPU parity of ffr_net_b200.RecNet (eval forward, CUDA path through the C ABI) against the fp32 CPU oracle.
+Tolerance: rectified embedding <= 1e-2 max relative error (max|e - e_ref| / max|e_ref|), cosine <= 1e-3 absolute."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import backbone as ob
+from oracle import recnet as orr
+from ffr_net_b200.recnet import RecNet
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def models(lib):
+    sd = orr.synth_recnet_state_dict(0)
+    m = RecNet()
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    return sd, m
+
+
+def _rel(a, b):
+    return ((a - b).abs().max() / b.abs().max()).item()
+
+
+@pytest.mark.parametrize("n", [1, 3, 8])
+def test_recnet_eval_matches_oracle(models, n):
+    sd, m = models
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(n, 512, 7, 7, generator=g) * 0.3
+    with torch.no_grad():
+        v_ref, map_ref = orr.recnet_forward(sd, x)
+        v, fmap = m(x.cuda())
+    torch.cuda.synchronize()
+    v, fmap = v.cpu(), fmap.cpu()
+    assert v.shape == (n, 512) and fmap.shape == (n, 512, 7, 7)
+    assert torch.isfinite(v).all() and torch.isfinite(fmap).all()
+    print("n=%d feat_new_v rel err %.3e  feat_new rel err %.3e" % (n, _rel(v, v_ref), _rel(fmap, map_ref)))
+    assert _rel(v, v_ref) <= 1e-2
+    assert _rel(fmap, map_ref) <= 2e-2
+    assert (F.cosine_similarity(v, v_ref) - 1).abs().max().item() <= 1e-3
+
+
+def test_full_pipeline_matches_oracle(lib, models):
+    """images -> IR-SE50 -> RecNet embedding, CUDA vs oracle, incl. pair cosine of (clean, masked) pairs."""
+    from ffr_net_b200.backbone import Backbone
+    sd, m = models
+    bsd = ob.synth_backbone_state_dict(0)
+    enc = Backbone(50, 0.6, "ir_se")
+    enc.load_state_dict(bsd)
+    enc = enc.cuda().eval()
+    a = ob.synth_faces(4, seed=21)
+    b = ob.synth_faces(4, seed=21, masked=True)
+    with torch.no_grad():
+        ya, _ = ob.backbone_forward(bsd, a)
+        yb, _ = ob.backbone_forward(bsd, b)
+        va_ref, _ = orr.recnet_forward(sd, ya)
+        vb_ref, _ = orr.recnet_forward(sd, yb)
+        va = m.embed_from_images(enc, a.cuda()).cpu()
+        vb = m.embed_from_images(enc, b.cuda()).cpu()
+    print("pipeline rel err %.3e %.3e" % (_rel(va, va_ref), _rel(vb, vb_ref)))
+    assert _rel(va, va_ref) <= 1e-2 and _rel(vb, vb_ref) <= 1e-2
+    cos_ref = F.cosine_similarity(va_ref, vb_ref)
+    cos = F.cosine_similarity(va, vb)
+    assert (cos - cos_ref).abs().max().item() <= 1e-3
+
+
+def test_recnet_batch_invariance(models):
+    sd, m = models
+    g = torch.Generator().manual_seed(77)
+    x = (torch.randn(5, 512, 7, 7, generator=g) * 0.3).cuda()
+    with torch.no_grad():
+        v5, _ = m(x)
+        v1, _ = m(x[3:4])
+    assert (v5[3:4] - v1).abs().max().item() <= 1e-5 * v1.abs().max().item() + 1e-6
+
+
+def test_recnet_rejects_cpu_and_training(models):
+    sd, m = models
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 512, 7, 7))
+    m.train()
+    try:
+        with pytest.raises(NotImplementedError):
+            m(torch.zeros(2, 512, 7, 7, device="cuda"))
+    finally:
+        m.eval()
