@@ -25,6 +25,8 @@ _SIGNATURES = {
     "ffr_recnet_convlayer_fwd": (_i, [_p, _i, _i, _p, _i, _p, _p, _p, _i, _i, _p, _i, _p, _i, _i, _p, _p, _p]),
     "ffr_feat_space": (_i, [_p, _p, _p, _p, _i, _p]),
     "ffr_rows_to_nchw": (_i, [_p, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "ffr_pair_cosine": (_i, [_p, _p, _p, _i, _i, _p]),
+    "ffr_threshold_sweep": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "ffr_scale_f32": (_i, [_p, _p, _i64, ctypes.c_float, _p]),
     "ffr_conv3x3_bnpre_prelu_fwd": (_i, [_p, _i, _i, _i, _p, _i, _p, _p, _p, _i, _p]),
     "ffr_conv3x3_bn_pool_fwd": (_i, [_p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p]),

@@ -28,6 +28,10 @@ int feat_space_launch(const float* x, const float* mspace, void* cm, float* out_
 int rows_to_nchw_launch(const void* rows, int is_f32, int ld, int ch0, const float* scale, const float* shift, float* y,
                         int n, int S, int G, int off, int rows_per_img, int C, cudaStream_t stream);
 int scale_f32_launch(const float* in, float* out, long long count, float scale, cudaStream_t stream);
+int pair_cosine_launch(const float* f1, const float* f2, float* score, int pairs, int D, cudaStream_t stream);
+int threshold_sweep_launch(const float* score, const int* label, const double* thresholds, int n, int T, int folds,
+                           int* best_idx, double* best_thr, int* test_correct, int* train_correct,
+                           cudaStream_t stream);
 }  // namespace ffr
 
 using namespace ffr;
@@ -257,6 +261,20 @@ FFR_API int ffr_rows_to_nchw(const void* rows, int is_f32, int ld, int ch0, cons
 FFR_API int ffr_scale_f32(const float* in, float* out, int64_t count, float scale, ffr_stream_t stream) {
     FFR_CHECK_ARG(in && out, "ffr_scale_f32: null pointer");
     return scale_f32_launch(in, out, count, scale, S_(stream));
+}
+
+FFR_API int ffr_pair_cosine(const float* f1, const float* f2, float* score, int pairs, int D, ffr_stream_t stream) {
+    FFR_CHECK_ARG(pairs == 0 || (f1 && f2 && score), "ffr_pair_cosine: null pointer");
+    return pair_cosine_launch(f1, f2, score, pairs, D, S_(stream));
+}
+
+FFR_API int ffr_threshold_sweep(const float* score, const int* label, const double* thresholds, int n, int T, int folds,
+                                int* best_idx, double* best_thr, int* test_correct, int* train_correct,
+                                ffr_stream_t stream) {
+    FFR_CHECK_ARG(score && label && thresholds && best_idx && best_thr && test_correct && train_correct,
+                  "ffr_threshold_sweep: null pointer");
+    return threshold_sweep_launch(score, label, thresholds, n, T, folds, best_idx, best_thr, test_correct,
+                                  train_correct, S_(stream));
 }
 
 }  // extern "C"

@@ -138,6 +138,19 @@ FFR_API int ffr_rows_to_nchw(const void* rows, int is_f32, int ld, int ch0, cons
 /* out = in * scale (AvgPool2d(7) finish, recnet.py:423). */
 FFR_API int ffr_scale_f32(const float* in, float* out, int64_t count, float scale, ffr_stream_t stream);
 
+/* ---- LFW-style verification scoring (lfw/lfw_eval.py) ------------------------------------------------------ */
+
+/* score[i] = sum(f1[i]*f2[i]) / (|f1[i]|*|f2[i]| + 1e-8)  (lfw_eval.py:246,248); f1, f2 fp32 [pairs][D]. */
+FFR_API int ffr_pair_cosine(const float* f1, const float* f2, float* score, int pairs, int D, ffr_stream_t stream);
+
+/* K-fold threshold sweep (lfw_eval.py:110-118 KFold, :137-153 eval_acc, :155-162 find_best_threshold,
+ * :255-259 get_fold_accuracy): contiguous folds; "same" iff (double)score > thresholds[t]; per fold the LAST threshold
+ * with maximal training accuracy and the held-out accuracy at it. thresholds: fp64 [T] (upload np.arange(-1,1,.005)
+ * bit-for-bit); outputs per fold: best_idx, best_thr (fp64), test_correct, train_correct (integer counts). */
+FFR_API int ffr_threshold_sweep(const float* score, const int* label, const double* thresholds, int n, int T, int folds,
+                                int* best_idx, double* best_thr, int* test_correct, int* train_correct,
+                                ffr_stream_t stream);
+
 /* Debug/tuning: 1 (default) lets 3x3 stride-1 convolutions use the sliding-window kernel, 0 forces the
  * tile-per-tap kernel (the two must agree; tests run both). */
 FFR_API int ffr_debug_set_window(int enable);

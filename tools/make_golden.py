@@ -1,0 +1,127 @@
+"""Generates tests/golden/*.npz by running the REAL reference (imported from /root/reference, read-only) on the
+deterministic synthetic weights/inputs of oracle/. Run in the build container only:
+
+    python tools/make_golden.py
+
+The fixtures pin the oracle (and, through it, the CUDA path) to the reference's behaviour; the reference itself ships
+no tests or golden vectors. Modules the reference imports but this image lacks (imageio, skimage,
+tensorboardX, matplotlib) are stubbed — they are not on the hot path.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+sys.dont_write_bytecode = True
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+from oracle import backbone as ob  # noqa: E402
+from oracle import recnet as orr  # noqa: E402
+from oracle import scoring as osc  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+class _Stub(types.ModuleType):
+    """Module stand-in: any attribute is a no-op callable/class (the stubbed modules are never used on the hot path)."""
+    __path__ = []
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return type(name, (), {"__init__": lambda self, *a, **k: None, "__call__": lambda self, *a, **k: None})
+
+
+def stub_missing():
+    for name in ("imageio", "skimage", "skimage.transform", "skimage.io", "tensorboardX", "matplotlib",
+                 "matplotlib.pyplot", "h5py"):
+        ok = False
+        if name not in ("imageio",):
+            try:
+                __import__(name)
+                ok = True
+            except Exception:
+                ok = False
+        if not ok:
+            sys.modules[name] = _Stub(name)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    from pretrain.model_ir_se50 import Backbone
+    import models.recnet as mr
+
+    # ---- backbone ----
+    sd = ob.synth_backbone_state_dict(0)
+    ref = Backbone(50, 0.6, "ir_se").eval()
+    ref.load_state_dict(sd, strict=True)
+    x = ob.synth_faces(2, seed=1)
+    xm = ob.synth_faces(2, seed=1, masked=True)
+    with torch.no_grad():
+        y, f = ref(x)
+        ym, fm = ref(xm)
+    np.savez_compressed(os.path.join(OUT, "backbone_ref.npz"), f=f.numpy(), f_masked=fm.numpy(),
+                        y_slice=y[:, ::64, :, :].numpy(), y_abs_sum=np.float64(y.double().abs().sum().item()),
+                        ym_abs_sum=np.float64(ym.double().abs().sum().item()))
+
+    # ---- RecNet eval + train-mode (label) forward ----
+    rsd = orr.synth_recnet_state_dict(0)
+    rec = mr.RecNet()
+    rec.load_state_dict(rsd, strict=True)
+    g = torch.Generator().manual_seed(3)
+    fx = torch.randn(3, 512, 7, 7, generator=g) * 0.3
+    label = torch.randint(0, 10575, (3,), generator=g)
+    rec.eval()
+    with torch.no_grad():
+        v, fmap = rec(fx)
+    _z = torch.zeros
+    mr.torch.zeros = lambda *a, **k: _z(*a, **{kk: vv for kk, vv in k.items() if kk != "device"})  # recnet.py:262
+    rec.train()
+    with torch.no_grad():
+        out = rec(fx, label)
+    mr.torch.zeros = _z
+    tsd = rec.state_dict()
+    np.savez_compressed(
+        os.path.join(OUT, "recnet_ref.npz"), v=v.numpy(), fmap_slice=fmap[:, ::64].numpy(),
+        label=label.numpy(), t_v=out[0].numpy(), t_pred_loss_slice=out[1][:, ::97].numpy(),
+        t_pred_label_slice=out[2][:, ::97].numpy(), t_m_space=out[3].numpy(), t_m_channel_slice=out[4][:, ::37, ::41].numpy(),
+        t_feat_space_slice=out[5][:, ::64].numpy(), t_feat_channel_slice=out[6][:, ::64].numpy(),
+        t_run_mean_merge0=tsd["Conv4Merge.0.norm.norm.running_mean"].numpy(),
+        t_run_var_merge0=tsd["Conv4Merge.0.norm.norm.running_var"].numpy(),
+        t_nbt=np.int64(tsd["Conv4Merge.0.norm.norm.num_batches_tracked"].item()))
+
+    # ---- selfSimilarity ----
+    with torch.no_grad():
+        ss_s, ss_c = mr.selfSimilarity(fx)
+    np.savez_compressed(os.path.join(OUT, "selfsim_ref.npz"), ss_space=ss_s.numpy(), ss_channel_slice=ss_c[:, ::16, ::16].numpy())
+
+    # ---- scoring: the real lfw_eval functions on 6000 synthetic pairs ----
+    stub_missing()
+    import lfw.lfw_eval as le
+    scores, labels = osc.synth_pair_scores(6000, 0)
+    pred = np.array([scores.astype(np.float64).tolist(), labels.tolist(), list(range(6000))]).T
+    folds = le.KFold(n=6000, n_folds=10, shuffle=False)
+    best, acc = [], []
+    for fold in folds:
+        b, a = le.get_fold_accuracy(fold, pred, 0)
+        best.append(b)
+        acc.append(a)
+    f1 = torch.randn(16, 512, generator=g)
+    f2 = torch.randn(16, 512, generator=g) + 0.5 * f1
+    cos = torch.sum(f1 * f2, dim=1) / (f1.norm(dim=1) * f2.norm(dim=1) + 1e-8)     # lfw_eval.py:246 verbatim formula
+    np.savez_compressed(os.path.join(OUT, "scoring_ref.npz"), scores=scores, labels=labels, best_thr=np.array(best),
+                        test_acc=np.array(acc), avg_acc=np.float64(sum(acc) / 10), f1=f1.numpy(), f2=f2.numpy(),
+                        cos=cos.numpy())
+    print("golden fixtures written to", OUT)
+    for fn in sorted(os.listdir(OUT)):
+        print(fn, os.path.getsize(os.path.join(OUT, fn)))
+
+
+if __name__ == "__main__":
+    main()
