@@ -316,61 +316,64 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int kb_total = p.ntaps * p.kb_per_tap;
 
     if (warp == WARP_TMA) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
-                const int split = work % p.num_splits;
-                const int t = work / p.num_splits;
-                const int n_tile = t % p.num_n_tiles;
-                const int m_tile = t / p.num_n_tiles;
-                const int m0 = m_tile * BLOCK_M;
-                const int n0 = n_tile * BN;
-                const int kb0 = split * p.kb_per_split;
-                const int kb1 = min(kb0 + p.kb_per_split, kb_total);
-                int tap = kb0 / p.kb_per_tap;
-                int c = kb0 - tap * p.kb_per_tap;
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+        // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+            const int split = work % p.num_splits;
+            const int t = work / p.num_splits;
+            const int n_tile = t % p.num_n_tiles;
+            const int m_tile = t / p.num_n_tiles;
+            const int m0 = m_tile * BLOCK_M;
+            const int b_row = n_tile * BN + m_tile * p.b_rows_per_mtile;
+            const int kb0 = split * p.kb_per_split;
+            const int kb1 = min(kb0 + p.kb_per_split, kb_total);
+            int tap = kb0 / p.kb_per_tap;
+            int c = kb0 - tap * p.kb_per_tap;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                const int a_col = p.tap_ch_off[tap] + c * BLOCK_K;
+                const int a_row = m0 + p.tap_row_shift[tap];
+                if (elect_one_sync()) {
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                    tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], p.tap_ch_off[tap] + c * BLOCK_K,
-                                m0 + p.tap_row_shift[tap]);
-                    tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K,
-                                n0 + m_tile * p.b_rows_per_mtile);
-                    if (++c == p.kb_per_tap) { c = 0; ++tap; }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], a_col, a_row);
+                    tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, b_row);
                 }
+                __syncwarp();
+                if (++c == p.kb_per_tap) { c = 0; ++tap; }
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == WARP_MMA) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++it) {
-                const int split = work % p.num_splits;
-                const int kb0 = split * p.kb_per_split;
-                const int kb1 = min(kb0 + p.kb_per_split, kb_total);
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1;
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+        constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++it) {
+            const int split = work % p.num_splits;
+            const int kb0 = split * p.kb_per_split;
+            const int kb1 = min(kb0 + p.kb_per_split, kb_total);
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint64_t a_desc = umma_smem_desc_sw128(smem_u32(sA + stage * A_STAGE_BYTES));
-                    const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(sB + stage * Cfg::B_STAGE_BYTES));
+                const uint64_t a_desc = umma_smem_desc_sw128(smem_u32(sA + stage * A_STAGE_BYTES));
+                const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(sB + stage * Cfg::B_STAGE_BYTES));
+                const uint32_t first = (kb > kb0) ? 1u : 0u;
+                if (elect_one_sync()) {
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / 16; ++k)   // +32 B per K step == +2 in the (addr >> 4) field
-                        umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (k > 0) ? 1u : first);
+                    umma_commit(&empty_bar[stage]);          // frees the smem slot once these MMAs retire
+                    if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
                 }
-                umma_commit(&tfull_bar[acc]);        // accumulator complete -> epilogue
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp < 8) {
@@ -446,65 +449,73 @@ conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int chunks = p.kb_per_tap;
 
     if (warp == WARP_TMA) {
-        if (lane == 0) {
-            int sa = 0, sb = 0;
-            uint32_t pa = 0, pb = 0;
-            for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
-                const int n_tile = work % p.num_n_tiles;
-                const int m_tile = work / p.num_n_tiles;
-                const int row0 = m_tile * BLOCK_M - wc.G - 1;
-                const int n0 = n_tile * BN;
-                for (int c = 0; c < chunks; ++c) {
-                    mbar_wait(&a_empty[sa], pa ^ 1);
+        int sa = 0, sb = 0;
+        uint32_t pa = 0, pb = 0;
+        for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+            const int n_tile = work % p.num_n_tiles;
+            const int m_tile = work / p.num_n_tiles;
+            const int row0 = m_tile * BLOCK_M - wc.G - 1;
+            const int n0 = n_tile * BN;
+            for (int c = 0; c < chunks; ++c) {
+                mbar_wait(&a_empty[sa], pa ^ 1);
+                uint8_t* dst = sA + sa * win_bytes;
+                if (elect_one_sync()) {
                     mbar_arrive_expect_tx(&a_full[sa], win_bytes);
-                    uint8_t* dst = sA + sa * win_bytes;
                     tma_load_2d(dst, &tmA, &a_full[sa], c * BLOCK_K, row0);
                     if (wc.nbox == 2)
                         tma_load_2d(dst + wc.box_rows * 128, &tmA, &a_full[sa], c * BLOCK_K, row0 + wc.box_rows);
-                    if (++sa == wc.a_stages) { sa = 0; pa ^= 1; }
-                    for (int t = 0; t < 9; ++t) {
-                        mbar_wait(&b_empty[sb], pb ^ 1);
+                }
+                __syncwarp();
+                if (++sa == wc.a_stages) { sa = 0; pa ^= 1; }
+#pragma unroll 1
+                for (int t = 0; t < 9; ++t) {
+                    mbar_wait(&b_empty[sb], pb ^ 1);
+                    if (elect_one_sync()) {
                         mbar_arrive_expect_tx(&b_full[sb], B_STAGE_BYTES);
                         tma_load_2d(sB + sb * B_STAGE_BYTES, &tmB, &b_full[sb], (t * chunks + c) * BLOCK_K, n0);
-                        if (++sb == wc.b_stages) { sb = 0; pb ^= 1; }
                     }
+                    __syncwarp();
+                    if (++sb == wc.b_stages) { sb = 0; pb ^= 1; }
                 }
             }
         }
     } else if (warp == WARP_MMA) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN);
-            int sa = 0, sb = 0;
-            uint32_t pa = 0, pb = 0;
-            int it = 0;
-            for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++it) {
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1;
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN);
+        int sa = 0, sb = 0;
+        uint32_t pa = 0, pb = 0;
+        int it = 0;
+        for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int c = 0; c < chunks; ++c) {
+                mbar_wait(&a_full[sa], pa);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int c = 0; c < chunks; ++c) {
-                    mbar_wait(&a_full[sa], pa);
-                    tc_fence_after();
-                    const uint32_t win = smem_u32(sA + sa * win_bytes);
+                const uint32_t win = smem_u32(sA + sa * win_bytes);
 #pragma unroll 1
-                    for (int t = 0; t < 9; ++t) {
-                        mbar_wait(&b_full[sb], pb);
-                        tc_fence_after();
-                        const int r = t / 3, sx = t - 3 * r;
-                        const uint64_t a_desc =
-                            umma_smem_desc_sw128(win + static_cast<uint32_t>(r * wc.G + sx) * 128u);
-                        const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(sB + sb * B_STAGE_BYTES));
+                for (int t = 0; t < 9; ++t) {
+                    mbar_wait(&b_full[sb], pb);
+                    tc_fence_after();
+                    const int r = t / 3, sx = t - 3 * r;
+                    const uint64_t a_desc = umma_smem_desc_sw128(win + static_cast<uint32_t>(r * wc.G + sx) * 128u);
+                    const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(sB + sb * B_STAGE_BYTES));
+                    const uint32_t first = (c > 0 || t > 0) ? 1u : 0u;
+                    if (elect_one_sync()) {
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / 16; ++k)
-                            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (c > 0 || t > 0 || k > 0) ? 1u : 0u);
+                            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (k > 0) ? 1u : first);
                         umma_commit(&b_empty[sb]);
-                        if (++sb == wc.b_stages) { sb = 0; pb ^= 1; }
+                        if (t == 8) {
+                            umma_commit(&a_empty[sa]);
+                            if (c == chunks - 1) umma_commit(&tfull_bar[acc]);
+                        }
                     }
-                    umma_commit(&a_empty[sa]);
-                    if (++sa == wc.a_stages) { sa = 0; pa ^= 1; }
+                    __syncwarp();
+                    if (++sb == wc.b_stages) { sb = 0; pb ^= 1; }
                 }
-                umma_commit(&tfull_bar[acc]);
+                if (++sa == wc.a_stages) { sa = 0; pa ^= 1; }
             }
         }
     } else if (warp < 8) {

@@ -77,3 +77,58 @@ extern "C" FFR_API int ffr_debug_rowshift_probe(const void* a, const void* w, fl
     rowshift_probe_kernel<<<1, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tmA, tmB, out, row_off, variant);
     return launch_status("rowshift_probe_kernel");
 }
+
+// ----------------------------------------------------------------------------------------------------------
+// Micro-benchmark (debug): issue rate of tcgen05.mma.kind::f16 (SS mode, K = 16 per instruction) as a function of
+// the instruction shape and of how many independent accumulators the instruction stream alternates between.
+// Operands are whatever is in shared memory (timing only). out[0] = cycles for `iters` MMAs on one CTA.
+// ----------------------------------------------------------------------------------------------------------
+namespace ffr {
+__global__ void __launch_bounds__(128, 1) mma_bench_kernel(long long* out, int M, int N, int n_acc, int iters) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < (128 * 128 + 256 * 128) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    fence_proxy_async_smem();
+    if (warp == 0) tmem_alloc<512>(&tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = umma_idesc_bf16(M, N);
+        const uint64_t a_desc = umma_smem_desc_sw128(smem_u32(smem));
+        const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(smem + 128 * 128));
+        // warm-up
+        for (int i = 0; i < 8; ++i) umma_bf16(tmem_base, a_desc, b_desc, idesc, 1);
+        umma_commit(&bar);
+        mbar_wait(&bar, 0);
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            const int acc = i % n_acc;
+            umma_bf16(tmem_base + acc * N, a_desc + 2 * (i & 3), b_desc + 2 * (i & 3), idesc, 1);
+        }
+        umma_commit(&bar);
+        mbar_wait(&bar, 1);
+        const long long t1 = clock64();
+        out[blockIdx.x] = t1 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc<512>(tmem_base); }
+}
+}  // namespace ffr
+
+extern "C" FFR_API int ffr_debug_mma_bench(long long* out_cycles, int M, int N, int n_acc, int iters, int grid,
+                                           ffr_stream_t stream) {
+    using namespace ffr;
+    FFR_CHECK_ARG((M == 64 || M == 128) && N >= 16 && N <= 256 && N % 16 == 0 && n_acc >= 1 && n_acc * N <= 512,
+                  "mma_bench: bad shape");
+    const int smem = 1024 + 128 * 128 + 256 * 128;
+    FFR_CUDA(cudaFuncSetAttribute(mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    mma_bench_kernel<<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(out_cycles, M, N, n_acc, iters);
+    return launch_status("mma_bench_kernel");
+}

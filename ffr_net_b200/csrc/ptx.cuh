@@ -13,6 +13,21 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a converged warp is elected. Loops that issue TMA / tcgen05.mma must stay WARP-UNIFORM (all 32 lanes
+// run the loop, operands are computed by all lanes, only the issue itself is guarded by the election): the SASS
+// operands of UTCHMMA / UTMALDG are uniform registers, and code inside an `if (lane == 0)` region makes the
+// compiler wrap every issue in an ELECT / R2UR.BROADCAST / BRA.U.ANY serialisation loop (~150 cycles per MMA,
+// measured in profiles/r01_mma_issue.md).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------

@@ -160,6 +160,11 @@ FFR_API int ffr_debug_set_window(int enable);
 FFR_API int ffr_debug_rowshift_probe(const void* a, const void* w, float* out, int row_off, int variant,
                                      ffr_stream_t stream);
 
+/* Debug: tcgen05.mma issue-rate micro-benchmark (csrc/probe.cu). out_cycles[grid] = cycles for `iters` MMAs of shape
+ * M x N x 16 alternating between n_acc accumulators. */
+FFR_API int ffr_debug_mma_bench(long long* out_cycles, int M, int N, int n_acc, int iters, int grid,
+                                ffr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
