@@ -53,11 +53,12 @@ __device__ __forceinline__ void fast_divmod(int m, int d, float inv_d, int& q, i
 
 // ===================== Epilogue: TMEM -> registers -> fused ops -> global =====================
 // Runs on warps 0..7 (256 threads). Warp w reads TMEM lanes 32*(w%4).. (tile rows) and the column half w/4.
-template <int BN>
+// A work item is SUB consecutive 128-row tiles (SUB accumulators side by side in the TMEM buffer).
+template <int BN, int SUB>
 __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uint32_t tmem_base, uint64_t* tfull_bar,
                                               uint64_t* tempty_bar, float* sparam, const int warp, const int lane) {
     constexpr int HALF = BN / 2;                 // columns per epilogue warp
-    const int num_work = p.num_m_tiles * p.num_n_tiles * p.num_splits;
+    const int num_work = ((p.num_m_tiles + SUB - 1) / SUB) * p.num_n_tiles * p.num_splits;
     const int quad = warp & 3;                   // TMEM lane quadrant == warp % 4
     const int chalf = warp >> 2;                    // which half of the accumulator columns
     const int row_in_tile = quad * 32 + lane;
@@ -73,8 +74,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
     for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++it) {
         const int t = work / p.num_splits;
         const int n_tile = t % p.num_n_tiles;
-        const int m_tile = t / p.num_n_tiles;
-        const int m0 = m_tile * BLOCK_M;
+        const int m_group = t / p.num_n_tiles;
         const int n0 = n_tile * BN;
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
@@ -90,7 +90,9 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
             loaded_n_tile = n_tile;
         }
 
-        const int m = m0 + row_in_tile;
+#pragma unroll 1
+        for (int sub = 0; sub < SUB; ++sub) {
+        const int m = (m_group * SUB + sub) * BLOCK_M + row_in_tile;
         int n_img = 0, h = 0, w = 0, r_local = 0;
         bool valid = m < p.M;
         int cls = 0;
@@ -146,9 +148,11 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
         const int n_lo = __shfl_sync(0xffffffffu, n_img, 0);
         const int n_hi = __shfl_sync(0xffffffffu, n_img, 31);
 
-        mbar_wait(&tfull_bar[acc], acc_phase);
-        tc_fence_after();
-        const uint32_t t_row = tmem_base + acc * BN + chalf * HALF + (static_cast<uint32_t>(quad * 32) << 16);
+        if (sub == 0) {
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+        }
+        const uint32_t t_row = tmem_base + (acc * SUB + sub) * BN + chalf * HALF + (static_cast<uint32_t>(quad * 32) << 16);
 
         uint32_t vbuf[2][32];
         tmem_ld_32x32(t_row, vbuf[0]);
@@ -264,6 +268,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
                 }
             }
         }
+        }   // sub
         tc_fence_before();
         mbar_arrive(&tempty_bar[acc]);
     }
@@ -377,7 +382,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else if (warp < 8) {
-        epilogue_loop<BN>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane);
+        epilogue_loop<BN, 1>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane);
     }
 
     tc_fence_before();
@@ -398,20 +403,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // Weights stream through their own ring, one [BN x 64] tile per (chunk, tap).
 // ----------------------------------------------------------------------------------------------------------
 constexpr int WIN_MAX_A_STAGES = 4;
-constexpr int WIN_MAX_B_STAGES = 8;
+constexpr int WIN_MAX_B_STAGES = 9;
 
 struct WinCfg {
     int G;            // row pitch of the flat map
     int box_rows;     // rows per TMA box (multiple of 8, <= 256)
     int nbox;         // 1 or 2 boxes per window
     int a_stages, b_stages;
+    int b_resident;   // all 9 weight tiles of the (single) channel chunk stay in smem for the whole kernel
 };
 
-template <int BN>
+// SUB = 128-row sub-tiles per work item. With SUB = 2 every weight tile that lands in smem feeds two MMAs groups
+// (halving the weight traffic through shared memory, which is what bounds the 64/128-channel layers) and the
+// window halo is amortised over 256 rows. Needs 2*SUB*BN <= 512 TMEM columns.
+template <int BN, int SUB>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const ConvGemmParams p, const WinCfg wc) {
     constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
+    constexpr uint32_t TMEM_COLS = 2 * SUB * BN;
+    static_assert(TMEM_COLS <= 512, "accumulators do not fit TMEM");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int win_bytes = wc.box_rows * wc.nbox * 128;            // multiple of 1024
@@ -439,22 +450,24 @@ conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], EPI_THREADS); }
         fence_mbar_init();
     }
-    if (warp == WARP_ALLOC) tmem_alloc<2 * BN>(tmem_slot);
+    if (warp == WARP_ALLOC) tmem_alloc<TMEM_COLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int num_work = p.num_m_tiles * p.num_n_tiles;
+    const int num_work = ((p.num_m_tiles + SUB - 1) / SUB) * p.num_n_tiles;
     const int chunks = p.kb_per_tap;
+    const bool resident = wc.b_resident != 0;
 
     if (warp == WARP_TMA) {
         int sa = 0, sb = 0;
         uint32_t pa = 0, pb = 0;
+        bool b_loaded = false;
         for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
             const int n_tile = work % p.num_n_tiles;
-            const int m_tile = work / p.num_n_tiles;
-            const int row0 = m_tile * BLOCK_M - wc.G - 1;
+            const int m_group = work / p.num_n_tiles;
+            const int row0 = m_group * (SUB * BLOCK_M) - wc.G - 1;
             const int n0 = n_tile * BN;
             for (int c = 0; c < chunks; ++c) {
                 mbar_wait(&a_empty[sa], pa ^ 1);
@@ -467,9 +480,10 @@ conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
                 __syncwarp();
                 if (++sa == wc.a_stages) { sa = 0; pa ^= 1; }
+                if (resident && b_loaded) continue;
 #pragma unroll 1
                 for (int t = 0; t < 9; ++t) {
-                    mbar_wait(&b_empty[sb], pb ^ 1);
+                    if (!resident) mbar_wait(&b_empty[sb], pb ^ 1);
                     if (elect_one_sync()) {
                         mbar_arrive_expect_tx(&b_full[sb], B_STAGE_BYTES);
                         tma_load_2d(sB + sb * B_STAGE_BYTES, &tmB, &b_full[sb], (t * chunks + c) * BLOCK_K, n0);
@@ -478,6 +492,7 @@ conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (++sb == wc.b_stages) { sb = 0; pb ^= 1; }
                 }
             }
+            b_loaded = true;
         }
     } else if (warp == WARP_MMA) {
         constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN);
@@ -489,14 +504,14 @@ conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * BN;
+            const uint32_t d_tmem = tmem_base + acc * (SUB * BN);
             for (int c = 0; c < chunks; ++c) {
                 mbar_wait(&a_full[sa], pa);
                 tc_fence_after();
                 const uint32_t win = smem_u32(sA + sa * win_bytes);
 #pragma unroll 1
                 for (int t = 0; t < 9; ++t) {
-                    mbar_wait(&b_full[sb], pb);
+                    if (!resident || it == 0) mbar_wait(&b_full[sb], pb);
                     tc_fence_after();
                     const int r = t / 3, sx = t - 3 * r;
                     const uint64_t a_desc = umma_smem_desc_sw128(win + static_cast<uint32_t>(r * wc.G + sx) * 128u);
@@ -504,9 +519,12 @@ conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const uint32_t first = (c > 0 || t > 0) ? 1u : 0u;
                     if (elect_one_sync()) {
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / 16; ++k)
-                            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (k > 0) ? 1u : first);
-                        umma_commit(&b_empty[sb]);
+                        for (int sub = 0; sub < SUB; ++sub)
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 16; ++k)   // sub-tile: +128 rows = +1024 (>>4) in the address
+                                umma_bf16(d_tmem + sub * BN, a_desc + (sub * 1024 + 2 * k), b_desc + 2 * k, idesc,
+                                          (k > 0) ? 1u : first);
+                        if (!resident) umma_commit(&b_empty[sb]);
                         if (t == 8) {
                             umma_commit(&a_empty[sa]);
                             if (c == chunks - 1) umma_commit(&tfull_bar[acc]);
@@ -519,26 +537,26 @@ conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
     } else if (warp < 8) {
-        epilogue_loop<BN>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane);
+        epilogue_loop<BN, SUB>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane);
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == WARP_ALLOC) {
         tc_fence_after();
-        tmem_dealloc<2 * BN>(tmem_base);
+        tmem_dealloc<TMEM_COLS>(tmem_base);
     }
 }
 
-template <int BN>
+template <int BN, int SUB>
 static int launch_win(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, const WinCfg& wc,
                       int smem_bytes, int grid, cudaStream_t stream) {
-    static int attr_bytes = 0;
-    if (attr_bytes < smem_bytes) {
-        FFR_CUDA(cudaFuncSetAttribute(conv_win_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        attr_bytes = 232448;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FFR_CUDA(cudaFuncSetAttribute(conv_win_kernel<BN, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        attr_set = true;
     }
-    conv_win_kernel<BN><<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, p, wc);
+    conv_win_kernel<BN, SUB><<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, p, wc);
     return launch_status("conv_win_kernel");
 }
 
@@ -608,27 +626,35 @@ int conv_gemm_launch(const void* a, long long a_rows, int a_cols, int a_ld, cons
     if (window_eligible(p, &G)) {
         WinCfg wc;
         wc.G = G;
-        const int need = BLOCK_M + 2 * G + 2;
+        const int SUB = (BN <= 128) ? 2 : 1;
+        const int need = SUB * BLOCK_M + 2 * G + 2;
         if (need <= 256) { wc.nbox = 1; wc.box_rows = (need + 7) & ~7; }
         else             { wc.nbox = 2; wc.box_rows = (((need + 1) / 2) + 7) & ~7; }
         const int win_bytes = wc.box_rows * wc.nbox * 128;
         const int b_stage = BN * BLOCK_K * 2;
         const int fixed = 1024 + 512 + 10 * BN * 4;
-        const int budget = 225 * 1024 - fixed;
-        // weights ring: up to ~96 KB; windows get the rest (at least 2 stages)
-        wc.b_stages = (96 * 1024) / b_stage;
-        if (wc.b_stages > WIN_MAX_B_STAGES) wc.b_stages = WIN_MAX_B_STAGES;
-        if (wc.b_stages < 2) wc.b_stages = 2;
+        const int budget = 226 * 1024 - fixed;
+        // weights: resident if all 9 tiles of a single-chunk layer fit next to two windows, else a ring that takes
+        // what two windows leave (deep enough to cover the TMA latency); windows take the rest.
+        wc.b_resident = (p.kb_per_tap == 1 && p.num_n_tiles == 1 && 9 * b_stage + 2 * win_bytes <= budget) ? 1 : 0;
+        if (wc.b_resident) {
+            wc.b_stages = 9;
+        } else {
+            wc.b_stages = (budget - 2 * win_bytes) / b_stage;
+            if (wc.b_stages > 8) wc.b_stages = 8;
+        }
         wc.a_stages = (budget - wc.b_stages * b_stage) / win_bytes;
         if (wc.a_stages > WIN_MAX_A_STAGES) wc.a_stages = WIN_MAX_A_STAGES;
-        if (wc.a_stages >= 2 && wc.box_rows <= 256) {
+        if (wc.a_stages >= 2 && wc.b_stages >= 3 && wc.box_rows <= 256) {
             rc = make_tmap_2d_bf16(&tmA, a, (uint64_t)a_rows, (uint64_t)a_cols, (uint64_t)a_ld, wc.box_rows);
             if (rc) return rc;
             const int smem_bytes = fixed + wc.a_stages * win_bytes + wc.b_stages * b_stage;
+            const long long work = (long long)((p.num_m_tiles + SUB - 1) / SUB) * p.num_n_tiles;
+            const int wgrid = (int)((work < num_sms()) ? work : num_sms());
             switch (BN) {
-                case 256: return launch_win<256>(tmA, tmB, p, wc, smem_bytes, grid, stream);
-                case 128: return launch_win<128>(tmA, tmB, p, wc, smem_bytes, grid, stream);
-                default:  return launch_win<64>(tmA, tmB, p, wc, smem_bytes, grid, stream);
+                case 256: return launch_win<256, 1>(tmA, tmB, p, wc, smem_bytes, wgrid, stream);
+                case 128: return launch_win<128, 2>(tmA, tmB, p, wc, smem_bytes, wgrid, stream);
+                default:  return launch_win<64, 2>(tmA, tmB, p, wc, smem_bytes, wgrid, stream);
             }
         }
     }

@@ -98,23 +98,31 @@ __global__ void __launch_bounds__(128, 1) mma_bench_kernel(long long* out, int M
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
-    if (threadIdx.x == 0) {
+    if (warp == 1) {   // warp-uniform issue loop, one elected lane issues (see ptx.cuh: elect_one_sync)
         const uint32_t idesc = umma_idesc_bf16(M, N);
         const uint64_t a_desc = umma_smem_desc_sw128(smem_u32(smem));
         const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(smem + 128 * 128));
-        // warm-up
-        for (int i = 0; i < 8; ++i) umma_bf16(tmem_base, a_desc, b_desc, idesc, 1);
-        umma_commit(&bar);
+        if (elect_one_sync()) {
+            for (int i = 0; i < 8; ++i) umma_bf16(tmem_base, a_desc, b_desc, idesc, 1);
+            umma_commit(&bar);
+        }
+        __syncwarp();
         mbar_wait(&bar, 0);
         const long long t0 = clock64();
-        for (int i = 0; i < iters; ++i) {
-            const int acc = i % n_acc;
-            umma_bf16(tmem_base + acc * N, a_desc + 2 * (i & 3), b_desc + 2 * (i & 3), idesc, 1);
+        const uint32_t mask = n_acc - 1;
+        for (int i = 0; i < iters; i += 4) {
+            const uint32_t d0 = tmem_base + ((i >> 2) & mask) * N;
+            if (elect_one_sync()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(d0, a_desc + 2 * k, b_desc + 2 * k, idesc, 1);
+            }
+            __syncwarp();
         }
-        umma_commit(&bar);
+        if (elect_one_sync()) umma_commit(&bar);
+        __syncwarp();
         mbar_wait(&bar, 1);
         const long long t1 = clock64();
-        out[blockIdx.x] = t1 - t0;
+        if (threadIdx.x == 32) out[blockIdx.x] = t1 - t0;
     }
     tc_fence_before();
     __syncthreads();
