@@ -18,6 +18,7 @@ int export_nchw_launch(const void* h, const float* scale, const float* shift, fl
                        cudaStream_t stream);
 int bias_l2norm_launch(const float* acc, const float* bias, float* f, int rows, int D, cudaStream_t stream);
 void set_use_window(bool on);
+void set_debug_counters(unsigned long long* dptr);
 struct PrepParams {
     const float* x; const float* w0aT; const float* w0bT; const float* b0; const float* slope1; const float* A1;
     const float* c1; const float* slope4; const float* A2; const float* c2; const float* slope7;
@@ -70,6 +71,11 @@ FFR_API const char* ffr_last_error(void) { return last_error_buf(); }
 FFR_API long long ffr_launch_count(void) { return launch_count(); }
 
 FFR_API int ffr_debug_set_window(int enable) { set_use_window(enable != 0); return 0; }
+
+FFR_API int ffr_debug_set_counters(void* counters) {
+    set_debug_counters(reinterpret_cast<unsigned long long*>(counters));
+    return 0;
+}
 
 FFR_API int ffr_conv_gemm(const void* a, int64_t a_rows, int a_cols, int a_ld, const void* wp, int Cin, int Cout, int ntaps,
                   const int* tap_row_shift, const int* tap_ch_off, int M, int rows_per_img, int Wp, int S, int h0,

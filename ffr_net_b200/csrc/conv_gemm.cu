@@ -25,6 +25,14 @@ struct GemmCfg {
     static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 256 /*barriers*/ + PARAM_FLOATS * 4;
 };
 
+// mbarrier wait that adds the time spent to a counter when profiling counters are enabled
+__device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, bool timed, long long& acc) {
+    if (!timed) { mbar_wait(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+}
+
 __device__ __forceinline__ float sigmoidf_fast(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 // Column sums across the 32 lanes of a warp for 32 per-lane values: after the call lane L holds, in x[0],
@@ -71,6 +79,9 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
     const float inv_wp = 1.0f / (float)max(p.Wp, 1);
     int loaded_n_tile = -1;
     int it = 0;
+    const bool timed = p.dbg != nullptr;
+    long long w_e = 0;
+    const long long t_begin = clock64();
     for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++it) {
         const int t = work / p.num_splits;
         const int n_tile = t % p.num_n_tiles;
@@ -149,7 +160,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
         const int n_hi = __shfl_sync(0xffffffffu, n_img, 31);
 
         if (sub == 0) {
-            mbar_wait(&tfull_bar[acc], acc_phase);
+            mbar_wait_timed(&tfull_bar[acc], acc_phase, timed, w_e);
             tc_fence_after();
         }
         const uint32_t t_row = tmem_base + (acc * SUB + sub) * BN + chalf * HALF + (static_cast<uint32_t>(quad * 32) << 16);
@@ -271,6 +282,10 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
         }   // sub
         tc_fence_before();
         mbar_arrive(&tempty_bar[acc]);
+    }
+    if (timed && threadIdx.x == 0) {
+        atomicAdd(p.dbg + DBG_EPI_WAIT, (unsigned long long)w_e);
+        atomicAdd(p.dbg + DBG_EPI_TOTAL, (unsigned long long)(clock64() - t_begin));
     }
 }
 
@@ -416,7 +431,10 @@ struct WinCfg {
 // SUB = 128-row sub-tiles per work item. With SUB = 2 every weight tile that lands in smem feeds two MMAs groups
 // (halving the weight traffic through shared memory, which is what bounds the 64/128-channel layers) and the
 // window halo is amortised over 256 rows. Needs 2*SUB*BN <= 512 TMEM columns.
-template <int BN, int SUB>
+// TB = taps per MMA issue batch. The tensor pipe buffers only ~one instruction, so whatever the issuing lane does
+// between two batches (barrier wait, descriptor arithmetic, ~250 cycles) is exposed unless a batch is long: TB weight
+// stages are awaited together and their TB*SUB*4 MMAs go out as straight-line code (b_stages is a multiple of TB).
+template <int BN, int SUB, int TB>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const ConvGemmParams p, const WinCfg wc) {
@@ -464,13 +482,16 @@ conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         int sa = 0, sb = 0;
         uint32_t pa = 0, pb = 0;
         bool b_loaded = false;
+        const bool timed = p.dbg != nullptr;
+        long long w_a = 0, w_b = 0;
+        const long long t_begin = clock64();
         for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
             const int n_tile = work % p.num_n_tiles;
             const int m_group = work / p.num_n_tiles;
             const int row0 = m_group * (SUB * BLOCK_M) - wc.G - 1;
             const int n0 = n_tile * BN;
             for (int c = 0; c < chunks; ++c) {
-                mbar_wait(&a_empty[sa], pa ^ 1);
+                mbar_wait_timed(&a_empty[sa], pa ^ 1, timed, w_a);
                 uint8_t* dst = sA + sa * win_bytes;
                 if (elect_one_sync()) {
                     mbar_arrive_expect_tx(&a_full[sa], win_bytes);
@@ -483,7 +504,7 @@ conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (resident && b_loaded) continue;
 #pragma unroll 1
                 for (int t = 0; t < 9; ++t) {
-                    if (!resident) mbar_wait(&b_empty[sb], pb ^ 1);
+                    if (!resident) mbar_wait_timed(&b_empty[sb], pb ^ 1, timed, w_b);
                     if (elect_one_sync()) {
                         mbar_arrive_expect_tx(&b_full[sb], B_STAGE_BYTES);
                         tma_load_2d(sB + sb * B_STAGE_BYTES, &tmB, &b_full[sb], (t * chunks + c) * BLOCK_K, n0);
@@ -494,47 +515,72 @@ conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             b_loaded = true;
         }
+        if (timed && lane == 0) {
+            atomicAdd(p.dbg + DBG_TMA_WAIT_A, (unsigned long long)w_a);
+            atomicAdd(p.dbg + DBG_TMA_WAIT_B, (unsigned long long)w_b);
+            atomicAdd(p.dbg + DBG_TMA_TOTAL, (unsigned long long)(clock64() - t_begin));
+        }
     } else if (warp == WARP_MMA) {
         constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN);
         int sa = 0, sb = 0;
         uint32_t pa = 0, pb = 0;
         int it = 0;
+        const bool timed = p.dbg != nullptr;
+        long long w_t = 0, w_a = 0, w_b = 0;
+        const long long t_begin = clock64();
         for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            mbar_wait_timed(&tempty_bar[acc], acc_phase ^ 1, timed, w_t);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * (SUB * BN);
             for (int c = 0; c < chunks; ++c) {
-                mbar_wait(&a_full[sa], pa);
+                mbar_wait_timed(&a_full[sa], pa, timed, w_a);
                 tc_fence_after();
-                const uint32_t win = smem_u32(sA + sa * win_bytes);
+                const uint32_t win_lo = static_cast<uint32_t>(umma_smem_desc_sw128(smem_u32(sA + sa * win_bytes)));
 #pragma unroll 1
-                for (int t = 0; t < 9; ++t) {
-                    if (!resident || it == 0) mbar_wait(&b_full[sb], pb);
+                for (int tb = 0; tb < 9 / TB; ++tb) {
+                    if (!resident || it == 0) {
+#pragma unroll
+                        for (int j = 0; j < TB; ++j) mbar_wait_timed(&b_full[sb + j], pb, timed, w_b);
+                    }
                     tc_fence_after();
-                    const int r = t / 3, sx = t - 3 * r;
-                    const uint64_t a_desc = umma_smem_desc_sw128(win + static_cast<uint32_t>(r * wc.G + sx) * 128u);
-                    const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(sB + sb * B_STAGE_BYTES));
-                    const uint32_t first = (c > 0 || t > 0) ? 1u : 0u;
+                    const uint32_t b_lo = static_cast<uint32_t>(umma_smem_desc_sw128(smem_u32(sB + sb * B_STAGE_BYTES)));
+                    // tap t = tb*TB + j = (r, sx): A rows start (r*G + sx) rows into the window, 8 (>>4 units) per row
+                    const uint32_t a_lo = win_lo + static_cast<uint32_t>((TB == 3 ? tb * wc.G : tb) * 8);
+                    const uint32_t g8 = static_cast<uint32_t>(wc.G * 8);
+                    const uint32_t first = (c > 0 || tb > 0) ? 1u : 0u;
                     if (elect_one_sync()) {
 #pragma unroll
-                        for (int sub = 0; sub < SUB; ++sub)
+                        for (int j = 0; j < TB; ++j) {
+                            const uint32_t a_tap = (TB == 9) ? a_lo + (j / 3) * g8 + (j % 3) * 8 : a_lo + j * 8;
 #pragma unroll
-                            for (int k = 0; k < BLOCK_K / 16; ++k)   // sub-tile: +128 rows = +1024 (>>4) in the address
-                                umma_bf16(d_tmem + sub * BN, a_desc + (sub * 1024 + 2 * k), b_desc + 2 * k, idesc,
-                                          (k > 0) ? 1u : first);
-                        if (!resident) umma_commit(&b_empty[sb]);
-                        if (t == 8) {
+                            for (int sub = 0; sub < SUB; ++sub)
+#pragma unroll
+                                for (int k = 0; k < BLOCK_K / 16; ++k)
+                                    umma_bf16(d_tmem + sub * BN, UMMA_DESC_HI | (a_tap + sub * 1024 + 2 * k),
+                                              UMMA_DESC_HI | (b_lo + j * (B_STAGE_BYTES >> 4) + 2 * k), idesc,
+                                              (j > 0 || k > 0) ? 1u : first);
+                            if (!resident) umma_commit(&b_empty[sb + j]);
+                        }
+                        if (tb == 9 / TB - 1) {
                             umma_commit(&a_empty[sa]);
                             if (c == chunks - 1) umma_commit(&tfull_bar[acc]);
                         }
                     }
                     __syncwarp();
-                    if (++sb == wc.b_stages) { sb = 0; pb ^= 1; }
+                    sb += TB;
+                    if (sb == wc.b_stages) { sb = 0; pb ^= 1; }
                 }
                 if (++sa == wc.a_stages) { sa = 0; pa ^= 1; }
             }
+        }
+        if (timed && lane == 0) {
+            atomicAdd(p.dbg + DBG_MMA_WAIT_TMEM, (unsigned long long)w_t);
+            atomicAdd(p.dbg + DBG_MMA_WAIT_A, (unsigned long long)w_a);
+            atomicAdd(p.dbg + DBG_MMA_WAIT_B, (unsigned long long)w_b);
+            atomicAdd(p.dbg + DBG_MMA_TOTAL, (unsigned long long)(clock64() - t_begin));
+            atomicAdd(p.dbg + DBG_CTAS, 1ull);
         }
     } else if (warp < 8) {
         epilogue_loop<BN, SUB>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane);
@@ -548,20 +594,23 @@ conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
 }
 
-template <int BN, int SUB>
+template <int BN, int SUB, int TB>
 static int launch_win(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, const WinCfg& wc,
                       int smem_bytes, int grid, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        FFR_CUDA(cudaFuncSetAttribute(conv_win_kernel<BN, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        FFR_CUDA(cudaFuncSetAttribute(conv_win_kernel<BN, SUB, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      232448));
         attr_set = true;
     }
-    conv_win_kernel<BN, SUB><<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, p, wc);
+    conv_win_kernel<BN, SUB, TB><<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, p, wc);
     return launch_status("conv_win_kernel");
 }
 
 static bool g_use_window = true;
 void set_use_window(bool on) { g_use_window = on; }
+static unsigned long long* g_dbg = nullptr;
+void set_debug_counters(unsigned long long* dptr) { g_dbg = dptr; }
 
 // Is this launch a plain 3x3/stride-1 flat convolution (taps (r-1)*G + (s-1), no channel offsets)?
 static bool window_eligible(const ConvGemmParams& p, int* G_out) {
@@ -594,6 +643,7 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
 // fields must be set by the caller).
 int conv_gemm_launch(const void* a, long long a_rows, int a_cols, int a_ld, const void* wp, int Cin, ConvGemmParams p,
                      int num_splits, cudaStream_t stream) {
+    p.dbg = g_dbg;
     FFR_CHECK_ARG(Cin % BLOCK_K == 0, "conv_gemm: Cin=%d not a multiple of 64", Cin);
     FFR_CHECK_ARG(p.Cout % 64 == 0, "conv_gemm: Cout=%d not a multiple of 64", p.Cout);
     FFR_CHECK_ARG(p.ntaps >= 1 && p.ntaps <= 9, "conv_gemm: ntaps=%d", p.ntaps);
@@ -637,24 +687,28 @@ int conv_gemm_launch(const void* a, long long a_rows, int a_cols, int a_ld, cons
         // weights: resident if all 9 tiles of a single-chunk layer fit next to two windows, else a ring that takes
         // what two windows leave (deep enough to cover the TMA latency); windows take the rest.
         wc.b_resident = (p.kb_per_tap == 1 && p.num_n_tiles == 1 && 9 * b_stage + 2 * win_bytes <= budget) ? 1 : 0;
+        const int TB = (BN == 256) ? 1 : (wc.b_resident ? 9 : 3);
         if (wc.b_resident) {
             wc.b_stages = 9;
         } else {
             wc.b_stages = (budget - 2 * win_bytes) / b_stage;
-            if (wc.b_stages > 8) wc.b_stages = 8;
+            if (wc.b_stages > 9) wc.b_stages = 9;
+            wc.b_stages -= wc.b_stages % TB;
         }
         wc.a_stages = (budget - wc.b_stages * b_stage) / win_bytes;
         if (wc.a_stages > WIN_MAX_A_STAGES) wc.a_stages = WIN_MAX_A_STAGES;
-        if (wc.a_stages >= 2 && wc.b_stages >= 3 && wc.box_rows <= 256) {
+        if (wc.a_stages >= 2 && wc.b_stages >= 3 && wc.b_stages % TB == 0 && wc.box_rows <= 256) {
             rc = make_tmap_2d_bf16(&tmA, a, (uint64_t)a_rows, (uint64_t)a_cols, (uint64_t)a_ld, wc.box_rows);
             if (rc) return rc;
             const int smem_bytes = fixed + wc.a_stages * win_bytes + wc.b_stages * b_stage;
             const long long work = (long long)((p.num_m_tiles + SUB - 1) / SUB) * p.num_n_tiles;
             const int wgrid = (int)((work < num_sms()) ? work : num_sms());
             switch (BN) {
-                case 256: return launch_win<256, 1>(tmA, tmB, p, wc, smem_bytes, wgrid, stream);
-                case 128: return launch_win<128, 2>(tmA, tmB, p, wc, smem_bytes, wgrid, stream);
-                default:  return launch_win<64, 2>(tmA, tmB, p, wc, smem_bytes, wgrid, stream);
+                case 256: return launch_win<256, 1, 1>(tmA, tmB, p, wc, smem_bytes, wgrid, stream);
+                case 128: return launch_win<128, 2, 3>(tmA, tmB, p, wc, smem_bytes, wgrid, stream);
+                default:
+                    if (wc.b_resident) return launch_win<64, 2, 9>(tmA, tmB, p, wc, smem_bytes, wgrid, stream);
+                    return launch_win<64, 2, 3>(tmA, tmB, p, wc, smem_bytes, wgrid, stream);
             }
         }
     }

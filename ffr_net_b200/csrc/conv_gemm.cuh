@@ -60,6 +60,12 @@ struct ConvGemmParams {
     int scatter_n;         // 1..8
     int out_rows_per_img;  // rows per image of the destination matrix
     int b_rows_per_mtile;  // batched B: weight-matrix row offset added per M tile (0 = shared weights)
+    unsigned long long* dbg;  // optional: per-role wait-cycle counters (ffr_debug_set_counters), else nullptr
 };
+
+// dbg slots (cycles summed over CTAs): MMA warp waits, producer waits, epilogue waits, totals
+enum DbgSlot { DBG_MMA_WAIT_TMEM = 0, DBG_MMA_WAIT_A = 1, DBG_MMA_WAIT_B = 2, DBG_MMA_TOTAL = 3,
+               DBG_TMA_WAIT_A = 4, DBG_TMA_WAIT_B = 5, DBG_TMA_TOTAL = 6, DBG_EPI_WAIT = 8, DBG_EPI_TOTAL = 9,
+               DBG_CTAS = 10 };
 
 }  // namespace ffr

@@ -155,6 +155,11 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t saddr, uint32_
     return d;
 }
 
+// High word of the SWIZZLE_128B K-major descriptor (SBO = 1024 B, version 1, layout type 2); the low word is
+// (addr >> 4) | LBO<<16 and can be advanced with plain 32-bit adds.
+constexpr uint64_t UMMA_DESC_HI = (static_cast<uint64_t>(1024 >> 4) << 32) | (static_cast<uint64_t>(1) << 46) |
+                                  (static_cast<uint64_t>(2) << 61);
+
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns.
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(

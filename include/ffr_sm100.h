@@ -155,6 +155,10 @@ FFR_API int ffr_threshold_sweep(const float* score, const int* label, const doub
  * tile-per-tap kernel (the two must agree; tests run both). */
 FFR_API int ffr_debug_set_window(int enable);
 
+/* Debug/tuning: device buffer of 16 uint64 that the sliding-window kernel fills with per-role barrier-wait cycle
+ * counts (summed over CTAs; slots in csrc/conv_gemm.cuh DbgSlot); NULL (default) disables the counters. */
+FFR_API int ffr_debug_set_counters(void* counters);
+
 /* Debug: hardware-semantics probe for row-offset UMMA descriptors (csrc/probe.cu); not on the product path.
  * a [256][64] bf16, w [64][64] bf16, out [128][64] fp32 = a[row_off : row_off+128] @ w^T. */
 FFR_API int ffr_debug_rowshift_probe(const void* a, const void* w, float* out, int row_off, int variant,
