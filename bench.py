@@ -290,7 +290,7 @@ def run_ours(args):
             roof = {"bound": "tensor", "kernel": "conv_gemm_kernel<256> (3x3 256->256 @14x14, %d launches/step)" % len(durs),
                     "achieved": achieved, "peak": peak, "peak_source": peak_src + " (sustained: timed inside the step)",
                     "unit": "TFLOP/s", "frac": achieved / peak, "avg_launch_ms": avg_ms,
-                    "share_of_step": sum(durs) / total if total > 0 else None,
+                    "share_of_step": sum(durs) / (ms / args.steps),
                     "traffic": _ncu_traffic()}
         if world == 1:
             cpu = cpu_baseline(with_recnet)

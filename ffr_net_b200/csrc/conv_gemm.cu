@@ -547,7 +547,8 @@ conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     tc_fence_after();
                     const uint32_t b_lo = static_cast<uint32_t>(umma_smem_desc_sw128(smem_u32(sB + sb * B_STAGE_BYTES)));
                     // tap t = tb*TB + j = (r, sx): A rows start (r*G + sx) rows into the window, 8 (>>4 units) per row
-                    const uint32_t a_lo = win_lo + static_cast<uint32_t>((TB == 3 ? tb * wc.G : tb) * 8);
+                    const uint32_t a_lo =
+                        win_lo + static_cast<uint32_t>((TB == 9 ? 0 : (TB == 3 ? tb * wc.G : (tb / 3) * wc.G + tb % 3)) * 8);
                     const uint32_t g8 = static_cast<uint32_t>(wc.G * 8);
                     const uint32_t first = (c > 0 || tb > 0) ? 1u : 0u;
                     if (elect_one_sync()) {
