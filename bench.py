@@ -287,7 +287,7 @@ def run_ours(args):
             avg_ms = sum(durs) / len(durs)
             achieved = flop / (avg_ms * 1e-3) / 1e12
             peak = peaks.get("bf16_tflops_sustained", 1400.0)
-            roof = {"bound": "tensor", "kernel": "conv_gemm_kernel<256> (3x3 256->256 @14x14, %d launches/step)" % len(durs),
+            roof = {"bound": "tensor", "kernel": "conv_win_kernel<256,1,1> (3x3 256->256 @14x14, %d launches/step)" % len(durs),
                     "achieved": achieved, "peak": peak, "peak_source": peak_src + " (sustained: timed inside the step)",
                     "unit": "TFLOP/s", "frac": achieved / peak, "avg_launch_ms": avg_ms,
                     "share_of_step": sum(durs) / (ms / args.steps),
