@@ -25,6 +25,11 @@ _SIGNATURES = {
     "ffr_recnet_convlayer_fwd": (_i, [_p, _i, _i, _p, _i, _p, _p, _p, _i, _i, _p, _i, _p, _i, _i, _p, _p, _p]),
     "ffr_feat_space": (_i, [_p, _p, _p, _p, _i, _p]),
     "ffr_rows_to_nchw": (_i, [_p, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "ffr_wgrad3x3": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "ffr_bn_prelu_fwd": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _p]),
+    "ffr_bn_prelu_bwd": (_i, [_p, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _i, _p, _p, _i, _i, _i, _p]),
+    "ffr_nchw_to_h9": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    "ffr_h9_to_nchw": (_i, [_p, _i, _i, _p, _i, _i, _i, _p]),
     "ffr_pair_cosine": (_i, [_p, _p, _p, _i, _i, _p]),
     "ffr_threshold_sweep": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "ffr_scale_f32": (_i, [_p, _p, _i64, ctypes.c_float, _p]),
@@ -37,6 +42,7 @@ _SIGNATURES = {
     "ffr_export_nchw_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "ffr_head_fwd": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "ffr_debug_set_window": (_i, [_i]),
+    "ffr_debug_mn_probe": (_i, [_p, _p, _p, _i, _i, _p]),
     "ffr_debug_set_counters": (_i, [_p]),
     "ffr_debug_mma_bench": (_i, [_p, _i, _i, _i, _i, _i, _p]),
     "ffr_debug_rowshift_probe": (_i, [_p, _p, _p, _i, _i, _p]),

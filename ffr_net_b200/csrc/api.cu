@@ -29,6 +29,17 @@ int feat_space_launch(const float* x, const float* mspace, void* cm, float* out_
 int rows_to_nchw_launch(const void* rows, int is_f32, int ld, int ch0, const float* scale, const float* shift, float* y,
                         int n, int S, int G, int off, int rows_per_img, int C, cudaStream_t stream);
 int scale_f32_launch(const float* in, float* out, long long count, float scale, cudaStream_t stream);
+int wgrad_launch(const void* dz, int ld_dz, const void* x, int ld_x, int x_ch0, int P, int Cout, int Cin, int G,
+                 float* dw, cudaStream_t stream);
+int bn_prelu_fwd_launch(const void* z, int ldz, const float* mean, const float* rstd, const float* gamma,
+                        const float* beta, const float* slope, const void* res, int ldres, void* out, int ldo,
+                        const int* scatter, int scatter_n, int n_img, int C, cudaStream_t stream);
+int bn_prelu_bwd_launch(const void* da, int ldda, const int* scatter, int scatter_n, const void* z, int ldz,
+                        const float* mean, const float* rstd, const float* gamma, const float* beta, const float* slope,
+                        void* dy, int lddy, void* dres, int lddres, float* sums, void* dz, int lddz, int n_img, int C,
+                        cudaStream_t stream);
+int nchw_to_h9_launch(const float* x, void* out, int ld, int ch0, int n_img, int C, int mirror, cudaStream_t stream);
+int h9_to_nchw_launch(const void* in, int ld, int ch0, float* y, int n_img, int C, int fold, cudaStream_t stream);
 int pair_cosine_launch(const float* f1, const float* f2, float* score, int pairs, int D, cudaStream_t stream);
 int threshold_sweep_launch(const float* score, const int* label, const double* thresholds, int n, int T, int folds,
                            int* best_idx, double* best_thr, int* test_correct, int* train_correct,
@@ -267,6 +278,41 @@ FFR_API int ffr_rows_to_nchw(const void* rows, int is_f32, int ld, int ch0, cons
 FFR_API int ffr_scale_f32(const float* in, float* out, int64_t count, float scale, ffr_stream_t stream) {
     FFR_CHECK_ARG(in && out, "ffr_scale_f32: null pointer");
     return scale_f32_launch(in, out, count, scale, S_(stream));
+}
+
+FFR_API int ffr_wgrad3x3(const void* dz, int ld_dz, const void* x, int ld_x, int x_ch0, int n, int Cout, int Cin,
+                         float* dw, ffr_stream_t stream) {
+    FFR_CHECK_ARG(dz && x && dw, "ffr_wgrad3x3: null pointer");
+    FFR_CHECK_ARG(ld_dz % 64 == 0 && ld_x % 8 == 0 && x_ch0 % 8 == 0, "ffr_wgrad3x3: bad pitches");
+    return wgrad_launch(dz, ld_dz, x, ld_x, x_ch0, n * 81, Cout, Cin, 9, dw, S_(stream));
+}
+
+FFR_API int ffr_bn_prelu_fwd(const void* z, int ldz, const float* mean, const float* rstd, const float* gamma,
+                             const float* beta, const float* slope, const void* res, int ldres, void* out, int ldo,
+                             const int* scatter, int scatter_n, int n, int C, ffr_stream_t stream) {
+    FFR_CHECK_ARG(z && mean && rstd && gamma && beta && slope && out && scatter, "ffr_bn_prelu_fwd: null pointer");
+    return bn_prelu_fwd_launch(z, ldz, mean, rstd, gamma, beta, slope, res, ldres, out, ldo, scatter, scatter_n, n, C,
+                               S_(stream));
+}
+
+FFR_API int ffr_bn_prelu_bwd(const void* da, int ldda, const int* scatter, int scatter_n, const void* z, int ldz,
+                             const float* mean, const float* rstd, const float* gamma, const float* beta,
+                             const float* slope, void* dy, int lddy, void* dres, int lddres, float* sums, void* dz,
+                             int lddz, int n, int C, ffr_stream_t stream) {
+    FFR_CHECK_ARG(da && scatter && z && mean && rstd && gamma && beta && slope && dy && sums && dz,
+                  "ffr_bn_prelu_bwd: null pointer");
+    return bn_prelu_bwd_launch(da, ldda, scatter, scatter_n, z, ldz, mean, rstd, gamma, beta, slope, dy, lddy, dres,
+                               lddres, sums, dz, lddz, n, C, S_(stream));
+}
+
+FFR_API int ffr_nchw_to_h9(const float* x, void* out, int ld, int ch0, int n, int C, int mirror, ffr_stream_t stream) {
+    FFR_CHECK_ARG(x && out, "ffr_nchw_to_h9: null pointer");
+    return nchw_to_h9_launch(x, out, ld, ch0, n, C, mirror, S_(stream));
+}
+
+FFR_API int ffr_h9_to_nchw(const void* in, int ld, int ch0, float* y, int n, int C, int fold, ffr_stream_t stream) {
+    FFR_CHECK_ARG(in && y, "ffr_h9_to_nchw: null pointer");
+    return h9_to_nchw_launch(in, ld, ch0, y, n, C, fold, S_(stream));
 }
 
 FFR_API int ffr_pair_cosine(const float* f1, const float* f2, float* score, int pairs, int D, ffr_stream_t stream) {

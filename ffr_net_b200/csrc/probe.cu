@@ -140,3 +140,90 @@ extern "C" FFR_API int ffr_debug_mma_bench(long long* out_cycles, int M, int N, 
     mma_bench_kernel<<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(out_cycles, M, N, n_acc, iters);
     return launch_status("mma_bench_kernel");
 }
+
+// ----------------------------------------------------------------------------------------------------------
+// Probe (debug): MN-major operands (the weight-gradient GEMM contracts over pixels, i.e. over the ROWS of the
+// row-major activation matrices). a: [96][128] bf16 (k rows, m contiguous), b: [96][64] bf16 (k rows, n contiguous);
+// out[128][64] = sum_{k<64} a[k][m] * b[r0 + k][n]. variant 0: LBO = MN-block stride, SBO = 8-row K-group stride;
+// variant 1: the two swapped.
+// ----------------------------------------------------------------------------------------------------------
+namespace ffr {
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(128, 1)
+mn_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* out, int r0,
+                int variant) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;                   // 2 blocks x [64 k rows][128 B]
+    uint8_t* sB = smem + 2 * 8192;        // [96 k rows][128 B]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * 8192 + 96 * 128);
+    uint64_t* mma_bar = bar + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(mma_bar, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc<64>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp == 1) {
+        if (elect_one_sync()) {
+            mbar_arrive_expect_tx(bar, 2 * 8192 + 96 * 128);
+            tma_load_2d(sA, &tmA, bar, 0, 0);
+            tma_load_2d(sA + 8192, &tmA, bar, 64, 0);
+            tma_load_2d(sB, &tmB, bar, 0, 0);
+        }
+        __syncwarp();
+        mbar_wait(bar, 0);
+        tc_fence_after();
+        // instruction descriptor with both operands MN-major
+        const uint32_t idesc = umma_idesc_bf16(128, 64) | (1u << 15) | (1u << 16);
+        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB) + r0 * 128;
+        if (elect_one_sync()) {
+            for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t ad = variant ? umma_desc_mn_sw128(a0 + ks * 2048, 1024, 8192)
+                                            : umma_desc_mn_sw128(a0 + ks * 2048, 8192, 1024);
+                const uint64_t bd = variant ? umma_desc_mn_sw128(b0 + ks * 2048, 1024, 8192)
+                                            : umma_desc_mn_sw128(b0 + ks * 2048, 8192, 1024);
+                umma_bf16(tmem_base, ad, bd, idesc, ks > 0);
+            }
+            umma_commit(mma_bar);
+        }
+        __syncwarp();
+    }
+    mbar_wait(mma_bar, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + c0 + (static_cast<uint32_t>(warp * 32) << 16), v);
+        tmem_ld_wait();
+        for (int j = 0; j < 32; ++j) out[(warp * 32 + lane) * 64 + c0 + j] = __uint_as_float(v[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc<64>(tmem_base); }
+}
+}  // namespace ffr
+
+extern "C" FFR_API int ffr_debug_mn_probe(const void* a, const void* b, float* out, int r0, int variant,
+                                          ffr_stream_t stream) {
+    using namespace ffr;
+    CUtensorMap tmA, tmB;
+    int rc = make_tmap_2d_bf16(&tmA, a, 96, 128, 128, 64);     // box: 64 k-rows x 64 m
+    if (rc) return rc;
+    rc = make_tmap_2d_bf16(&tmB, b, 96, 64, 64, 96);           // box: 96 k-rows x 64 n
+    if (rc) return rc;
+    const int smem = 1024 + 2 * 8192 + 96 * 128 + 64;
+    FFR_CUDA(cudaFuncSetAttribute(mn_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    mn_probe_kernel<<<1, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tmA, tmB, out, r0, variant);
+    return launch_status("mn_probe_kernel");
+}

@@ -1,0 +1,431 @@
+// RecNet training kernels (models/recnet.py ConvLayer in train mode + its backward, models/trainer.py:154-187):
+//   - wgrad_kernel: weight gradient of a reflection-padded 3x3 conv as a tcgen05 GEMM that contracts over PIXELS.
+//     Both operands are read straight from their row-major (pixel-major) H9 matrices as MN-major UMMA operands
+//     (profiles/r01_probe_mn_major.json); a tap is a TMA row-coordinate shift of the x operand.
+//   - bn_prelu_fwd_kernel: batch-statistics BatchNorm + PReLU (+ residual) on the raw conv output, scattered into H9.
+//   - bn_prelu_bwd_reduce_kernel / bn_prelu_bwd_dz_kernel: gradient fold of the reflection mirrors, PReLU and
+//     BatchNorm backward (per-channel reductions, then dz).
+#include "host.h"
+#include "ptx.cuh"
+
+namespace ffr {
+
+// ------------------------------------------------------------------------------------------------------------
+// wgrad: dW[co][ci][t] += sum_p dz[p][co] * x[p + shift_t][ci]
+// ------------------------------------------------------------------------------------------------------------
+constexpr int WG_THREADS = 352;     // warps 0-7 epilogue, 8 TMEM alloc, 9 TMA, 10 MMA (same roles as conv_gemm.cu)
+constexpr int WG_STAGES = 4;
+constexpr int WG_BN = 256;          // ci tile
+constexpr int WG_STAGE_BYTES = 2 * 8192 + (WG_BN / 64) * 8192;   // dz: 2 x [64 p][64 co], x: 4 x [64 p][64 ci]
+
+struct WgradParams {
+    int P;                 // pixel rows (n * 81)
+    int Cout, Cin;         // real channel counts (gradient tensor is [Cout][Cin][3][3] fp32)
+    int m_tiles, n_tiles;  // over padded Cout (128) and padded Cin (256)
+    int splits, kb_per_split, kb_total;
+    int tap_shift[9];
+    float* dw;
+};
+
+__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t saddr) {   // LBO = 8192 B between 64-wide MN blocks, SBO = 1024 B
+    return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(8192 >> 4) << 16) |
+           (static_cast<uint64_t>(1024 >> 4) << 32) | (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61);
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + WG_STAGES;
+    uint64_t* tfull_bar = bars + 2 * WG_STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 9 && lane == 0) { tma_prefetch_desc(&tmDZ); tma_prefetch_desc(&tmX); }
+    if (warp == 10 && lane == 0) {
+        for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 256); }
+        fence_mbar_init();
+    }
+    if (warp == 8) tmem_alloc<2 * WG_BN>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int num_work = 9 * p.m_tiles * p.n_tiles * p.splits;
+
+    // work -> (split, n_tile, m_tile, tap); tap slowest so concurrently running CTAs share the dz / x tiles in L2
+    if (warp == 9) {
+        int stage = 0; uint32_t phase = 0;
+        for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+            int w = work;
+            const int split = w % p.splits; w /= p.splits;
+            const int n_tile = w % p.n_tiles; w /= p.n_tiles;
+            const int m_tile = w % p.m_tiles; w /= p.m_tiles;
+            const int shift = p.tap_shift[w];
+            const int kb0 = split * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* s = smem + stage * WG_STAGE_BYTES;
+                if (elect_one_sync()) {
+                    mbar_arrive_expect_tx(&full_bar[stage], WG_STAGE_BYTES);
+                    tma_load_2d(s, &tmDZ, &full_bar[stage], m_tile * 128, kb * 64);
+                    tma_load_2d(s + 8192, &tmDZ, &full_bar[stage], m_tile * 128 + 64, kb * 64);
+#pragma unroll
+                    for (int j = 0; j < WG_BN / 64; ++j)
+                        tma_load_2d(s + 16384 + j * 8192, &tmX, &full_bar[stage], n_tile * WG_BN + j * 64,
+                                    kb * 64 + shift);
+                }
+                __syncwarp();
+                if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 10) {
+        const uint32_t idesc = umma_idesc_bf16(128, WG_BN) | (1u << 15) | (1u << 16);   // both operands MN-major
+        int stage = 0; uint32_t phase = 0; int it = 0;
+        for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++it) {
+            const int split = work % p.splits;
+            const int kb0 = split * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+            const int acc = it & 1;
+            mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * WG_BN;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint64_t a_desc = desc_mn_sw128(smem_u32(smem + stage * WG_STAGE_BYTES));
+                const uint64_t b_desc = desc_mn_sw128(smem_u32(smem + stage * WG_STAGE_BYTES + 16384));
+                const uint32_t first = (kb > kb0) ? 1u : 0u;
+                if (elect_one_sync()) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)      // 16 pixel rows = 2048 B = +128 in the (addr >> 4) field
+                        umma_bf16(d_tmem, a_desc + 128 * ks, b_desc + 128 * ks, idesc, ks > 0 ? 1u : first);
+                    umma_commit(&empty_bar[stage]);
+                    if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
+                }
+                __syncwarp();
+                if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp < 8) {
+        const int quad = warp & 3, chalf = warp >> 2;
+        int it = 0;
+        for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++it) {
+            int w = work / p.splits;
+            const int n_tile = w % p.n_tiles; w /= p.n_tiles;
+            const int m_tile = w % p.m_tiles; w /= p.m_tiles;
+            const int tap = w;
+            const int acc = it & 1;
+            const int co = m_tile * 128 + quad * 32 + lane;
+            mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + acc * WG_BN + chalf * (WG_BN / 2) + (static_cast<uint32_t>(quad * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < WG_BN / 2; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_row + c0, v);
+                tmem_ld_wait();
+                const int ci0 = n_tile * WG_BN + chalf * (WG_BN / 2) + c0;
+                if (co < p.Cout) {
+                    float* o = p.dw + ((long long)co * p.Cin + ci0) * 9 + tap;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (ci0 + j < p.Cin) atomicAdd(o + j * 9, __uint_as_float(v[j]));
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) { tc_fence_after(); tmem_dealloc<2 * WG_BN>(tmem_base); }
+}
+
+// dz: [P][ld_dz] bf16 (zeros on halo rows), x: [P][ld_x] bf16 H9 (with halo), dw: fp32 [Cout][Cin][3][3], pre-zeroed.
+int wgrad_launch(const void* dz, int ld_dz, const void* x, int ld_x, int x_ch0, int P, int Cout, int Cin, int G,
+                 float* dw, cudaStream_t stream) {
+    WgradParams p;
+    p.P = P; p.Cout = Cout; p.Cin = Cin; p.dw = dw;
+    p.m_tiles = (Cout + 127) / 128;
+    p.n_tiles = (Cin + WG_BN - 1) / WG_BN;
+    p.kb_total = (P + 63) / 64;
+    const int base_work = 9 * p.m_tiles * p.n_tiles;
+    int splits = (2 * num_sms() + base_work - 1) / base_work;      // aim at >= 2 waves
+    if (splits > p.kb_total / 8) splits = p.kb_total / 8;
+    if (splits < 1) splits = 1;
+    p.kb_per_split = (p.kb_total + splits - 1) / splits;
+    p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+    for (int r = 0; r < 3; ++r)
+        for (int s = 0; s < 3; ++s) p.tap_shift[r * 3 + s] = (r - 1) * G + (s - 1);
+    CUtensorMap tmDZ, tmX;
+    int rc = make_tmap_2d_bf16(&tmDZ, dz, (uint64_t)P, (uint64_t)ld_dz, (uint64_t)ld_dz, 64);
+    if (rc) return rc;
+    // the x map starts at channel x_ch0 of a possibly wider (concatenated) matrix and exposes Cin padded to 64 columns
+    const int cin_cols = (Cin + 63) / 64 * 64;
+    rc = make_tmap_2d_bf16(&tmX, reinterpret_cast<const __nv_bfloat16*>(x) + x_ch0, (uint64_t)P, (uint64_t)cin_cols,
+                           (uint64_t)ld_x, 64);
+    if (rc) return rc;
+    const int smem = 1024 + WG_STAGES * WG_STAGE_BYTES + 256;
+    static bool attr = false;
+    if (!attr) {
+        FFR_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    const int num_work = base_work * p.splits;
+    const int grid = num_work < num_sms() ? num_work : num_sms();
+    wgrad_kernel<<<grid, WG_THREADS, smem, stream>>>(tmDZ, tmX, p);
+    return launch_status("wgrad_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// BatchNorm(batch statistics) + PReLU (+ residual) forward on the raw conv output z (rows of the H9 grid).
+// stats: [2][C] = per-channel sum and sum of squares over the n*49 valid rows (accumulated by the conv epilogue).
+// Writes a = prelu(gamma*(z-mean)*rstd + beta) (+ res) to every destination of the scatter table (self + mirrors).
+// grid.x covers rows*C/8 work items of 8 channels.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bn_prelu_fwd_kernel(const __nv_bfloat16* __restrict__ z, int ldz, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    const float* __restrict__ slope, const __nv_bfloat16* __restrict__ res, int ldres,
+                    __nv_bfloat16* __restrict__ out, int ldo, const int2* __restrict__ scatter, int scatter_n,
+                    int n_img, int C) {
+    const int c8n = C / 8;
+    const long long total = (long long)n_img * 49 * c8n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % c8n);
+        const long long pr = i / c8n;
+        const int n = (int)(pr / 49), pix = (int)(pr - (long long)n * 49);
+        const int r_local = (pix / 7 + 1) * 9 + (pix % 7 + 1);
+        const long long row = (long long)n * 81 + r_local;
+        const uint4 zv = __ldg(reinterpret_cast<const uint4*>(z + row * ldz) + c8);
+        float v[8] = {bf16lo(zv.x), bf16hi(zv.x), bf16lo(zv.y), bf16hi(zv.y), bf16lo(zv.z), bf16hi(zv.z), bf16lo(zv.w), bf16hi(zv.w)};
+        float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (res) {
+            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(res + row * ldres) + c8);
+            r[0] = bf16lo(rv.x); r[1] = bf16hi(rv.x); r[2] = bf16lo(rv.y); r[3] = bf16hi(rv.y);
+            r[4] = bf16lo(rv.z); r[5] = bf16hi(rv.z); r[6] = bf16lo(rv.w); r[7] = bf16hi(rv.w);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = c8 * 8 + j;
+            float y = (v[j] - mean[c]) * rstd[c] * gamma[c] + beta[c];
+            y = fmaxf(y, 0.f) + slope[c] * fminf(y, 0.f);
+            v[j] = y + r[j];
+        }
+        const uint4 o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        for (int k = 0; k < scatter_n; ++k) {
+            const int2 e = __ldg(scatter + r_local * scatter_n + k);
+            if (e.x >= 0) *(reinterpret_cast<uint4*>(out + ((long long)n * 81 + e.x) * ldo + e.y) + c8) = o;
+        }
+    }
+}
+
+int bn_prelu_fwd_launch(const void* z, int ldz, const float* mean, const float* rstd, const float* gamma,
+                        const float* beta, const float* slope, const void* res, int ldres, void* out, int ldo,
+                        const int* scatter, int scatter_n, int n_img, int C, cudaStream_t stream) {
+    FFR_CHECK_ARG(C % 8 == 0, "bn_prelu_fwd: C=%d", C);
+    const long long total = (long long)n_img * 49 * (C / 8);
+    int grid = (int)((total + 255) / 256);
+    if (grid > num_sms() * 8) grid = num_sms() * 8;
+    bn_prelu_fwd_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(z), ldz, mean, rstd, gamma, beta,
+                                                  slope, reinterpret_cast<const __nv_bfloat16*>(res), ldres,
+                                                  reinterpret_cast<__nv_bfloat16*>(out), ldo,
+                                                  reinterpret_cast<const int2*>(scatter), scatter_n, n_img, C);
+    return launch_status("bn_prelu_fwd_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Backward, pass 1. da_h9 is the gradient w.r.t. the H9 OUTPUT tensor (own row + mirror rows, possibly a channel
+// slot of a wider matrix): fold it (sum over the scatter destinations), then
+//   dy = da * prelu'(y);   sums[0][c] += dy;  sums[1][c] += dy * zhat;  sums[2][c] += da * min(y, 0)
+// and store dy (bf16, plain rows) for pass 2; optionally store the folded da as the residual-branch gradient.
+// One CTA handles a slab of valid rows for 64 channels; per-channel partial sums are reduced in shared memory.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bn_prelu_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, int ldda, const int2* __restrict__ scatter, int scatter_n,
+                           const __nv_bfloat16* __restrict__ z, int ldz, const float* __restrict__ mean,
+                           const float* __restrict__ rstd, const float* __restrict__ gamma,
+                           const float* __restrict__ beta, const float* __restrict__ slope,
+                           __nv_bfloat16* __restrict__ dy, int lddy, __nv_bfloat16* __restrict__ dres, int lddres,
+                           float* __restrict__ sums, int n_img, int C) {
+    __shared__ float red[3][32][65];
+    const int c0 = blockIdx.y * 64;
+    const int c2 = (threadIdx.x & 31) * 2;          // channel pair within the 64-channel slab
+    const int rlane = threadIdx.x >> 5;              // 8 row lanes
+    const long long rows = (long long)n_img * 49;
+    float s0[2] = {0, 0}, s1[2] = {0, 0}, s2[2] = {0, 0};
+    float m[2], rs[2], g[2], b[2], sl[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int c = c0 + c2 + j;
+        m[j] = mean[c]; rs[j] = rstd[c]; g[j] = gamma[c]; b[j] = beta[c]; sl[j] = slope[c];
+    }
+    for (long long pr = (long long)blockIdx.x * 8 + rlane; pr < rows; pr += (long long)gridDim.x * 8) {
+        const int n = (int)(pr / 49), pix = (int)(pr - (long long)n * 49);
+        const int r_local = (pix / 7 + 1) * 9 + (pix % 7 + 1);
+        float a[2] = {0, 0};
+        for (int k = 0; k < scatter_n; ++k) {
+            const int2 e = __ldg(scatter + r_local * scatter_n + k);
+            if (e.x >= 0) {
+                const uint32_t u = *reinterpret_cast<const uint32_t*>(da + ((long long)n * 81 + e.x) * ldda + e.y + c0 + c2);
+                a[0] += bf16lo(u); a[1] += bf16hi(u);
+            }
+        }
+        const long long row = (long long)n * 81 + r_local;
+        const uint32_t zu = *reinterpret_cast<const uint32_t*>(z + row * ldz + c0 + c2);
+        const float zz[2] = {bf16lo(zu), bf16hi(zu)};
+        float d[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float zh = (zz[j] - m[j]) * rs[j];
+            const float y = zh * g[j] + b[j];
+            d[j] = a[j] * (y > 0.f ? 1.f : sl[j]);
+            s0[j] += d[j];
+            s1[j] += d[j] * zh;
+            s2[j] += a[j] * fminf(y, 0.f);
+        }
+        *reinterpret_cast<uint32_t*>(dy + row * lddy + c0 + c2) = pack_bf16x2(d[0], d[1]);
+        if (dres) *reinterpret_cast<uint32_t*>(dres + row * lddres + c0 + c2) = pack_bf16x2(a[0], a[1]);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        red[0][rlane][c2 + j] = s0[j]; red[1][rlane][c2 + j] = s1[j]; red[2][rlane][c2 + j] = s2[j];
+    }
+    __syncthreads();
+    if (threadIdx.x < 192) {
+        const int q = threadIdx.x / 64, c = threadIdx.x % 64;
+        float t = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t += red[q][r][c];
+        atomicAdd(sums + q * C + c0 + c, t);
+    }
+}
+
+// Pass 2: dz = gamma * rstd * (dy - sum(dy)/cnt - zhat * sum(dy*zhat)/cnt), written to the valid rows of dz_h9
+// (halo rows of that buffer stay zero: the dgrad / wgrad GEMMs read it as a zero-padded map).
+__global__ void __launch_bounds__(256)
+bn_prelu_bwd_dz_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, const __nv_bfloat16* __restrict__ z, int ldz,
+                       const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                       const float* __restrict__ sums, __nv_bfloat16* __restrict__ dz, int lddz, int n_img, int C) {
+    const int c8n = C / 8;
+    const float inv_cnt = 1.0f / (float)(n_img * 49);
+    const long long total = (long long)n_img * 49 * c8n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % c8n);
+        const long long pr = i / c8n;
+        const int n = (int)(pr / 49), pix = (int)(pr - (long long)n * 49);
+        const long long row = (long long)n * 81 + (pix / 7 + 1) * 9 + (pix % 7 + 1);
+        const uint4 dv = __ldg(reinterpret_cast<const uint4*>(dy + row * lddy) + c8);
+        const uint4 zv = __ldg(reinterpret_cast<const uint4*>(z + row * ldz) + c8);
+        const float d[8] = {bf16lo(dv.x), bf16hi(dv.x), bf16lo(dv.y), bf16hi(dv.y), bf16lo(dv.z), bf16hi(dv.z), bf16lo(dv.w), bf16hi(dv.w)};
+        const float zz[8] = {bf16lo(zv.x), bf16hi(zv.x), bf16lo(zv.y), bf16hi(zv.y), bf16lo(zv.z), bf16hi(zv.z), bf16lo(zv.w), bf16hi(zv.w)};
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = c8 * 8 + j;
+            const float zh = (zz[j] - mean[c]) * rstd[c];
+            o[j] = gamma[c] * rstd[c] * (d[j] - sums[c] * inv_cnt - zh * sums[C + c] * inv_cnt);
+        }
+        *(reinterpret_cast<uint4*>(dz + row * lddz) + c8) =
+            make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    }
+}
+
+int bn_prelu_bwd_launch(const void* da, int ldda, const int* scatter, int scatter_n, const void* z, int ldz,
+                        const float* mean, const float* rstd, const float* gamma, const float* beta, const float* slope,
+                        void* dy, int lddy, void* dres, int lddres, float* sums, void* dz, int lddz, int n_img, int C,
+                        cudaStream_t stream) {
+    FFR_CHECK_ARG(C % 64 == 0, "bn_prelu_bwd: C=%d", C);
+    FFR_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 3 * C, stream));
+    const long long rows = (long long)n_img * 49;
+    int gx = (int)((rows + 63) / 64);
+    if (gx > num_sms() * 2) gx = num_sms() * 2;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, C / 64);
+    bn_prelu_bwd_reduce_kernel<<<grid, 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(da), ldda, reinterpret_cast<const int2*>(scatter), scatter_n,
+        reinterpret_cast<const __nv_bfloat16*>(z), ldz, mean, rstd, gamma, beta, slope,
+        reinterpret_cast<__nv_bfloat16*>(dy), lddy, reinterpret_cast<__nv_bfloat16*>(dres), lddres, sums, n_img, C);
+    int rc = launch_status("bn_prelu_bwd_reduce_kernel");
+    if (rc) return rc;
+    const long long total = rows * (C / 8);
+    int g2 = (int)((total + 255) / 256);
+    if (g2 > num_sms() * 8) g2 = num_sms() * 8;
+    bn_prelu_bwd_dz_kernel<<<g2, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy), lddy,
+                                                   reinterpret_cast<const __nv_bfloat16*>(z), ldz, mean, rstd, gamma, sums,
+                                                   reinterpret_cast<__nv_bfloat16*>(dz), lddz, n_img, C);
+    return launch_status("bn_prelu_bwd_dz_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Layout converters with gradients: fp32 NCHW (n,C,7,7) <-> bf16 H9.
+//   nchw_to_h9: scatter each pixel to its own row and mirrors, channel slot ch0 of a matrix with row pitch ld.
+//   h9_to_nchw_fold: out[n][c][pix] = sum over the scatter destinations of pix (gradient fold), or just the own row.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+nchw_to_h9_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int ld, int ch0, int n_img, int C,
+                  int mirror) {
+    __shared__ float tile[49][65];
+    const int n = blockIdx.y, c0 = blockIdx.x * 64;
+    for (int i = threadIdx.x; i < 64 * 49; i += 256) {
+        const int c = i / 49, pix = i - c * 49;
+        tile[pix][c] = (c0 + c < C) ? x[((long long)n * C + c0 + c) * 49 + pix] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 81 * 32; i += 256) {
+        const int pos = i >> 5, cp = (i & 31) * 2;
+        const int hp = pos / 9, wp = pos - hp * 9;
+        const int sh = hp == 0 ? 1 : (hp == 8 ? 5 : hp - 1), sw = wp == 0 ? 1 : (wp == 8 ? 5 : wp - 1);
+        const int pix = sh * 7 + sw;
+        const bool halo = (hp == 0 || hp == 8 || wp == 0 || wp == 8);
+        *reinterpret_cast<uint32_t*>(out + ((long long)n * 81 + pos) * ld + ch0 + c0 + cp) =
+            (halo && !mirror) ? 0u : pack_bf16x2(tile[pix][cp], tile[pix][cp + 1]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+h9_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, int ld, int ch0, float* __restrict__ y, int n_img, int C,
+                  int fold) {
+    __shared__ float tile[49][65];
+    const int n = blockIdx.y, c0 = blockIdx.x * 64;
+    for (int i = threadIdx.x; i < 49 * 32; i += 256) {
+        const int pix = i >> 5, cp = (i & 31) * 2;
+        const int h = pix / 7, w = pix - h * 7;
+        const int mh = fold ? ((h == 1) ? -2 : ((h == 5) ? 2 : 0)) : 0;
+        const int mw = fold ? ((w == 1) ? -2 : ((w == 5) ? 2 : 0)) : 0;
+        const long long base = (long long)n * 81 + (h + 1) * 9 + (w + 1);
+        float a = 0.f, b = 0.f;
+        auto add = [&](long long row) {
+            const uint32_t u = *reinterpret_cast<const uint32_t*>(in + row * ld + ch0 + c0 + cp);
+            a += bf16lo(u); b += bf16hi(u);
+        };
+        add(base);
+        if (mh) add(base + mh * 9);
+        if (mw) add(base + mw);
+        if (mh && mw) add(base + mh * 9 + mw);
+        tile[pix][cp] = a; tile[pix][cp + 1] = b;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 49; i += 256) {
+        const int c = i / 49, pix = i - c * 49;
+        if (c0 + c < C) y[((long long)n * C + c0 + c) * 49 + pix] = tile[pix][c];
+    }
+}
+
+int nchw_to_h9_launch(const float* x, void* out, int ld, int ch0, int n_img, int C, int mirror, cudaStream_t stream) {
+    dim3 grid((C + 63) / 64, n_img);
+    nchw_to_h9_kernel<<<grid, 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out), ld, ch0, n_img, C, mirror);
+    return launch_status("nchw_to_h9_kernel");
+}
+
+int h9_to_nchw_launch(const void* in, int ld, int ch0, float* y, int n_img, int C, int fold, cudaStream_t stream) {
+    dim3 grid((C + 63) / 64, n_img);
+    h9_to_nchw_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), ld, ch0, y, n_img, C, fold);
+    return launch_status("h9_to_nchw_kernel");
+}
+
+}  // namespace ffr

@@ -260,6 +260,12 @@ class RecNet(nn.Module):
         self._packed = pk
         return pk
 
+    def _train_tables(self, device):
+        key = str(device)
+        if getattr(self, "_ttab", None) is None or self._ttab[0] != key:
+            self._ttab = (key, (_h9_scatter(0, device),))
+        return self._ttab[1]
+
     def _workspace(self, n, device):
         key = (n, str(device))
         ws = self._ws.get(key)

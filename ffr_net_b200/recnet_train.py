@@ -1,19 +1,234 @@
-"""Training-mode RecNet (batch-statistics BatchNorm, CosFace head, autograd) — under construction.
+"""RecNet in training mode (batch-statistics BatchNorm, label head) with autograd — models/recnet.py:398-429 as used
+by models/trainer.py:139-187.
 
-The eval/no-grad forward lives in recnet.py and runs fully on the sm_100a library. Until the backward kernels
-(dgrad/wgrad implicit GEMMs, BN/PReLU/reflection backward) land, the training entry points fail loudly rather than
-fall back to another implementation."""
+What runs where (round 1):
+  * the 15 ConvLayers (97 % of RecNet's FLOPs) — forward conv + BN-stat reduction, BN/PReLU/residual apply, and the
+    whole backward (gradient fold of the reflection mirrors, PReLU/BN backward, dgrad, wgrad) — are hand-written
+    sm_100a kernels behind `torch.autograd.Function`s (libffr_sm100: ffr_conv_gemm, ffr_bn_prelu_fwd/bwd,
+    ffr_wgrad3x3, ffr_nchw_to_h9 / ffr_h9_to_nchw);
+  * the thin remainder (selfSimilarity, the Conv4Channel MLP, the two per-sample matmuls, the CosFace head and the
+    losses) are library ops (ATen/cuBLAS under autograd) for now — fused kernels for them are the next step
+    (DESIGN.md §7). Nothing falls back to the CPU; CPU tensors raise.
+"""
+import ctypes
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib, packing
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+_EPI_GEOM, _EPI_STATS = 0x8, 0x400
+_TAPS9 = (ctypes.c_int * 9)(*[(r - 1) * 9 + (s - 1) for r in range(3) for s in range(3)])
+_ZERO9 = (ctypes.c_int * 9)(*([0] * 9))
 
 
-def forward_train(model, input, label):
-    raise NotImplementedError(
-        "ffr_net_b200.RecNet: training-mode / label forward is not implemented yet in the sm_100a library "
-        "(eval forward with label=None is); there is deliberately no PyTorch fallback")
+def _ceil64(c):
+    return (c + 63) // 64 * 64
+
+
+def _pad1(t, n):
+    out = torch.zeros(n, dtype=torch.float32, device=t.device)
+    out[: t.numel()] = t.detach().float()
+    return out
+
+
+def _conv_gemm(lib, a, wp, cin, cout, m, n_img, flags, out, stats=None, geom=True):
+    """3x3 taps on the H9 grid (pitch 9); plain bf16 rows out."""
+    rc = lib.ffr_conv_gemm(_lib.ptr(a), a.shape[0], a.shape[1], a.stride(0), _lib.ptr(wp), cin, cout, 9, _TAPS9, _ZERO9,
+                           m, 81, 9, 7, 1, n_img, flags, None, None, _lib.ptr(out), out.stride(0), 0, None, None, None,
+                           0, _lib.ptr(stats), 1, None, 0, 0, 0, _lib.stream_ptr())
+    _lib.check(rc, "ffr_conv_gemm")
+
+
+class _ConvLayerTrain(torch.autograd.Function):
+    """ReflectionPad2d(1) -> Conv2d 3x3 -> BatchNorm2d(batch stats) -> PReLU [+ residual] on H9 bf16 rows."""
+
+    @staticmethod
+    def forward(ctx, x_h9, weight, gamma, beta, slope, res_h9, layer, tab):
+        lib = _lib.load()
+        n = x_h9.shape[0] // 81
+        cin_p = x_h9.shape[1]
+        cout, cin = weight.shape[0], weight.shape[1]
+        cout_p = _ceil64(cout)
+        dev = x_h9.device
+        x_h9 = x_h9.contiguous()
+        wp = torch.zeros(cout_p, 9 * cin_p, dtype=torch.bfloat16, device=dev)
+        wp[:cout] = packing.pack_conv(weight.detach(), cin_pad=cin_p)
+        z = torch.empty(n * 81, cout_p, dtype=torch.bfloat16, device=dev)
+        stats = torch.zeros(2, cout_p, dtype=torch.float32, device=dev)
+        _conv_gemm(lib, x_h9, wp, cin_p, cout_p, n * 81, n, _EPI_GEOM | _EPI_STATS, z, stats)
+        cnt = float(n * 49)
+        mean = stats[0] / cnt
+        var = (stats[1] / cnt - mean * mean).clamp_min_(0.0)
+        rstd = torch.rsqrt(var + BN_EPS)
+        bn = layer.norm.norm
+        with torch.no_grad():                       # running statistics (momentum 0.1, unbiased variance)
+            bn.running_mean.mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * mean[:cout])
+            bn.running_var.mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * var[:cout] * (cnt / max(cnt - 1.0, 1.0)))
+            bn.num_batches_tracked += 1
+        g_p, b_p, s_p = _pad1(gamma, cout_p), _pad1(beta, cout_p), _pad1(slope, cout_p)
+        out = torch.empty(n * 81, cout_p, dtype=torch.bfloat16, device=dev)
+        res = res_h9.contiguous() if res_h9 is not None else None
+        _lib.check(lib.ffr_bn_prelu_fwd(_lib.ptr(z), cout_p, _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(g_p), _lib.ptr(b_p),
+                                        _lib.ptr(s_p), _lib.ptr(res), cout_p if res is not None else 0, _lib.ptr(out),
+                                        cout_p, _lib.ptr(tab), 4, n, cout_p, _lib.stream_ptr()), "ffr_bn_prelu_fwd")
+        ctx.save_for_backward(x_h9, weight, z, mean, rstd, g_p, b_p, s_p, tab)
+        ctx.has_res = res is not None
+        ctx.dims = (n, cin, cin_p, cout, cout_p)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        x_h9, weight, z, mean, rstd, g_p, b_p, s_p, tab = ctx.saved_tensors
+        n, cin, cin_p, cout, cout_p = ctx.dims
+        dev = dout.device
+        dout = dout.contiguous()
+        dy = torch.empty(n * 81, cout_p, dtype=torch.bfloat16, device=dev)
+        dz = torch.zeros(n * 81, cout_p, dtype=torch.bfloat16, device=dev)       # halo rows must be zero
+        dres = torch.zeros(n * 81, cout_p, dtype=torch.bfloat16, device=dev) if ctx.has_res else None
+        sums = torch.empty(3, cout_p, dtype=torch.float32, device=dev)
+        _lib.check(lib.ffr_bn_prelu_bwd(_lib.ptr(dout), cout_p, _lib.ptr(tab), 4, _lib.ptr(z), cout_p, _lib.ptr(mean),
+                                        _lib.ptr(rstd), _lib.ptr(g_p), _lib.ptr(b_p), _lib.ptr(s_p), _lib.ptr(dy), cout_p,
+                                        _lib.ptr(dres), cout_p, _lib.ptr(sums), _lib.ptr(dz), cout_p, n, cout_p,
+                                        _lib.stream_ptr()), "ffr_bn_prelu_bwd")
+        dw = torch.zeros(cout, cin, 3, 3, dtype=torch.float32, device=dev)
+        _lib.check(lib.ffr_wgrad3x3(_lib.ptr(dz), cout_p, _lib.ptr(x_h9), cin_p, 0, n, cout, cin, _lib.ptr(dw),
+                                    _lib.stream_ptr()), "ffr_wgrad3x3")
+        dx = None
+        if ctx.needs_input_grad[0]:
+            # dgrad = the same shifted-row conv with spatially flipped, transposed weights: WT[ci][(8-t)*Cout_p + co]
+            wt = torch.zeros(cin_p, 3, 3, cout_p, dtype=torch.bfloat16, device=dev)
+            wt[:cin, :, :, :cout] = weight.detach().flip(2, 3).permute(1, 2, 3, 0).to(torch.bfloat16)
+            dx = torch.empty(n * 81, cin_p, dtype=torch.bfloat16, device=dev)
+            _conv_gemm(lib, dz, wt.reshape(cin_p, 9 * cout_p), cout_p, cin_p, n * 81, n, 0, dx)
+        return dx, dw, sums[1, :cout].clone(), sums[0, :cout].clone(), sums[2, :cout].clone(), dres, None, None
+
+
+class _NchwToH9(torch.autograd.Function):
+    """fp32 (N,C,7,7) -> bf16 H9 [N*81, cpad] with the reflection halo filled; backward folds the mirrors."""
+
+    @staticmethod
+    def forward(ctx, x, cpad):
+        lib = _lib.load()
+        n, c = x.shape[0], x.shape[1]
+        x = x.contiguous().float()
+        alloc = torch.empty if cpad == _ceil64(c) else torch.zeros      # the kernel writes channels [0, ceil64(C))
+        out = alloc(n * 81, cpad, dtype=torch.bfloat16, device=x.device)
+        _lib.check(lib.ffr_nchw_to_h9(_lib.ptr(x), _lib.ptr(out), cpad, 0, n, c, 1, _lib.stream_ptr()), "ffr_nchw_to_h9")
+        ctx.dims = (n, c, cpad)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        n, c, cpad = ctx.dims
+        g = g.contiguous()
+        dx = torch.empty(n, c, 7, 7, dtype=torch.float32, device=g.device)
+        _lib.check(lib.ffr_h9_to_nchw(_lib.ptr(g), cpad, 0, _lib.ptr(dx), n, c, 1, _lib.stream_ptr()), "ffr_h9_to_nchw")
+        return dx, None
+
+
+class _H9ToNchw(torch.autograd.Function):
+    """bf16 H9 [N*81, cpad] -> fp32 (N,C,7,7) (valid pixels); backward writes the gradient with a zero halo."""
+
+    @staticmethod
+    def forward(ctx, h9, c):
+        lib = _lib.load()
+        n, cpad = h9.shape[0] // 81, h9.shape[1]
+        h9 = h9.contiguous()
+        y = torch.empty(n, c, 7, 7, dtype=torch.float32, device=h9.device)
+        _lib.check(lib.ffr_h9_to_nchw(_lib.ptr(h9), cpad, 0, _lib.ptr(y), n, c, 0, _lib.stream_ptr()), "ffr_h9_to_nchw")
+        ctx.dims = (n, c, cpad)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        n, c, cpad = ctx.dims
+        g = g.contiguous().float()
+        d = torch.zeros(n * 81, cpad, dtype=torch.bfloat16, device=g.device)
+        _lib.check(lib.ffr_nchw_to_h9(_lib.ptr(g), _lib.ptr(d), cpad, 0, n, c, 0, _lib.stream_ptr()), "ffr_nchw_to_h9")
+        return d, None
 
 
 def cosine_sim(x1, x2, dim=1):
-    raise NotImplementedError("ffr_net_b200.cosine_sim: not implemented yet in the sm_100a library")
+    """recnet.py:220-224."""
+    x1 = F.normalize(x1, dim=2)
+    x2 = F.normalize(x2, dim=2)
+    return torch.bmm(x1, x2.permute(0, 2, 1))
 
 
 def self_similarity(x):
-    raise NotImplementedError("ffr_net_b200.selfSimilarity: not implemented yet in the sm_100a library")
+    """selfSimilarity, recnet.py:226-236 (ATen/cuBLAS under autograd: used by the trainer's loss terms)."""
+    if not x.is_cuda:
+        raise RuntimeError("ffr_net_b200.selfSimilarity runs only on CUDA")
+    h, w = x.size(2), x.size(3)
+    v = x.reshape(x.size(0), x.size(1), -1)
+    ss_space = cosine_sim(v.permute(0, 2, 1), v.permute(0, 2, 1))
+    ss_channel = cosine_sim(v, v)
+    return ss_space.reshape(ss_space.size(0), ss_space.size(1), h, w), ss_channel
+
+
+def add_margin_product(weight, x, label, s=30.0, m=0.40):
+    """AddMarginProduct.forward, recnet.py:257-270 (one-hot built on the input's device)."""
+    cosine = F.linear(F.normalize(x), F.normalize(weight))
+    one_hot = torch.zeros_like(cosine)
+    one_hot.scatter_(1, label.view(-1, 1).long(), 1)
+    output = (one_hot * (cosine - m)) + ((1.0 - one_hot) * cosine)
+    return output * s, cosine
+
+
+def forward_train(model, x, label):
+    """RecNet.forward for training / label inputs (recnet.py:398-429)."""
+    if not x.is_cuda:
+        raise RuntimeError("ffr_net_b200.RecNet runs only on CUDA (sm_100a); there is no CPU fallback")
+    if not model.training:
+        raise NotImplementedError("RecNet(label=...) in eval mode is not implemented (the reference only calls the "
+                                  "label path while training, models/trainer.py:144-145)")
+    pk = model._train_tables(x.device)
+    tab = pk[0]
+    n = x.shape[0]
+    x = x.contiguous().float()
+
+    def conv(layer, h, res=None):
+        return _ConvLayerTrain.apply(h, layer.conv2d.weight, layer.norm.norm.weight, layer.norm.norm.bias,
+                                     layer.relu.func.weight, res, layer, tab)
+
+    def resblock(blk, h):
+        return conv(blk.conv2, conv(blk.conv1, h), res=h)
+
+    ss_space, ss_channel = self_similarity(x)                                            # :399
+    flat = x.reshape(n, 512, 49)
+    s = model.Conv4Space
+    h = _NchwToH9.apply(torch.cat((x, ss_space), 1), 576)                                # :401
+    h = resblock(s[1], conv(s[0], h))
+    h = resblock(s[3], conv(s[2], h))
+    h = resblock(s[5], conv(s[4], h))
+    m_space = torch.sigmoid(_H9ToNchw.apply(h, 49)).reshape(n, 49, 49)                   # :404-405
+
+    c = model.Conv4Channel
+    g = torch.cat((flat, ss_channel), 2)                                                 # :402
+    for i in (0, 3, 6):
+        g = F.linear(g, c[i].weight, c[i].bias)
+        g = F.prelu(g, c[i + 1].func.weight)
+        g = F.linear(g, c[i + 2].weight, c[i + 2].bias)
+    m_channel = torch.sigmoid(g)                                                         # :406
+
+    feat_space = torch.matmul(flat, m_space).reshape(n, 512, 7, 7)                       # :409,412
+    feat_channel = torch.matmul(m_channel, flat).reshape(n, 512, 7, 7)                   # :410,413
+    fm = _NchwToH9.apply(torch.cat((torch.flip(feat_channel, [3]), feat_channel), 1), 1024)   # :416-417
+    f = model.ChannelFlipMerge
+    fc_h9 = resblock(f[1], conv(f[0], fm))                                               # :418
+    feat_channel_out = _H9ToNchw.apply(fc_h9, 512)
+    cat_h9 = torch.cat((_NchwToH9.apply(feat_space, 512), fc_h9, _NchwToH9.apply(x, 512)), 1)   # :420
+    mg = model.Conv4Merge
+    feat_new = _H9ToNchw.apply(resblock(mg[1], conv(mg[0], cat_h9)), 512)                # :421
+    feat_new_v = feat_new.mean(dim=(2, 3))                                               # :423
+    if label is None:
+        return feat_new_v, feat_new
+    pred_loss, pred_label = add_margin_product(model.classifier.weight, feat_new_v, label)   # :428
+    return feat_new_v, pred_loss, pred_label, m_space, m_channel, feat_space, feat_channel_out

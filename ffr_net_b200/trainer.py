@@ -1,0 +1,137 @@
+"""Training step — mirror of the hot part of `models/trainer.py` (TripletLoss :31-43, Trainer.forward :139-152,
+backward :154-180, optimizer_parameters :182-187, update_learning_rate :235-238) for one process per GPU.
+
+Data parallelism replaces the reference's single-process `nn.parallel.data_parallel` (trainer.py:70,72): every rank
+runs the frozen encoder and RecNet on its batch shard, the 76 RecNet/head gradient tensors are averaged with ONE NCCL
+all-reduce over a flat bucket before clip_grad_value_ and Adam (losses are batch means, so the mean of per-rank
+gradients equals the gradient of the global mean; BatchNorm statistics stay per rank like per-replica DP).
+"""
+import types
+
+import torch
+import torch.nn.functional as F
+from torch import nn, optim
+
+from .backbone import Backbone
+from .recnet import RecNet, init_weights, selfSimilarity
+
+
+class TripletLoss(nn.Module):
+    def forward(self, x_feat, y_feat, z_feat):
+        margin = 0.1
+        pos_cos = 1 - torch.sum(F.normalize(x_feat) * F.normalize(y_feat), 1)
+        neg_cos = 1 - torch.sum(F.normalize(x_feat) * F.normalize(z_feat), 1)
+        return F.relu((pos_cos - neg_cos) + margin).mean(), pos_cos.mean(), neg_cos.mean()
+
+
+def default_opts(**kw):
+    """The hyper-parameters run.py passes (run.py:10-28)."""
+    o = types.SimpleNamespace(phase="train", lr=0.1, beta1=0.9, beta2=0.999, weight_decay=0.0, optimizer="adam",
+                              loss_weight=[1.0, 1.0, 1.0, 1.0], device="cuda", continue_train=False)
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+class Trainer:
+    def __init__(self, opts, encoder=None, recnet=None, encoder_weights=None):
+        self.opts = opts
+        self.isTrain = opts.phase.lower() == "train"
+        self.lr = opts.lr
+        dev = torch.device(opts.device)
+        self.encoder = encoder if encoder is not None else Backbone(50, 0.6, "ir_se")
+        if encoder_weights is not None:
+            self.encoder.load_state_dict(encoder_weights)
+        if recnet is None:
+            recnet = RecNet(norm_type="bn", relu_type="prelu")
+            init_weights(recnet, "kaiming")
+        self.recnet = recnet
+        for p in self.encoder.parameters():
+            p.requires_grad = False
+        self.encoder.to(dev).eval()
+        self.recnet.to(dev)
+        if self.isTrain:
+            self.recnet.train()
+            params = [p for p in self.recnet.parameters() if p.requires_grad]
+            if opts.optimizer.lower() != "adam":
+                raise NotImplementedError("run.py uses Adam (run.py:11)")
+            self.optim = optim.Adam(params, opts.lr, betas=(opts.beta1, opts.beta2), weight_decay=opts.weight_decay)
+            self.sch = optim.lr_scheduler.MultiStepLR(self.optim, [5000, 10000, 15000], gamma=0.5)
+        else:
+            self.recnet.eval()
+        self.mse_loss = nn.MSELoss()
+        self.triplet = TripletLoss()
+        self.cross_entropy = nn.CrossEntropyLoss()
+        self._flat = None
+
+    def set_input(self, img1, img2, label):
+        self.nonocl, self.ocl, self.gt_label = img1, img2, label
+
+    def forward(self):
+        with torch.no_grad():
+            self.feat_map_non, self.feat_extract_non = self.encoder(self.nonocl)
+            self.feat_map_ocl, self.feat_extract_ocl = self.encoder(self.ocl)
+        (self.f_non, self.pred_loss_non, self.pred_label_non, self.M_space_non, self.M_channel_non, self.space_non,
+         self.channel_non) = self.recnet(self.feat_map_non, self.gt_label)
+        (self.f_ocl, self.pred_loss_ocl, self.pred_label_ocl, self.M_space_ocl, self.M_channel_ocl, self.space_ocl,
+         self.channel_ocl) = self.recnet(self.feat_map_ocl, self.gt_label)
+        pred = self.pred_label_ocl.detach().argmax(1)
+        self.pred_label = pred
+        self._correct = pred.eq(self.gt_label).sum()          # no host sync here; .item() in get_current_values
+
+    def backward(self):
+        ss_space, ss_channel = selfSimilarity(self.feat_map_non)
+        ss_space_non, _ = selfSimilarity(self.space_non)
+        ss_space_ocl, _ = selfSimilarity(self.space_ocl)
+        _, ss_channel_non = selfSimilarity(self.channel_non)
+        _, ss_channel_ocl = selfSimilarity(self.channel_ocl)
+        mse = self.mse_loss
+        l_space = (mse(ss_space, ss_space_non) + mse(ss_space, ss_space_ocl)) / 2
+        l_channel = (mse(ss_channel, ss_channel_non) + mse(ss_channel, ss_channel_ocl)) / 2
+        items = [(l_space + l_channel) / 2]
+        t, self.pos_loss, self.neg_loss = self.triplet(self.f_ocl, self.feat_extract_non, self.feat_extract_ocl)
+        items.append(t)
+        items.append((mse(self.f_non, self.feat_extract_non) + mse(self.f_ocl, self.feat_extract_non)) / 2)
+        items.append(self.cross_entropy(self.pred_loss_non, self.gt_label) / (1e-8 + self.opts.loss_weight[3])
+                     + self.cross_entropy(self.pred_loss_ocl, self.gt_label))
+        self.loss_items = [l * w for l, w in zip(items, self.opts.loss_weight)]
+        sum(self.loss_items).backward()
+
+    def allreduce_gradients(self):
+        """Average the RecNet/head gradients over ranks with one all-reduce of a flat fp32 bucket."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        params = [p for p in self.recnet.parameters() if p.grad is not None]
+        n = sum(p.numel() for p in params)
+        if self._flat is None or self._flat.numel() != n:
+            self._flat = torch.empty(n, dtype=torch.float32, device=params[0].device)
+        off = 0
+        for p in params:
+            self._flat[off:off + p.numel()].copy_(p.grad.reshape(-1))
+            off += p.numel()
+        dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
+        self._flat.div_(dist.get_world_size())
+        off = 0
+        for p in params:
+            p.grad.copy_(self._flat[off:off + p.numel()].view_as(p.grad))
+            off += p.numel()
+
+    def optimizer_parameters(self, cur_iters=0):
+        self.optim.zero_grad()
+        self.backward()
+        self.allreduce_gradients()                     # before clipping, as reduce-then-clip in the reference
+        nn.utils.clip_grad_value_(self.recnet.parameters(), 1.0)
+        self.optim.step()
+
+    def get_current_values(self):
+        keys = ["SelfSimilarityLoss", "TripletLoss", "IdentityLoss", "ClassifierLoss"]
+        d = {k: "{:.4f}".format(v.item()) for k, v in zip(keys, self.loss_items)}
+        self.accuracy = self._correct.item() / self.pred_label.shape[0]
+        d["TrainAcc"] = "{:.4f}".format(self.accuracy)
+        return d
+
+    def update_learning_rate(self):
+        self.sch.step()
+        for g in self.optim.param_groups:
+            self.lr = g["lr"]

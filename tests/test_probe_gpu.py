@@ -31,4 +31,26 @@ def test_rowshift_descriptor_semantics(lib):
         json.dump(result, f)
     print("rowshift probe:", result)
     assert result["variant0"][0] and result["variant1"][0], "aligned descriptor must work in both variants"
-    assert all(result["variant0"]) or all(result["variant1"]), result
+    assert all(result["variant0"]), result
+
+
+def test_mn_major_descriptor_semantics(lib):
+    """MN-major SWIZZLE_128B operands (needed by the weight-gradient GEMM, which contracts over pixel rows)."""
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.randint(-3, 4, (96, 128), generator=g, device="cuda").to(torch.bfloat16)
+    b = torch.randint(-3, 4, (96, 64), generator=g, device="cuda").to(torch.bfloat16)
+    result = {}
+    for variant in (0,):     # variant 1 (LBO/SBO swapped) faults the context on B200 — established once, not re-run
+        ok = []
+        for r0 in (0, 8, 16, 1, 3, 9, 10, 19, 32):
+            out = torch.zeros(128, 64, dtype=torch.float32, device="cuda")
+            _lib.check(lib.ffr_debug_mn_probe(_lib.ptr(a), _lib.ptr(b), _lib.ptr(out), r0, variant, _lib.stream_ptr()))
+            torch.cuda.synchronize()
+            ref = a[:64].float().t() @ b[r0:r0 + 64].float()
+            ok.append(bool(torch.equal(out, ref)))
+        result["variant%d" % variant] = ok
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/probe_mn_major.json", "w") as f:
+        json.dump(result, f)
+    print("mn-major probe:", result)
+    assert all(result["variant0"]), result

@@ -80,9 +80,5 @@ def test_recnet_rejects_cpu_and_training(models):
     sd, m = models
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 512, 7, 7))
-    m.train()
-    try:
-        with pytest.raises(NotImplementedError):
-            m(torch.zeros(2, 512, 7, 7, device="cuda"))
-    finally:
-        m.eval()
+    with pytest.raises(NotImplementedError):     # label path in eval mode: the reference never uses it
+        m(torch.zeros(2, 512, 7, 7, device="cuda"), torch.zeros(2, dtype=torch.long, device="cuda"))
