@@ -28,6 +28,9 @@ METRIC = "IR-SE50+RecBlock embeddings/s (bs512)"
 UNIT = "img/s"
 
 
+_emit = print
+
+
 def _peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -155,7 +158,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(json.dumps(line))
 
 
 def _have_recnet():
@@ -315,7 +318,7 @@ def run_ours(args):
             "tflops_whole_step": value * gflop / 1e3,
             "roofline": roof, "cpu_baseline": cpu, "train": train,
         }
-        print(json.dumps(line))
+        _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -374,6 +377,17 @@ def main():
     ap.add_argument("--no-train", dest="no_train", action="store_true", help="skip the secondary training-step line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE JSON line: anything libraries print to fd 1 meanwhile (e.g. NCCL's version banner)
+    # is routed to stderr, and fd 1 is restored for the final print.
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+    def _emit(line):
+        sys.stdout.flush()
+        os.dup2(saved_fd, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
