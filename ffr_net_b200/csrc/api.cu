@@ -39,6 +39,8 @@ int bn_prelu_bwd_launch(const void* da, int ldda, const int* scatter, int scatte
                         void* dy, int lddy, void* dres, int lddres, float* sums, void* dz, int lddz, int n_img, int C,
                         cudaStream_t stream);
 int nchw_to_h9_launch(const float* x, void* out, int ld, int ch0, int n_img, int C, int mirror, cudaStream_t stream);
+int pack_conv3x3_launch(const float* w, int cout, int cin, int cout_p, int cin_p, void* fwd, void* dgrad,
+                        cudaStream_t stream);
 int h9_to_nchw_launch(const void* in, int ld, int ch0, float* y, int n_img, int C, int fold, cudaStream_t stream);
 int pair_cosine_launch(const float* f1, const float* f2, float* score, int pairs, int D, cudaStream_t stream);
 int threshold_sweep_launch(const float* score, const int* label, const double* thresholds, int n, int T, int folds,
@@ -303,6 +305,12 @@ FFR_API int ffr_bn_prelu_bwd(const void* da, int ldda, const int* scatter, int s
                   "ffr_bn_prelu_bwd: null pointer");
     return bn_prelu_bwd_launch(da, ldda, scatter, scatter_n, z, ldz, mean, rstd, gamma, beta, slope, dy, lddy, dres,
                                lddres, sums, dz, lddz, n, C, S_(stream));
+}
+
+FFR_API int ffr_pack_conv3x3(const float* w, int cout, int cin, int cout_p, int cin_p, void* fwd, void* dgrad,
+                             ffr_stream_t stream) {
+    FFR_CHECK_ARG(w && fwd, "ffr_pack_conv3x3: null pointer");
+    return pack_conv3x3_launch(w, cout, cin, cout_p, cin_p, fwd, dgrad, S_(stream));
 }
 
 FFR_API int ffr_nchw_to_h9(const float* x, void* out, int ld, int ch0, int n, int C, int mirror, ffr_stream_t stream) {

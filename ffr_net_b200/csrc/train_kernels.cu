@@ -305,20 +305,27 @@ bn_prelu_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, int ldda, const
     }
 }
 
-// Pass 2: dz = gamma * rstd * (dy - sum(dy)/cnt - zhat * sum(dy*zhat)/cnt), written to the valid rows of dz_h9
-// (halo rows of that buffer stay zero: the dgrad / wgrad GEMMs read it as a zero-padded map).
+// Pass 2: dz = gamma * rstd * (dy - sum(dy)/cnt - zhat * sum(dy*zhat)/cnt) on the valid rows of dz_h9 and ZERO on its
+// halo rows (the dgrad / wgrad GEMMs read dz as a zero-padded map); the residual-branch gradient buffer gets its
+// halo rows zeroed here as well (its valid rows were written by pass 1).
 __global__ void __launch_bounds__(256)
 bn_prelu_bwd_dz_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, const __nv_bfloat16* __restrict__ z, int ldz,
                        const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
-                       const float* __restrict__ sums, __nv_bfloat16* __restrict__ dz, int lddz, int n_img, int C) {
+                       const float* __restrict__ sums, __nv_bfloat16* __restrict__ dz, int lddz,
+                       __nv_bfloat16* __restrict__ dres, int lddres, int n_img, int C) {
     const int c8n = C / 8;
     const float inv_cnt = 1.0f / (float)(n_img * 49);
-    const long long total = (long long)n_img * 49 * c8n;
+    const long long total = (long long)n_img * 81 * c8n;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int c8 = (int)(i % c8n);
-        const long long pr = i / c8n;
-        const int n = (int)(pr / 49), pix = (int)(pr - (long long)n * 49);
-        const long long row = (long long)n * 81 + (pix / 7 + 1) * 9 + (pix % 7 + 1);
+        const long long row = i / c8n;
+        const int pos = (int)(row % 81);
+        const int hp = pos / 9, wp = pos - hp * 9;
+        if (hp == 0 || hp == 8 || wp == 0 || wp == 8) {
+            *(reinterpret_cast<uint4*>(dz + row * lddz) + c8) = make_uint4(0, 0, 0, 0);
+            if (dres) *(reinterpret_cast<uint4*>(dres + row * lddres) + c8) = make_uint4(0, 0, 0, 0);
+            continue;
+        }
         const uint4 dv = __ldg(reinterpret_cast<const uint4*>(dy + row * lddy) + c8);
         const uint4 zv = __ldg(reinterpret_cast<const uint4*>(z + row * ldz) + c8);
         const float d[8] = {bf16lo(dv.x), bf16hi(dv.x), bf16lo(dv.y), bf16hi(dv.y), bf16lo(dv.z), bf16hi(dv.z), bf16lo(dv.w), bf16hi(dv.w)};
@@ -352,12 +359,13 @@ int bn_prelu_bwd_launch(const void* da, int ldda, const int* scatter, int scatte
         reinterpret_cast<__nv_bfloat16*>(dy), lddy, reinterpret_cast<__nv_bfloat16*>(dres), lddres, sums, n_img, C);
     int rc = launch_status("bn_prelu_bwd_reduce_kernel");
     if (rc) return rc;
-    const long long total = rows * (C / 8);
+    const long long total = (long long)n_img * 81 * (C / 8);
     int g2 = (int)((total + 255) / 256);
     if (g2 > num_sms() * 8) g2 = num_sms() * 8;
     bn_prelu_bwd_dz_kernel<<<g2, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy), lddy,
                                                    reinterpret_cast<const __nv_bfloat16*>(z), ldz, mean, rstd, gamma, sums,
-                                                   reinterpret_cast<__nv_bfloat16*>(dz), lddz, n_img, C);
+                                                   reinterpret_cast<__nv_bfloat16*>(dz), lddz,
+                                                   reinterpret_cast<__nv_bfloat16*>(dres), lddres, n_img, C);
     return launch_status("bn_prelu_bwd_dz_kernel");
 }
 
@@ -414,6 +422,37 @@ h9_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, int ld, int ch0, float* 
         const int c = i / 49, pix = i - c * 49;
         if (c0 + c < C) y[((long long)n * C + c0 + c) * 49 + pix] = tile[pix][c];
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Weight packing for one ConvLayer in a single launch (done once per optimizer step, cached by the host):
+//   fwd  [cout_p][9*cin_p]  : fwd[co][t*cin_p + ci]          = w[co][ci][t]
+//   dgrad[cin_p][9*cout_p]  : dgrad[ci][(8-t)*cout_p + co]   = w[co][ci][t]   (spatially flipped, transposed)
+// Padded rows/columns are written as zeros.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_conv3x3_kernel(const float* __restrict__ w, int cout, int cin, int cout_p, int cin_p,
+                    __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ dgrad) {
+    const long long total = (long long)cout_p * cin_p * 9;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % cin_p);
+        const int t = (int)((i / cin_p) % 9);
+        const int co = (int)(i / ((long long)cin_p * 9));
+        const float v = (co < cout && ci < cin) ? w[((long long)co * cin + ci) * 9 + t] : 0.f;
+        const __nv_bfloat16 b = __float2bfloat16(v);
+        fwd[i] = b;                                                      // i == (co*9 + t)*cin_p + ci
+        if (dgrad) dgrad[((long long)ci * 9 + (8 - t)) * cout_p + co] = b;
+    }
+}
+
+int pack_conv3x3_launch(const float* w, int cout, int cin, int cout_p, int cin_p, void* fwd, void* dgrad,
+                        cudaStream_t stream) {
+    const long long total = (long long)cout_p * cin_p * 9;
+    int grid = (int)((total + 255) / 256);
+    if (grid > num_sms() * 16) grid = num_sms() * 16;
+    pack_conv3x3_kernel<<<grid, 256, 0, stream>>>(w, cout, cin, cout_p, cin_p, reinterpret_cast<__nv_bfloat16*>(fwd),
+                                                  reinterpret_cast<__nv_bfloat16*>(dgrad));
+    return launch_status("pack_conv3x3_kernel");
 }
 
 int nchw_to_h9_launch(const float* x, void* out, int ld, int ch0, int n_img, int C, int mirror, cudaStream_t stream) {

@@ -30,9 +30,32 @@ def _ceil64(c):
 
 
 def _pad1(t, n):
+    t = t.detach()
+    if t.numel() == n and t.dtype == torch.float32 and t.is_contiguous():
+        return t                                   # the kernels only read it
     out = torch.zeros(n, dtype=torch.float32, device=t.device)
-    out[: t.numel()] = t.detach().float()
+    out[: t.numel()] = t.float()
     return out
+
+
+def _packed_weights(layer, weight, cin_p, cout_p):
+    """bf16 K-major weights for the forward GEMM and the dgrad GEMM, packed by one kernel and cached until the
+    parameter changes (the two RecNet calls of a step and the backward share them)."""
+    key = (weight.data_ptr(), weight._version, cin_p, cout_p)
+    cache = getattr(layer, "_ffr_pack", None)
+    if cache is not None and cache[0] == key:
+        return cache[1], cache[2]
+    lib = _lib.load()
+    cout, cin = weight.shape[0], weight.shape[1]
+    dev = weight.device
+    wp = torch.empty(cout_p, 9 * cin_p, dtype=torch.bfloat16, device=dev)
+    wt = torch.empty(cin_p, 9 * cout_p, dtype=torch.bfloat16, device=dev)
+    w = weight.detach()
+    w = w if (w.dtype == torch.float32 and w.is_contiguous()) else w.float().contiguous()
+    _lib.check(lib.ffr_pack_conv3x3(_lib.ptr(w), cout, cin, cout_p, cin_p, _lib.ptr(wp), _lib.ptr(wt),
+                                    _lib.stream_ptr()), "ffr_pack_conv3x3")
+    layer._ffr_pack = (key, wp, wt)
+    return wp, wt
 
 
 def _conv_gemm(lib, a, wp, cin, cout, m, n_img, flags, out, stats=None, geom=True):
@@ -55,8 +78,7 @@ class _ConvLayerTrain(torch.autograd.Function):
         cout_p = _ceil64(cout)
         dev = x_h9.device
         x_h9 = x_h9.contiguous()
-        wp = torch.zeros(cout_p, 9 * cin_p, dtype=torch.bfloat16, device=dev)
-        wp[:cout] = packing.pack_conv(weight.detach(), cin_pad=cin_p)
+        wp, wt = _packed_weights(layer, weight, cin_p, cout_p)
         z = torch.empty(n * 81, cout_p, dtype=torch.bfloat16, device=dev)
         stats = torch.zeros(2, cout_p, dtype=torch.float32, device=dev)
         _conv_gemm(lib, x_h9, wp, cin_p, cout_p, n * 81, n, _EPI_GEOM | _EPI_STATS, z, stats)
@@ -75,7 +97,7 @@ class _ConvLayerTrain(torch.autograd.Function):
         _lib.check(lib.ffr_bn_prelu_fwd(_lib.ptr(z), cout_p, _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(g_p), _lib.ptr(b_p),
                                         _lib.ptr(s_p), _lib.ptr(res), cout_p if res is not None else 0, _lib.ptr(out),
                                         cout_p, _lib.ptr(tab), 4, n, cout_p, _lib.stream_ptr()), "ffr_bn_prelu_fwd")
-        ctx.save_for_backward(x_h9, weight, z, mean, rstd, g_p, b_p, s_p, tab)
+        ctx.save_for_backward(x_h9, weight, z, mean, rstd, g_p, b_p, s_p, tab, wt)
         ctx.has_res = res is not None
         ctx.dims = (n, cin, cin_p, cout, cout_p)
         return out
@@ -83,13 +105,13 @@ class _ConvLayerTrain(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         lib = _lib.load()
-        x_h9, weight, z, mean, rstd, g_p, b_p, s_p, tab = ctx.saved_tensors
+        x_h9, weight, z, mean, rstd, g_p, b_p, s_p, tab, wt = ctx.saved_tensors
         n, cin, cin_p, cout, cout_p = ctx.dims
         dev = dout.device
         dout = dout.contiguous()
         dy = torch.empty(n * 81, cout_p, dtype=torch.bfloat16, device=dev)
-        dz = torch.zeros(n * 81, cout_p, dtype=torch.bfloat16, device=dev)       # halo rows must be zero
-        dres = torch.zeros(n * 81, cout_p, dtype=torch.bfloat16, device=dev) if ctx.has_res else None
+        dz = torch.empty(n * 81, cout_p, dtype=torch.bfloat16, device=dev)       # halo rows zeroed by the kernel
+        dres = torch.empty(n * 81, cout_p, dtype=torch.bfloat16, device=dev) if ctx.has_res else None
         sums = torch.empty(3, cout_p, dtype=torch.float32, device=dev)
         _lib.check(lib.ffr_bn_prelu_bwd(_lib.ptr(dout), cout_p, _lib.ptr(tab), 4, _lib.ptr(z), cout_p, _lib.ptr(mean),
                                         _lib.ptr(rstd), _lib.ptr(g_p), _lib.ptr(b_p), _lib.ptr(s_p), _lib.ptr(dy), cout_p,
@@ -101,11 +123,9 @@ class _ConvLayerTrain(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             # dgrad = the same shifted-row conv with spatially flipped, transposed weights: WT[ci][(8-t)*Cout_p + co]
-            wt = torch.zeros(cin_p, 3, 3, cout_p, dtype=torch.bfloat16, device=dev)
-            wt[:cin, :, :, :cout] = weight.detach().flip(2, 3).permute(1, 2, 3, 0).to(torch.bfloat16)
             dx = torch.empty(n * 81, cin_p, dtype=torch.bfloat16, device=dev)
-            _conv_gemm(lib, dz, wt.reshape(cin_p, 9 * cout_p), cout_p, cin_p, n * 81, n, 0, dx)
-        return dx, dw, sums[1, :cout].clone(), sums[0, :cout].clone(), sums[2, :cout].clone(), dres, None, None
+            _conv_gemm(lib, dz, wt, cout_p, cin_p, n * 81, n, 0, dx)
+        return dx, dw, sums[1, :cout], sums[0, :cout], sums[2, :cout], dres, None, None
 
 
 class _NchwToH9(torch.autograd.Function):

@@ -59,6 +59,10 @@ class Trainer:
             self.sch = optim.lr_scheduler.MultiStepLR(self.optim, [5000, 10000, 15000], gamma=0.5)
         else:
             self.recnet.eval()
+        # The thin library-op remainder of the step (Conv4Channel MLP, per-sample matmuls, CosFace head; see
+        # recnet_train.py) would otherwise run as fp32 SIMT GEMMs: let cuBLAS use TF32 tensor cores for it.
+        if getattr(opts, "tf32_glue", True):
+            torch.backends.cuda.matmul.allow_tf32 = True
         self.mse_loss = nn.MSELoss()
         self.triplet = TripletLoss()
         self.cross_entropy = nn.CrossEntropyLoss()

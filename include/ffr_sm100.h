@@ -161,6 +161,11 @@ FFR_API int ffr_bn_prelu_bwd(const void* da, int ldda, const int* scatter, int s
                              const float* slope, void* dy, int lddy, void* dres, int lddres, float* sums, void* dz,
                              int lddz, int n, int C, ffr_stream_t stream);
 
+/* Packs one 3x3 conv weight (fp32 OIHW) for the forward GEMM and (optionally) for its dgrad in a single launch:
+ * fwd [cout_p][9*cin_p], dgrad [cin_p][9*cout_p] (spatially flipped + transposed), zero padded. */
+FFR_API int ffr_pack_conv3x3(const float* w, int cout, int cin, int cout_p, int cin_p, void* fwd, void* dgrad,
+                             ffr_stream_t stream);
+
 /* fp32 NCHW (n,C,7,7) -> bf16 H9 channel slot (mirror != 0: reflection halo filled, else halo zero) and back
  * (fold != 0: sums the mirror rows into the pixel, i.e. the gradient of the mirrored scatter). */
 FFR_API int ffr_nchw_to_h9(const float* x, void* out, int ld, int ch0, int n, int C, int mirror, ffr_stream_t stream);

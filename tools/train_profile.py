@@ -1,0 +1,49 @@
+"""torch.profiler breakdown of one training step (GPU box): which kernels / ops dominate. Writes gpurun_out/train_profile.txt."""
+import os
+import sys
+
+import torch
+from torch.profiler import ProfilerActivity, profile
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import backbone as ob
+from oracle import recnet as orr
+from ffr_net_b200.backbone import Backbone
+from ffr_net_b200.recnet import RecNet
+from ffr_net_b200.trainer import Trainer, default_opts
+
+dev = torch.device("cuda")
+enc = Backbone(50, 0.6, "ir_se")
+enc.load_state_dict(ob.synth_backbone_state_dict(0))
+rec = RecNet()
+rec.load_state_dict(orr.synth_recnet_state_dict(0))
+tr = Trainer(default_opts(lr=1e-4), encoder=enc, recnet=rec)
+pairs = 256
+a = ob.synth_faces(64, seed=1).repeat(4, 1, 1, 1).to(dev)
+b = ob.synth_faces(64, seed=1, masked=True).repeat(4, 1, 1, 1).to(dev)
+label = torch.randint(0, 10575, (pairs,)).to(dev)
+
+
+def step():
+    tr.set_input(a, b, label)
+    tr.forward()
+    tr.optimizer_parameters(0)
+    tr.update_learning_rate()
+
+
+for _ in range(3):
+    step()
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    step()
+    torch.cuda.synchronize()
+os.makedirs("gpurun_out", exist_ok=True)
+txt = prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70)
+open("gpurun_out/train_profile.txt", "w").write(txt)
+print(txt)
+import time
+t0 = time.perf_counter()
+for _ in range(5):
+    step()
+torch.cuda.synchronize()
+print("wall ms/step", (time.perf_counter() - t0) / 5 * 1e3)
