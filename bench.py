@@ -254,14 +254,38 @@ def run_ours(args):
     value = world * BATCH * args.steps / (ms * 1e-3)
 
     # ---- end to end through the module API with host buffers ----
+    # Every step copies its batch from pinned host memory (77 MB) and reads its embeddings back (1 MB), all inside the
+    # timed region. The copies run on a side stream into a double-buffered staging tensor so the H2D of step i+1
+    # overlaps the kernels of step i (what any host loop around the public forward() would do).
     out_host = torch.empty(BATCH, 512, dtype=torch.float32).pin_memory()
-    x_stage = torch.empty_like(x_dev)
+    x_stage = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
+    copy_stream = torch.cuda.Stream()
+    ev_in = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_free = [torch.cuda.Event(), torch.cuda.Event()]
+    main_stream = torch.cuda.current_stream()
+    state = {"i": 0, "primed": False}
+
+    def issue_copy(buf):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_free[buf])           # the step that last read this buffer has finished
+            x_stage[buf].copy_(x_host, non_blocking=True)
+            ev_in[buf].record(copy_stream)
 
     def e2e_step():
-        x_stage.copy_(x_host, non_blocking=True)
-        f = step(x_stage)
+        i = state["i"]
+        buf = i & 1
+        if not state["primed"]:
+            issue_copy(buf)
+            state["primed"] = True
+        issue_copy(buf ^ 1)                                # prefetch the next step's batch
+        main_stream.wait_event(ev_in[buf])
+        f = step(x_stage[buf])
         out_host.copy_(f, non_blocking=True)
+        ev_free[buf].record(main_stream)
+        state["i"] = i + 1
 
+    for b in (0, 1):
+        ev_free[b].record(main_stream)
     for _ in range(3):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
@@ -313,7 +337,8 @@ def run_ours(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": _config(with_recnet),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
-                    "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": ms_e2e / args.steps,
+                    "pipeline": "H2D of step i+1 on a side stream overlaps step i (double-buffered staging)"},
             "gpu_launches": int(launches), "clocks": clocks,
             "tflops_whole_step": value * gflop / 1e3,
             "roofline": roof, "cpu_baseline": cpu, "train": train,

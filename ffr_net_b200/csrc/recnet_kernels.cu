@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(512, 1) recnet_prep_kernel(const PrepParams p)
     float* inv_c = xs + 512 * 49;        // [512]
     float* inv_s = inv_c + 512;          // [64]
     float* Gs = inv_s + 64;              // [49][49]
-    float* T = Gs + 49 * 49 + 3;         // [49][32]
+    float* T = Gs + 49 * 49 + 3;         // [49][32]   (49*49 + 3 = 2404: keeps T, W0a, A1s, A2s 16-byte aligned)
     float* W0a = T + 49 * 32;            // [49][32]
     float* A1s = W0a + 49 * 32;          // [32][32]
     float* A2s = A1s + 1024;             // [32][32]
@@ -80,21 +80,44 @@ __global__ void __launch_bounds__(512, 1) recnet_prep_kernel(const PrepParams p)
     }
     __syncthreads();
 
-    // spatial self-similarity Gram (49x49 over C)
-    for (int o = tid; o < 49 * 49; o += 512) {
-        const int i = o / 49, j = o - i * 49;
-        float a = 0.f;
-#pragma unroll 8
-        for (int c = 0; c < 512; ++c) a = fmaf(xs[c * 49 + i], xs[c * 49 + j], a);
-        Gs[o] = a * inv_s[i] * inv_s[j];
-    }
-    // T[hw][j] = sum_c Xh[c][hw] * W0b[j][c]
-    for (int o = tid; o < 49 * 32; o += 512) {
-        const int hw = o >> 5, j = o & 31;
-        float a = 0.f;
+    // The three phases below are bound by shared-memory instruction throughput (every FMA wants an operand from
+    // smem), so each thread register-tiles its outputs: 4 Gram columns per row value, 7 pixels per weight value.
+
+    // spatial self-similarity Gram (49x49 over C): work item = (row i, block of 4 columns j0..j0+3)
+    for (int o = tid; o < 49 * 13; o += 512) {
+        const int i = o / 13, j0 = (o - i * 13) * 4;
+        const int j1 = min(j0 + 1, 48), j2 = min(j0 + 2, 48), j3 = min(j0 + 3, 48);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 4
-        for (int c = 0; c < 512; ++c) a = fmaf(xs[c * 49 + hw] * inv_c[c], __ldg(p.w0bT + c * 32 + j), a);
-        T[o] = a;
+        for (int c = 0; c < 512; ++c) {
+            const float* xr = xs + c * 49;
+            const float xi = xr[i];
+            a0 = fmaf(xi, xr[j0], a0); a1 = fmaf(xi, xr[j1], a1);
+            a2 = fmaf(xi, xr[j2], a2); a3 = fmaf(xi, xr[j3], a3);
+        }
+        const float si = inv_s[i];
+        Gs[i * 49 + j0] = a0 * si * inv_s[j0];
+        if (j0 + 1 < 49) Gs[i * 49 + j0 + 1] = a1 * si * inv_s[j1];
+        if (j0 + 2 < 49) Gs[i * 49 + j0 + 2] = a2 * si * inv_s[j2];
+        if (j0 + 3 < 49) Gs[i * 49 + j0 + 3] = a3 * si * inv_s[j3];
+    }
+    // T[hw][j] = sum_c Xh[c][hw] * W0b[j][c]: work item = (7 consecutive pixels, j, half of the channel range);
+    // the two halves are combined with shared-memory atomics (T zero-initialised first)
+    for (int o = tid; o < 49 * 32; o += 512) T[o] = 0.f;
+    __syncthreads();
+    if (tid < 448) {
+        const int j = tid & 31, hg = (tid >> 5) % 7, half = tid / 224;
+        float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const int c_lo = half * 256;
+#pragma unroll 4
+        for (int c = c_lo; c < c_lo + 256; ++c) {
+            const float wj = __ldg(p.w0bT + c * 32 + j) * inv_c[c];
+            const float* xr = xs + c * 49 + hg * 7;
+#pragma unroll
+            for (int q = 0; q < 7; ++q) acc[q] = fmaf(xr[q], wj, acc[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 7; ++q) atomicAdd(&T[(hg * 7 + q) * 32 + j], acc[q]);
     }
     __syncthreads();
 
@@ -132,10 +155,15 @@ __global__ void __launch_bounds__(512, 1) recnet_prep_kernel(const PrepParams p)
         for (int j = 0; j < 32; ++j) { h[j] = misc[j]; g[j] = 0.f; }
         for (int hw = 0; hw < 49; ++hw) {
             const float xv = xs[c * 49 + hw];
+            const float4* wa = reinterpret_cast<const float4*>(W0a + hw * 32);
+            const float4* tt = reinterpret_cast<const float4*>(T + hw * 32);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                h[j] = fmaf(xv, W0a[hw * 32 + j], h[j]);
-                g[j] = fmaf(xv, T[hw * 32 + j], g[j]);
+            for (int q = 0; q < 8; ++q) {
+                const float4 a4 = wa[q], t4 = tt[q];
+                h[q * 4 + 0] = fmaf(xv, a4.x, h[q * 4 + 0]); h[q * 4 + 1] = fmaf(xv, a4.y, h[q * 4 + 1]);
+                h[q * 4 + 2] = fmaf(xv, a4.z, h[q * 4 + 2]); h[q * 4 + 3] = fmaf(xv, a4.w, h[q * 4 + 3]);
+                g[q * 4 + 0] = fmaf(xv, t4.x, g[q * 4 + 0]); g[q * 4 + 1] = fmaf(xv, t4.y, g[q * 4 + 1]);
+                g[q * 4 + 2] = fmaf(xv, t4.z, g[q * 4 + 2]); g[q * 4 + 3] = fmaf(xv, t4.w, g[q * 4 + 3]);
             }
         }
         const float ic = inv_c[c];
@@ -148,15 +176,25 @@ __global__ void __launch_bounds__(512, 1) recnet_prep_kernel(const PrepParams p)
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             float a = misc[32 + j];
+            const float4* ar = reinterpret_cast<const float4*>(A1s + j * 32);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) a = fmaf(A1s[j * 32 + i], h[i], a);
+            for (int q = 0; q < 8; ++q) {
+                const float4 a4 = ar[q];
+                a = fmaf(a4.x, h[q * 4 + 0], a); a = fmaf(a4.y, h[q * 4 + 1], a);
+                a = fmaf(a4.z, h[q * 4 + 2], a); a = fmaf(a4.w, h[q * 4 + 3], a);
+            }
             g[j] = a > 0.f ? a : a * s4;
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             float a = misc[64 + j];
+            const float4* ar = reinterpret_cast<const float4*>(A2s + j * 32);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) a = fmaf(A2s[j * 32 + i], g[i], a);
+            for (int q = 0; q < 8; ++q) {
+                const float4 a4 = ar[q];
+                a = fmaf(a4.x, g[q * 4 + 0], a); a = fmaf(a4.y, g[q * 4 + 1], a);
+                a = fmaf(a4.z, g[q * 4 + 2], a); a = fmaf(a4.w, g[q * 4 + 3], a);
+            }
             h[j] = a > 0.f ? a : a * s7;
         }
         uint4* o = reinterpret_cast<uint4*>(p.h5 + ((long long)n * 512 + c) * 64);
