@@ -29,6 +29,8 @@ _SIGNATURES = {
     "ffr_bn_prelu_fwd": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _p]),
     "ffr_bn_prelu_bwd": (_i, [_p, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _i, _p, _p, _i, _i, _i, _p]),
     "ffr_pack_conv3x3": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
+    "ffr_clip_adam": (_i, [_p, _p, _i, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                           _i, ctypes.c_float, _p]),
     "ffr_nchw_to_h9": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "ffr_h9_to_nchw": (_i, [_p, _i, _i, _p, _i, _i, _i, _p]),
     "ffr_pair_cosine": (_i, [_p, _p, _p, _i, _i, _p]),

@@ -5,48 +5,9 @@
 
 #include "conv_gemm.cuh"
 #include "host.h"
+#include "kernels.h"
 
-namespace ffr {
-int conv_gemm_launch(const void* a, long long a_rows, int a_cols, int a_ld, const void* wp, int Cin, ConvGemmParams p,
-                     int num_splits, cudaStream_t stream);
-int stem_launch(const float* x, const float* w, const float* b, const float* a, void* out, int n_img, int S,
-                cudaStream_t stream);
-int se_residual_launch(const void* u, const float* pool, const float* w1, const float* w2, const void* sc,
-                       int shortcut_mode, void* y, int n_img, int S, int C, cudaStream_t stream);
-int subsample2_launch(const void* x, void* out, int n_img, int So, int C, cudaStream_t stream);
-int export_nchw_launch(const void* h, const float* scale, const float* shift, float* y, int n_img, int S, int C,
-                       cudaStream_t stream);
-int bias_l2norm_launch(const float* acc, const float* bias, float* f, int rows, int D, cudaStream_t stream);
-void set_use_window(bool on);
-void set_debug_counters(unsigned long long* dptr);
-struct PrepParams {
-    const float* x; const float* w0aT; const float* w0bT; const float* b0; const float* slope1; const float* A1;
-    const float* c1; const float* slope4; const float* A2; const float* c2; const float* slope7;
-    __nv_bfloat16* s0; __nv_bfloat16* cm; __nv_bfloat16* xt; __nv_bfloat16* h5; float* ss_space;
-};
-int recnet_prep_launch(const PrepParams& p, int n, cudaStream_t stream);
-int feat_space_launch(const float* x, const float* mspace, void* cm, float* out_nchw, int n, cudaStream_t stream);
-int rows_to_nchw_launch(const void* rows, int is_f32, int ld, int ch0, const float* scale, const float* shift, float* y,
-                        int n, int S, int G, int off, int rows_per_img, int C, cudaStream_t stream);
-int scale_f32_launch(const float* in, float* out, long long count, float scale, cudaStream_t stream);
-int wgrad_launch(const void* dz, int ld_dz, const void* x, int ld_x, int x_ch0, int P, int Cout, int Cin, int G,
-                 float* dw, cudaStream_t stream);
-int bn_prelu_fwd_launch(const void* z, int ldz, const float* mean, const float* rstd, const float* gamma,
-                        const float* beta, const float* slope, const void* res, int ldres, void* out, int ldo,
-                        const int* scatter, int scatter_n, int n_img, int C, cudaStream_t stream);
-int bn_prelu_bwd_launch(const void* da, int ldda, const int* scatter, int scatter_n, const void* z, int ldz,
-                        const float* mean, const float* rstd, const float* gamma, const float* beta, const float* slope,
-                        void* dy, int lddy, void* dres, int lddres, float* sums, void* dz, int lddz, int n_img, int C,
-                        cudaStream_t stream);
-int nchw_to_h9_launch(const float* x, void* out, int ld, int ch0, int n_img, int C, int mirror, cudaStream_t stream);
-int pack_conv3x3_launch(const float* w, int cout, int cin, int cout_p, int cin_p, void* fwd, void* dgrad,
-                        cudaStream_t stream);
-int h9_to_nchw_launch(const void* in, int ld, int ch0, float* y, int n_img, int C, int fold, cudaStream_t stream);
-int pair_cosine_launch(const float* f1, const float* f2, float* score, int pairs, int D, cudaStream_t stream);
-int threshold_sweep_launch(const float* score, const int* label, const double* thresholds, int n, int T, int folds,
-                           int* best_idx, double* best_thr, int* test_correct, int* train_correct,
-                           cudaStream_t stream);
-}  // namespace ffr
+
 
 using namespace ffr;
 
@@ -311,6 +272,13 @@ FFR_API int ffr_pack_conv3x3(const float* w, int cout, int cin, int cout_p, int 
                              ffr_stream_t stream) {
     FFR_CHECK_ARG(w && fwd, "ffr_pack_conv3x3: null pointer");
     return pack_conv3x3_launch(w, cout, cin, cout_p, cin_p, fwd, dgrad, S_(stream));
+}
+
+FFR_API int ffr_clip_adam(const void* table, const int* chunks, int n_chunks, float lr, float beta1, float beta2,
+                          float eps, float weight_decay, int step, float clip, ffr_stream_t stream) {
+    FFR_CHECK_ARG(n_chunks == 0 || (table && chunks), "ffr_clip_adam: null pointer");
+    FFR_CHECK_ARG(step >= 1, "ffr_clip_adam: step=%d", step);
+    return clip_adam_launch(table, chunks, n_chunks, lr, beta1, beta2, eps, weight_decay, step, clip, S_(stream));
 }
 
 FFR_API int ffr_nchw_to_h9(const float* x, void* out, int ld, int ch0, int n, int C, int mirror, ffr_stream_t stream) {

@@ -3,6 +3,7 @@
 // All activations are bf16 in the halo-shared flat NHWC layout: image n, pixel (h, w) of an SxS map
 // lives in row n*(S+1)^2 + h*(S+1) + w; rows with h == S or w == S are zero padding.
 #include "host.h"
+#include "kernels.h"
 #include "ptx.cuh"
 
 namespace ffr {

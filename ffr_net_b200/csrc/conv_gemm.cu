@@ -1,5 +1,6 @@
 #include "conv_gemm.cuh"
 #include "host.h"
+#include "kernels.h"
 #include "ptx.cuh"
 
 namespace ffr {

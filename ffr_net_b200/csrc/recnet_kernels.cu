@@ -7,6 +7,7 @@
 //   XT  : X^T per sample, bf16 [n*128][512] (rows hw < 49 valid) — the A operand of feat_channel = M_channel @ X.
 //   H5  : input of the last Conv4Channel linear, bf16 [n*512][64] (32 valid columns).
 #include "host.h"
+#include "kernels.h"
 #include "ptx.cuh"
 
 namespace ffr {
@@ -21,24 +22,9 @@ __device__ __forceinline__ int reflect_src(int p) {  // padded index 0..8 -> sou
     return p == 0 ? 1 : (p == 8 ? 5 : p - 1);
 }
 
-struct PrepParams {
-    const float* x;        // [n][512][49] fp32 (NCHW feature map from the backbone)
-    const float* w0aT;     // [49][32]   Conv4Channel.0.weight[:, :49]^T
-    const float* w0bT;     // [512][32]  Conv4Channel.0.weight[:, 49:]^T
-    const float* b0;       // [32]
-    const float* slope1;   // [512] PReLU over the 512 rows (recnet.py:374; nn.PReLU(512) acts on dim 1)
-    const float* A1;       // [32][32]   Conv4Channel.3.weight @ Conv4Channel.2.weight
-    const float* c1;       // [32]       Conv4Channel.3.weight @ Conv4Channel.2.bias + Conv4Channel.3.bias
-    const float* slope4;   // [512]
-    const float* A2;       // [32][32]   Conv4Channel.6.weight @ Conv4Channel.5.weight
-    const float* c2;       // [32]
-    const float* slope7;   // [512]
-    __nv_bfloat16* s0;     // H9 [n*81][576]: X | ss_space | 0        (input of Conv4Space.0, recnet.py:401)
-    __nv_bfloat16* cm;     // H9 [n*81][1536]: slot [1024,1536) <- X  (input of Conv4Merge.0, recnet.py:420)
-    __nv_bfloat16* xt;     // XT [n*128][512]
-    __nv_bfloat16* h5;     // H5 [n*512][64]
-    float* ss_space;       // optional fp32 [n][49][49]   (selfSimilarity outputs for callers that want them)
-};
+// PrepParams (kernels.h): x fp32 [n][512][49]; w0aT [49][32], w0bT [512][32] = Conv4Channel.0.weight split and
+// transposed; b0; slope1/4/7 [512] (PReLU over the 512 rows, recnet.py:374); A1 = W3 W2, c1 = W3 b2 + b3, A2 = W6 W5,
+// c2 = W6 b5 + b6 (folded 32x32 maps); outputs s0 / cm / xt / h5 (layouts above), optional fp32 ss_space [n][49][49].
 
 // One CTA per sample: self-similarity (recnet.py:220-236), layout fan-out of X, and the thin part of the channel
 // rectifier Conv4Channel (recnet.py:372-385) up to the input of its last Linear.

@@ -1,6 +1,7 @@
 // LFW-style verification scoring (lfw/lfw_eval.py): row-wise cosine of embedding pairs and the 10-fold threshold
 // sweep, both on the device.
 #include "host.h"
+#include "kernels.h"
 #include "ptx.cuh"
 
 namespace ffr {

@@ -6,7 +6,10 @@
 //   - bn_prelu_bwd_reduce_kernel / bn_prelu_bwd_dz_kernel: gradient fold of the reflection mirrors, PReLU and
 //     BatchNorm backward (per-channel reductions, then dz).
 #include "host.h"
+#include "kernels.h"
 #include "ptx.cuh"
+
+#include <cmath>
 
 namespace ffr {
 
@@ -467,4 +470,45 @@ int h9_to_nchw_launch(const void* in, int ld, int ch0, float* y, int n_img, int 
     return launch_status("h9_to_nchw_kernel");
 }
 
+}  // namespace ffr
+
+// ------------------------------------------------------------------------------------------------------------
+// Fused clip_grad_value_ + Adam over a table of tensors in ONE launch (models/trainer.py:182-187 with
+// torch.optim.Adam semantics, no amsgrad): g = clamp(g, +-clip) (written back), optional L2 weight decay,
+// m = b1 m + (1-b1) g, v = b2 v + (1-b2) g^2, p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps).
+// ------------------------------------------------------------------------------------------------------------
+namespace ffr {
+struct AdamTensor { float* p; float* g; float* m; float* v; long long n; };
+constexpr int ADAM_CHUNK = 4096;   // elements per CTA (256 threads x 4 float4)
+
+__global__ void __launch_bounds__(256)
+clip_adam_kernel(const AdamTensor* __restrict__ tab, const int2* __restrict__ chunks, float lr_over_bc1,
+                 float inv_sqrt_bc2, float b1, float b2, float eps, float wd, float clip) {
+    const int2 ch = chunks[blockIdx.x];
+    const AdamTensor t = tab[ch.x];
+    const long long base = (long long)ch.y * ADAM_CHUNK;
+    for (int k = 0; k < ADAM_CHUNK / 256; ++k) {
+        const long long i = base + k * 256 + threadIdx.x;
+        if (i >= t.n) break;
+        float g = fminf(fmaxf(t.g[i], -clip), clip);
+        t.g[i] = g;
+        const float p = t.p[i];
+        g = fmaf(wd, p, g);
+        const float m = fmaf(b1, t.m[i], (1.f - b1) * g);
+        const float v = fmaf(b2, t.v[i], (1.f - b2) * g * g);
+        t.m[i] = m;
+        t.v[i] = v;
+        t.p[i] = p - lr_over_bc1 * m / (sqrtf(v) * inv_sqrt_bc2 + eps);
+    }
+}
+
+int clip_adam_launch(const void* table, const int* chunks, int n_chunks, float lr, float b1, float b2, float eps,
+                     float wd, int step, float clip, cudaStream_t stream) {
+    if (n_chunks == 0) return 0;
+    const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
+    clip_adam_kernel<<<n_chunks, 256, 0, stream>>>(reinterpret_cast<const AdamTensor*>(table),
+                                                  reinterpret_cast<const int2*>(chunks), (float)(lr / bc1),
+                                                  (float)(1.0 / sqrt(bc2)), b1, b2, eps, wd, clip);
+    return launch_status("clip_adam_kernel");
+}
 }  // namespace ffr

@@ -13,6 +13,7 @@ import torch.nn.functional as F
 from torch import nn, optim
 
 from .backbone import Backbone
+from .optim import FusedClipAdam
 from .recnet import RecNet, init_weights, selfSimilarity
 
 
@@ -55,7 +56,9 @@ class Trainer:
             params = [p for p in self.recnet.parameters() if p.requires_grad]
             if opts.optimizer.lower() != "adam":
                 raise NotImplementedError("run.py uses Adam (run.py:11)")
-            self.optim = optim.Adam(params, opts.lr, betas=(opts.beta1, opts.beta2), weight_decay=opts.weight_decay)
+            # clip_grad_value_(1.0) + Adam fused into one kernel launch over all RecNet/head tensors
+            self.optim = FusedClipAdam(params, opts.lr, betas=(opts.beta1, opts.beta2),
+                                       weight_decay=opts.weight_decay, clip_value=1.0)
             self.sch = optim.lr_scheduler.MultiStepLR(self.optim, [5000, 10000, 15000], gamma=0.5)
         else:
             self.recnet.eval()
@@ -125,8 +128,7 @@ class Trainer:
         self.optim.zero_grad()
         self.backward()
         self.allreduce_gradients()                     # before clipping, as reduce-then-clip in the reference
-        nn.utils.clip_grad_value_(self.recnet.parameters(), 1.0)
-        self.optim.step()
+        self.optim.step()                              # clip_grad_value_(1.0) + Adam, one fused launch
 
     def get_current_values(self):
         keys = ["SelfSimilarityLoss", "TripletLoss", "IdentityLoss", "ClassifierLoss"]

@@ -95,6 +95,31 @@ def test_convlayer_train_function(lib, cin, cout, with_res):
         assert e <= 2e-2, k
 
 
+def test_fused_clip_adam_matches_torch(lib):
+    """ffr_clip_adam == clip_grad_value_(1.0) + torch.optim.Adam over several steps (fp32, <= 1e-6 relative)."""
+    from ffr_net_b200.optim import FusedClipAdam
+    g = torch.Generator().manual_seed(0)
+    shapes = [(512, 1536, 3, 3), (49,), (10575, 512), (32, 561), (1,)]
+    pa = [torch.nn.Parameter(torch.randn(s, generator=g).cuda()) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    oa = FusedClipAdam(pa, lr=0.1, betas=(0.9, 0.999), weight_decay=0.01, clip_value=1.0)
+    ob_ = torch.optim.Adam(pb, lr=0.1, betas=(0.9, 0.999), weight_decay=0.01)
+    sch = torch.optim.lr_scheduler.MultiStepLR(oa, [2], gamma=0.5)
+    schb = torch.optim.lr_scheduler.MultiStepLR(ob_, [2], gamma=0.5)
+    for it in range(4):
+        for x, y in zip(pa, pb):
+            gr = torch.randn(x.shape, generator=g).cuda() * 3
+            x.grad, y.grad = gr.clone(), gr.clone()
+        oa.step()
+        torch.nn.utils.clip_grad_value_(pb, 1.0)
+        ob_.step()
+        sch.step()
+        schb.step()
+        for x, y in zip(pa, pb):
+            assert rel_l2(x.detach().cpu(), y.detach().cpu()) <= 1e-6
+            assert torch.equal(x.grad, y.grad)           # clipped gradients are written back
+
+
 @pytest.fixture(scope="module")
 def models(lib):
     rsd = orr.synth_recnet_state_dict(0)
