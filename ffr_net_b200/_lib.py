@@ -29,8 +29,8 @@ _SIGNATURES = {
     "ffr_bn_prelu_fwd": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _p]),
     "ffr_bn_prelu_bwd": (_i, [_p, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _i, _p, _p, _i, _i, _i, _p]),
     "ffr_pack_conv3x3": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
-    "ffr_clip_adam": (_i, [_p, _p, _i, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
-                           _i, ctypes.c_float, _p]),
+    "ffr_clip_adam": (_i, [_p, _p, _i, _p, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                           ctypes.c_float, _p]),
     "ffr_nchw_to_h9": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "ffr_h9_to_nchw": (_i, [_p, _i, _i, _p, _i, _i, _i, _p]),
     "ffr_pair_cosine": (_i, [_p, _p, _p, _i, _i, _p]),
@@ -80,6 +80,20 @@ def check(rc, what=""):
     if rc != 0:
         msg = load().ffr_last_error()
         raise RuntimeError("libffr_sm100 %s failed (rc=%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+# Parameter tensors are updated in place by the fused optimizer kernel through raw pointers, which torch's
+# per-tensor version counters do not see; packed-weight caches key on this generation counter as well.
+_weights_generation = 0
+
+
+def weights_generation():
+    return _weights_generation
+
+
+def bump_weights_generation():
+    global _weights_generation
+    _weights_generation += 1
 
 
 def ptr(t):

@@ -103,7 +103,8 @@ class Backbone(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def _cache_key(self):
-        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        return (_lib.weights_generation(),) + tuple((t.data_ptr(), t._version)
+                                                    for t in list(self.parameters()) + list(self.buffers()))
 
     def _pack(self, device):
         key = (str(device),) + self._cache_key()

@@ -274,11 +274,10 @@ FFR_API int ffr_pack_conv3x3(const float* w, int cout, int cin, int cout_p, int 
     return pack_conv3x3_launch(w, cout, cin, cout_p, cin_p, fwd, dgrad, S_(stream));
 }
 
-FFR_API int ffr_clip_adam(const void* table, const int* chunks, int n_chunks, float lr, float beta1, float beta2,
-                          float eps, float weight_decay, int step, float clip, ffr_stream_t stream) {
-    FFR_CHECK_ARG(n_chunks == 0 || (table && chunks), "ffr_clip_adam: null pointer");
-    FFR_CHECK_ARG(step >= 1, "ffr_clip_adam: step=%d", step);
-    return clip_adam_launch(table, chunks, n_chunks, lr, beta1, beta2, eps, weight_decay, step, clip, S_(stream));
+FFR_API int ffr_clip_adam(const void* table, const int* chunks, int n_chunks, const float* hyper, float beta1,
+                          float beta2, float eps, float weight_decay, float clip, ffr_stream_t stream) {
+    FFR_CHECK_ARG(n_chunks == 0 || (table && chunks && hyper), "ffr_clip_adam: null pointer");
+    return clip_adam_launch(table, chunks, n_chunks, hyper, beta1, beta2, eps, weight_decay, clip, S_(stream));
 }
 
 FFR_API int ffr_nchw_to_h9(const float* x, void* out, int ld, int ch0, int n, int C, int mirror, ffr_stream_t stream) {

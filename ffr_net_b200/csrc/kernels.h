@@ -41,8 +41,8 @@ int nchw_to_h9_launch(const float* x, void* out, int ld, int ch0, int n_img, int
 int pack_conv3x3_launch(const float* w, int cout, int cin, int cout_p, int cin_p, void* fwd, void* dgrad,
                         cudaStream_t stream);
 int h9_to_nchw_launch(const void* in, int ld, int ch0, float* y, int n_img, int C, int fold, cudaStream_t stream);
-int clip_adam_launch(const void* table, const int* chunks, int n_chunks, float lr, float b1, float b2, float eps,
-                     float wd, int step, float clip, cudaStream_t stream);
+int clip_adam_launch(const void* table, const int* chunks, int n_chunks, const float* hyper, float b1, float b2,
+                     float eps, float wd, float clip, cudaStream_t stream);
 int pair_cosine_launch(const float* f1, const float* f2, float* score, int pairs, int D, cudaStream_t stream);
 int threshold_sweep_launch(const float* score, const int* label, const double* thresholds, int n, int T, int folds,
                            int* best_idx, double* best_thr, int* test_correct, int* train_correct,

@@ -481,11 +481,16 @@ namespace ffr {
 struct AdamTensor { float* p; float* g; float* m; float* v; long long n; };
 constexpr int ADAM_CHUNK = 4096;   // elements per CTA (256 threads x 4 float4)
 
+// hyper[0] = learning rate, hyper[1] = step count (1-based, as float): device-resident so that a captured CUDA graph
+// of the training step stays valid when the host scheduler changes the rate / the step advances.
 __global__ void __launch_bounds__(256)
-clip_adam_kernel(const AdamTensor* __restrict__ tab, const int2* __restrict__ chunks, float lr_over_bc1,
-                 float inv_sqrt_bc2, float b1, float b2, float eps, float wd, float clip) {
+clip_adam_kernel(const AdamTensor* __restrict__ tab, const int2* __restrict__ chunks, const float* __restrict__ hyper,
+                 float b1, float b2, float eps, float wd, float clip) {
     const int2 ch = chunks[blockIdx.x];
     const AdamTensor t = tab[ch.x];
+    const float lr = hyper[0], step = hyper[1];
+    const float lr_over_bc1 = lr / (1.f - powf(b1, step));
+    const float inv_sqrt_bc2 = rsqrtf(1.f - powf(b2, step));
     const long long base = (long long)ch.y * ADAM_CHUNK;
     for (int k = 0; k < ADAM_CHUNK / 256; ++k) {
         const long long i = base + k * 256 + threadIdx.x;
@@ -502,13 +507,11 @@ clip_adam_kernel(const AdamTensor* __restrict__ tab, const int2* __restrict__ ch
     }
 }
 
-int clip_adam_launch(const void* table, const int* chunks, int n_chunks, float lr, float b1, float b2, float eps,
-                     float wd, int step, float clip, cudaStream_t stream) {
+int clip_adam_launch(const void* table, const int* chunks, int n_chunks, const float* hyper, float b1, float b2,
+                     float eps, float wd, float clip, cudaStream_t stream) {
     if (n_chunks == 0) return 0;
-    const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
     clip_adam_kernel<<<n_chunks, 256, 0, stream>>>(reinterpret_cast<const AdamTensor*>(table),
-                                                  reinterpret_cast<const int2*>(chunks), (float)(lr / bc1),
-                                                  (float)(1.0 / sqrt(bc2)), b1, b2, eps, wd, clip);
+                                                  reinterpret_cast<const int2*>(chunks), hyper, b1, b2, eps, wd, clip);
     return launch_status("clip_adam_kernel");
 }
 }  // namespace ffr

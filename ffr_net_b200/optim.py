@@ -33,8 +33,19 @@ class FusedClipAdam(torch.optim.Optimizer):
         dev = params[0].device
         table = torch.from_numpy(np.array(rows, dtype=np.int64)).to(dev)
         chunk_t = torch.from_numpy(np.array(chunks, dtype=np.int32)).to(dev)
-        self._tables[gi] = (key, table, chunk_t, len(chunks))
-        return table, chunk_t, len(chunks)
+        hyper = torch.zeros(2, dtype=torch.float32, device=dev)      # [lr, step] (device-resident: graph-capturable)
+        if cached is not None:
+            hyper.copy_(cached[4])
+        self._tables[gi] = (key, table, chunk_t, len(chunks), hyper)
+        return table, chunk_t, len(chunks), hyper
+
+    def sync_lr(self):
+        """Push the (scheduler-updated) learning rates to the device; call outside graph capture/replay."""
+        for gi, group in enumerate(self.param_groups):
+            t = self._tables.get(gi)
+            if t is not None and group.get("_lr_on_device") != group["lr"]:
+                t[4][0:1].fill_(float(group["lr"]))
+                group["_lr_on_device"] = group["lr"]
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -42,10 +53,18 @@ class FusedClipAdam(torch.optim.Optimizer):
         for gi, group in enumerate(self.param_groups):
             if not any(p.grad is not None for p in group["params"]):
                 continue
-            table, chunk_t, n_chunks = self._table(gi, group)
-            group["step"] = group.get("step", 0) + 1
+            table, chunk_t, n_chunks, hyper = self._table(gi, group)
+            # lr: pushed to the device only when the scheduler changed it (a host->device copy is not capturable);
+            # step: advanced on the device, so a replayed CUDA graph keeps counting
+            if group.get("_lr_on_device") != group["lr"]:
+                if torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError("learning rate changed while capturing: call step() once before capture")
+                hyper[0:1].fill_(float(group["lr"]))
+                group["_lr_on_device"] = group["lr"]
+            hyper[1:2].add_(1.0)
             b1, b2 = group["betas"]
-            _lib.check(lib.ffr_clip_adam(_lib.ptr(table), _lib.ptr(chunk_t), n_chunks, float(group["lr"]), float(b1),
-                                         float(b2), float(group["eps"]), float(group["weight_decay"]), group["step"],
+            _lib.check(lib.ffr_clip_adam(_lib.ptr(table), _lib.ptr(chunk_t), n_chunks, _lib.ptr(hyper), float(b1),
+                                         float(b2), float(group["eps"]), float(group["weight_decay"]),
                                          float(group["clip_value"]), _lib.stream_ptr()), "ffr_clip_adam")
+        _lib.bump_weights_generation()       # packed bf16 weight caches must be rebuilt
         return None

@@ -212,7 +212,8 @@ class RecNet(nn.Module):
         return out
 
     def _cache_key(self):
-        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        return (_lib.weights_generation(),) + tuple((t.data_ptr(), t._version)
+                                                    for t in list(self.parameters()) + list(self.buffers()))
 
     def _pack_eval(self, device):
         key = (str(device),) + self._cache_key()

@@ -41,7 +41,7 @@ def _pad1(t, n):
 def _packed_weights(layer, weight, cin_p, cout_p):
     """bf16 K-major weights for the forward GEMM and the dgrad GEMM, packed by one kernel and cached until the
     parameter changes (the two RecNet calls of a step and the backward share them)."""
-    key = (weight.data_ptr(), weight._version, cin_p, cout_p)
+    key = (weight.data_ptr(), weight._version, _lib.weights_generation(), cin_p, cout_p)
     cache = getattr(layer, "_ffr_pack", None)
     if cache is not None and cache[0] == key:
         return cache[1], cache[2]

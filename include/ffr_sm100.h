@@ -168,9 +168,10 @@ FFR_API int ffr_pack_conv3x3(const float* w, int cout, int cin, int cout_p, int 
 
 /* clip_grad_value_(clip) + Adam.step() for a whole parameter set in one launch (models/trainer.py:185-187,
  * torch.optim.Adam semantics). table: device array of {float* p, g, m, v; int64 n} per tensor; chunks: device array of
- * (tensor index, chunk index) pairs, one per 4096 elements; step = 1-based step count (bias correction). */
-FFR_API int ffr_clip_adam(const void* table, const int* chunks, int n_chunks, float lr, float beta1, float beta2,
-                          float eps, float weight_decay, int step, float clip, ffr_stream_t stream);
+ * (tensor index, chunk index) pairs, one per 4096 elements; hyper: DEVICE float[2] = {learning rate, 1-based step count}
+ * (device-resident so a captured CUDA graph of the training step survives LR-schedule and step changes). */
+FFR_API int ffr_clip_adam(const void* table, const int* chunks, int n_chunks, const float* hyper, float beta1,
+                          float beta2, float eps, float weight_decay, float clip, ffr_stream_t stream);
 
 /* fp32 NCHW (n,C,7,7) -> bf16 H9 channel slot (mirror != 0: reflection halo filled, else halo zero) and back
  * (fold != 0: sums the mirror rows into the pixel, i.e. the gradient of the mirrored scatter). */
