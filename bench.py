@@ -365,11 +365,12 @@ def _bench_train(args, enc, dev, world, rank, timed):
     label = torch.randint(0, 10575, (pairs,), generator=torch.Generator().manual_seed(rank)).to(dev)
 
     def step():
-        tr.set_input(a, b, label)
-        tr.forward()
-        tr.optimizer_parameters(0)
-        tr.update_learning_rate()
+        tr.step(a, b, label)
 
+    mode = "eager"
+    if world == 1 and not args.no_graph:
+        tr.capture_step(a, b, label, warmup=3)          # the whole iteration replayed as one CUDA graph
+        mode = "cuda-graph replay of the whole iteration"
     for _ in range(2):
         step()
     k = max(3, min(args.steps, 8))
@@ -377,10 +378,10 @@ def _bench_train(args, enc, dev, world, rank, timed):
     vals = tr.get_current_values()
     pairs_s = world * pairs * k / (ms * 1e-3)
     return {"value": 2 * pairs_s, "unit": "img/s", "pairs_per_s": pairs_s, "ms_per_step": ms / k, "steps": k,
-            "batch_pairs_per_gpu": pairs, "gflop_per_pair": 39.9, "tflops": pairs_s * 39.9 / 1e3,
+            "batch_pairs_per_gpu": pairs, "gflop_per_pair": 39.9, "launch_mode": mode, "tflops": pairs_s * 39.9 / 1e3,
             "grad_allreduce": ("nccl, one flat fp32 bucket of 29.9 M elements" if world > 1 else "none (1 GPU)"),
-            "note": "ConvLayer fwd/bwd (conv, dgrad, wgrad, BN/PReLU) hand-written; Conv4Channel MLP, bmm, head, losses "
-                    "and Adam are ATen/cuBLAS ops this round", "losses": vals}
+            "note": "ConvLayer fwd/bwd (conv, dgrad, wgrad, BN/PReLU) and clip+Adam hand-written; Conv4Channel MLP, bmm, "
+                    "head and losses are ATen/cuBLAS ops this round", "losses": vals}
 
 
 def _ncu_traffic():
@@ -400,6 +401,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-train", dest="no_train", action="store_true", help="skip the secondary training-step line")
+    ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="run the training step eagerly")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     # stdout carries exactly ONE JSON line: anything libraries print to fd 1 meanwhile (e.g. NCCL's version banner)

@@ -219,8 +219,9 @@ def test_train_step_gradients_match_oracle(lib):
 
 
 def test_cuda_graph_step_matches_eager(lib):
-    """Trainer.capture_step(): replaying the captured iteration gives the same parameters as eager iterations
-    (same kernels, same order; fp32 atomics in wgrad / BN sums make it equal only up to round-off)."""
+    """Trainer.capture_step(): ONE replay of the captured iteration from a given state equals ONE eager iteration from
+    the same state (parameters, BN buffers, Adam moments, step count) up to the round-off of the fp32 atomics.
+    (Multi-step trajectories are not compared: Adam's sign-like update amplifies that round-off chaotically.)"""
     from ffr_net_b200.backbone import Backbone
     from ffr_net_b200.trainer import Trainer, default_opts
     bsd, rsd = ob.synth_backbone_state_dict(0), orr.synth_recnet_state_dict(0)
@@ -234,15 +235,31 @@ def test_cuda_graph_step_matches_eager(lib):
         rec.load_state_dict(rsd)
         return Trainer(default_opts(lr=1e-3), encoder=enc, recnet=rec)
     eager, graphed = make(), make()
-    for _ in range(5):
+    for _ in range(2):
         eager.step(img1, img2, label)
-    graphed.capture_step(img1, img2, label, warmup=2)      # 2 eager warm-up iterations + 1 captured (also executed? no)
-    # capture does not execute; the two warm-up iterations already advanced the state by 2 steps
-    for _ in range(3):
-        graphed.step(img1, img2, label)
+    graphed.capture_step(img1, img2, label, warmup=2)
+    # put `graphed` into exactly the state of `eager` (in place: the graph holds the tensor addresses)
+    with torch.no_grad():
+        for a, b in zip(graphed.recnet.parameters(), eager.recnet.parameters()):
+            a.copy_(b)
+            sa, sb = graphed.optim.state[a], eager.optim.state[b]
+            sa["exp_avg"].copy_(sb["exp_avg"])
+            sa["exp_avg_sq"].copy_(sb["exp_avg_sq"])
+        for a, b in zip(graphed.recnet.buffers(), eager.recnet.buffers()):
+            a.copy_(b)
+        graphed.optim._tables[0][4].copy_(eager.optim._tables[0][4])
+    before = [p.detach().clone() for p in eager.recnet.parameters()]
+    eager.step(img1, img2, label)
+    graphed.step(img1, img2, label)
     torch.cuda.synchronize()
-    worst = max(rel_l2(a.detach().cpu(), b.detach().cpu())
-                for a, b in zip(graphed.recnet.parameters(), eager.recnet.parameters()))
-    print("graph vs eager after 5 steps: worst parameter rel L2 %.3e" % worst)
-    assert worst <= 2e-2
-    assert int(graphed.recnet.state_dict()["Conv4Merge.0.norm.norm.num_batches_tracked"]) == 10
+    # compare the UPDATES (parameter deltas), relative to the update size
+    num = den = 0.0
+    for a, b, p0 in zip(graphed.recnet.parameters(), eager.recnet.parameters(), before):
+        num += float(((a.detach() - b.detach()).double() ** 2).sum())
+        den += float(((b.detach() - p0).double() ** 2).sum())
+    rel = (num / den) ** 0.5
+    print("graph replay vs eager step: relative difference of the parameter update %.3e" % rel)
+    assert den > 0 and rel <= 5e-2
+    assert float(graphed.optim._tables[0][4][1]) == float(eager.optim._tables[0][4][1]) == 3.0
+    k = "Conv4Merge.0.norm.norm.num_batches_tracked"
+    assert int(graphed.recnet.state_dict()[k]) == int(eager.recnet.state_dict()[k]) == 6
