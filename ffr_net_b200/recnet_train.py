@@ -193,6 +193,20 @@ def self_similarity(x):
     return ss_space.reshape(ss_space.size(0), ss_space.size(1), h, w), ss_channel
 
 
+def self_similarity_space(x):
+    """Only the spatial Gram of selfSimilarity (recnet.py:231,234): (N,C,H,W) -> (N,HW,H,W)."""
+    h, w = x.size(2), x.size(3)
+    v = x.reshape(x.size(0), x.size(1), -1).permute(0, 2, 1)
+    ss = cosine_sim(v, v)
+    return ss.reshape(ss.size(0), ss.size(1), h, w)
+
+
+def self_similarity_channel(x):
+    """Only the channel Gram of selfSimilarity (recnet.py:232): (N,C,H,W) -> (N,C,C)."""
+    v = x.reshape(x.size(0), x.size(1), -1)
+    return cosine_sim(v, v)
+
+
 def add_margin_product(weight, x, label, s=30.0, m=0.40):
     """AddMarginProduct.forward, recnet.py:257-270 (one-hot built on the input's device)."""
     cosine = F.linear(F.normalize(x), F.normalize(weight))
@@ -221,7 +235,7 @@ def forward_train(model, x, label):
     def resblock(blk, h):
         return conv(blk.conv2, conv(blk.conv1, h), res=h)
 
-    ss_space, ss_channel = self_similarity(x)                                            # :399
+    ss_space = self_similarity_space(x)                                                  # :399 (spatial half)
     flat = x.reshape(n, 512, 49)
     s = model.Conv4Space
     h = _NchwToH9.apply(torch.cat((x, ss_space), 1), 576)                                # :401
@@ -230,9 +244,17 @@ def forward_train(model, x, label):
     h = resblock(s[5], conv(s[4], h))
     m_space = torch.sigmoid(_H9ToNchw.apply(h, 49)).reshape(n, 49, 49)                   # :404-405
 
+    # Conv4Channel on cat(X, ss_channel) (:402,:406). ss_channel = Xh Xh^T (Xh = rows of X normalised over HW) is not
+    # materialised: Linear(561->32)(cat(X, Xh Xh^T)) = X W0a^T + Xh (Xh^T W0b^T) + b0 by associativity — the same
+    # function of (X, W0, b0), so autograd yields the same gradients; saves three (N,512,512) fp32 round trips.
     c = model.Conv4Channel
-    g = torch.cat((flat, ss_channel), 2)                                                 # :402
-    for i in (0, 3, 6):
+    w0 = c[0].weight
+    xh = F.normalize(flat, dim=2)
+    g = torch.matmul(flat, w0[:, :49].t()) + torch.matmul(xh, torch.matmul(xh.transpose(1, 2), w0[:, 49:].t())) \
+        + c[0].bias
+    g = F.prelu(g, c[1].func.weight)
+    g = F.linear(g, c[2].weight, c[2].bias)
+    for i in (3, 6):
         g = F.linear(g, c[i].weight, c[i].bias)
         g = F.prelu(g, c[i + 1].func.weight)
         g = F.linear(g, c[i + 2].weight, c[i + 2].bias)

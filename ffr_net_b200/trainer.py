@@ -126,11 +126,14 @@ class Trainer:
         self._correct = pred.eq(self.gt_label).sum()          # no host sync here; .item() in get_current_values
 
     def backward(self):
+        # trainer.py:157-161 calls selfSimilarity five times and discards one of the two Grams in four of them;
+        # only the Gram that enters a loss term is computed here (same values, half the work)
+        from .recnet_train import self_similarity_channel, self_similarity_space
         ss_space, ss_channel = selfSimilarity(self.feat_map_non)
-        ss_space_non, _ = selfSimilarity(self.space_non)
-        ss_space_ocl, _ = selfSimilarity(self.space_ocl)
-        _, ss_channel_non = selfSimilarity(self.channel_non)
-        _, ss_channel_ocl = selfSimilarity(self.channel_ocl)
+        ss_space_non = self_similarity_space(self.space_non)
+        ss_space_ocl = self_similarity_space(self.space_ocl)
+        ss_channel_non = self_similarity_channel(self.channel_non)
+        ss_channel_ocl = self_similarity_channel(self.channel_ocl)
         mse = self.mse_loss
         l_space = (mse(ss_space, ss_space_non) + mse(ss_space, ss_space_ocl)) / 2
         l_channel = (mse(ss_channel, ss_channel_non) + mse(ss_channel, ss_channel_ocl)) / 2
