@@ -103,8 +103,9 @@ class Backbone(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def _cache_key(self):
-        return (_lib.weights_generation(),) + tuple((t.data_ptr(), t._version)
-                                                    for t in list(self.parameters()) + list(self.buffers()))
+        # The backbone is frozen (models/trainer.py:62-63): its packed weights depend only on its own tensors. (The
+        # fused optimizer's generation counter is deliberately NOT part of the key: it only ever updates RecNet.)
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
 
     def _pack(self, device):
         key = (str(device),) + self._cache_key()

@@ -19,6 +19,7 @@ from . import _lib, packing
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
+ASSOCIATIVE_CONV4CHANNEL = True     # see forward_train
 
 _EPI_GEOM, _EPI_STATS = 0x8, 0x400
 _TAPS9 = (ctypes.c_int * 9)(*[(r - 1) * 9 + (s - 1) for r in range(3) for s in range(3)])
@@ -248,10 +249,13 @@ def forward_train(model, x, label):
     # materialised: Linear(561->32)(cat(X, Xh Xh^T)) = X W0a^T + Xh (Xh^T W0b^T) + b0 by associativity — the same
     # function of (X, W0, b0), so autograd yields the same gradients; saves three (N,512,512) fp32 round trips.
     c = model.Conv4Channel
-    w0 = c[0].weight
-    xh = F.normalize(flat, dim=2)
-    g = torch.matmul(flat, w0[:, :49].t()) + torch.matmul(xh, torch.matmul(xh.transpose(1, 2), w0[:, 49:].t())) \
-        + c[0].bias
+    if ASSOCIATIVE_CONV4CHANNEL:
+        w0 = c[0].weight
+        xh = F.normalize(flat, dim=2)
+        t = torch.matmul(xh.transpose(1, 2).contiguous(), w0[:, 49:].t())                # (N,49,32)
+        g = torch.matmul(flat, w0[:, :49].t()) + torch.bmm(xh, t) + c[0].bias
+    else:                                                                                # literal form (validation)
+        g = F.linear(torch.cat((flat, self_similarity_channel(x)), 2), c[0].weight, c[0].bias)
     g = F.prelu(g, c[1].func.weight)
     g = F.linear(g, c[2].weight, c[2].bias)
     for i in (3, 6):

@@ -34,13 +34,15 @@ def step():
 for _ in range(3):
     step()
 torch.cuda.synchronize()
-with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
     step()
     torch.cuda.synchronize()
 os.makedirs("gpurun_out", exist_ok=True)
 txt = prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70)
 open("gpurun_out/train_profile.txt", "w").write(txt)
 print(txt)
+shp = prof.key_averages(group_by_input_shape=True).table(sort_by="cuda_time_total", row_limit=30, max_name_column_width=40)
+open("gpurun_out/train_profile_shapes.txt", "w").write(shp)
 import time
 t0 = time.perf_counter()
 for _ in range(5):
