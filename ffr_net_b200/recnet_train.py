@@ -256,12 +256,15 @@ def forward_train(model, x, label):
         g = torch.matmul(flat, w0[:, :49].t()) + torch.bmm(xh, t) + c[0].bias
     else:                                                                                # literal form (validation)
         g = F.linear(torch.cat((flat, self_similarity_channel(x)), 2), c[0].weight, c[0].bias)
+    # Linear(32->512) directly followed by Linear(512->32) (c[2]->c[3], c[5]->c[6]; no activation in between,
+    # recnet.py:375-380) is applied as the composed 32x32 map W_b W_a, W_b b_a + b_b: same function of the four
+    # parameter tensors (autograd differentiates through the small product), without two (N,512,512) intermediates.
     g = F.prelu(g, c[1].func.weight)
-    g = F.linear(g, c[2].weight, c[2].bias)
-    for i in (3, 6):
-        g = F.linear(g, c[i].weight, c[i].bias)
-        g = F.prelu(g, c[i + 1].func.weight)
-        g = F.linear(g, c[i + 2].weight, c[i + 2].bias)
+    for a_, b_, p_ in ((2, 3, 4), (5, 6, 7)):
+        w_ab = torch.matmul(c[b_].weight, c[a_].weight)                                  # (32, 32)
+        b_ab = torch.mv(c[b_].weight, c[a_].bias) + c[b_].bias
+        g = F.prelu(F.linear(g, w_ab, b_ab), c[p_].func.weight)
+    g = F.linear(g, c[8].weight, c[8].bias)
     m_channel = torch.sigmoid(g)                                                         # :406
 
     feat_space = torch.matmul(flat, m_space).reshape(n, 512, 7, 7)                       # :409,412
