@@ -180,6 +180,9 @@ class Backbone(nn.Module):
             raise RuntimeError("ffr_net_b200.Backbone runs only on CUDA (sm_100a); there is no CPU fallback")
         if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != self.IMG or x.shape[3] != self.IMG:
             raise ValueError("expected input (N,3,112,112), got %s" % (tuple(x.shape),))
+        if x.shape[0] == 0:                          # empty batch: nothing to launch
+            return (torch.empty(0, 512, 7, 7, dtype=torch.float32, device=x.device),
+                    torch.empty(0, 512, dtype=torch.float32, device=x.device))
         y, f, _ = self.forward_internal(x)
         return y, f
 

@@ -88,15 +88,6 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
-        "[%2];" ::"r"(smem_u32(dst)),
-        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-
 // ----------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ----------------------------------------------------------------------------------------------
@@ -143,7 +134,9 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
 
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle:
 // rows are 128 B (64 bf16) apart, 8-row groups are 1024 B apart (SBO), LBO unused for swizzled K-major.
-// `row_phase` = (start_address >> 7) & 7 goes into base_offset when the start is not 1024 B aligned.
+// The start address may be any multiple of 128 B (a row offset into a TMA-written tile): the hardware swizzles on
+// absolute shared-memory address bits, so base_offset stays 0 (profiles/r01_probe_rowshift.json; setting it to
+// (addr >> 7) & 7 is WRONG for row offsets that are not multiples of 8).
 __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t saddr, uint32_t base_offset = 0) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);          // start address  [0,14)

@@ -303,6 +303,9 @@ class RecNet(nn.Module):
         if self.training or label is not None or (torch.is_grad_enabled() and input.requires_grad):
             from . import recnet_train
             return recnet_train.forward_train(self, input, label)
+        if input.shape[0] == 0:                      # empty batch: nothing to launch
+            return (torch.empty(0, 512, dtype=torch.float32, device=input.device),
+                    torch.empty(0, 512, 7, 7, dtype=torch.float32, device=input.device))
         v, feat_new = self._forward_eval(input, want_map=True)
         return v, feat_new
 

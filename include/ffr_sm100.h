@@ -35,19 +35,22 @@ typedef void* ffr_stream_t; /* cudaStream_t */
 #define FFR_API
 #endif
 
-/* Epilogue flags of the implicit-GEMM kernel (values mirror ffr::EpiFlags). */
-#define FFR_EPI_BIAS           (1u << 0)
-#define FFR_EPI_BORDER_BIAS    (1u << 1)
-#define FFR_EPI_PRELU          (1u << 2)
-#define FFR_EPI_GEOM           (1u << 3)
-#define FFR_EPI_POOL           (1u << 4)
-#define FFR_EPI_OUT_S2D        (1u << 5)
-#define FFR_EPI_OUT_F32_ATOMIC (1u << 6)
+/* Epilogue flags of the implicit-GEMM kernel (values mirror ffr::EpiFlags in csrc/conv_gemm.cuh).
+ * Order of application: bias -> PReLU -> residual -> sigmoid -> zero on invalid rows -> outputs / reductions. */
+#define FFR_EPI_BIAS           (1u << 0)  /* + bias[co] */
+#define FFR_EPI_BORDER_BIAS    (1u << 1)  /* + bias9[border class of (h,w)][co] (BatchNorm before a zero-padded conv) */
+#define FFR_EPI_PRELU          (1u << 2)  /* max(x,0) + slope[co]*min(x,0) */
+#define FFR_EPI_GEOM           (1u << 3)  /* rows carry (image, h, w): row = n*rows_per_img + h*Wp + w; a row is valid iff
+                                             h0 <= h < h0+S and h0 <= w < h0+S (or, with SCATTER, iff it has a destination) */
+#define FFR_EPI_POOL           (1u << 4)  /* atomically add per-(image,co) sums of the valid rows into pool[n_img][Cout] */
+#define FFR_EPI_OUT_S2D        (1u << 5)  /* bf16 rows go to the space-to-depth map of the following stride-2 conv */
+#define FFR_EPI_OUT_F32_ATOMIC (1u << 6)  /* split-K: atomicAdd fp32 into out_f32[M][Cout] */
 #define FFR_EPI_SIGMOID        (1u << 7)
-#define FFR_EPI_OUT_REFLECT    (1u << 8)
-#define FFR_EPI_RESIDUAL       (1u << 9)
-#define FFR_EPI_STATS          (1u << 10)
-#define FFR_EPI_OUT_F32        (1u << 11)
+#define FFR_EPI_SCATTER        (1u << 8)  /* bf16 rows go to up to scatter_n table destinations (reflection mirrors,
+                                             concat slots, W-flip); see ffr_conv_gemm */
+#define FFR_EPI_RESIDUAL       (1u << 9)  /* + res[m][co] (bf16, same row grid) */
+#define FFR_EPI_STATS          (1u << 10) /* atomically add per-co sum and sum of squares of valid rows into stats[2][Cout] */
+#define FFR_EPI_OUT_F32        (1u << 11) /* plain fp32 rows to out_f32[M][Cout] */
 
 FFR_API int ffr_version(void);
 FFR_API const char* ffr_last_error(void);
@@ -68,12 +71,13 @@ FFR_API int ffr_conv_gemm(const void* a, int64_t a_rows, int a_cols, int a_ld, c
 
 /* Conv2d(Cin,Cout,3,stride 1,pad 1) on a flat SxS map (model_ir_se50.py:67 with the BatchNorm of :66 folded:
  * scale into wp, shift into the 9-class border bias table `bias9` [9][Cout]) + PReLU (:68).
- * out_s2d != 0 writes the space-to-depth layout consumed by ffr_conv3x3_s2_fwd. */
+ * out_s2d != 0 writes the space-to-depth layout consumed by ffr_conv3x3_bn_pool_fwd(stride = 2). */
 FFR_API int ffr_conv3x3_bnpre_prelu_fwd(const void* x, int n_img, int S, int Cin, const void* wp, int Cout,
                                 const float* bias9, const float* slope, void* out, int out_s2d, ffr_stream_t stream);
 
 /* Conv2d(C,Cout,3,stride,pad 1) + BatchNorm (model_ir_se50.py:69-70; scale folded into wp, shift = bias) and the
- * SE squeeze: per-(image,channel) sums of the result are atomically added into pool[n_img][Cout] (:31, zero it first).
+ * SE squeeze: per-(image,channel) sums of the result land in pool[n_img][Cout] (:31; the call zeroes it, then the
+ * epilogue adds atomically).
  * stride 1: x is flat SxS. stride 2: x is the space-to-depth map written by ffr_conv3x3_bnpre_prelu_fwd
  * (rows of the (S/2+1)^2 grid, 4*C channels); S is the INPUT size. Output is flat (S/stride)x(S/stride). */
 FFR_API int ffr_conv3x3_bn_pool_fwd(const void* x, int n_img, int S, int C, int stride, const void* wp, int Cout,
@@ -142,7 +146,8 @@ FFR_API int ffr_scale_f32(const float* in, float* out, int64_t count, float scal
 
 /* Weight gradient of ReflectionPad2d(1)+Conv2d(3x3) (autograd of recnet.py:82): dw[co][ci][r][s] +=
  * sum_p dz[p][co] * x[p + (r-1)*9 + (s-1)][x_ch0 + ci] over the P = n*81 rows of the H9 grid (dz is zero on halo rows).
- * dz [P][ld_dz] bf16, x [P][ld_x] bf16, dw fp32 [Cout][Cin][3][3] (accumulated with atomics: zero it first). */
+ * dz [P][ld_dz] bf16, x [P][ld_x] bf16, dw fp32 [Cout][Cin][3][3]: ACCUMULATED with atomics (split-K), so the
+ * caller zeroes it for a fresh gradient or leaves the running .grad in it to accumulate. */
 FFR_API int ffr_wgrad3x3(const void* dz, int ld_dz, const void* x, int ld_x, int x_ch0, int n, int Cout, int Cin,
                          float* dw, ffr_stream_t stream);
 

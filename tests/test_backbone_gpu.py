@@ -110,3 +110,18 @@ def test_stem_kernel(lib, n, S):
     got = layout.from_flat(out, n, S, 64)
     assert (got - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
     assert layout.flat_pad_rows(out, n, S, 64).abs().max().item() == 0.0
+
+
+def test_empty_and_odd_batches(models):
+    """Edge cases: empty batch, batch sizes that leave ragged last tiles (rows not a multiple of 128/256)."""
+    sd, m = models
+    with torch.no_grad():
+        y, f = m(torch.zeros(0, 3, 112, 112, device="cuda"))
+        assert y.shape == (0, 512, 7, 7) and f.shape == (0, 512)
+        x = ob.synth_faces(7, seed=4)
+        y7, f7 = m(x.cuda())
+        y3, f3 = m(x[:3].cuda())
+    assert torch.isfinite(f7).all()
+    assert (f7[:3] - f3).abs().max().item() <= 1e-3
+    with pytest.raises(ValueError):
+        m(torch.zeros(2, 3, 96, 112, device="cuda"))
