@@ -23,6 +23,7 @@ _SIGNATURES = {
                            _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _p]),
     "ffr_recnet_prep": (_i, [_p, _i] + [_p] * 15 + [_p]),
     "ffr_recnet_convlayer_fwd": (_i, [_p, _i, _i, _p, _i, _p, _p, _p, _i, _i, _p, _i, _p, _i, _i, _p, _p, _p]),
+    "ffr_self_similarity": (_i, [_p, _i, _p, _p, _p]),
     "ffr_feat_space": (_i, [_p, _p, _p, _p, _i, _p]),
     "ffr_rows_to_nchw": (_i, [_p, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "ffr_wgrad3x3": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _p, _p]),

@@ -12,7 +12,7 @@ from collections import namedtuple
 import torch
 from torch import nn
 
-from . import _lib, packing
+from . import _lib, packing, streams
 
 
 class Flatten(nn.Module):
@@ -143,11 +143,11 @@ class Backbone(nn.Module):
         self._packed = pk
         return pk
 
-    def _workspace(self, n, device):
+    def _workspace(self, n, device, slot=0):
         key = (n, str(device))
-        ws = self._ws.get(key)
-        if ws is not None:
-            return ws
+        held = self._ws.get(slot)
+        if held is not None and held[0] == key:
+            return held[1]
         ws = _Packed()
         S = self.IMG
         big = n * (S + 1) * (S + 1) * 64                     # elements of the largest flat map (112x112x64)
@@ -168,7 +168,7 @@ class Backbone(nn.Module):
                 res = so
         ws.pool = torch.empty(n * 512, dtype=torch.float32, device=device)
         ws.acc = torch.empty(n * 512, dtype=torch.float32, device=device)
-        self._ws = {key: ws}                                  # keep one batch size resident
+        self._ws[slot] = (key, ws)                            # keep one batch size resident per stream slot
         return ws
 
     # ------------------------------------------------------------------------------------------
@@ -183,11 +183,18 @@ class Backbone(nn.Module):
         if x.shape[0] == 0:                          # empty batch: nothing to launch
             return (torch.empty(0, 512, 7, 7, dtype=torch.float32, device=x.device),
                     torch.empty(0, 512, dtype=torch.float32, device=x.device))
-        y, f, _ = self.forward_internal(x)
+        n = x.shape[0]
+        y = torch.empty(n, 512, 7, 7, dtype=torch.float32, device=x.device)
+        f = torch.empty(n, 512, dtype=torch.float32, device=x.device)
+        x = x.contiguous().float()
+        streams.fork_join(streams.chunk_bounds(n), x.device,
+                          lambda i, lo, hi: self.forward_internal(x[lo:hi], slot=i, out_y=y[lo:hi], out_f=f[lo:hi]))
         return y, f
 
-    def forward_internal(self, x, want_y=True):
-        """Returns (y, f, h) where h is the flat bf16 body output (N*64 rows x 512) for a fused RecNet consumer."""
+    def forward_internal(self, x, want_y=True, slot=0, out_y=None, out_f=None):
+        """One chunk of images on the current stream. Returns (y, f, h) where h is the flat bf16 body output
+        (N*64 rows x 512). `slot` picks the workspace (one per concurrent stream, streams.py); `out_y` / `out_f` are
+        optional preallocated (contiguous) destinations."""
         lib = _lib.load()
         P = _lib.ptr
         prof = self._profile
@@ -204,7 +211,7 @@ class Backbone(nn.Module):
         x = x.contiguous().float()
         n, dev = x.shape[0], x.device
         pk = self._pack(dev)
-        ws = self._workspace(n, dev)
+        ws = self._workspace(n, dev, slot)
         st = _lib.stream_ptr()
         S = self.IMG
         L.check(lib.ffr_stem_fwd(P(x), P(pk.stem_w), P(pk.stem_b), P(pk.stem_a), P(ws.a), n, S, st), "stem")
@@ -234,9 +241,9 @@ class Backbone(nn.Module):
             S = so
         y = None
         if want_y:
-            y = torch.empty(n, 512, S, S, dtype=torch.float32, device=dev)
+            y = out_y if out_y is not None else torch.empty(n, 512, S, S, dtype=torch.float32, device=dev)
             L.check(lib.ffr_export_nchw_fwd(P(cur), P(pk.bn_scale), P(pk.bn_shift), P(y), n, S, 512, st), "export")
-        f = torch.empty(n, 512, dtype=torch.float32, device=dev)
+        f = out_f if out_f is not None else torch.empty(n, 512, dtype=torch.float32, device=dev)
         L.check(lib.ffr_head_fwd(P(cur), n, S, 512, P(pk.head_w), P(pk.head_b), P(ws.acc), P(f), st), "head")
         return y, f, cur
 

@@ -227,6 +227,12 @@ FFR_API int ffr_recnet_convlayer_fwd(const void* x, int n, int Cin, const void* 
     return conv_gemm_launch(x, (long long)p.M, Cin, Cin, wp, Cin, p, 1, S_(stream));
 }
 
+FFR_API int ffr_self_similarity(const float* x, int n, float* ss_space, float* ss_channel, ffr_stream_t stream) {
+    FFR_CHECK_ARG(n == 0 || x, "ffr_self_similarity: null input");
+    FFR_CHECK_ARG(ss_space || ss_channel, "ffr_self_similarity: no output requested");
+    return self_similarity_launch(x, n, ss_space, ss_channel, S_(stream));
+}
+
 FFR_API int ffr_feat_space(const float* x, const float* mspace, void* cm, float* out_nchw, int n, ffr_stream_t stream) {
     FFR_CHECK_ARG(x && mspace && cm, "ffr_feat_space: null pointer");
     return feat_space_launch(x, mspace, cm, out_nchw, n, S_(stream));

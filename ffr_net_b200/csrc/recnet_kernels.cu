@@ -308,3 +308,120 @@ int scale_f32_launch(const float* in, float* out, long long count, float scale, 
 }
 
 }  // namespace ffr
+
+// ------------------------------------------------------------------------------------------------------------
+// selfSimilarity (recnet.py:226-236) as a standalone forward op in fp32 (used for the no-grad targets of the
+// training loss, models/trainer.py:157): x (n,512,7,7) ->
+//   ss_space  (n,49,49)  : cosine between pixel columns  (normalised over C,  eps 1e-12)
+//   ss_channel(n,512,512): cosine between channel rows   (normalised over HW, eps 1e-12)
+// ------------------------------------------------------------------------------------------------------------
+namespace ffr {
+
+// one CTA per sample; x in shared memory; 4 Gram columns per thread (as in recnet_prep_kernel)
+__global__ void __launch_bounds__(512, 1) selfsim_space_kernel(const float* __restrict__ x, float* __restrict__ ss) {
+    extern __shared__ float sm[];
+    float* xs = sm;                 // [512][49]
+    float* inv_s = xs + 512 * 49;   // [64]
+    const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* xp = x + (long long)n * 512 * 49;
+    for (int i = tid; i < 512 * 49; i += 512) xs[i] = xp[i];
+    __syncthreads();
+    for (int hw = warp; hw < 49; hw += 16) {
+        float s = 0.f;
+        for (int c = lane; c < 512; c += 32) { const float v = xs[c * 49 + hw]; s = fmaf(v, v, s); }
+        s = warp_sum_r(s);
+        if (lane == 0) inv_s[hw] = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+    }
+    __syncthreads();
+    for (int o = tid; o < 49 * 13; o += 512) {
+        const int i = o / 13, j0 = (o - i * 13) * 4;
+        const int j1 = min(j0 + 1, 48), j2 = min(j0 + 2, 48), j3 = min(j0 + 3, 48);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+        for (int c = 0; c < 512; ++c) {
+            const float* xr = xs + c * 49;
+            const float xi = xr[i];
+            a0 = fmaf(xi, xr[j0], a0); a1 = fmaf(xi, xr[j1], a1);
+            a2 = fmaf(xi, xr[j2], a2); a3 = fmaf(xi, xr[j3], a3);
+        }
+        float* o_ = ss + (long long)n * 2401 + i * 49;
+        const float si = inv_s[i];
+        o_[j0] = a0 * si * inv_s[j0];
+        if (j0 + 1 < 49) o_[j0 + 1] = a1 * si * inv_s[j1];
+        if (j0 + 2 < 49) o_[j0 + 2] = a2 * si * inv_s[j2];
+        if (j0 + 3 < 49) o_[j0 + 3] = a3 * si * inv_s[j3];
+    }
+}
+
+// grid (16, n): CTA (tile, sample) computes a 128x128 tile of the 512x512 channel Gram; 8x8 outputs per thread
+__global__ void __launch_bounds__(256) selfsim_channel_kernel(const float* __restrict__ x, float* __restrict__ ss) {
+    extern __shared__ __align__(16) float ssm[];
+    float (*a_s)[132] = reinterpret_cast<float (*)[132]>(ssm);              // [k][row], rows of the tile, normalised
+    float (*b_s)[132] = reinterpret_cast<float (*)[132]>(ssm + 49 * 132);   // pitch 132 keeps float4 alignment
+    const int n = blockIdx.y, tr = blockIdx.x >> 2, tc = blockIdx.x & 3;
+    const int tid = threadIdx.x;
+    const float* xp = x + (long long)n * 512 * 49;
+    if (tid < 256) {
+        const int which = tid >> 7, r = tid & 127;               // 128 threads load+normalise A rows, 128 B rows
+        const float* row = xp + (long long)((which ? tc : tr) * 128 + r) * 49;
+        float v[49], s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 49; ++k) { v[k] = __ldg(row + k); s = fmaf(v[k], v[k], s); }
+        const float inv = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+#pragma unroll
+        for (int k = 0; k < 49; ++k) (which ? b_s : a_s)[k][r] = v[k] * inv;
+    }
+    __syncthreads();
+    const int ty = tid >> 4, tx = tid & 15;                       // 16 x 16 threads, 8 x 8 outputs each
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int k = 0; k < 49; ++k) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&a_s[k][ty * 8]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&a_s[k][ty * 8 + 4]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&b_s[k][tx * 8]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&b_s[k][tx * 8 + 4]);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    float* out = ss + ((long long)n * 512 + tr * 128 + ty * 8) * 512 + tc * 128 + tx * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        *reinterpret_cast<float4*>(out + (long long)i * 512) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        *reinterpret_cast<float4*>(out + (long long)i * 512 + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+    }
+}
+
+int self_similarity_launch(const float* x, int n, float* ss_space, float* ss_channel, cudaStream_t stream) {
+    if (n == 0) return 0;
+    if (ss_space) {
+        const int smem = (512 * 49 + 64) * (int)sizeof(float);
+        static bool attr = false;
+        if (!attr) {
+            FFR_CUDA(cudaFuncSetAttribute(selfsim_space_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr = true;
+        }
+        selfsim_space_kernel<<<n, 512, smem, stream>>>(x, ss_space);
+        int rc = launch_status("selfsim_space_kernel");
+        if (rc) return rc;
+    }
+    if (ss_channel) {
+        const int smem = 2 * 49 * 132 * (int)sizeof(float);
+        static bool attr = false;
+        if (!attr) {
+            FFR_CUDA(cudaFuncSetAttribute(selfsim_channel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr = true;
+        }
+        selfsim_channel_kernel<<<dim3(16, n), 256, smem, stream>>>(x, ss_channel);
+        return launch_status("selfsim_channel_kernel");
+    }
+    return 0;
+}
+
+}  // namespace ffr

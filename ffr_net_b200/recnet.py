@@ -15,7 +15,7 @@ import torch.nn.functional as F
 from torch import nn
 from torch.nn import init
 
-from . import _lib, packing
+from . import _lib, packing, streams
 
 READY = True   # bench.py includes the RecBlock stage when this module is importable and READY
 
@@ -267,11 +267,11 @@ class RecNet(nn.Module):
             self._ttab = (key, (_h9_scatter(0, device),))
         return self._ttab[1]
 
-    def _workspace(self, n, device):
+    def _workspace(self, n, device, slot=0):
         key = (n, str(device))
-        ws = self._ws.get(key)
-        if ws is not None:
-            return ws
+        held = self._ws.get(slot)
+        if held is not None and held[0] == key:
+            return held[1]
         ws = _Obj()
         bf = dict(dtype=torch.bfloat16, device=device)
 
@@ -290,7 +290,7 @@ class RecNet(nn.Module):
         ws.c512 = [h9(512) for _ in range(2)]
         ws.d512 = [h9(512) for _ in range(3)]
         ws.pool = torch.empty(n, 512, dtype=torch.float32, device=device)
-        self._ws = {key: ws}
+        self._ws[slot] = (key, ws)
         return ws
 
     # ------------------------------------------------------------------------------------------
@@ -306,16 +306,32 @@ class RecNet(nn.Module):
         if input.shape[0] == 0:                      # empty batch: nothing to launch
             return (torch.empty(0, 512, dtype=torch.float32, device=input.device),
                     torch.empty(0, 512, 7, 7, dtype=torch.float32, device=input.device))
-        v, feat_new = self._forward_eval(input, want_map=True)
+        n = input.shape[0]
+        x = input.contiguous().float()
+        v = torch.empty(n, 512, dtype=torch.float32, device=x.device)
+        feat_new = torch.empty(n, 512, 7, 7, dtype=torch.float32, device=x.device)
+        streams.fork_join(streams.chunk_bounds(n), x.device,
+                          lambda i, lo, hi: self._forward_eval(x[lo:hi], True, slot=i, out_v=v[lo:hi],
+                                                               out_map=feat_new[lo:hi]))
         return v, feat_new
 
     def embed_from_images(self, encoder, x):
-        """encoder(x) -> RecNet -> rectified embedding, the per-image path of lfw_eval.calculate_distance:241-242."""
-        y, _, _ = encoder.forward_internal(x, want_y=True)
-        v, _ = self._forward_eval(y, want_map=False)
+        """encoder(x) -> RecNet -> rectified embedding, the per-image path of lfw_eval.calculate_distance:241-242.
+        The batch is cut into chunks that run concurrently on side streams (streams.py): the tail wave of one chunk's
+        kernel is filled by the other chunk's next kernel, and HBM-bound passes overlap tensor-bound ones."""
+        n = x.shape[0]
+        x = x.contiguous().float()
+        v = torch.empty(n, 512, dtype=torch.float32, device=x.device)
+        if n == 0:
+            return v
+
+        def chunk(i, lo, hi):
+            y, _, _ = encoder.forward_internal(x[lo:hi], want_y=True, slot=i)
+            self._forward_eval(y, want_map=False, slot=i, out_v=v[lo:hi])
+        streams.fork_join(streams.chunk_bounds(n), x.device, chunk)
         return v
 
-    def _forward_eval(self, x, want_map=True):
+    def _forward_eval(self, x, want_map=True, slot=0, out_v=None, out_map=None):
         lib = _lib.load()
         P = _lib.ptr
         prof = self._profile
@@ -330,7 +346,7 @@ class RecNet(nn.Module):
         x = x.contiguous().float()
         n, dev = x.shape[0], x.device
         pk = self._pack_eval(dev)
-        ws = self._workspace(n, dev)
+        ws = self._workspace(n, dev, slot)
         st = _lib.stream_ptr()
 
         chk(lib.ffr_recnet_prep(P(x), n, P(pk.w0aT), P(pk.w0bT), P(pk.b0), P(pk.slope1), P(pk.A1), P(pk.c1),
@@ -373,11 +389,11 @@ class RecNet(nn.Module):
         conv("Conv4Merge.1.conv1", ws.d512[0], ws.d512[1])
         conv("Conv4Merge.1.conv2", ws.d512[1], ws.d512[2], res=ws.d512[0], pool=ws.pool)
 
-        v = torch.empty(n, 512, dtype=torch.float32, device=dev)
+        v = out_v if out_v is not None else torch.empty(n, 512, dtype=torch.float32, device=dev)
         chk(lib.ffr_scale_f32(P(ws.pool), P(v), n * 512, 1.0 / 49.0, st), "avgpool")
         feat_new = None
         if want_map:
-            feat_new = torch.empty(n, 512, 7, 7, dtype=torch.float32, device=dev)
+            feat_new = out_map if out_map is not None else torch.empty(n, 512, 7, 7, dtype=torch.float32, device=dev)
             chk(lib.ffr_rows_to_nchw(P(ws.d512[2]), 0, 512, 0, None, None, P(feat_new), n, 7, 9, 1, 81, 512, st),
                 "export")
         return v, feat_new

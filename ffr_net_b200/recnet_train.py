@@ -184,9 +184,20 @@ def cosine_sim(x1, x2, dim=1):
 
 
 def self_similarity(x):
-    """selfSimilarity, recnet.py:226-236 (ATen/cuBLAS under autograd: used by the trainer's loss terms)."""
+    """selfSimilarity, recnet.py:226-236. Without autograd (the no-grad targets of the loss, trainer.py:157, or any
+    inference use) both Grams come from the library's fp32 kernels; when a gradient is required the ATen/cuBLAS ops
+    below run under autograd."""
     if not x.is_cuda:
         raise RuntimeError("ffr_net_b200.selfSimilarity runs only on CUDA")
+    if not (torch.is_grad_enabled() and x.requires_grad) and tuple(x.shape[1:]) == (512, 7, 7):
+        lib = _lib.load()
+        xc = x.detach().contiguous().float()
+        n = xc.shape[0]
+        ss_s = torch.empty(n, 49, 7, 7, dtype=torch.float32, device=x.device)
+        ss_c = torch.empty(n, 512, 512, dtype=torch.float32, device=x.device)
+        _lib.check(lib.ffr_self_similarity(_lib.ptr(xc), n, _lib.ptr(ss_s), _lib.ptr(ss_c), _lib.stream_ptr()),
+                   "ffr_self_similarity")
+        return ss_s, ss_c
     h, w = x.size(2), x.size(3)
     v = x.reshape(x.size(0), x.size(1), -1)
     ss_space = cosine_sim(v.permute(0, 2, 1), v.permute(0, 2, 1))

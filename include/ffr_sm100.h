@@ -132,6 +132,10 @@ FFR_API int ffr_recnet_convlayer_fwd(const void* x, int n, int Cin, const void* 
                                      const int* scatter, int scatter_n, int out_rows_per_img, float* out_f32,
                                      float* pool, ffr_stream_t stream);
 
+/* selfSimilarity forward (recnet.py:226-236) in fp32: x (n,512,7,7) -> ss_space (n,49,49) [viewed (n,49,7,7) by the
+ * caller] and/or ss_channel (n,512,512); either output may be NULL. */
+FFR_API int ffr_self_similarity(const float* x, int n, float* ss_space, float* ss_channel, ffr_stream_t stream);
+
 /* feat_space = X @ M_space (recnet.py:409) -> slot [0,512) of cm (H9 + mirrors); optional fp32 NCHW copy. */
 FFR_API int ffr_feat_space(const float* x, const float* mspace, void* cm, float* out_nchw, int n, ffr_stream_t stream);
 

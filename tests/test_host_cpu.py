@@ -165,3 +165,11 @@ def test_head_fold_is_exact_in_fp32():
     flat = layout.to_flat(h, torch.float32).reshape(2, -1)
     got2 = flat @ wp.float().t() + bp
     assert float((got2 - o).abs().max()) <= 1e-2 * float(o.abs().max())
+
+
+def test_chunk_bounds():
+    from ffr_net_b200 import streams
+    assert streams.chunk_bounds(512, 2) == [(0, 256), (256, 512)]
+    assert streams.chunk_bounds(11, 3) == [(0, 11)]          # below FFR_MIN_CHUNK: one chunk
+    assert streams.chunk_bounds(200, 3) == [(0, 67), (67, 134), (134, 200)]
+    assert streams.chunk_bounds(0, 4) == [(0, 0)]

@@ -82,3 +82,56 @@ def test_recnet_rejects_cpu_and_training(models):
         m(torch.zeros(1, 512, 7, 7))
     with pytest.raises(NotImplementedError):     # label path in eval mode: the reference never uses it
         m(torch.zeros(2, 512, 7, 7, device="cuda"), torch.zeros(2, dtype=torch.long, device="cuda"))
+
+
+@pytest.mark.parametrize("n", [1, 3])
+def test_self_similarity_kernel(lib, n):
+    """ffr_self_similarity (through the public selfSimilarity) vs the oracle: fp32, <= 2e-6 absolute on cosines."""
+    import numpy as np
+    import os
+    from ffr_net_b200.recnet import selfSimilarity
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(3, 512, 7, 7, generator=g) * 0.3
+    x = x[:n]
+    ref_s, ref_c = orr.self_similarity(x)
+    got_s, got_c = selfSimilarity(x.cuda())
+    assert got_s.shape == (n, 49, 7, 7) and got_c.shape == (n, 512, 512)
+    assert (got_s.cpu() - ref_s).abs().max().item() <= 2e-6
+    assert (got_c.cpu() - ref_c).abs().max().item() <= 2e-6
+    if n == 3:   # golden vector from the real reference (tests/golden/selfsim_ref.npz)
+        gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "selfsim_ref.npz"))
+        assert np.abs(got_s.cpu().numpy() - gold["ss_space"]).max() <= 2e-6
+        assert np.abs(got_c.cpu()[:, ::16, ::16].numpy() - gold["ss_channel_slice"]).max() <= 2e-6
+    xg = x.cuda().requires_grad_(True)          # autograd path still available
+    s2, c2 = selfSimilarity(xg)
+    (s2.sum() + c2.sum()).backward()
+    assert xg.grad is not None and torch.isfinite(xg.grad).all()
+
+
+def test_chunked_streams_match_single_stream(models, monkeypatch):
+    """streams.py: the batch cut into concurrent chunks (2 and 3 side streams, uneven chunk sizes) gives the same
+    embeddings as one chunk on one stream, within the batch-invariance bound (fp32 atomics order only)."""
+    from ffr_net_b200.backbone import Backbone
+    sd, m = models
+    enc = Backbone(50, 0.6, "ir_se")
+    enc.load_state_dict(ob.synth_backbone_state_dict(0))
+    enc = enc.cuda().eval()
+    x = ob.synth_faces(11, seed=12).cuda()
+    with torch.no_grad():
+        monkeypatch.setenv("FFR_STREAMS", "1")
+        v1 = m.embed_from_images(enc, x)
+        y1, f1 = enc(x)
+        r1, map1 = m(y1)
+        monkeypatch.setenv("FFR_MIN_CHUNK", "2")
+        for k in ("2", "3"):
+            monkeypatch.setenv("FFR_STREAMS", k)
+            vk = m.embed_from_images(enc, x)
+            yk, fk = enc(x)
+            rk, mapk = m(y1)
+            torch.cuda.synchronize()
+            assert (vk - v1).abs().max().item() <= 1e-3 * max(1.0, v1.abs().max().item())
+            assert (fk - f1).abs().max().item() <= 1e-3
+            assert (yk - y1).abs().max().item() <= 1e-2 * y1.abs().max().item()
+            assert (rk - r1).abs().max().item() <= 1e-3 * max(1.0, r1.abs().max().item())
+            assert (mapk - map1).abs().max().item() <= 1e-2 * map1.abs().max().item()
+
