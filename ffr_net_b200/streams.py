@@ -8,7 +8,10 @@ chunks, each chunk's kernel sequence goes to its own CUDA stream, and the hardwa
 chunk's kernel frees with the other chunk's next kernel. Chunk 0 stays on the caller's stream; the side streams fork
 from it and join back through events, which also makes the pattern capturable in a CUDA graph (trainer.capture_step).
 
-FFR_STREAMS (default 2) sets the number of concurrent chunks; a chunk is never smaller than FFR_MIN_CHUNK images.
+FFR_STREAMS sets the number of concurrent chunks (a chunk is never smaller than FFR_MIN_CHUNK images). The default
+is 1: measured on a B200 at batch 512 (tools/streams_sweep.py, profiles/r01_streams_sweep_512.json) 2 chunks give the
+same throughput as 1 (8.51 vs 8.45 ms backbone, 11.44 vs 11.09 ms with RecNet) and 3-4 chunks are 5-8 % slower — the
+half-batch kernels lose to their own tail waves (and extra launches) what the overlap wins. Kept as an opt-in.
 """
 import os
 
@@ -18,7 +21,7 @@ _side = {}
 
 
 def num_streams():
-    return max(1, int(os.environ.get("FFR_STREAMS", "2")))
+    return max(1, int(os.environ.get("FFR_STREAMS", "1")))
 
 
 def min_chunk():
