@@ -280,6 +280,53 @@ FFR_API int ffr_pack_conv3x3(const float* w, int cout, int cin, int cout_p, int 
     return pack_conv3x3_launch(w, cout, cin, cout_p, cin_p, fwd, dgrad, S_(stream));
 }
 
+FFR_API int ffr_cosface_pack(const float* x, int rows, int rows_pad, int mode, void* packed, void* transposed, int t_ld,
+                             ffr_stream_t stream) {
+    FFR_CHECK_ARG((rows == 0 || x) && packed, "ffr_cosface_pack: null pointer");
+    FFR_CHECK_ARG(rows >= 0 && rows_pad >= rows && rows_pad % 64 == 0, "ffr_cosface_pack: rows=%d rows_pad=%d", rows, rows_pad);
+    FFR_CHECK_ARG(!transposed || (t_ld >= rows_pad && t_ld % 8 == 0), "ffr_cosface_pack: t_ld=%d", t_ld);
+    return cosface_pack_launch(x, rows, rows_pad, mode, packed, transposed, t_ld, S_(stream));
+}
+
+FFR_API int ffr_cosface_ce_fwd(const void* v_packed, int n, const void* w_packed, int c_pad, int classes, const int* label,
+                               float s, float m, float* cos_out, float* sumexp, float* zlabel,
+                               unsigned long long* argkey, ffr_stream_t stream) {
+    FFR_CHECK_ARG(v_packed && w_packed && label && cos_out && sumexp && zlabel && argkey, "ffr_cosface_ce_fwd: null pointer");
+    FFR_CHECK_ARG(n > 0 && c_pad % 256 == 0 && classes > 0 && classes <= c_pad, "ffr_cosface_ce_fwd: n=%d c_pad=%d classes=%d",
+                  n, c_pad, classes);
+    FFR_CUDA(cudaMemsetAsync(sumexp, 0, sizeof(float) * (size_t)n, S_(stream)));
+    FFR_CUDA(cudaMemsetAsync(argkey, 0, sizeof(unsigned long long) * (size_t)n, S_(stream)));
+    ConvGemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = n;
+    p.Cout = c_pad;
+    p.ntaps = 1;
+    p.flags = EPI_OUT_F32 | EPI_COSFACE;
+    p.out_f32 = cos_out;
+    p.ce_label = label; p.ce_sumexp = sumexp; p.ce_zlabel = zlabel; p.ce_argkey = argkey;
+    p.ce_classes = classes; p.ce_s = s; p.ce_m = m;
+    return conv_gemm_launch(v_packed, (long long)n, 1536, 1536, w_packed, 1536, p, 1, S_(stream));
+}
+
+FFR_API int ffr_cosface_ce_finish(const float* sumexp, const float* zlabel, const unsigned long long* argkey, int n, float s,
+                                  float* loss, long long* pred, ffr_stream_t stream) {
+    FFR_CHECK_ARG(sumexp && zlabel && argkey && loss && n > 0, "ffr_cosface_ce_finish: bad argument");
+    return cosface_finish_launch(sumexp, zlabel, argkey, n, s, loss, pred, S_(stream));
+}
+
+FFR_API int ffr_cosface_ce_bwd(const float* cos_in, int c_pad, int classes, int n, int n_pad, const int* label,
+                               const float* sumexp, const float* gloss, float s, float m, void* dcos, void* dcosT,
+                               ffr_stream_t stream) {
+    FFR_CHECK_ARG(cos_in && label && sumexp && gloss && dcos && dcosT, "ffr_cosface_ce_bwd: null pointer");
+    FFR_CHECK_ARG(c_pad % 64 == 0 && n_pad % 64 == 0 && n_pad >= n && classes <= c_pad, "ffr_cosface_ce_bwd: bad shape");
+    return cosface_bwd_launch(cos_in, c_pad, classes, n, n_pad, label, sumexp, gloss, s, m, dcos, dcosT, S_(stream));
+}
+
+FFR_API int ffr_normalize_bwd(const float* x, const float* dxh, int rows, float* dx, ffr_stream_t stream) {
+    FFR_CHECK_ARG(rows == 0 || (x && dxh && dx), "ffr_normalize_bwd: null pointer");
+    return normalize_bwd_launch(x, dxh, rows, dx, S_(stream));
+}
+
 FFR_API int ffr_clip_adam(const void* table, const int* chunks, int n_chunks, const float* hyper, float beta1,
                           float beta2, float eps, float weight_decay, float clip, ffr_stream_t stream) {
     FFR_CHECK_ARG(n_chunks == 0 || (table && chunks && hyper), "ffr_clip_adam: null pointer");

@@ -166,6 +166,11 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
         }
         const uint32_t t_row = tmem_base + (acc * SUB + sub) * BN + chalf * HALF + (static_cast<uint32_t>(quad * 32) << 16);
 
+        // EPI_COSFACE per-row running values (one row per thread, HALF classes per tile)
+        const int ce_lab = ((flags & EPI_COSFACE) && m < p.M) ? __ldg(p.ce_label + m) : -1;
+        float ce_sum = 0.f, ce_zl = 0.f, ce_best = -3.0e38f;
+        int ce_bestc = 0;
+
         uint32_t vbuf[2][32];
         tmem_ld_32x32(t_row, vbuf[0]);
 #pragma unroll
@@ -213,6 +218,19 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
             if (!valid) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) x[j] = 0.f;
+            }
+            if (flags & EPI_COSFACE) {
+                const int cbase = nc0 + c0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int c = cbase + j;
+                    if (c < p.ce_classes) {
+                        const float z = p.ce_s * (x[j] - ((c == ce_lab) ? p.ce_m : 0.f));
+                        ce_sum += __expf(z - p.ce_s);
+                        if (c == ce_lab) ce_zl = z;
+                        if (x[j] > ce_best) { ce_best = x[j]; ce_bestc = c; }
+                    }
+                }
             }
             if (flags & EPI_OUT_F32_ATOMIC) {
                 if (valid) {
@@ -278,6 +296,15 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
                     if (n_lo < p.n_img) atomicAdd(p.pool + (long long)n_lo * p.Cout + nc0 + c0 + lane, sa);
                     if (n_hi < p.n_img) atomicAdd(p.pool + (long long)n_hi * p.Cout + nc0 + c0 + lane, sb);
                 }
+            }
+        }
+        if ((flags & EPI_COSFACE) && m < p.M) {
+            atomicAdd(p.ce_sumexp + m, ce_sum);
+            if (ce_lab >= nc0 && ce_lab < nc0 + HALF) p.ce_zlabel[m] = ce_zl;
+            if (nc0 < p.ce_classes) {
+                uint32_t u = __float_as_uint(ce_best);
+                u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);            // monotone map float -> uint
+                atomicMax(p.ce_argkey + m, ((unsigned long long)u << 32) | (0xFFFFFFFFu - (uint32_t)ce_bestc));
             }
         }
         }   // sub

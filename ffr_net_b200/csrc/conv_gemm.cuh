@@ -29,6 +29,9 @@ enum EpiFlags : uint32_t {
     EPI_RESIDUAL    = 1u << 9,   // + res[m, co] (bf16, same row grid) after PReLU
     EPI_STATS       = 1u << 10,  // atomically accumulate per-co sum and sum of squares of valid rows (batch-stat BN)
     EPI_OUT_F32     = 1u << 11,  // plain fp32 store to out_f32[m, co] (no atomics)
+    EPI_COSFACE     = 1u << 12,  // rows = samples, columns = classes, accumulator = cosine: per row accumulate
+                                 // sum_c exp(z_c - s) with z_c = s*(cos_c - m*[c == label]) (|cos| <= 1, so the fixed
+                                 // shift s replaces the running maximum), record z_label and the arg-max of cos
 };
 
 struct ConvGemmParams {
@@ -60,6 +63,13 @@ struct ConvGemmParams {
     int scatter_n;         // 1..8
     int out_rows_per_img;  // rows per image of the destination matrix
     int b_rows_per_mtile;  // batched B: weight-matrix row offset added per M tile (0 = shared weights)
+    // EPI_COSFACE (AddMarginProduct + CrossEntropy, recnet.py:257-270, trainer.py:173-176)
+    const int* ce_label;            // [M]
+    float* ce_sumexp;               // [M], zeroed by the caller
+    float* ce_zlabel;               // [M]
+    unsigned long long* ce_argkey;  // [M], zeroed by the caller: (orderable cos bits << 32) | (0xFFFFFFFF - class)
+    int ce_classes;                 // real class count (columns >= ce_classes are padding)
+    float ce_s, ce_m;
     unsigned long long* dbg;  // optional: per-role wait-cycle counters (ffr_debug_set_counters), else nullptr
 };
 

@@ -27,6 +27,13 @@ int recnet_prep_launch(const PrepParams& p, int n, cudaStream_t stream);
 int feat_space_launch(const float* x, const float* mspace, void* cm, float* out_nchw, int n, cudaStream_t stream);
 int rows_to_nchw_launch(const void* rows, int is_f32, int ld, int ch0, const float* scale, const float* shift, float* y,
                         int n, int S, int G, int off, int rows_per_img, int C, cudaStream_t stream);
+int cosface_pack_launch(const float* x, int rows, int rows_pad, int mode, void* packed, void* transposed, int t_ld,
+                        cudaStream_t stream);
+int cosface_finish_launch(const float* sumexp, const float* zlabel, const unsigned long long* argkey, int n, float s,
+                          float* loss, long long* pred, cudaStream_t stream);
+int cosface_bwd_launch(const float* cosv, int c_pad, int classes, int n, int n_pad, const int* label, const float* sumexp,
+                       const float* gloss, float s, float m, void* dcos, void* dcosT, cudaStream_t stream);
+int normalize_bwd_launch(const float* x, const float* dxh, int rows, float* dx, cudaStream_t stream);
 int self_similarity_launch(const float* x, int n, float* ss_space, float* ss_channel, cudaStream_t stream);
 int scale_f32_launch(const float* in, float* out, long long count, float scale, cudaStream_t stream);
 int wgrad_launch(const void* dz, int ld_dz, const void* x, int ld_x, int x_ch0, int P, int Cout, int Cin, int G,

@@ -228,8 +228,10 @@ def add_margin_product(weight, x, label, s=30.0, m=0.40):
     return output * s, cosine
 
 
-def forward_train(model, x, label):
-    """RecNet.forward for training / label inputs (recnet.py:398-429)."""
+def forward_train(model, x, label, fused_ce=False):
+    """RecNet.forward for training / label inputs (recnet.py:398-429). fused_ce: the `pred_loss` and `pred_label` slots
+    of the 7-tuple hold one head.FusedCE (CE loss + predicted classes, csrc/head_kernels.cu) instead of the two
+    (N,10575) tensors — the form the Trainer consumes."""
     if not x.is_cuda:
         raise RuntimeError("ffr_net_b200.RecNet runs only on CUDA (sm_100a); there is no CPU fallback")
     if not model.training:
@@ -290,5 +292,10 @@ def forward_train(model, x, label):
     feat_new_v = feat_new.mean(dim=(2, 3))                                               # :423
     if label is None:
         return feat_new_v, feat_new
+    if fused_ce:
+        from . import head
+        fused = head.FusedCE(*head.cosface_ce(model.classifier.weight, feat_new_v, label, model.classifier.s,
+                                              model.classifier.m))
+        return feat_new_v, fused, fused, m_space, m_channel, feat_space, feat_channel_out
     pred_loss, pred_label = add_margin_product(model.classifier.weight, feat_new_v, label)   # :428
     return feat_new_v, pred_loss, pred_label, m_space, m_channel, feat_space, feat_channel_out

@@ -13,6 +13,7 @@ import torch.nn.functional as F
 from torch import nn, optim
 
 from .backbone import Backbone
+from .head import FusedCE
 from .optim import FusedClipAdam
 from .recnet import RecNet, init_weights, selfSimilarity
 
@@ -66,6 +67,9 @@ class Trainer:
         # recnet_train.py) would otherwise run as fp32 SIMT GEMMs: let cuBLAS use TF32 tensor cores for it.
         if getattr(opts, "tf32_glue", True):
             torch.backends.cuda.matmul.allow_tf32 = True
+        # CosFace head + CrossEntropy as one fused forward/backward (head.py); opts.fused_head=False keeps the
+        # reference's op sequence on library kernels (two (N,10575) tensors + nn.CrossEntropyLoss)
+        self.fused_head = bool(getattr(opts, "fused_head", True))
         self.mse_loss = nn.MSELoss()
         self.triplet = TripletLoss()
         self.cross_entropy = nn.CrossEntropyLoss()
@@ -117,11 +121,19 @@ class Trainer:
         with torch.no_grad():
             self.feat_map_non, self.feat_extract_non = self.encoder(self.nonocl)
             self.feat_map_ocl, self.feat_extract_ocl = self.encoder(self.ocl)
+        if self.fused_head and self.recnet.training:
+            from .recnet_train import forward_train
+            rec = lambda fmap: forward_train(self.recnet, fmap, self.gt_label, fused_ce=True)
+        else:
+            rec = lambda fmap: self.recnet(fmap, self.gt_label)
         (self.f_non, self.pred_loss_non, self.pred_label_non, self.M_space_non, self.M_channel_non, self.space_non,
-         self.channel_non) = self.recnet(self.feat_map_non, self.gt_label)
+         self.channel_non) = rec(self.feat_map_non)
         (self.f_ocl, self.pred_loss_ocl, self.pred_label_ocl, self.M_space_ocl, self.M_channel_ocl, self.space_ocl,
-         self.channel_ocl) = self.recnet(self.feat_map_ocl, self.gt_label)
-        pred = self.pred_label_ocl.detach().argmax(1)
+         self.channel_ocl) = rec(self.feat_map_ocl)
+        if isinstance(self.pred_label_ocl, FusedCE):
+            pred = self.pred_label_ocl.pred
+        else:
+            pred = self.pred_label_ocl.detach().argmax(1)
         self.pred_label = pred
         self._correct = pred.eq(self.gt_label).sum()          # no host sync here; .item() in get_current_values
 
@@ -141,8 +153,9 @@ class Trainer:
         t, self.pos_loss, self.neg_loss = self.triplet(self.f_ocl, self.feat_extract_non, self.feat_extract_ocl)
         items.append(t)
         items.append((mse(self.f_non, self.feat_extract_non) + mse(self.f_ocl, self.feat_extract_non)) / 2)
-        items.append(self.cross_entropy(self.pred_loss_non, self.gt_label) / (1e-8 + self.opts.loss_weight[3])
-                     + self.cross_entropy(self.pred_loss_ocl, self.gt_label))
+        def ce(logits):
+            return logits.loss if isinstance(logits, FusedCE) else self.cross_entropy(logits, self.gt_label)
+        items.append(ce(self.pred_loss_non) / (1e-8 + self.opts.loss_weight[3]) + ce(self.pred_loss_ocl))
         self.loss_items = [l * w for l, w in zip(items, self.opts.loss_weight)]
         sum(self.loss_items).backward()
 

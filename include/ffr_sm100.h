@@ -182,6 +182,36 @@ FFR_API int ffr_pack_conv3x3(const float* w, int cout, int cin, int cout_p, int 
 FFR_API int ffr_clip_adam(const void* table, const int* chunks, int n_chunks, const float* hyper, float beta1,
                           float beta2, float eps, float weight_decay, float clip, ffr_stream_t stream);
 
+/* ---- CosFace head + CrossEntropy, training path (AddMarginProduct recnet.py:238-270, trainer.py:173-176) ------ */
+
+/* Rows of x (fp32 [rows][512]) -> F.normalize'd (eps 1e-12) bf16 hi/lo split, packed [rows_pad][1536]:
+ * mode 0 (samples) = [hi | lo | hi], mode 1 (classes) = [hi | hi | lo]; rows in [rows, rows_pad) are zero.
+ * transposed (may be NULL): [512][t_ld] bf16, hi part, column index = row (K-major operand of the backward GEMMs). */
+FFR_API int ffr_cosface_pack(const float* x, int rows, int rows_pad, int mode, void* packed, void* transposed, int t_ld,
+                             ffr_stream_t stream);
+
+/* cos[n][c_pad] (fp32) = v_packed . w_packed^T on the tcgen05 GEMM (K = 1536: hi.hi + lo.hi + hi.lo), with the fused
+ * epilogue: sumexp[i] = sum_{c < classes} exp(z_ic - s), z_ic = s*(cos_ic - m*[c == label_i]); zlabel[i] = z at the
+ * label; argkey[i] = arg-max_c cos_ic packed as (orderable bits << 32) | (0xFFFFFFFF - c) (first maximum wins, as
+ * torch.argmax). c_pad must be a multiple of 256; label is int32. sumexp and argkey are zeroed here. */
+FFR_API int ffr_cosface_ce_fwd(const void* v_packed, int n, const void* w_packed, int c_pad, int classes, const int* label,
+                               float s, float m, float* cos_out, float* sumexp, float* zlabel,
+                               unsigned long long* argkey, ffr_stream_t stream);
+
+/* loss = mean_i(log(sumexp[i]) + s - zlabel[i]) (device scalar); pred[i] = arg-max class (int64, may be NULL). */
+FFR_API int ffr_cosface_ce_finish(const float* sumexp, const float* zlabel, const unsigned long long* argkey, int n, float s,
+                                  float* loss, long long* pred, ffr_stream_t stream);
+
+/* dcos[i][c] = s * (softmax(z_i)[c] - [c == label_i]) * gloss[0] / n as bf16 [n][c_pad] and transposed [c_pad][n_pad]
+ * (pads zero). gloss: DEVICE scalar, the upstream gradient of the mean CE loss. The two backward contractions
+ * (dv^ = dcos . W^, K = c_pad;  dW^ = dcos^T . v^, K = n_pad) are plain ffr_conv_gemm calls on these operands. */
+FFR_API int ffr_cosface_ce_bwd(const float* cos_in, int c_pad, int classes, int n, int n_pad, const int* label,
+                               const float* sumexp, const float* gloss, float s, float m, void* dcos, void* dcosT,
+                               ffr_stream_t stream);
+
+/* Jacobian of F.normalize(x, dim=1) on rows of 512: dx = (dxh - xh (xh . dxh)) / max(|x|, 1e-12). */
+FFR_API int ffr_normalize_bwd(const float* x, const float* dxh, int rows, float* dx, ffr_stream_t stream);
+
 /* fp32 NCHW (n,C,7,7) -> bf16 H9 channel slot (mirror != 0: reflection halo filled, else halo zero) and back
  * (fold != 0: sums the mirror rows into the pixel, i.e. the gradient of the mirrored scatter). */
 FFR_API int ffr_nchw_to_h9(const float* x, void* out, int ld, int ch0, int n, int C, int mirror, ffr_stream_t stream);

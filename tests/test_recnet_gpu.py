@@ -129,9 +129,14 @@ def test_chunked_streams_match_single_stream(models, monkeypatch):
             yk, fk = enc(x)
             rk, mapk = m(y1)
             torch.cuda.synchronize()
-            assert (vk - v1).abs().max().item() <= 1e-3 * max(1.0, v1.abs().max().item())
-            assert (fk - f1).abs().max().item() <= 1e-3
-            assert (yk - y1).abs().max().item() <= 1e-2 * y1.abs().max().item()
-            assert (rk - r1).abs().max().item() <= 1e-3 * max(1.0, r1.abs().max().item())
-            assert (mapk - map1).abs().max().item() <= 1e-2 * map1.abs().max().item()
+            dv = (vk - v1).abs().max().item() / v1.abs().max().item()
+            df = (fk - f1).abs().max().item()
+            dy = (yk - y1).abs().max().item() / y1.abs().max().item()
+            dr = (rk - r1).abs().max().item() / r1.abs().max().item()
+            dm = (mapk - map1).abs().max().item() / map1.abs().max().item()
+            print("streams=%s: embed %.2e backbone f %.2e y %.2e | recnet v %.2e map %.2e" % (k, dv, df, dy, dr, dm))
+            # backbone: batch-invariance bound of test_backbone_batch_invariance (chunking changes the tile partition);
+            # RecNet on identical input: bound of test_recnet_batch_invariance
+            assert dy <= 1e-2 and df <= 1e-3 and dv <= 1e-2
+            assert dr <= 1e-5 + 1e-6 and dm <= 1e-2
 
