@@ -26,7 +26,7 @@ _SIGNATURES = {
     "ffr_self_similarity": (_i, [_p, _i, _p, _p, _p]),
     "ffr_feat_space": (_i, [_p, _p, _p, _p, _i, _p]),
     "ffr_rows_to_nchw": (_i, [_p, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
-    "ffr_wgrad3x3": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "ffr_wgrad3x3": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "ffr_bn_prelu_fwd": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _p]),
     "ffr_bn_prelu_bwd": (_i, [_p, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _i, _p, _p, _i, _i, _i, _p]),
     "ffr_pack_conv3x3": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
@@ -53,6 +53,9 @@ _SIGNATURES = {
     "ffr_debug_set_window": (_i, [_i]),
     "ffr_debug_mn_probe": (_i, [_p, _p, _p, _i, _i, _p]),
     "ffr_debug_set_counters": (_i, [_p]),
+    "ffr_debug_set_wgrad_splits": (None, [_i]),
+    "ffr_pixmajor_profitable": (_i, [_i]),
+    "ffr_debug_set_pixmajor": (None, [_i]),
     "ffr_debug_mma_bench": (_i, [_p, _i, _i, _i, _i, _i, _p]),
     "ffr_debug_rowshift_probe": (_i, [_p, _p, _p, _i, _i, _p]),
 }

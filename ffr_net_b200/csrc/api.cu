@@ -223,9 +223,13 @@ FFR_API int ffr_recnet_convlayer_fwd(const void* x, int n, int Cin, const void* 
     p.scatter = reinterpret_cast<const int2*>(scatter); p.scatter_n = scatter_n; p.out_rows_per_img = out_rows_per_img;
     p.out_f32 = out_f32;
     p.pool = pool;
+    if (pixmajor_profitable(n)) p.flags |= EPI_PIXMAJOR;
     if (pool) FFR_CUDA(cudaMemsetAsync(pool, 0, sizeof(float) * (size_t)n * Cout, S_(stream)));
     return conv_gemm_launch(x, (long long)p.M, Cin, Cin, wp, Cin, p, 1, S_(stream));
 }
+
+FFR_API int ffr_pixmajor_profitable(int n) { return pixmajor_profitable(n) ? 1 : 0; }
+FFR_API void ffr_debug_set_pixmajor(int mode) { set_pixmajor_mode(mode); }
 
 FFR_API int ffr_self_similarity(const float* x, int n, float* ss_space, float* ss_channel, ffr_stream_t stream) {
     FFR_CHECK_ARG(n == 0 || x, "ffr_self_similarity: null input");
@@ -250,11 +254,13 @@ FFR_API int ffr_scale_f32(const float* in, float* out, int64_t count, float scal
 }
 
 FFR_API int ffr_wgrad3x3(const void* dz, int ld_dz, const void* x, int ld_x, int x_ch0, int n, int Cout, int Cin,
-                         float* dw, ffr_stream_t stream) {
-    FFR_CHECK_ARG(dz && x && dw, "ffr_wgrad3x3: null pointer");
+                         float* dw, float* workspace, ffr_stream_t stream) {
+    FFR_CHECK_ARG(dz && x && dw && workspace, "ffr_wgrad3x3: null pointer");
     FFR_CHECK_ARG(ld_dz % 64 == 0 && ld_x % 8 == 0 && x_ch0 % 8 == 0, "ffr_wgrad3x3: bad pitches");
-    return wgrad_launch(dz, ld_dz, x, ld_x, x_ch0, n * 81, Cout, Cin, 9, dw, S_(stream));
+    return wgrad_launch(dz, ld_dz, x, ld_x, x_ch0, n * 81, Cout, Cin, 9, dw, workspace, S_(stream));
 }
+
+FFR_API void ffr_debug_set_wgrad_splits(int splits) { set_wgrad_splits(splits); }
 
 FFR_API int ffr_bn_prelu_fwd(const void* z, int ldz, const float* mean, const float* rstd, const float* gamma,
                              const float* beta, const float* slope, const void* res, int ldres, void* out, int ldo,

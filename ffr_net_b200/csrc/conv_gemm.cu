@@ -63,6 +63,28 @@ __device__ __forceinline__ void fast_divmod(int m, int d, float inv_d, int& q, i
 // ===================== Epilogue: TMEM -> registers -> fused ops -> global =====================
 // Runs on warps 0..7 (256 threads). Warp w reads TMEM lanes 32*(w%4).. (tile rows) and the column half w/4.
 // A work item is SUB consecutive 128-row tiles (SUB accumulators side by side in the TMEM buffer).
+// EPI_PIXMAJOR: M tile -> (output pixel, first image, mask of taps whose source pixel exists)
+struct PixTile { int ho, wo, img0; uint32_t tapmask; };
+__device__ __forceinline__ PixTile pix_tile(const ConvGemmParams& p, int m_tile) {
+    PixTile t;
+    const int q = m_tile / p.pix_iblocks;
+    t.img0 = (m_tile - q * p.pix_iblocks) * BLOCK_M;
+    const int qh = q / p.pix_side;
+    t.ho = qh + p.pix_off;
+    t.wo = q - qh * p.pix_side + p.pix_off;
+    t.tapmask = 0;
+    for (int tap = 0; tap < p.ntaps; ++tap) {
+        const int r = (p.ntaps == 9) ? tap / 3 : 1, s = (p.ntaps == 9) ? tap % 3 : 1;
+        const int hs = t.ho + r - 1, ws = t.wo + s - 1;
+        if (hs >= p.pix_src_lo && hs <= p.pix_src_hi && ws >= p.pix_src_lo && ws <= p.pix_src_hi) t.tapmask |= 1u << tap;
+    }
+    return t;
+}
+
+__device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 template <int BN, int SUB>
 __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uint32_t tmem_base, uint64_t* tfull_bar,
                                               uint64_t* tempty_bar, float* sparam, const int warp, const int lane) {
@@ -104,11 +126,21 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
 
 #pragma unroll 1
         for (int sub = 0; sub < SUB; ++sub) {
-        const int m = (m_group * SUB + sub) * BLOCK_M + row_in_tile;
+        int m = (m_group * SUB + sub) * BLOCK_M + row_in_tile;
         int n_img = 0, h = 0, w = 0, r_local = 0;
         bool valid = m < p.M;
         int cls = 0;
-        if (flags & EPI_GEOM) {
+        if (flags & EPI_PIXMAJOR) {              // row = image (img0 + row_in_tile) at the tile's pixel
+            const PixTile pt = pix_tile(p, m_group);
+            n_img = pt.img0 + row_in_tile;
+            r_local = pt.ho * p.Wp + pt.wo;
+            m = n_img * p.rows_per_img + r_local;
+            valid = n_img < p.n_img;
+            if (!valid) m = p.M;                 // keeps every "m < p.M" guard below false
+            h = pt.ho - p.h0;
+            w = pt.wo - p.h0;
+            if ((flags & EPI_GEOM) && !(flags & EPI_SCATTER)) valid = valid && h >= 0 && h < p.S && w >= 0 && w < p.S;
+        } else if (flags & EPI_GEOM) {
             if (small_m) {
                 fast_divmod(m, p.rows_per_img, inv_rpi, n_img, r_local);
                 fast_divmod(r_local, p.Wp, inv_wp, h, w);
@@ -280,7 +312,13 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
                 atomicAdd(p.stats + nc0 + c0 + lane, s1);
                 atomicAdd(p.stats + p.Cout + nc0 + c0 + lane, s2);
             }
-            if (flags & EPI_POOL) {    // x is already zero on invalid rows
+            if ((flags & EPI_POOL) && (flags & EPI_PIXMAJOR)) {   // every row is a different image
+                if (valid) {
+                    float* o = p.pool + (long long)n_img * p.Cout + nc0 + c0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) red_add_f32x4(o + q * 4, x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
+                }
+            } else if (flags & EPI_POOL) {    // x is already zero on invalid rows
                 if (n_lo == n_hi) {
                     const float s = warp_colsum32(x, lane);
                     if (n_lo < p.n_img) atomicAdd(p.pool + (long long)n_lo * p.Cout + nc0 + c0 + lane, s);
@@ -374,6 +412,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int m_tile = t / p.num_n_tiles;
             const int m0 = m_tile * BLOCK_M;
             const int b_row = n_tile * BN + m_tile * p.b_rows_per_mtile;
+            if (p.flags & EPI_PIXMAJOR) {        // A tile = 128 images at the tap's source pixel; taps outside are skipped
+                const PixTile pt = pix_tile(p, m_tile);
+                for (int tap = 0; tap < p.ntaps; ++tap) {
+                    if (!((pt.tapmask >> tap) & 1u)) continue;
+                    const int r = (p.ntaps == 9) ? tap / 3 : 1, s = (p.ntaps == 9) ? tap % 3 : 1;
+                    for (int c = 0; c < p.kb_per_tap; ++c) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        if (elect_one_sync()) {
+                            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                            tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], p.tap_ch_off[tap] + c * BLOCK_K,
+                                        pt.wo + s - 1, pt.ho + r - 1, pt.img0);
+                            tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage],
+                                        (tap * p.kb_per_tap + c) * BLOCK_K, b_row);
+                        }
+                        __syncwarp();
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+                continue;
+            }
             const int kb0 = split * p.kb_per_split;
             const int kb1 = min(kb0 + p.kb_per_split, kb_total);
             int tap = kb0 / p.kb_per_tap;
@@ -400,8 +458,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int it = 0;
         for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++it) {
             const int split = work % p.num_splits;
-            const int kb0 = split * p.kb_per_split;
-            const int kb1 = min(kb0 + p.kb_per_split, kb_total);
+            int kb0 = split * p.kb_per_split;
+            int kb1 = min(kb0 + p.kb_per_split, kb_total);
+            if (p.flags & EPI_PIXMAJOR) {        // the producer streams only the taps whose source pixel exists
+                kb0 = 0;
+                kb1 = __popc(pix_tile(p, (work / p.num_splits) / p.num_n_tiles).tapmask) * p.kb_per_tap;
+            }
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -670,19 +732,59 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
 // Host entry used by every C-ABI wrapper. `a`: activation matrix [a_rows, a_ld]; `wp`: packed weights
 // [Cout, ntaps*Cin]. Fills the tiling fields of `p` (M, Cout, ntaps, kb_per_tap, taps, geometry and epilogue
 // fields must be set by the caller).
+// Pixel-major tiles pay off once 49 pixel tiles of 128 images undercut the row-major tile count (81 rows per image, of
+// which 32 are halo) by more than what the sliding-window kernel wins back (~8 %): n >= ~96 except just above a
+// multiple of 128. g_pix_mode: -1 = this rule, 0 / 1 = forced off / on (ffr_debug_set_pixmajor, tests and tuning).
+static int g_pix_mode = -1;
+void set_pixmajor_mode(int mode) { g_pix_mode = mode; }
+bool pixmajor_profitable(int n_img) {
+    if (g_pix_mode >= 0) return g_pix_mode != 0;
+    const long long pix = 49LL * ((n_img + BLOCK_M - 1) / BLOCK_M);
+    const long long rowmajor = (81LL * n_img + BLOCK_M - 1) / BLOCK_M;
+    return pix * 108 < rowmajor * 100;
+}
+
+// same question for a contraction over pixels in k-blocks of 64 rows (wgrad): 49 * ceil(n/64) against ceil(81 n / 64)
+bool pixmajor_profitable_k64(int n_img) {
+    if (g_pix_mode >= 0) return g_pix_mode != 0;
+    return 49LL * ((n_img + 63) / 64) * 105 < ((81LL * n_img + 63) / 64) * 100;
+}
+
 int conv_gemm_launch(const void* a, long long a_rows, int a_cols, int a_ld, const void* wp, int Cin, ConvGemmParams p,
                      int num_splits, cudaStream_t stream) {
     p.dbg = g_dbg;
     FFR_CHECK_ARG(Cin % BLOCK_K == 0, "conv_gemm: Cin=%d not a multiple of 64", Cin);
     FFR_CHECK_ARG(p.Cout % 64 == 0, "conv_gemm: Cout=%d not a multiple of 64", p.Cout);
     FFR_CHECK_ARG(p.ntaps >= 1 && p.ntaps <= 9, "conv_gemm: ntaps=%d", p.ntaps);
-    const int BN = (p.Cout % 256 == 0) ? 256 : ((p.Cout % 128 == 0) ? 128 : 64);
+    int BN = (p.Cout % 256 == 0) ? 256 : ((p.Cout % 128 == 0) ? 128 : 64);
+    const bool pix = (p.flags & EPI_PIXMAJOR) != 0;
+    if (pix) {
+        FFR_CHECK_ARG(p.rows_per_img == 81 && p.Wp == 9 && p.n_img > 0 && (p.ntaps == 9 || p.ntaps == 1) &&
+                      num_splits <= 1 && p.b_rows_per_mtile == 0, "conv_gemm: pixel-major tiles need an H9 map");
+        const bool dgrad = (p.flags & EPI_PIX_DGRAD) != 0;
+        p.pix_iblocks = (p.n_img + BLOCK_M - 1) / BLOCK_M;
+        p.pix_side = dgrad ? 9 : 7;
+        p.pix_off = dgrad ? 0 : 1;
+        p.pix_src_lo = dgrad ? 1 : 0;
+        p.pix_src_hi = dgrad ? 7 : 8;
+        p.M = p.n_img * 81;
+        // N tile: fewest (waves x cycles per MMA) over the SMs; the measured issue rates are 128 / 64 / 48 cycles
+        const int m_tiles = p.pix_side * p.pix_side * p.pix_iblocks;
+        long long best = -1;
+        const int cand[3] = {256, 128, 64}, rate[3] = {128, 64, 48};
+        for (int i = 0; i < 3; ++i) {
+            if (p.Cout % cand[i]) continue;
+            const long long tiles = (long long)m_tiles * (p.Cout / cand[i]);
+            const long long cost = ((tiles + num_sms() - 1) / num_sms()) * (rate[i] + 8);
+            if (best < 0 || cost < best) { best = cost; BN = cand[i]; }
+        }
+    }
     p.kb_per_tap = Cin / BLOCK_K;
     const int kb_total = p.ntaps * p.kb_per_tap;
     if (num_splits < 1) num_splits = 1;
     p.kb_per_split = (kb_total + num_splits - 1) / num_splits;
     p.num_splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
-    p.num_m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+    p.num_m_tiles = pix ? p.pix_side * p.pix_side * p.pix_iblocks : (p.M + BLOCK_M - 1) / BLOCK_M;
     p.num_n_tiles = p.Cout / BN;
     FFR_CHECK_ARG(p.num_splits == 1 || (p.flags & EPI_OUT_F32_ATOMIC), "conv_gemm: split-K needs the atomic epilogue");
     if (p.flags & EPI_SCATTER)
@@ -702,6 +804,15 @@ int conv_gemm_launch(const void* a, long long a_rows, int a_cols, int a_ld, cons
     if (rc) return rc;
 
     int G = 0;
+    if (pix) {
+        rc = make_tmap_h9_pixel_bf16(&tmA, a, (uint64_t)p.n_img, (uint64_t)a_cols, (uint64_t)a_ld, BLOCK_M);
+        if (rc) return rc;
+        switch (BN) {
+            case 256: return launch_cfg<256>(tmA, tmB, p, grid, stream);
+            case 128: return launch_cfg<128>(tmA, tmB, p, grid, stream);
+            default:  return launch_cfg<64>(tmA, tmB, p, grid, stream);
+        }
+    }
     if (window_eligible(p, &G)) {
         WinCfg wc;
         wc.G = G;

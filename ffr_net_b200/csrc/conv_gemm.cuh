@@ -32,6 +32,11 @@ enum EpiFlags : uint32_t {
     EPI_COSFACE     = 1u << 12,  // rows = samples, columns = classes, accumulator = cosine: per row accumulate
                                  // sum_c exp(z_c - s) with z_c = s*(cos_c - m*[c == label]) (|cos| <= 1, so the fixed
                                  // shift s replaces the running maximum), record z_label and the arg-max of cos
+    EPI_PIXMAJOR    = 1u << 13,  // H9 maps only (rows_per_img 81, Wp 9): an M tile is 128 IMAGES at one pixel instead of
+                                 // 128 consecutive rows, so only the 49 interior pixels are computed (the H9 halo rows
+                                 // are 40 % of a row-major tile). A taps are 4-D TMA boxes (channel, w, h, image).
+    EPI_PIX_DGRAD   = 1u << 14,  // with EPI_PIXMAJOR: outputs cover all 81 grid points, and a tap is skipped when its
+                                 // source pixel is a halo point (the operand is zero there: dz of a reflection-padded conv)
 };
 
 struct ConvGemmParams {
@@ -63,6 +68,10 @@ struct ConvGemmParams {
     int scatter_n;         // 1..8
     int out_rows_per_img;  // rows per image of the destination matrix
     int b_rows_per_mtile;  // batched B: weight-matrix row offset added per M tile (0 = shared weights)
+    // EPI_PIXMAJOR (filled in by conv_gemm_launch)
+    int pix_iblocks;                // image blocks of 128 per pixel
+    int pix_side, pix_off;          // output pixels: side x side, starting at (off, off) in H9 coordinates
+    int pix_src_lo, pix_src_hi;     // a tap is skipped when its source pixel leaves [lo, hi]^2
     // EPI_COSFACE (AddMarginProduct + CrossEntropy, recnet.py:257-270, trainer.py:173-176)
     const int* ce_label;            // [M]
     float* ce_sumexp;               // [M], zeroed by the caller

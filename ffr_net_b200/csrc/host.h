@@ -32,6 +32,8 @@ long long launch_count();
 // (64 bf16 = 128 B = one SWIZZLE_128B row). Out-of-bounds elements read as zero.
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                       uint32_t box_rows, uint32_t box_cols = 64);
+int make_tmap_h9_pixel_bf16(CUtensorMap* out, const void* base, uint64_t n_img, uint64_t cols, uint64_t ld_elems,
+                            uint32_t box_imgs);
 
 int num_sms();
 

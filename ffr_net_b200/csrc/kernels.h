@@ -37,7 +37,11 @@ int normalize_bwd_launch(const float* x, const float* dxh, int rows, float* dx, 
 int self_similarity_launch(const float* x, int n, float* ss_space, float* ss_channel, cudaStream_t stream);
 int scale_f32_launch(const float* in, float* out, long long count, float scale, cudaStream_t stream);
 int wgrad_launch(const void* dz, int ld_dz, const void* x, int ld_x, int x_ch0, int P, int Cout, int Cin, int G,
-                 float* dw, cudaStream_t stream);
+                 float* dw, float* ws, cudaStream_t stream);
+void set_wgrad_splits(int s);
+void set_pixmajor_mode(int mode);
+bool pixmajor_profitable(int n_img);
+bool pixmajor_profitable_k64(int n_img);
 int bn_prelu_fwd_launch(const void* z, int ldz, const float* mean, const float* rstd, const float* gamma,
                         const float* beta, const float* slope, const void* res, int ldres, void* out, int ldo,
                         const int* scatter, int scatter_n, int n_img, int C, cudaStream_t stream);

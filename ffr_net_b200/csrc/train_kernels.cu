@@ -16,6 +16,7 @@ namespace ffr {
 // ------------------------------------------------------------------------------------------------------------
 // wgrad: dW[co][ci][t] += sum_p dz[p][co] * x[p + shift_t][ci]
 // ------------------------------------------------------------------------------------------------------------
+static int g_wgrad_splits = 0;      // > 0: override of the split heuristic (ffr_debug_set_wgrad_splits, tuning only)
 constexpr int WG_THREADS = 352;     // warps 0-7 epilogue, 8 TMEM alloc, 9 TMA, 10 MMA (same roles as conv_gemm.cu)
 constexpr int WG_STAGES = 4;
 constexpr int WG_BN = 256;          // ci tile
@@ -27,8 +28,14 @@ struct WgradParams {
     int m_tiles, n_tiles;  // over padded Cout (128) and padded Cin (256)
     int splits, kb_per_split, kb_total;
     int tap_shift[9];
-    float* dw;
+    int pix_iblocks;       // > 0: pixel-major contraction (k-block = 64 images at one interior pixel, 4-D TMA boxes)
+    float* ws;             // staging, fp32 [9][cout_p][cin_p] (tap-major so that a thread's 32 columns are contiguous)
+    int cout_p, cin_p;     // m_tiles * 128, n_tiles * WG_BN
 };
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 __device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t saddr) {   // LBO = 8192 B between 64-wide MN blocks, SBO = 1024 B
     return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(8192 >> 4) << 16) |
@@ -70,17 +77,29 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant__ C
             const int m_tile = w % p.m_tiles; w /= p.m_tiles;
             const int shift = p.tap_shift[w];
             const int kb0 = split * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+            const int tap_r = w / 3, tap_s = w - tap_r * 3;
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* s = smem + stage * WG_STAGE_BYTES;
                 if (elect_one_sync()) {
                     mbar_arrive_expect_tx(&full_bar[stage], WG_STAGE_BYTES);
-                    tma_load_2d(s, &tmDZ, &full_bar[stage], m_tile * 128, kb * 64);
-                    tma_load_2d(s + 8192, &tmDZ, &full_bar[stage], m_tile * 128 + 64, kb * 64);
+                    if (p.pix_iblocks > 0) {       // 64 images at interior pixel q: dz at (h, w), x at the tap's source
+                        const int q = kb / p.pix_iblocks, img0 = (kb - q * p.pix_iblocks) * 64;
+                        const int qh = q / 7, hh = qh + 1, ww = q - qh * 7 + 1;
+                        tma_load_4d(s, &tmDZ, &full_bar[stage], m_tile * 128, ww, hh, img0);
+                        tma_load_4d(s + 8192, &tmDZ, &full_bar[stage], m_tile * 128 + 64, ww, hh, img0);
 #pragma unroll
-                    for (int j = 0; j < WG_BN / 64; ++j)
-                        tma_load_2d(s + 16384 + j * 8192, &tmX, &full_bar[stage], n_tile * WG_BN + j * 64,
-                                    kb * 64 + shift);
+                        for (int j = 0; j < WG_BN / 64; ++j)
+                            tma_load_4d(s + 16384 + j * 8192, &tmX, &full_bar[stage], n_tile * WG_BN + j * 64,
+                                        ww + tap_s - 1, hh + tap_r - 1, img0);
+                    } else {
+                        tma_load_2d(s, &tmDZ, &full_bar[stage], m_tile * 128, kb * 64);
+                        tma_load_2d(s + 8192, &tmDZ, &full_bar[stage], m_tile * 128 + 64, kb * 64);
+#pragma unroll
+                        for (int j = 0; j < WG_BN / 64; ++j)
+                            tma_load_2d(s + 16384 + j * 8192, &tmX, &full_bar[stage], n_tile * WG_BN + j * 64,
+                                        kb * 64 + shift);
+                    }
                 }
                 __syncwarp();
                 if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
@@ -132,11 +151,20 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant__ C
                 tmem_ld_32x32(t_row + c0, v);
                 tmem_ld_wait();
                 const int ci0 = n_tile * WG_BN + chalf * (WG_BN / 2) + c0;
-                if (co < p.Cout) {
-                    float* o = p.dw + ((long long)co * p.Cin + ci0) * 9 + tap;
+                // one 128-byte run per thread: plain vector stores when the tile is complete, vector reductions
+                // (REDG.ADD.F32x4) when the pixel axis is split over several CTAs
+                float* o = p.ws + ((long long)tap * p.cout_p + co) * p.cin_p + ci0;
+                if (p.splits == 1) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (ci0 + j < p.Cin) atomicAdd(o + j * 9, __uint_as_float(v[j]));
+                    for (int q = 0; q < 8; ++q)
+                        reinterpret_cast<float4*>(o)[q] =
+                            make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
+                                        __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        red_add_v4(o + q * 4, __uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
+                                   __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
                 }
             }
             tc_fence_before();
@@ -148,29 +176,71 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant__ C
     if (warp == 8) { tc_fence_after(); tmem_dealloc<2 * WG_BN>(tmem_base); }
 }
 
-// dz: [P][ld_dz] bf16 (zeros on halo rows), x: [P][ld_x] bf16 H9 (with halo), dw: fp32 [Cout][Cin][3][3], pre-zeroed.
+// staging [9][cout_p][cin_p] -> dw [Cout][Cin][3][3] (OIHW); one CTA per output channel
+__global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restrict__ ws, int cout_p, int cin_p, int Cout, int Cin,
+                                                           float* __restrict__ dw) {
+    const int co = blockIdx.x;
+    for (int ci = threadIdx.x; ci < Cin; ci += blockDim.x) {
+        float v[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) v[t] = __ldg(ws + ((long long)t * cout_p + co) * cin_p + ci);
+        float* o = dw + ((long long)co * Cin + ci) * 9;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) o[t] = v[t];
+    }
+}
+
+// Work items = 9 taps x m_tiles x n_tiles x splits on a persistent grid: pick the split count that minimises
+// (waves over the SMs) x (k-blocks per item + a fixed per-item cost), so the big layers run in one or two full waves.
+static int wgrad_pick_splits(int base_work, int kb_total, int sms) {
+    int best = 1;
+    long long best_cost = -1;
+    const int max_splits = kb_total / 8 > 1 ? kb_total / 8 : 1;
+    for (int s = 1; s <= max_splits; ++s) {
+        const int kps = (kb_total + s - 1) / s;
+        const int real = (kb_total + kps - 1) / kps;
+        const long long waves = ((long long)base_work * real + sms - 1) / sms;
+        const long long cost = waves * (kps + 4) + (real > 1 ? 1 : 0);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = real; }
+    }
+    return best;
+}
+
+// dz: [P][ld_dz] bf16 (zeros on halo rows), x: [P][ld_x] bf16 H9 (with halo), dw: fp32 [Cout][Cin][3][3] (overwritten),
+// ws: fp32 staging of 9 * ceil128(Cout) * ceil256(Cin) elements.
 int wgrad_launch(const void* dz, int ld_dz, const void* x, int ld_x, int x_ch0, int P, int Cout, int Cin, int G,
-                 float* dw, cudaStream_t stream) {
+                 float* dw, float* ws, cudaStream_t stream) {
     WgradParams p;
-    p.P = P; p.Cout = Cout; p.Cin = Cin; p.dw = dw;
+    p.P = P; p.Cout = Cout; p.Cin = Cin; p.ws = ws;
     p.m_tiles = (Cout + 127) / 128;
     p.n_tiles = (Cin + WG_BN - 1) / WG_BN;
-    p.kb_total = (P + 63) / 64;
+    p.cout_p = p.m_tiles * 128;
+    p.cin_p = p.n_tiles * WG_BN;
+    const int n_img = P / 81;
+    const bool pix = (G == 9) && (P % 81 == 0) && pixmajor_profitable_k64(n_img);
+    p.pix_iblocks = pix ? (n_img + 63) / 64 : 0;
+    p.kb_total = pix ? 49 * p.pix_iblocks : (P + 63) / 64;
     const int base_work = 9 * p.m_tiles * p.n_tiles;
-    int splits = (2 * num_sms() + base_work - 1) / base_work;      // aim at >= 2 waves
-    if (splits > p.kb_total / 8) splits = p.kb_total / 8;
-    if (splits < 1) splits = 1;
+    int splits = wgrad_pick_splits(base_work, p.kb_total, num_sms());
+    if (g_wgrad_splits > 0) splits = g_wgrad_splits;
     p.kb_per_split = (p.kb_total + splits - 1) / splits;
     p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
     for (int r = 0; r < 3; ++r)
         for (int s = 0; s < 3; ++s) p.tap_shift[r * 3 + s] = (r - 1) * G + (s - 1);
     CUtensorMap tmDZ, tmX;
-    int rc = make_tmap_2d_bf16(&tmDZ, dz, (uint64_t)P, (uint64_t)ld_dz, (uint64_t)ld_dz, 64);
-    if (rc) return rc;
     // the x map starts at channel x_ch0 of a possibly wider (concatenated) matrix and exposes Cin padded to 64 columns
     const int cin_cols = (Cin + 63) / 64 * 64;
-    rc = make_tmap_2d_bf16(&tmX, reinterpret_cast<const __nv_bfloat16*>(x) + x_ch0, (uint64_t)P, (uint64_t)cin_cols,
-                           (uint64_t)ld_x, 64);
+    const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x) + x_ch0;
+    int rc;
+    if (pix) {
+        rc = make_tmap_h9_pixel_bf16(&tmDZ, dz, (uint64_t)n_img, (uint64_t)ld_dz, (uint64_t)ld_dz, 64);
+        if (rc) return rc;
+        rc = make_tmap_h9_pixel_bf16(&tmX, xb, (uint64_t)n_img, (uint64_t)cin_cols, (uint64_t)ld_x, 64);
+    } else {
+        rc = make_tmap_2d_bf16(&tmDZ, dz, (uint64_t)P, (uint64_t)ld_dz, (uint64_t)ld_dz, 64);
+        if (rc) return rc;
+        rc = make_tmap_2d_bf16(&tmX, xb, (uint64_t)P, (uint64_t)cin_cols, (uint64_t)ld_x, 64);
+    }
     if (rc) return rc;
     const int smem = 1024 + WG_STAGES * WG_STAGE_BYTES + 256;
     static bool attr = false;
@@ -178,11 +248,18 @@ int wgrad_launch(const void* dz, int ld_dz, const void* x, int ld_x, int x_ch0, 
         FFR_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr = true;
     }
+    if (p.splits > 1)
+        FFR_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 9ull * p.cout_p * p.cin_p, stream));
     const int num_work = base_work * p.splits;
     const int grid = num_work < num_sms() ? num_work : num_sms();
     wgrad_kernel<<<grid, WG_THREADS, smem, stream>>>(tmDZ, tmX, p);
-    return launch_status("wgrad_kernel");
+    rc = launch_status("wgrad_kernel");
+    if (rc) return rc;
+    wgrad_finish_kernel<<<Cout, 256, 0, stream>>>(ws, p.cout_p, p.cin_p, Cout, Cin, dw);
+    return launch_status("wgrad_finish_kernel");
 }
+
+void set_wgrad_splits(int s) { g_wgrad_splits = s; }
 
 // ------------------------------------------------------------------------------------------------------------
 // BatchNorm(batch statistics) + PReLU (+ residual) forward on the raw conv output z (rows of the H9 grid).

@@ -21,13 +21,18 @@ BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 ASSOCIATIVE_CONV4CHANNEL = True     # see forward_train
 
-_EPI_GEOM, _EPI_STATS = 0x8, 0x400
+_EPI_GEOM, _EPI_STATS, _EPI_PIXMAJOR, _EPI_PIX_DGRAD = 0x8, 0x400, 0x2000, 0x4000
 _TAPS9 = (ctypes.c_int * 9)(*[(r - 1) * 9 + (s - 1) for r in range(3) for s in range(3)])
 _ZERO9 = (ctypes.c_int * 9)(*([0] * 9))
 
 
 def _ceil64(c):
     return (c + 63) // 64 * 64
+
+
+def wgrad_workspace_elems(cout, cin):
+    """Per-tap staging elements ffr_wgrad3x3 needs: ceil128(Cout) * ceil256(Cin) (x9 taps)."""
+    return ((cout + 127) // 128 * 128) * ((cin + 255) // 256 * 256)
 
 
 def _pad1(t, n):
@@ -60,7 +65,11 @@ def _packed_weights(layer, weight, cin_p, cout_p):
 
 
 def _conv_gemm(lib, a, wp, cin, cout, m, n_img, flags, out, stats=None, geom=True):
-    """3x3 taps on the H9 grid (pitch 9); plain bf16 rows out."""
+    """3x3 taps on the H9 grid (pitch 9); plain bf16 rows out. Large batches use pixel-major tiles (128 images at one
+    pixel, csrc/conv_gemm.cuh EPI_PIXMAJOR): only the 49 interior pixels (forward) / the taps with a non-halo source
+    (dgrad, `flags` without geometry) are computed."""
+    if lib.ffr_pixmajor_profitable(n_img):
+        flags |= _EPI_PIXMAJOR | (0 if (flags & _EPI_GEOM) else _EPI_PIX_DGRAD)
     rc = lib.ffr_conv_gemm(_lib.ptr(a), a.shape[0], a.shape[1], a.stride(0), _lib.ptr(wp), cin, cout, 9, _TAPS9, _ZERO9,
                            m, 81, 9, 7, 1, n_img, flags, None, None, _lib.ptr(out), out.stride(0), 0, None, None, None,
                            0, _lib.ptr(stats), 1, None, 0, 0, 0, _lib.stream_ptr())
@@ -118,9 +127,10 @@ class _ConvLayerTrain(torch.autograd.Function):
                                         _lib.ptr(rstd), _lib.ptr(g_p), _lib.ptr(b_p), _lib.ptr(s_p), _lib.ptr(dy), cout_p,
                                         _lib.ptr(dres), cout_p, _lib.ptr(sums), _lib.ptr(dz), cout_p, n, cout_p,
                                         _lib.stream_ptr()), "ffr_bn_prelu_bwd")
-        dw = torch.zeros(cout, cin, 3, 3, dtype=torch.float32, device=dev)
+        dw = torch.empty(cout, cin, 3, 3, dtype=torch.float32, device=dev)
+        ws = torch.empty(9 * wgrad_workspace_elems(cout, cin), dtype=torch.float32, device=dev)
         _lib.check(lib.ffr_wgrad3x3(_lib.ptr(dz), cout_p, _lib.ptr(x_h9), cin_p, 0, n, cout, cin, _lib.ptr(dw),
-                                    _lib.stream_ptr()), "ffr_wgrad3x3")
+                                    _lib.ptr(ws), _lib.stream_ptr()), "ffr_wgrad3x3")
         dx = None
         if ctx.needs_input_grad[0]:
             # dgrad = the same shifted-row conv with spatially flipped, transposed weights: WT[ci][(8-t)*Cout_p + co]

@@ -51,6 +51,12 @@ typedef void* ffr_stream_t; /* cudaStream_t */
 #define FFR_EPI_RESIDUAL       (1u << 9)  /* + res[m][co] (bf16, same row grid) */
 #define FFR_EPI_STATS          (1u << 10) /* atomically add per-co sum and sum of squares of valid rows into stats[2][Cout] */
 #define FFR_EPI_OUT_F32        (1u << 11) /* plain fp32 rows to out_f32[M][Cout] */
+#define FFR_EPI_COSFACE        (1u << 12) /* internal to ffr_cosface_ce_fwd (softmax denominator / label logit / arg-max) */
+#define FFR_EPI_PIXMAJOR       (1u << 13) /* H9 maps (rows_per_img 81, Wp 9, 9 taps or 1): an M tile is 128 IMAGES at one
+                                             pixel, so only the 49 interior pixels are computed (n_img must be given);
+                                             rows of the result are addressed exactly as in the row-major mode */
+#define FFR_EPI_PIX_DGRAD      (1u << 14) /* with PIXMAJOR: outputs on all 81 grid points, taps whose source pixel is a halo
+                                             point are skipped (operand zero there: dz of a reflection-padded conv) */
 
 FFR_API int ffr_version(void);
 FFR_API const char* ffr_last_error(void);
@@ -148,12 +154,12 @@ FFR_API int ffr_scale_f32(const float* in, float* out, int64_t count, float scal
 
 /* ---- RecNet training (models/recnet.py ConvLayer in train mode, models/trainer.py:154-187) ------------------- */
 
-/* Weight gradient of ReflectionPad2d(1)+Conv2d(3x3) (autograd of recnet.py:82): dw[co][ci][r][s] +=
+/* Weight gradient of ReflectionPad2d(1)+Conv2d(3x3) (autograd of recnet.py:82): dw[co][ci][r][s] =
  * sum_p dz[p][co] * x[p + (r-1)*9 + (s-1)][x_ch0 + ci] over the P = n*81 rows of the H9 grid (dz is zero on halo rows).
- * dz [P][ld_dz] bf16, x [P][ld_x] bf16, dw fp32 [Cout][Cin][3][3]: ACCUMULATED with atomics (split-K), so the
- * caller zeroes it for a fresh gradient or leaves the running .grad in it to accumulate. */
+ * dz [P][ld_dz] bf16, x [P][ld_x] bf16, dw fp32 [Cout][Cin][3][3] (OVERWRITTEN). workspace: fp32 staging of
+ * 9 * ceil128(Cout) * ceil256(Cin) elements (tap-major partial sums; vector reductions when the pixel axis is split). */
 FFR_API int ffr_wgrad3x3(const void* dz, int ld_dz, const void* x, int ld_x, int x_ch0, int n, int Cout, int Cin,
-                         float* dw, ffr_stream_t stream);
+                         float* dw, float* workspace, ffr_stream_t stream);
 
 /* Train-mode BatchNorm2d (batch statistics) + PReLU (+ residual) on the raw conv output z (recnet.py:83-84,217):
  * a = prelu(gamma*(z-mean)*rstd+beta) (+res), scattered to H9 rows (own row + reflection mirrors / concat slot). */
@@ -237,6 +243,15 @@ FFR_API int ffr_debug_set_window(int enable);
 /* Debug/tuning: device buffer of 16 uint64 that the sliding-window kernel fills with per-role barrier-wait cycle
  * counts (summed over CTAs; slots in csrc/conv_gemm.cuh DbgSlot); NULL (default) disables the counters. */
 FFR_API int ffr_debug_set_counters(void* counters);
+
+/* 1 when H9 convolutions over n images run with pixel-major tiles (FFR_EPI_PIXMAJOR): the rule the library applies in
+ * ffr_recnet_convlayer_fwd and that callers of ffr_conv_gemm / ffr_wgrad3x3 on H9 maps should follow. */
+FFR_API int ffr_pixmajor_profitable(int n);
+/* Tests / tuning: -1 = the rule above, 0 = never, 1 = always. */
+FFR_API void ffr_debug_set_pixmajor(int mode);
+
+/* Tuning only: splits > 0 overrides the split-count heuristic of ffr_wgrad3x3 (0 restores it). */
+FFR_API void ffr_debug_set_wgrad_splits(int splits);
 
 /* Debug: hardware-semantics probe for row-offset UMMA descriptors (csrc/probe.cu); not on the product path.
  * a [256][64] bf16, w [64][64] bf16, out [128][64] fp32 = a[row_off : row_off+128] @ w^T. */

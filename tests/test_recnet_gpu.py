@@ -140,3 +140,27 @@ def test_chunked_streams_match_single_stream(models, monkeypatch):
             assert dy <= 1e-2 and df <= 1e-3 and dv <= 1e-2
             assert dr <= 1e-5 + 1e-6 and dm <= 1e-2
 
+
+
+@pytest.mark.parametrize("n", [3, 130])
+def test_recnet_eval_pixmajor_tiles(lib, models, n):
+    """Pixel-major tiles (128 images at one pixel, EPI_PIXMAJOR) against row-major tiles on the same input (the K axis is
+    walked tap-major instead of chunk-major, so fp32 sums round differently and single bf16 ulps flip: compared within
+    the bf16 bound), and against the oracle. n=130 exercises a second, mostly empty image block."""
+    sd, m = models
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(n, 512, 7, 7, generator=g) * 0.3
+    try:
+        with torch.no_grad():
+            lib.ffr_debug_set_pixmajor(0)
+            v0, map0 = m(x.cuda())
+            lib.ffr_debug_set_pixmajor(1)
+            v1, map1 = m(x.cuda())
+            torch.cuda.synchronize()
+    finally:
+        lib.ffr_debug_set_pixmajor(-1)
+    print("pixmajor vs rowmajor: map %.2e v %.2e" % (_rel(map1, map0), _rel(v1, v0)))
+    assert _rel(map1, map0) <= 1e-2 and _rel(v1, v0) <= 1e-2
+    if n <= 8:
+        v_ref, map_ref = orr.recnet_forward(sd, x)
+        assert _rel(v1.cpu(), v_ref) <= 1e-2 and _rel(map1.cpu(), map_ref) <= 1e-2

@@ -14,11 +14,20 @@ from ffr_net_b200.recnet import RecNet
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["rowmajor", "pixmajor"])
+def tile_mode(request, lib):
+    """Runs a test with the H9 convolutions forced to row-major tiles (128 consecutive rows, sliding window) and to
+    pixel-major tiles (128 images at one pixel; what batches >= ~96 use) — ffr_debug_set_pixmajor."""
+    lib.ffr_debug_set_pixmajor(1 if request.param == "pixmajor" else 0)
+    yield request.param
+    lib.ffr_debug_set_pixmajor(-1)
+
+
 def rel_l2(a, b):
     return ((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)).item()
 
 
-def test_wgrad_and_dgrad_kernels(lib):
+def test_wgrad_and_dgrad_kernels(lib, tile_mode):
     """ffr_wgrad3x3 and the flipped-weight dgrad against autograd of F.conv2d(reflect-padded) on bf16 operands."""
     import torch.nn.functional as F
     from ffr_net_b200 import recnet_train as rt
@@ -33,8 +42,10 @@ def test_wgrad_and_dgrad_kernels(lib):
     z.backward(dzb)
     x_h9 = rt._NchwToH9.apply(x.cuda(), 128)
     dz_h9 = rt._H9ToNchw.backward(type("c", (), {"dims": (n, cout, 64)}), dz.cuda())[0]       # zero-halo H9
-    dw = torch.zeros(cout, cin, 3, 3, device="cuda")
-    _lib.check(lib.ffr_wgrad3x3(_lib.ptr(dz_h9), 64, _lib.ptr(x_h9), 128, 0, n, cout, cin, _lib.ptr(dw), _lib.stream_ptr()))
+    dw = torch.full((cout, cin, 3, 3), 7.0, device="cuda")                                   # overwritten, not accumulated
+    ws = torch.empty(9 * rt.wgrad_workspace_elems(cout, cin), device="cuda")
+    _lib.check(lib.ffr_wgrad3x3(_lib.ptr(dz_h9), 64, _lib.ptr(x_h9), 128, 0, n, cout, cin, _lib.ptr(dw), _lib.ptr(ws),
+                                _lib.stream_ptr()))
     torch.cuda.synchronize()
     assert rel_l2(dw.cpu(), wr.grad) <= 5e-3
     wt = torch.zeros(128, 3, 3, 64, dtype=torch.bfloat16, device="cuda")
@@ -48,7 +59,7 @@ def test_wgrad_and_dgrad_kernels(lib):
 
 
 @pytest.mark.parametrize("cin,cout,with_res", [(128, 128, True), (192, 49, False), (1536, 512, False)])
-def test_convlayer_train_function(lib, cin, cout, with_res):
+def test_convlayer_train_function(lib, cin, cout, with_res, tile_mode):
     """One train-mode ConvLayer (+ residual) through the autograd Function vs torch autograd in fp32 on the same
     bf16-rounded input: output and all five gradients."""
     import torch.nn.functional as F
@@ -148,7 +159,7 @@ def test_recnet_train_forward_matches_oracle(models):
     assert int(sd["Conv4Merge.0.norm.norm.num_batches_tracked"]) == 1
 
 
-def test_train_step_gradients_match_oracle(lib):
+def test_train_step_gradients_match_oracle(lib, tile_mode):
     """Full Trainer.forward + backward (2 encoder fwd, 2 RecNet fwd with label, 4 losses, backward).
 
     Two comparisons, RecNet fed with the oracle's backbone outputs so that only RecNet + losses are under test:

@@ -64,11 +64,37 @@ def trainer_grads(fused, feats, rsd, bsd, a, b, label):
     return outs, {k: p.grad.clone() for k, p in rec.named_parameters()}, [float(l.detach()) for l in tr.loss_items]
 
 
+def backward_twice(rsd, bsd, a, b, label, fused):
+    """One forward, two backward passes over the SAME saved graph: isolates the backward kernels' reproducibility."""
+    from ffr_net_b200.trainer import Trainer, default_opts
+    rec = RecNet()
+    rec.load_state_dict(rsd)
+    tr = Trainer(default_opts(fused_head=fused), recnet=rec, encoder_weights=bsd)
+    tr.set_input(a, b, label)
+    tr.forward()
+    orig = torch.Tensor.backward
+    torch.Tensor.backward = lambda self, *ar, **kw: orig(self, *ar, retain_graph=True, **kw)
+    try:
+        gs = []
+        for _ in range(2):
+            tr.optim.zero_grad(set_to_none=False)
+            tr.backward()
+            torch.cuda.synchronize()
+            gs.append({k: p.grad.clone() for k, p in rec.named_parameters()})
+    finally:
+        torch.Tensor.backward = orig
+    d = sorted(((rel(gs[1][k], gs[0][k]), k) for k in gs[0]), reverse=True)
+    print("backward twice on one saved forward (fused_head=%s): worst %s | median %.2e" %
+          (fused, ", ".join("%s %.2e" % (k, v) for v, k in d[:3]), d[len(d) // 2][0]))
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 4
     bsd, rsd = ob.synth_backbone_state_dict(0), orr.synth_recnet_state_dict(0)
     a, b = ob.synth_faces(n, seed=3).cuda(), ob.synth_faces(n, seed=3, masked=True).cuda()
     label = torch.randint(0, 10575, (n,), generator=torch.Generator().manual_seed(1)).cuda()
+    backward_twice(rsd, bsd, a, b, label, False)
+    backward_twice(rsd, bsd, a, b, label, True)
     feats = []
     base = None
     for tag, val in (("clean", None), ("clean2", None), ("poison=NaN", float("nan")), ("poison=1e4", 1.0e4),

@@ -41,6 +41,17 @@ os.makedirs("gpurun_out", exist_ok=True)
 txt = prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70)
 open("gpurun_out/train_profile.txt", "w").write(txt)
 print(txt)
+# kernels only (device-side events), with their share of the step
+from torch.autograd import DeviceType
+ks = [e for e in prof.key_averages() if e.device_type == DeviceType.CUDA]
+ks.sort(key=lambda e: -e.self_device_time_total)
+tot = sum(e.self_device_time_total for e in ks)
+lines = ["# kernels of one training step (256 pairs), device time %.3f ms over %d launches" %
+         (tot / 1e3, sum(e.count for e in ks)), "share,total_us,launches,kernel"]
+for e in ks[:60]:
+    lines.append("%.3f,%.1f,%d,%s" % (e.self_device_time_total / tot, e.self_device_time_total, e.count, e.key[:110]))
+open("gpurun_out/train_profile_kernels.csv", "w").write("\n".join(lines) + "\n")
+print("\n".join(lines[:45]))
 shp = prof.key_averages(group_by_input_shape=True).table(sort_by="cuda_time_total", row_limit=30, max_name_column_width=40)
 open("gpurun_out/train_profile_shapes.txt", "w").write(shp)
 import time
