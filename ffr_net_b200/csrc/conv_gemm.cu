@@ -34,7 +34,9 @@ __device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, 
     acc += clock64() - t0;
 }
 
-__device__ __forceinline__ float sigmoidf_fast(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// ex2.approx + rcp.approx (2 MUFU ops); an IEEE division here costs ~4x the whole epilogue of a K=64 GEMM
+// (tools/mchannel_bench.py: 369 us with, 138 us without the sigmoid before this change)
+__device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 // Column sums across the 32 lanes of a warp for 32 per-lane values: after the call lane L holds, in x[0],
 // sum over lanes of (their) x[L]. 31 shuffles (butterfly transpose-reduce).
