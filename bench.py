@@ -380,8 +380,9 @@ def _bench_train(args, enc, dev, world, rank, timed):
     return {"value": 2 * pairs_s, "unit": "img/s", "pairs_per_s": pairs_s, "ms_per_step": ms / k, "steps": k,
             "batch_pairs_per_gpu": pairs, "gflop_per_pair": 39.9, "launch_mode": mode, "tflops": pairs_s * 39.9 / 1e3,
             "grad_allreduce": ("nccl, one flat fp32 bucket of 29.9 M elements" if world > 1 else "none (1 GPU)"),
-            "note": "ConvLayer fwd/bwd (conv, dgrad, wgrad, BN/PReLU) and clip+Adam hand-written; Conv4Channel MLP, bmm, "
-                    "head and losses are ATen/cuBLAS ops this round", "losses": vals}
+            "note": "ConvLayer fwd/bwd (conv, dgrad, wgrad, BN/PReLU), CosFace head + cross-entropy fwd/bwd and clip+Adam "
+                    "hand-written; Conv4Channel MLP, per-sample matmuls and the similarity / triplet / MSE losses are "
+                    "ATen/cuBLAS ops under autograd", "losses": vals}
 
 
 def _ncu_traffic():
