@@ -47,6 +47,7 @@ _SIGNATURES = {
     "ffr_conv1x1_bn_fwd": (_i, [_p, _i, _i, _i, _p, _i, _p, _p, _p]),
     "ffr_subsample2": (_i, [_p, _p, _i, _i, _i, _p]),
     "ffr_stem_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _p]),
+    "ffr_stem_u8_fwd": (_i, [_p, _p, _i, _p, _p, _p, _p, _i, _i, _p]),
     "ffr_se_residual_fwd": (_i, [_p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _p]),
     "ffr_export_nchw_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "ffr_head_fwd": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),

@@ -178,6 +178,8 @@ class Backbone(nn.Module):
             raise RuntimeError("Backbone is frozen/forward-only (reference: models/trainer.py:75,79); call .eval()")
         if not x.is_cuda:
             raise RuntimeError("ffr_net_b200.Backbone runs only on CUDA (sm_100a); there is no CPU fallback")
+        if x.dtype == torch.uint8:
+            return self.forward_u8(x)
         if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != self.IMG or x.shape[3] != self.IMG:
             raise ValueError("expected input (N,3,112,112), got %s" % (tuple(x.shape),))
         if x.shape[0] == 0:                          # empty batch: nothing to launch
@@ -191,7 +193,32 @@ class Backbone(nn.Module):
                           lambda i, lo, hi: self.forward_internal(x[lo:hi], slot=i, out_y=y[lo:hi], out_f=f[lo:hi]))
         return y, f
 
-    def forward_internal(self, x, want_y=True, slot=0, out_y=None, out_f=None):
+    def forward_u8(self, img, flip=None, swap_rb=True):
+        """Decoded images in, preprocessing fused into the stem: img uint8 (N,112,112,3) HWC CUDA as PIL decodes them
+        (RGB); the reference's host pipeline — R/B channel swap (data/dataset.py:138-141), optional per-image
+        horizontal flip (dataset.py:149-152; `flip`: uint8/bool (N,) CUDA or None), ToTensor + Normalize(0.5, 0.5)
+        (data/dataloader.py:15-19) — runs inside the first kernel. Same outputs as forward(preprocessed fp32 NCHW)."""
+        if self.training:
+            raise RuntimeError("Backbone is frozen/forward-only (reference: models/trainer.py:75,79); call .eval()")
+        if not img.is_cuda or img.dtype != torch.uint8:
+            raise RuntimeError("forward_u8 expects a CUDA uint8 tensor; there is no CPU fallback")
+        if img.dim() != 4 or tuple(img.shape[1:]) != (self.IMG, self.IMG, 3):
+            raise ValueError("expected uint8 input (N,112,112,3), got %s" % (tuple(img.shape),))
+        n = img.shape[0]
+        y = torch.empty(n, 512, 7, 7, dtype=torch.float32, device=img.device)
+        f = torch.empty(n, 512, dtype=torch.float32, device=img.device)
+        if n == 0:
+            return y, f
+        img = img.contiguous()
+        if flip is not None:
+            flip = flip.to(device=img.device, dtype=torch.uint8).contiguous()
+        streams.fork_join(streams.chunk_bounds(n), img.device,
+                          lambda i, lo, hi: self.forward_internal(img[lo:hi], slot=i, out_y=y[lo:hi], out_f=f[lo:hi],
+                                                                  flip=None if flip is None else flip[lo:hi],
+                                                                  swap_rb=swap_rb))
+        return y, f
+
+    def forward_internal(self, x, want_y=True, slot=0, out_y=None, out_f=None, flip=None, swap_rb=True):
         """One chunk of images on the current stream. Returns (y, f, h) where h is the flat bf16 body output
         (N*64 rows x 512). `slot` picks the workspace (one per concurrent stream, streams.py); `out_y` / `out_f` are
         optional preallocated (contiguous) destinations."""
@@ -208,13 +235,18 @@ class Backbone(nn.Module):
                     e.record()
                     prof.append((what, e))
 
-        x = x.contiguous().float()
+        u8 = x.dtype == torch.uint8                # decoded HWC images: preprocessing fused into the stem
+        x = x.contiguous() if u8 else x.contiguous().float()
         n, dev = x.shape[0], x.device
         pk = self._pack(dev)
         ws = self._workspace(n, dev, slot)
         st = _lib.stream_ptr()
         S = self.IMG
-        L.check(lib.ffr_stem_fwd(P(x), P(pk.stem_w), P(pk.stem_b), P(pk.stem_a), P(ws.a), n, S, st), "stem")
+        if u8:
+            L.check(lib.ffr_stem_u8_fwd(P(x), P(flip), 1 if swap_rb else 0, P(pk.stem_w), P(pk.stem_b), P(pk.stem_a),
+                                        P(ws.a), n, S, st), "stem")
+        else:
+            L.check(lib.ffr_stem_fwd(P(x), P(pk.stem_w), P(pk.stem_b), P(pk.stem_a), P(ws.a), n, S, st), "stem")
         cur, nxt = ws.a, ws.b
         for i, u in enumerate(pk.units):
             so = S // u.stride

@@ -153,6 +153,12 @@ FFR_API int ffr_stem_fwd(const float* x, const float* w, const float* b, const f
     return stem_launch(x, w, b, a, out, n_img, S, S_(stream));
 }
 
+FFR_API int ffr_stem_u8_fwd(const unsigned char* img, const unsigned char* flip, int swap_rb, const float* w,
+                            const float* b, const float* a, void* out, int n_img, int S, ffr_stream_t stream) {
+    FFR_CHECK_ARG(img && w && b && a && out, "ffr_stem_u8_fwd: null pointer");
+    return stem_u8_launch(img, flip, swap_rb, w, b, a, out, n_img, S, S_(stream));
+}
+
 FFR_API int ffr_se_residual_fwd(const void* u, const float* pool, const float* w1, const float* w2, const void* shortcut,
                         int shortcut_mode, void* y, int n_img, int S, int C, ffr_stream_t stream) {
     FFR_CHECK_ARG(u && pool && w1 && w2 && shortcut && y, "ffr_se_residual_fwd: null pointer");

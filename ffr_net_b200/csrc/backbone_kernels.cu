@@ -31,10 +31,23 @@ __device__ __forceinline__ void mma_16816_bf16(float (&c)[4], const uint32_t (&a
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
+// U8 = true: the input is the decoded image itself, uint8 HWC (N,S,S,3), and the reference's host preprocessing
+// (data/dataset.py:135-155 channel swap + horizontal flip, data/dataloader.py:15-19 ToTensor + Normalize(0.5, 0.5))
+// is applied on the fly: value = (u/255 - 0.5)/0.5 through a 256-entry table computed with IEEE division (bit-equal to
+// torchvision), source channel 2-ci when swap_rb, source column S-1-w for images whose flip flag is set.
+template <bool U8>
+__global__ void __launch_bounds__(128) stem_kernel(const void* __restrict__ xin, const unsigned char* __restrict__ flip,
+                                                   int swap_rb, const float* __restrict__ w,
                                                    const float* __restrict__ b, const float* __restrict__ a,
                                                    __nv_bfloat16* __restrict__ out, int n_img, int S) {
     __shared__ __align__(16) uint32_t stage[4][16 * 32];   // per warp: 16 rows x 64 bf16
+    __shared__ float lut[U8 ? 256 : 1];
+    const float* x = reinterpret_cast<const float*>(xin);
+    const unsigned char* xu = reinterpret_cast<const unsigned char*>(xin);
+    if (U8) {
+        for (int i = threadIdx.x; i < 256; i += 128) lut[i] = __fdiv_rn(__fdiv_rn((float)i, 255.0f) - 0.5f, 0.5f);
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, tig = lane & 3;
     const int G = S + 1;
@@ -63,7 +76,7 @@ __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ x, 
         if (k < 27) {
             const int ci = k / 9, r = (k % 9) / 3, s = k % 3;
             kdr[j] = r - 1; kds[j] = s - 1;
-            koff[j] = ci * (int)plane + (r - 1) * S + (s - 1);
+            koff[j] = U8 ? (swap_rb ? 2 - ci : ci) : ci * (int)plane + (r - 1) * S + (s - 1);
         } else { kdr[j] = 1 << 20; kds[j] = 0; koff[j] = 0; }
     }
     // epilogue constants for this thread's channels nt*8 + tig*2 + {0,1}
@@ -83,8 +96,9 @@ __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ x, 
         const long long m_base = tile * 16;
         // rows handled by this thread's fragments: m_base + g and m_base + g + 8
         const float* px[2];
+        const unsigned char* pu[2];
         int ph[2], pw[2];
-        bool pv[2];
+        bool pv[2], pf[2];
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
             const long long m = m_base + g + rr * 8;
@@ -94,6 +108,8 @@ __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ x, 
             pw[rr] = rem - ph[rr] * G;
             pv[rr] = (m < total) && ph[rr] < S && pw[rr] < S;
             px[rr] = x + (long long)n * 3 * plane + (long long)ph[rr] * S + pw[rr];
+            pu[rr] = xu + (long long)n * 3 * plane;
+            pf[rr] = U8 && flip != nullptr && pv[rr] && flip[n] != 0;
         }
         uint32_t af[2][4];
 #pragma unroll
@@ -108,7 +124,12 @@ __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ x, 
                         const int j = ks * 4 + h * 2 + e;
                         const int hh = ph[rr] + kdr[j], ww = pw[rr] + kds[j];
                         const bool ok = pv[rr] && hh >= 0 && hh < S && ww >= 0 && ww < S;
-                        v[e] = ok ? __ldg(px[rr] + koff[j]) : 0.f;
+                        if (U8) {
+                            const int ws = pf[rr] ? S - 1 - ww : ww;
+                            v[e] = ok ? lut[__ldg(pu[rr] + ((long long)hh * S + ws) * 3 + koff[j])] : 0.f;
+                        } else {
+                            v[e] = ok ? __ldg(px[rr] + koff[j]) : 0.f;
+                        }
                     }
                     // A fragment order: a0:(g, k lo) a1:(g+8, k lo) a2:(g, k hi) a3:(g+8, k hi)
                     af[ks][h * 2 + rr] = pack_bf16x2(v[0], v[1]);
@@ -150,8 +171,19 @@ int stem_launch(const float* x, const float* w, const float* b, const float* a, 
     long long grid = (tiles + 3) / 4;
     const long long cap = (long long)num_sms() * 16;
     if (grid > cap) grid = cap;
-    stem_kernel<<<(int)grid, 128, 0, stream>>>(x, w, b, a, reinterpret_cast<__nv_bfloat16*>(out), n_img, S);
+    stem_kernel<false><<<(int)grid, 128, 0, stream>>>(x, nullptr, 0, w, b, a, reinterpret_cast<__nv_bfloat16*>(out), n_img, S);
     return launch_status("stem_kernel");
+}
+
+int stem_u8_launch(const unsigned char* img, const unsigned char* flip, int swap_rb, const float* w, const float* b,
+                   const float* a, void* out, int n_img, int S, cudaStream_t stream) {
+    const long long total = (long long)n_img * (S + 1) * (S + 1);
+    const long long tiles = (total + 15) / 16;
+    long long grid = (tiles + 3) / 4;
+    const long long cap = (long long)num_sms() * 16;
+    if (grid > cap) grid = cap;
+    stem_kernel<true><<<(int)grid, 128, 0, stream>>>(img, flip, swap_rb, w, b, a, reinterpret_cast<__nv_bfloat16*>(out), n_img, S);
+    return launch_status("stem_kernel<u8>");
 }
 
 // ----------------------------------------------------------------------------------------------

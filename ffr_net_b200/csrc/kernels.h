@@ -10,6 +10,8 @@ int conv_gemm_launch(const void* a, long long a_rows, int a_cols, int a_ld, cons
                      int num_splits, cudaStream_t stream);
 int stem_launch(const float* x, const float* w, const float* b, const float* a, void* out, int n_img, int S,
                 cudaStream_t stream);
+int stem_u8_launch(const unsigned char* img, const unsigned char* flip, int swap_rb, const float* w, const float* b,
+                   const float* a, void* out, int n_img, int S, cudaStream_t stream);
 int se_residual_launch(const void* u, const float* pool, const float* w1, const float* w2, const void* sc,
                        int shortcut_mode, void* y, int n_img, int S, int C, cudaStream_t stream);
 int subsample2_launch(const void* x, void* out, int n_img, int So, int C, cudaStream_t stream);

@@ -320,7 +320,8 @@ class RecNet(nn.Module):
         The batch is cut into chunks that run concurrently on side streams (streams.py): the tail wave of one chunk's
         kernel is filled by the other chunk's next kernel, and HBM-bound passes overlap tensor-bound ones."""
         n = x.shape[0]
-        x = x.contiguous().float()
+        u8 = x.dtype == torch.uint8                # decoded HWC images (Backbone.forward_u8): channel swap, no flip
+        x = x.contiguous() if u8 else x.contiguous().float()
         v = torch.empty(n, 512, dtype=torch.float32, device=x.device)
         if n == 0:
             return v

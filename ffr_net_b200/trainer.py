@@ -12,6 +12,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn, optim
 
+from . import _lib
 from .backbone import Backbone
 from .head import FusedCE
 from .optim import FusedClipAdam
@@ -29,7 +30,8 @@ class TripletLoss(nn.Module):
 def default_opts(**kw):
     """The hyper-parameters run.py passes (run.py:10-28)."""
     o = types.SimpleNamespace(phase="train", lr=0.1, beta1=0.9, beta2=0.999, weight_decay=0.0, optimizer="adam",
-                              loss_weight=[1.0, 1.0, 1.0, 1.0], device="cuda", continue_train=False)
+                              loss_weight=[1.0, 1.0, 1.0, 1.0], device="cuda", continue_train=False,
+                              ckpt_dir="./checkpoints")
     for k, v in kw.items():
         setattr(o, k, v)
     return o
@@ -158,6 +160,18 @@ class Trainer:
         items.append(ce(self.pred_loss_non) / (1e-8 + self.opts.loss_weight[3]) + ce(self.pred_loss_ocl))
         self.loss_items = [l * w for l, w in zip(items, self.opts.loss_weight)]
         sum(self.loss_items).backward()
+
+    def save_model(self, file_name, extra_info=None):
+        """models/trainer.py:216-224 (`<ckpt_dir>/<file_name>.pth.gzip`)."""
+        from . import checkpoint
+        return checkpoint.save_model(self.recnet, self.optim, self.opts.ckpt_dir, file_name, extra_info)
+
+    def load_model(self, file_name):
+        """models/trainer.py:201-214; sets self.start_point like the reference."""
+        from . import checkpoint
+        self.start_point = checkpoint.load_model(self.recnet, self.opts.ckpt_dir, file_name,
+                                                 map_location=self.opts.device)
+        _lib.bump_weights_generation()
 
     def allreduce_gradients(self):
         """Average the RecNet/head gradients over ranks with one all-reduce of a flat fp32 bucket."""

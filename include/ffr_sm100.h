@@ -101,6 +101,13 @@ FFR_API int ffr_subsample2(const void* x, void* out, int n_img, int So, int C, f
 FFR_API int ffr_stem_fwd(const float* x, const float* w, const float* b, const float* a, void* out, int n_img, int S,
                  ffr_stream_t stream);
 
+/* The same layer fed by decoded images: img uint8 HWC (n,S,S,3). Applies the reference's host-side preprocessing on the
+ * fly — channel swap (data/dataset.py:138-141, swap_rb != 0: source channel 2-c), horizontal flip for images with
+ * flip[i] != 0 (dataset.py:149-152; flip may be NULL), ToTensor + Normalize(0.5,0.5) (data/dataloader.py:15-19):
+ * (u/255 - 0.5)/0.5 with IEEE division, bit-equal to torchvision. 4x less host->device traffic than fp32 NCHW. */
+FFR_API int ffr_stem_u8_fwd(const unsigned char* img, const unsigned char* flip, int swap_rb, const float* w,
+                            const float* b, const float* a, void* out, int n_img, int S, ffr_stream_t stream);
+
 /* SEModule gate + residual add (model_ir_se50.py:29-36,73-76): y = u*sigmoid(W2 relu(W1 mean(u))) + shortcut.
  * pool = per-(image,channel) sums of u; shortcut_mode 0: same-grid x, 1: x on the 2Sx2S grid (MaxPool2d(1,2)),
  * 2: same-grid conv shortcut. w1 [C/16][C], w2 [C][C/16] fp32. */

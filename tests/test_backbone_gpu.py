@@ -2,6 +2,7 @@
 
 Tolerance (BASELINE.json north_star): embeddings <= 1e-2 max relative error in bf16 against fp32, measured as
 max|e - e_ref| / max|e_ref| over the batch; pair cosine <= 1e-3 absolute."""
+import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
@@ -125,3 +126,51 @@ def test_empty_and_odd_batches(models):
     assert (f7[:3] - f3).abs().max().item() <= 1e-3
     with pytest.raises(ValueError):
         m(torch.zeros(2, 3, 96, 112, device="cuda"))
+
+
+def test_stem_u8_fused_preprocessing(lib):
+    """ffr_stem_u8_fwd (decoded uint8 HWC images, channel swap + per-image flip + ToTensor/Normalize fused) produces
+    bit-identical stem activations to ffr_stem_fwd on the oracle-preprocessed fp32 NCHW tensor."""
+    from oracle import preprocess as opp
+    from ffr_net_b200 import packing
+    sd = ob.synth_backbone_state_dict(0)
+    from ffr_net_b200.backbone import Backbone, _bn_fold
+    m = Backbone(50, 0.6, "ir_se")
+    m.load_state_dict(sd)
+    conv, bn, prelu = m.input_layer[0], m.input_layer[1], m.input_layer[2]
+    w, b = packing.pack_stem(conv.weight.detach(), _bn_fold(bn))
+    w, b, a = w.cuda(), b.cuda(), prelu.weight.detach().float().cuda()
+    for n, S in ((3, 16), (2, 112)):
+        imgs = opp.synth_images_u8(n, S, seed=9)
+        flips = np.array([1, 0, 1][:n], dtype=np.uint8)
+        for swap in (1, 0):
+            x = opp.preprocess_batch(imgs, flips, swap_rb=bool(swap)).cuda()
+            rows = n * (S + 1) * (S + 1)
+            o0 = torch.empty(rows, 64, dtype=torch.bfloat16, device="cuda")
+            o1 = torch.empty(rows, 64, dtype=torch.bfloat16, device="cuda")
+            st = _lib.stream_ptr()
+            _lib.check(lib.ffr_stem_fwd(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(a), _lib.ptr(o0), n, S, st))
+            iu, fl = torch.from_numpy(imgs).cuda(), torch.from_numpy(flips).cuda()
+            _lib.check(lib.ffr_stem_u8_fwd(_lib.ptr(iu), _lib.ptr(fl), swap, _lib.ptr(w), _lib.ptr(b), _lib.ptr(a),
+                                           _lib.ptr(o1), n, S, st))
+            torch.cuda.synchronize()
+            assert torch.equal(o0, o1)
+
+
+def test_backbone_forward_u8_matches_fp32_input(models):
+    """Backbone(uint8 NHWC) == Backbone(preprocess(uint8)) (no flip, channel swap as data/dataset.py:138-141)."""
+    from oracle import preprocess as opp
+    sd, m = models
+    imgs = opp.synth_images_u8(3, 112, seed=4)
+    x = opp.preprocess_batch(imgs).cuda()
+    with torch.no_grad():
+        y0, f0 = m(x)
+        y1, f1 = m(torch.from_numpy(imgs).cuda())
+        flips = torch.tensor([1, 0, 1], dtype=torch.uint8)
+        y2, f2 = m.forward_u8(torch.from_numpy(imgs).cuda(), flip=flips.cuda())
+        y3, f3 = m(opp.preprocess_batch(imgs, flips.numpy()).cuda())
+    # same kernels on bit-identical stem inputs: only the fp32 atomics order of the SE / head sums differs
+    assert (f1 - f0).abs().max().item() <= 1e-3 and (y1 - y0).abs().max().item() <= 1e-2 * y0.abs().max().item()
+    assert (f2 - f3).abs().max().item() <= 1e-3 and (y2 - y3).abs().max().item() <= 1e-2 * y3.abs().max().item()
+    assert (f2[1] - f0[1]).abs().max().item() <= 1e-3          # image 1 is not flipped
+    assert (f2[0] - f0[0]).abs().max().item() > 1e-3            # image 0 is

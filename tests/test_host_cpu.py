@@ -173,3 +173,34 @@ def test_chunk_bounds():
     assert streams.chunk_bounds(11, 3) == [(0, 11)]          # below FFR_MIN_CHUNK: one chunk
     assert streams.chunk_bounds(200, 3) == [(0, 67), (67, 134), (134, 200)]
     assert streams.chunk_bounds(0, 4) == [(0, 0)]
+
+
+def test_checkpoint_container_matches_reference(tmp_path):
+    """ffr_net_b200.checkpoint reads a file written by the real utils.save (golden), resolves 'latest' like
+    Trainer.load_model (models/trainer.py:201-214), and round-trips the {'RecNet','optimizer','epoch','iter'} layout
+    (non-strict load, optimizer state not restored)."""
+    import gzip
+    import os
+    import shutil
+    import torch
+    from ffr_net_b200 import checkpoint as ck
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiny_ckpt_ref.pth.gzip")
+    w = ck.load(gold)
+    g = torch.Generator().manual_seed(11)
+    assert w["epoch"] == 3 and w["iter"] == 1234 and int(w["RecNet"]["a.norm.num_batches_tracked"]) == 7
+    assert torch.equal(w["RecNet"]["a.weight"], torch.randn(3, 4, generator=g))
+    # save_model / load_model on a small module with the reference's container keys
+    net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.BatchNorm1d(3))
+    opt = torch.optim.Adam(net.parameters(), lr=0.1)
+    d = str(tmp_path)
+    p1 = ck.save_model(net, opt, d, "epoch_001", {"epoch": 1, "iter": 10})
+    with gzip.open(p1, "rb") as f:                                  # a gzip stream around a torch.save payload
+        assert f.read(2) in (b"PK", b"\x80\x02")
+    ck.save_model(net, opt, d, "latest", {"epoch": 2, "iter": 20})
+    shutil.copy(gold, os.path.join(d, "zz_other.bin"))             # not a *.pth.gzip: ignored by 'latest'
+    assert ck.resolve(d, "latest").endswith("latest.pth.gzip") and ck.resolve(d, "a/b") == "a/b.pth.gzip"
+    net2 = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.BatchNorm1d(3), torch.nn.Linear(3, 2))   # extra keys: strict=False
+    start = ck.load_model(net2, d, "latest")
+    assert start == {"epoch": 2, "iter": 20}
+    assert torch.equal(net2[0].weight, net[0].weight)
+    assert set(ck.load(p1).keys()) == {"RecNet", "optimizer", "epoch", "iter"}

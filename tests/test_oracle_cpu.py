@@ -103,3 +103,15 @@ def test_scoring_literal_equals_vectorised():
         assert [b for _, b in lit] == vec["test_acc"]
     thr = osc.thresholds_grid()
     assert len(thr) == 400 and thr[0] == -1.0 and thr[259] != 0.295      # not a round decimal
+
+
+def test_preprocess_oracle_matches_reference_golden():
+    """oracle.preprocess reproduces the real data/dataset.py CASIA.__getitem__ + dataloader transform bit for bit
+    (channel swap, flips drawn by the reference, ToTensor, Normalize)."""
+    from oracle import preprocess as opp
+    g = _load("preprocess_ref.npz")
+    assert np.array_equal(g["imgs"], opp.synth_images_u8(4, 16, seed=5))
+    got1 = opp.preprocess_batch(g["imgs"], g["flips"]).numpy()
+    got2 = opp.preprocess_batch(g["masks"], g["flips"]).numpy()
+    assert np.array_equal(got1, g["img1"]) and np.array_equal(got2, g["img2"])
+    assert g["flips"].any() and not g["flips"].all()

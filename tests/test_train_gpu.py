@@ -274,3 +274,33 @@ def test_cuda_graph_step_matches_eager(lib):
     assert float(graphed.optim._tables[0][4][1]) == float(eager.optim._tables[0][4][1]) == 3.0
     k = "Conv4Merge.0.norm.norm.num_batches_tracked"
     assert int(graphed.recnet.state_dict()[k]) == int(eager.recnet.state_dict()[k]) == 6
+
+
+def test_trainer_checkpoint_roundtrip(lib, tmp_path):
+    """Trainer.save_model / load_model (models/trainer.py:201-224): `<ckpt_dir>/<name>.pth.gzip` with the reference's
+    container keys; a fresh trainer that loads it continues from the same weights (the packed bf16 caches are rebuilt)."""
+    from ffr_net_b200 import checkpoint as ck
+    from ffr_net_b200.trainer import Trainer, default_opts
+    bsd, rsd = ob.synth_backbone_state_dict(0), orr.synth_recnet_state_dict(0)
+    a, b = ob.synth_faces(4, seed=3).cuda(), ob.synth_faces(4, seed=3, masked=True).cuda()
+    label = torch.tensor([5, 17, 10000, 3], device="cuda")
+    rec = RecNet()
+    rec.load_state_dict(rsd)
+    tr = Trainer(default_opts(lr=1e-3, ckpt_dir=str(tmp_path)), recnet=rec, encoder_weights=bsd)
+    tr.step(a, b, label)
+    path = tr.save_model("epoch_000_iter_000001", {"epoch": 0, "iter": 1})
+    w = ck.load(path, map_location="cpu")
+    assert set(w.keys()) == {"RecNet", "optimizer", "epoch", "iter"} and len(w["RecNet"]) == 121
+    rec2 = RecNet()
+    tr2 = Trainer(default_opts(lr=1e-3, ckpt_dir=str(tmp_path)), recnet=rec2, encoder_weights=bsd)
+    tr2.load_model("latest")
+    assert tr2.start_point == {"epoch": 0, "iter": 1}
+    for (k, p), (_, q) in zip(rec.state_dict().items(), rec2.state_dict().items()):
+        assert torch.equal(p, q), k
+    tr.recnet.eval()
+    tr2.recnet.eval()
+    with torch.no_grad():
+        y, _ = tr.encoder(a)
+        v1, _ = tr.recnet(y)
+        v2, _ = tr2.recnet(y)
+    assert (v1 - v2).abs().max().item() <= 1e-5 * v1.abs().max().item() + 1e-6

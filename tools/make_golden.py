@@ -51,8 +51,77 @@ def stub_missing():
             sys.modules[name] = _Stub(name)
 
 
+def golden_preprocess():
+    """data/dataset.py CASIA.__getitem__ (the REAL class, on a temporary PNG dataset) + the transform of
+    data/dataloader.py:15-19 -> tests/golden/preprocess_ref.npz."""
+    import random
+    import shutil
+    import tempfile
+    from PIL import Image
+    from torchvision import transforms
+    from oracle import preprocess as opp
+    try:
+        import cv2  # noqa: F401
+    except Exception:
+        sys.modules["cv2"] = _Stub("cv2")              # imported at module top by data/dataset.py, unused on this path
+    from data import dataset as rds
+    tmp = tempfile.mkdtemp(prefix="ffr_golden_ds_")
+    try:
+        size = 16
+        imgs = opp.synth_images_u8(4, size, seed=5)
+        masks = opp.synth_images_u8(4, size, seed=6)
+        os.makedirs(os.path.join(tmp, "id0"))
+        lines = []
+        for i in range(4):
+            os.makedirs(os.path.join(tmp, "p%d" % i))
+            Image.fromarray(imgs[i]).save(os.path.join(tmp, "p%d" % i, "%03d.png" % i))
+            Image.fromarray(masks[i]).save(os.path.join(tmp, "p%d" % i, "%03d_mask.png" % i))
+            lines.append("p%d/%03d.png %d" % (i, i, 100 + i))
+        lst = os.path.join(tmp, "list.txt")
+        open(lst, "w").write("\n".join(lines) + "\n")
+        tf_transform = transforms.Compose([transforms.ToTensor(),                      # data/dataloader.py:15-19
+                                           transforms.Normalize([0.5, 0.5, 0.5], [0.5, 0.5, 0.5])])
+        ds = rds.CASIA(tmp, lst, transform=tf_transform, shuffle=False, size=(size, size))
+        out1, out2, flips, labels = [], [], [], []
+        for i in range(4):
+            random.seed(40 + i)
+            flips.append(random.random() < 0.5)        # the draw __getitem__ makes (dataset.py:147-149)
+            random.seed(40 + i)
+            sample = ds[i]
+            out1.append(sample["img1"].numpy())
+            out2.append(sample["img2"].numpy())
+            labels.append(int(sample["label"]))
+        assert any(flips) and not all(flips), flips
+        np.savez_compressed(os.path.join(OUT, "preprocess_ref.npz"), imgs=imgs, masks=masks,
+                            flips=np.array(flips, dtype=np.uint8), img1=np.stack(out1), img2=np.stack(out2),
+                            labels=np.array(labels))
+        print("preprocess_ref.npz: flips", flips, "labels", labels)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def golden_checkpoint():
+    """A tiny checkpoint written by the REAL utils.save (utils/utils.py:110-115) with the container layout of
+    Trainer.save_model (models/trainer.py:216-224) -> tests/golden/tiny_ckpt_ref.pth.gzip."""
+    stub_missing()
+    try:
+        import cv2  # noqa: F401
+    except Exception:
+        sys.modules["cv2"] = _Stub("cv2")
+    from utils import utils as ru
+    g = torch.Generator().manual_seed(11)
+    obj = {"RecNet": {"a.weight": torch.randn(3, 4, generator=g), "a.norm.num_batches_tracked": torch.tensor(7)},
+           "optimizer": {"state": {}, "param_groups": [{"lr": 0.05, "betas": (0.9, 0.999), "params": [0]}]},
+           "epoch": 3, "iter": 1234}
+    ru.save(obj, os.path.join(OUT, "tiny_ckpt_ref.pth.gzip"))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "preprocess":
+        return golden_preprocess()
+    if len(sys.argv) > 1 and sys.argv[1] == "checkpoint":
+        return golden_checkpoint()
     torch.set_num_threads(os.cpu_count() or 1)
     from pretrain.model_ir_se50 import Backbone
     import models.recnet as mr
@@ -100,6 +169,10 @@ def main():
     with torch.no_grad():
         ss_s, ss_c = mr.selfSimilarity(fx)
     np.savez_compressed(os.path.join(OUT, "selfsim_ref.npz"), ss_space=ss_s.numpy(), ss_channel_slice=ss_c[:, ::16, ::16].numpy())
+
+    # ---- preprocessing, checkpoint container ----
+    golden_preprocess()
+    golden_checkpoint()
 
     # ---- scoring: the real lfw_eval functions on 6000 synthetic pairs ----
     stub_missing()
