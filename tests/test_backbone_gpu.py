@@ -8,6 +8,7 @@ import torch
 import torch.nn.functional as F
 
 from oracle import backbone as ob
+from ffr_net_b200 import _lib
 from ffr_net_b200.backbone import Backbone
 
 pytestmark = pytest.mark.gpu
