@@ -383,9 +383,10 @@ def _bench_train(args, enc, dev, world, rank, timed):
         tr.step(a, b, label)
 
     mode = "eager"
-    if world == 1 and not args.no_graph:
-        tr.capture_step(a, b, label, warmup=3)          # the whole iteration replayed as one CUDA graph
-        mode = "cuda-graph replay of the whole iteration"
+    if not args.no_graph:
+        tr.capture_step(a, b, label, warmup=3)          # the iteration replayed from CUDA graphs
+        mode = ("cuda-graph replay of the whole iteration" if world == 1 else
+                "cuda graphs: forward+backward into the flat gradient buffer | eager NCCL all-reduce | clip+Adam")
     for _ in range(2):
         step()
     k = max(3, min(args.steps, 8))
@@ -394,7 +395,8 @@ def _bench_train(args, enc, dev, world, rank, timed):
     pairs_s = world * pairs * k / (ms * 1e-3)
     return {"value": 2 * pairs_s, "unit": "img/s", "pairs_per_s": pairs_s, "ms_per_step": ms / k, "steps": k,
             "batch_pairs_per_gpu": pairs, "gflop_per_pair": 39.9, "launch_mode": mode, "tflops": pairs_s * 39.9 / 1e3,
-            "grad_allreduce": ("nccl, one flat fp32 bucket of 29.9 M elements" if world > 1 else "none (1 GPU)"),
+            "grad_allreduce": ("nccl, in place on one flat fp32 buffer of 29.9 M elements (gradients are views of it)"
+                               if world > 1 else "none (1 GPU)"),
             "note": "ConvLayer fwd/bwd (conv, dgrad, wgrad, BN/PReLU), CosFace head + cross-entropy fwd/bwd and clip+Adam "
                     "hand-written; Conv4Channel MLP, per-sample matmuls and the similarity / triplet / MSE losses are "
                     "ATen/cuBLAS ops under autograd", "losses": vals}

@@ -76,7 +76,9 @@ class Trainer:
         self.triplet = TripletLoss()
         self.cross_entropy = nn.CrossEntropyLoss()
         self._flat = None
+        self._flat_bound = False
         self._graph = None
+        self._graph_opt = None
         self._static = None
 
     # ------------------------------------------------------------------------------------------------------
@@ -93,12 +95,34 @@ class Trainer:
             for dst, src in zip(self._static, (img1, img2, label)):
                 dst.copy_(src, non_blocking=True)
             self._graph.replay()
+            if self._graph_opt is not None:            # data parallel: the exchange runs between the two graphs
+                self.allreduce_gradients()
+                self._graph_opt.replay()
         self.update_learning_rate()
 
-    def capture_step(self, img1, img2, label, warmup=3):
+    def bind_flat_gradients(self):
+        """Make every RecNet/head .grad a view into ONE flat fp32 buffer: the data-parallel exchange is then a single
+        all-reduce of that buffer with no pack / unpack copies (autograd accumulates into existing .grad in place)."""
+        params = [p for p in self.recnet.parameters() if p.requires_grad]
+        n = sum(p.numel() for p in params)
+        self._flat = torch.zeros(n, dtype=torch.float32, device=params[0].device)
+        off = 0
+        for p in params:
+            p.grad = self._flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self._flat_bound = True
+
+    def capture_step(self, img1, img2, label, warmup=3, split_optimizer=None):
+        """Record the iteration into CUDA graphs. One GPU: a single graph (forward, losses, backward, clip+Adam).
+        Data parallel: graph 1 = forward + backward into the flat gradient buffer, then the NCCL all-reduce of that
+        buffer runs eagerly on the same stream, then graph 2 = clip+Adam (models/trainer.py:182-187 order:
+        backward -> [reduce] -> clip -> step)."""
         import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            raise NotImplementedError("graph capture of the NCCL all-reduce is not enabled; use eager steps under DP")
+        dp = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if split_optimizer is not None:                # tests: exercise the two-graph path on one GPU
+            dp = bool(split_optimizer)
+        if dp and not self._flat_bound:
+            self.bind_flat_gradients()
         self._static = (img1.clone(), img2.clone(), label.clone())
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -113,7 +137,16 @@ class Trainer:
         with torch.cuda.graph(graph):
             self.set_input(*self._static)
             self.forward()
-            self.optimizer_parameters(0)
+            if dp:
+                self.optim.zero_grad(set_to_none=False)
+                self.backward()
+            else:
+                self.optimizer_parameters(0)
+        if dp:
+            graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph_opt, pool=graph.pool()):
+                self.optim.step()
+            self._graph_opt = graph_opt
         self._graph = graph
 
     def set_input(self, img1, img2, label):
@@ -174,9 +207,14 @@ class Trainer:
         _lib.bump_weights_generation()
 
     def allreduce_gradients(self):
-        """Average the RecNet/head gradients over ranks with one all-reduce of a flat fp32 bucket."""
+        """Average the RecNet/head gradients over ranks with one all-reduce of a flat fp32 bucket (in place when the
+        gradients are views of it, bind_flat_gradients; otherwise packed into and unpacked from it)."""
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        if getattr(self, "_flat_bound", False):
+            dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
+            self._flat.div_(dist.get_world_size())
             return
         params = [p for p in self.recnet.parameters() if p.grad is not None]
         n = sum(p.numel() for p in params)

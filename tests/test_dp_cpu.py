@@ -38,6 +38,25 @@ def _worker(rank, world, port, ret):
         dist.all_gather(parts, local[i])
         exp.append(sum(parts) / world)
     ok = all(torch.allclose(p.grad, e, atol=1e-6) for p, e in zip(net.parameters(), exp))
+    # flat-bound gradients (what capture_step uses under DP): .grad tensors are views of one buffer, autograd
+    # accumulates into them in place, and the exchange is a single in-place all-reduce with no copies
+    t2 = Trainer.__new__(Trainer)
+    net2 = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.PReLU(5), torch.nn.Linear(5, 3))
+    net2.load_state_dict(net.state_dict())
+    t2.recnet, t2._flat, t2._flat_bound = net2, None, False
+    t2.bind_flat_gradients()
+    x = torch.randn(4, 7, generator=g)
+    net2(x).square().sum().backward()
+    base = t2._flat.data_ptr()
+    ok = ok and all(p.grad.data_ptr() >= base and p.grad.data_ptr() < base + 4 * t2._flat.numel()
+                    for p in net2.parameters())
+    local2 = [p.grad.clone() for p in net2.parameters()]
+    ok = ok and all(float(l.abs().sum()) > 0 for l in local2)
+    t2.allreduce_gradients()
+    for i, p in enumerate(net2.parameters()):
+        parts = [torch.zeros_like(local2[i]) for _ in range(world)]
+        dist.all_gather(parts, local2[i])
+        ok = ok and torch.allclose(p.grad, sum(parts) / world, atol=1e-6)
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 

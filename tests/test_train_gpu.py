@@ -229,8 +229,11 @@ def test_train_step_gradients_match_oracle(lib, tile_mode):
     assert abs(float(vals["ClassifierLoss"]) - items_ref[3]) <= 2e-2 * items_ref[3]
 
 
-def test_cuda_graph_step_matches_eager(lib):
-    """Trainer.capture_step(): ONE replay of the captured iteration from a given state equals ONE eager iteration from
+@pytest.mark.parametrize("split", [False, True])
+def test_cuda_graph_step_matches_eager(lib, split):
+    """split=True: the data-parallel form (graph 1 = forward + backward into the flat gradient buffer, [all-reduce],
+    graph 2 = clip+Adam) exercised on one GPU.
+    Trainer.capture_step(): ONE replay of the captured iteration from a given state equals ONE eager iteration from
     the same state (parameters, BN buffers, Adam moments, step count) up to the round-off of the fp32 atomics.
     (Multi-step trajectories are not compared: Adam's sign-like update amplifies that round-off chaotically.)"""
     from ffr_net_b200.backbone import Backbone
@@ -248,7 +251,8 @@ def test_cuda_graph_step_matches_eager(lib):
     eager, graphed = make(), make()
     for _ in range(2):
         eager.step(img1, img2, label)
-    graphed.capture_step(img1, img2, label, warmup=2)
+    graphed.capture_step(img1, img2, label, warmup=2, split_optimizer=split)
+    assert (graphed._graph_opt is not None) == split and graphed._flat_bound == split
     # put `graphed` into exactly the state of `eager` (in place: the graph holds the tensor addresses)
     with torch.no_grad():
         for a, b in zip(graphed.recnet.parameters(), eager.recnet.parameters()):
