@@ -54,6 +54,7 @@ class Trainer:
             p.requires_grad = False
         self.encoder.to(dev).eval()
         self.recnet.to(dev)
+        self._flat, self._flat_bound = None, False
         if self.isTrain:
             self.recnet.train()
             params = [p for p in self.recnet.parameters() if p.requires_grad]
@@ -63,6 +64,8 @@ class Trainer:
             self.optim = FusedClipAdam(params, opts.lr, betas=(opts.beta1, opts.beta2),
                                        weight_decay=opts.weight_decay, clip_value=1.0)
             self.sch = optim.lr_scheduler.MultiStepLR(self.optim, [5000, 10000, 15000], gamma=0.5)
+            if dev.type == "cuda":
+                self.bind_flat_gradients()         # every .grad is a view of one flat buffer from the start
         else:
             self.recnet.eval()
         # The thin library-op remainder of the step (Conv4Channel MLP, per-sample matmuls, CosFace head; see
@@ -75,8 +78,6 @@ class Trainer:
         self.mse_loss = nn.MSELoss()
         self.triplet = TripletLoss()
         self.cross_entropy = nn.CrossEntropyLoss()
-        self._flat = None
-        self._flat_bound = False
         self._graph = None
         self._graph_opt = None
         self._static = None
@@ -99,6 +100,24 @@ class Trainer:
                 self.allreduce_gradients()
                 self._graph_opt.replay()
         self.update_learning_rate()
+
+    def zero_grad(self):
+        """One memset of the flat gradient buffer (76 tensors are views of it); per-tensor zeroing before it is bound."""
+        if self._flat_bound and self._grads_bound():
+            self._flat.zero_()
+        elif self._flat_bound:                         # someone replaced / dropped a .grad (e.g. zero_grad(set_to_none=True))
+            self.bind_flat_gradients()
+        else:
+            self.optim.zero_grad(set_to_none=False)
+
+    def _grads_bound(self):
+        off, base, ok = 0, self._flat.data_ptr(), True
+        for p in self.recnet.parameters():
+            if not p.requires_grad:
+                continue
+            ok = ok and p.grad is not None and p.grad.data_ptr() == base + 4 * off
+            off += p.numel()
+        return ok
 
     def bind_flat_gradients(self):
         """Make every RecNet/head .grad a view into ONE flat fp32 buffer: the data-parallel exchange is then a single
@@ -138,7 +157,7 @@ class Trainer:
             self.set_input(*self._static)
             self.forward()
             if dp:
-                self.optim.zero_grad(set_to_none=False)
+                self.zero_grad()
                 self.backward()
             else:
                 self.optimizer_parameters(0)
@@ -212,7 +231,7 @@ class Trainer:
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return
-        if getattr(self, "_flat_bound", False):
+        if getattr(self, "_flat_bound", False) and self._grads_bound():
             dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
             self._flat.div_(dist.get_world_size())
             return
@@ -232,7 +251,7 @@ class Trainer:
             off += p.numel()
 
     def optimizer_parameters(self, cur_iters=0):
-        self.optim.zero_grad(set_to_none=False)        # keep gradient storage (addresses are cached by the optimizer)
+        self.zero_grad()                               # keeps gradient storage (addresses are cached by the optimizer)
         self.backward()
         self.allreduce_gradients()                     # before clipping, as reduce-then-clip in the reference
         self.optim.step()                              # clip_grad_value_(1.0) + Adam, one fused launch

@@ -101,7 +101,7 @@ def test_trainer_fused_head_matches_library_head(lib):
         tr.encoder = _FixedEncoder()
         tr.set_input(a, b, label)
         tr.forward()
-        tr.optim.zero_grad(set_to_none=False)
+        tr.zero_grad()
         tr.backward()
         torch.cuda.synchronize()
         res.append(([float(l.detach()) for l in tr.loss_items], {k: p.grad.clone() for k, p in rec.named_parameters()},

@@ -195,7 +195,7 @@ def test_train_step_gradients_match_oracle(lib, tile_mode):
      tr.channel_non) = rec(tr.feat_map_non, tr.gt_label)
     (tr.f_ocl, tr.pred_loss_ocl, tr.pred_label_ocl, tr.M_space_ocl, tr.M_channel_ocl, tr.space_ocl,
      tr.channel_ocl) = rec(tr.feat_map_ocl, tr.gt_label)
-    tr.optim.zero_grad()
+    tr.zero_grad()
     tr.backward()
     torch.cuda.synchronize()
     items = [float(v) for v in tr.loss_items]
@@ -252,7 +252,7 @@ def test_cuda_graph_step_matches_eager(lib, split):
     for _ in range(2):
         eager.step(img1, img2, label)
     graphed.capture_step(img1, img2, label, warmup=2, split_optimizer=split)
-    assert (graphed._graph_opt is not None) == split and graphed._flat_bound == split
+    assert (graphed._graph_opt is not None) == split and graphed._flat_bound
     # put `graphed` into exactly the state of `eager` (in place: the graph holds the tensor addresses)
     with torch.no_grad():
         for a, b in zip(graphed.recnet.parameters(), eager.recnet.parameters()):

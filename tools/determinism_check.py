@@ -58,7 +58,7 @@ def trainer_grads(fused, feats, rsd, bsd, a, b, label):
     outs = {"f_non": tr.f_non.detach().clone(), "M_space_non": tr.M_space_non.detach().clone(),
             "M_channel_non": tr.M_channel_non.detach().clone(), "space_non": tr.space_non.detach().clone(),
             "channel_non": tr.channel_non.detach().clone(), "f_ocl": tr.f_ocl.detach().clone()}
-    tr.optim.zero_grad(set_to_none=False)
+    tr.zero_grad()
     tr.backward()
     torch.cuda.synchronize()
     return outs, {k: p.grad.clone() for k, p in rec.named_parameters()}, [float(l.detach()) for l in tr.loss_items]
@@ -77,7 +77,7 @@ def backward_twice(rsd, bsd, a, b, label, fused):
     try:
         gs = []
         for _ in range(2):
-            tr.optim.zero_grad(set_to_none=False)
+            tr.zero_grad()
             tr.backward()
             torch.cuda.synchronize()
             gs.append({k: p.grad.clone() for k, p in rec.named_parameters()})
