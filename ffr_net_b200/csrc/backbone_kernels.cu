@@ -36,7 +36,7 @@ __device__ __forceinline__ void mma_16816_bf16(float (&c)[4], const uint32_t (&a
 // is applied on the fly: value = (u/255 - 0.5)/0.5 through a 256-entry table computed with IEEE division (bit-equal to
 // torchvision), source channel 2-ci when swap_rb, source column S-1-w for images whose flip flag is set.
 template <bool U8>
-__global__ void __launch_bounds__(128) stem_kernel(const void* __restrict__ xin, const unsigned char* __restrict__ flip,
+__global__ void __launch_bounds__(128, 4) stem_kernel(const void* __restrict__ xin, const unsigned char* __restrict__ flip,
                                                    int swap_rb, const float* __restrict__ w,
                                                    const float* __restrict__ b, const float* __restrict__ a,
                                                    __nv_bfloat16* __restrict__ out, int n_img, int S) {

@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(512, 1) recnet_prep_kernel(const PrepParams p)
     float* A1s = W0a + 49 * 32;          // [32][32]
     float* A2s = A1s + 1024;             // [32][32]
     float* misc = A2s + 1024;            // b0, c1, c2 [3][32]
+    float* Gpart = misc + 96;            // [8][49*49] per-channel-slice partial Grams
     const int n = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* x = p.x + (long long)n * 512 * 49;
@@ -69,23 +70,42 @@ __global__ void __launch_bounds__(512, 1) recnet_prep_kernel(const PrepParams p)
     // The three phases below are bound by shared-memory instruction throughput (every FMA wants an operand from
     // smem), so each thread register-tiles its outputs: 4 Gram columns per row value, 7 pixels per weight value.
 
-    // spatial self-similarity Gram (49x49 over C): work item = (row i, block of 4 columns j0..j0+3)
-    for (int o = tid; o < 49 * 13; o += 512) {
-        const int i = o / 13, j0 = (o - i * 13) * 4;
-        const int j1 = min(j0 + 1, 48), j2 = min(j0 + 2, 48), j3 = min(j0 + 3, 48);
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
-        for (int c = 0; c < 512; ++c) {
+    // spatial self-similarity Gram (49x49 over C): work item = (7x7 output block, one eighth of the channels) on
+    // 392 threads — 49 FMAs per 14 shared-memory loads (the 4-column version spent half of the kernel here on LSU
+    // wavefronts); the eight channel slices go to their own shared-memory planes and are summed in a fixed order
+    // (deterministic: the embedding of an image must not depend on the run or on its batch)
+    if (tid < 392) {
+        const int item = tid % 49, split = tid / 49;
+        const int bi = (item / 7) * 7, bj = (item % 7) * 7;
+        float acc[7][7];
+#pragma unroll
+        for (int a = 0; a < 7; ++a)
+#pragma unroll
+            for (int q = 0; q < 7; ++q) acc[a][q] = 0.f;
+#pragma unroll 2
+        for (int c = split * 64; c < split * 64 + 64; ++c) {
             const float* xr = xs + c * 49;
-            const float xi = xr[i];
-            a0 = fmaf(xi, xr[j0], a0); a1 = fmaf(xi, xr[j1], a1);
-            a2 = fmaf(xi, xr[j2], a2); a3 = fmaf(xi, xr[j3], a3);
+            float va[7], vb[7];
+#pragma unroll
+            for (int q = 0; q < 7; ++q) { va[q] = xr[bi + q]; vb[q] = xr[bj + q]; }
+#pragma unroll
+            for (int a = 0; a < 7; ++a)
+#pragma unroll
+                for (int q = 0; q < 7; ++q) acc[a][q] = fmaf(va[a], vb[q], acc[a][q]);
         }
-        const float si = inv_s[i];
-        Gs[i * 49 + j0] = a0 * si * inv_s[j0];
-        if (j0 + 1 < 49) Gs[i * 49 + j0 + 1] = a1 * si * inv_s[j1];
-        if (j0 + 2 < 49) Gs[i * 49 + j0 + 2] = a2 * si * inv_s[j2];
-        if (j0 + 3 < 49) Gs[i * 49 + j0 + 3] = a3 * si * inv_s[j3];
+        float* gp = Gpart + split * 2401;
+#pragma unroll
+        for (int a = 0; a < 7; ++a)
+#pragma unroll
+            for (int q = 0; q < 7; ++q) gp[(bi + a) * 49 + bj + q] = acc[a][q];
+    }
+    __syncthreads();
+    for (int o = tid; o < 49 * 49; o += 512) {
+        const int i = o / 49, j = o - i * 49;
+        float g = 0.f;
+#pragma unroll
+        for (int sp = 0; sp < 8; ++sp) g += Gpart[sp * 2401 + o];
+        Gs[o] = g * inv_s[i] * inv_s[j];
     }
     // T[hw][j] = sum_c Xh[c][hw] * W0b[j][c]: work item = (7 consecutive pixels, j, half of the channel range);
     // the two halves are combined with shared-memory atomics (T zero-initialised first)
@@ -194,7 +214,7 @@ __global__ void __launch_bounds__(512, 1) recnet_prep_kernel(const PrepParams p)
 }
 
 int recnet_prep_launch(const PrepParams& p, int n, cudaStream_t stream) {
-    const int smem = (512 * 49 + 512 + 64 + 49 * 49 + 3 + 49 * 32 * 2 + 2048 + 96) * (int)sizeof(float);
+    const int smem = (512 * 49 + 512 + 64 + 49 * 49 + 3 + 49 * 32 * 2 + 2048 + 96 + 8 * 2401) * (int)sizeof(float);
     static bool attr = false;
     if (!attr) {
         FFR_CUDA(cudaFuncSetAttribute(recnet_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -332,35 +332,38 @@ bn_prelu_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, int ldda, const
                            const float* __restrict__ beta, const float* __restrict__ slope,
                            __nv_bfloat16* __restrict__ dy, int lddy, __nv_bfloat16* __restrict__ dres, int lddres,
                            float* __restrict__ sums, int n_img, int C) {
+    // 256 threads = 32 row lanes x 8 channel groups of 8 (16-byte accesses; a row's 64-channel slab is one 128-byte line)
     __shared__ float red[3][32][65];
     const int c0 = blockIdx.y * 64;
-    const int c2 = (threadIdx.x & 31) * 2;          // channel pair within the 64-channel slab
-    const int rlane = threadIdx.x >> 5;              // 8 row lanes
+    const int cg = (threadIdx.x & 7) * 8;            // first channel of this thread's group within the slab
+    const int rlane = threadIdx.x >> 3;              // 32 row lanes
     const long long rows = (long long)n_img * 49;
-    float s0[2] = {0, 0}, s1[2] = {0, 0}, s2[2] = {0, 0};
-    float m[2], rs[2], g[2], b[2], sl[2];
+    float s0[8], s1[8], s2[8], m[8], rs[8], g[8], b[8], sl[8];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int c = c0 + c2 + j;
+    for (int j = 0; j < 8; ++j) {
+        const int c = c0 + cg + j;
+        s0[j] = s1[j] = s2[j] = 0.f;
         m[j] = mean[c]; rs[j] = rstd[c]; g[j] = gamma[c]; b[j] = beta[c]; sl[j] = slope[c];
     }
-    for (long long pr = (long long)blockIdx.x * 8 + rlane; pr < rows; pr += (long long)gridDim.x * 8) {
+    for (long long pr = (long long)blockIdx.x * 32 + rlane; pr < rows; pr += (long long)gridDim.x * 32) {
         const int n = (int)(pr / 49), pix = (int)(pr - (long long)n * 49);
         const int r_local = (pix / 7 + 1) * 9 + (pix % 7 + 1);
-        float a[2] = {0, 0};
+        const long long row = (long long)n * 81 + r_local;
+        const uint4 zv = __ldg(reinterpret_cast<const uint4*>(z + row * ldz + c0 + cg));
+        float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int k = 0; k < scatter_n; ++k) {
             const int2 e = __ldg(scatter + r_local * scatter_n + k);
             if (e.x >= 0) {
-                const uint32_t u = *reinterpret_cast<const uint32_t*>(da + ((long long)n * 81 + e.x) * ldda + e.y + c0 + c2);
-                a[0] += bf16lo(u); a[1] += bf16hi(u);
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(da + ((long long)n * 81 + e.x) * ldda + e.y + c0 + cg));
+                a[0] += bf16lo(u.x); a[1] += bf16hi(u.x); a[2] += bf16lo(u.y); a[3] += bf16hi(u.y);
+                a[4] += bf16lo(u.z); a[5] += bf16hi(u.z); a[6] += bf16lo(u.w); a[7] += bf16hi(u.w);
             }
         }
-        const long long row = (long long)n * 81 + r_local;
-        const uint32_t zu = *reinterpret_cast<const uint32_t*>(z + row * ldz + c0 + c2);
-        const float zz[2] = {bf16lo(zu), bf16hi(zu)};
-        float d[2];
+        const float zz[8] = {bf16lo(zv.x), bf16hi(zv.x), bf16lo(zv.y), bf16hi(zv.y),
+                             bf16lo(zv.z), bf16hi(zv.z), bf16lo(zv.w), bf16hi(zv.w)};
+        float d[8];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < 8; ++j) {
             const float zh = (zz[j] - m[j]) * rs[j];
             const float y = zh * g[j] + b[j];
             d[j] = a[j] * (y > 0.f ? 1.f : sl[j]);
@@ -368,19 +371,22 @@ bn_prelu_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, int ldda, const
             s1[j] += d[j] * zh;
             s2[j] += a[j] * fminf(y, 0.f);
         }
-        *reinterpret_cast<uint32_t*>(dy + row * lddy + c0 + c2) = pack_bf16x2(d[0], d[1]);
-        if (dres) *reinterpret_cast<uint32_t*>(dres + row * lddres + c0 + c2) = pack_bf16x2(a[0], a[1]);
+        *reinterpret_cast<uint4*>(dy + row * lddy + c0 + cg) =
+            make_uint4(pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]), pack_bf16x2(d[4], d[5]), pack_bf16x2(d[6], d[7]));
+        if (dres)
+            *reinterpret_cast<uint4*>(dres + row * lddres + c0 + cg) =
+                make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
     }
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        red[0][rlane][c2 + j] = s0[j]; red[1][rlane][c2 + j] = s1[j]; red[2][rlane][c2 + j] = s2[j];
+    for (int j = 0; j < 8; ++j) {
+        red[0][rlane][cg + j] = s0[j]; red[1][rlane][cg + j] = s1[j]; red[2][rlane][cg + j] = s2[j];
     }
     __syncthreads();
     if (threadIdx.x < 192) {
         const int q = threadIdx.x / 64, c = threadIdx.x % 64;
         float t = 0.f;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) t += red[q][r][c];
+        for (int r = 0; r < 32; ++r) t += red[q][r][c];
         atomicAdd(sums + q * C + c0 + c, t);
     }
 }
@@ -429,8 +435,10 @@ int bn_prelu_bwd_launch(const void* da, int ldda, const int* scatter, int scatte
     FFR_CHECK_ARG(C % 64 == 0, "bn_prelu_bwd: C=%d", C);
     FFR_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 3 * C, stream));
     const long long rows = (long long)n_img * 49;
+    // ~8 CTAs per SM in total: enough rows in flight to cover the HBM latency, few enough atomics at the end
     int gx = (int)((rows + 63) / 64);
-    if (gx > num_sms() * 2) gx = num_sms() * 2;
+    const int cap = (num_sms() * 8 + C / 64 - 1) / (C / 64);
+    if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
     dim3 grid(gx, C / 64);
     bn_prelu_bwd_reduce_kernel<<<grid, 256, 0, stream>>>(
