@@ -33,6 +33,30 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert rc < 0 and b"null pointer" in lib.ffr_last_error()
     with pytest.raises(RuntimeError):
         _lib.check(rc, "conv")
+    # every family of entry points validates before it touches the device: negative code + message, no exception
+    one = ctypes.c_void_p(16)                                     # a non-null, never dereferenced "device pointer"
+    cases = [
+        (lambda: lib.ffr_conv_gemm(one, 128, 64, 64, one, 64, 64, 0, None, None, 128, 0, 0, 0, 0, 0, 0, None, None, one, 64, 0,
+                           None, None, None, 0, None, 1, None, 0, 0, 0, None), b"ntaps"),
+        (lambda: lib.ffr_conv_gemm(one, 128, 60, 60, one, 60, 64, 1, None, None, 128, 0, 0, 0, 0, 0, 0, None, None, one, 64, 0,
+                           None, None, None, 0, None, 1, None, 0, 0, 0, None), b"multiple of 64"),
+        (lambda: lib.ffr_conv_gemm(one, 128, 64, 64, one, 64, 64, 1, None, None, 128, 0, 0, 0, 0, 0, 0x1, None, None, one, 64, 0,
+                           None, None, None, 0, None, 1, None, 0, 0, 0, None), b"bias"),
+        (lambda: lib.ffr_conv_gemm(one, 81, 64, 64, one, 64, 64, 9, None, None, 81, 80, 9, 7, 1, 1, 0x2000, None, None, one, 64,
+                           0, None, None, None, 0, None, 1, None, 0, 0, 0, None), b"pixel-major"),
+        (lambda: lib.ffr_conv3x3_bnpre_prelu_fwd(one, 1, 13, 64, one, 64, one, one, one, 1, None), b"even S"),
+        (lambda: lib.ffr_cosface_pack(one, 5, 70, 0, one, None, 0, None), b"rows_pad"),
+        (lambda: lib.ffr_cosface_ce_fwd(one, 4, one, 300, 300, one, 30.0, 0.4, one, one, one, one, None), b"c_pad"),
+        (lambda: lib.ffr_cosface_ce_bwd(one, 320, 300, 4, 60, one, one, one, 30.0, 0.4, one, one, None), b"bad shape"),
+        (lambda: lib.ffr_wgrad3x3(one, 60, one, 64, 0, 1, 64, 64, one, one, None), b"pitches"),
+        (lambda: lib.ffr_self_similarity(one, 1, None, None, None), b"no output"),
+        (lambda: lib.ffr_stem_u8_fwd(None, None, 1, one, one, one, one, 1, 112, None), b"null pointer"),
+    ]
+    for call, needle in cases:
+        rc = call()
+        assert rc < 0 and needle in lib.ffr_last_error(), (rc, needle, lib.ffr_last_error())
+    assert lib.ffr_pixmajor_profitable(4) == 0 and lib.ffr_pixmajor_profitable(512) == 1
+    assert lib.ffr_pixmajor_profitable(130) == 0                  # a second, nearly empty image block does not pay
 
 
 def test_state_dict_layout_matches_reference():
