@@ -263,6 +263,18 @@ class Trainer:
         d["TrainAcc"] = "{:.4f}".format(self.accuracy)
         return d
 
+    def get_lr(self):
+        """models/trainer.py:226-227."""
+        return {"LR": "{:.6f}".format(self.lr)}
+
+    def get_pos(self):
+        """models/trainer.py:229-230: mean (1 - cos) of the positive pairs of the triplet term."""
+        return self.pos_loss
+
+    def get_neg(self):
+        """models/trainer.py:232-233."""
+        return self.neg_loss
+
     def update_learning_rate(self):
         self.sch.step()
         for g in self.optim.param_groups:
