@@ -30,6 +30,8 @@ _SIGNATURES = {
     "ffr_bn_prelu_fwd": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _p]),
     "ffr_bn_prelu_bwd": (_i, [_p, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _i, _p, _p, _i, _i, _i, _p]),
     "ffr_pack_conv3x3": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
+    "ffr_gallery_cosine": (_i, [_p, _i, _p, _i, _i, _p, _p, _p]),
+    "ffr_roc_hist": (_i, [_p, _i, _i, _i, _p, _p, _p, _i, _p, _p]),
     "ffr_cosface_pack": (_i, [_p, _i, _i, _i, _p, _p, _i, _p]),
     "ffr_cosface_ce_fwd": (_i, [_p, _i, _p, _i, _i, _p, ctypes.c_float, ctypes.c_float, _p, _p, _p, _p, _p]),
     "ffr_cosface_ce_finish": (_i, [_p, _p, _p, _i, ctypes.c_float, _p, _p, _p]),

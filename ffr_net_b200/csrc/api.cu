@@ -339,6 +339,32 @@ FFR_API int ffr_normalize_bwd(const float* x, const float* dxh, int rows, float*
     return normalize_bwd_launch(x, dxh, rows, dx, S_(stream));
 }
 
+FFR_API int ffr_gallery_cosine(const void* probe_packed, int P, const void* gallery_packed, int g_pad, int G,
+                               float* cos_out, unsigned long long* argkey, ffr_stream_t stream) {
+    FFR_CHECK_ARG(probe_packed && gallery_packed && cos_out, "ffr_gallery_cosine: null pointer");
+    FFR_CHECK_ARG(P > 0 && g_pad % 256 == 0 && G > 0 && G <= g_pad, "ffr_gallery_cosine: P=%d g_pad=%d G=%d", P, g_pad, G);
+    ConvGemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = P;
+    p.Cout = g_pad;
+    p.ntaps = 1;
+    p.flags = EPI_OUT_F32;
+    p.out_f32 = cos_out;
+    if (argkey) {                                  // rank-1 match per probe through the arg-max part of EPI_COSFACE
+        FFR_CUDA(cudaMemsetAsync(argkey, 0, sizeof(unsigned long long) * (size_t)P, S_(stream)));
+        p.flags |= EPI_COSFACE;
+        p.ce_label = nullptr; p.ce_sumexp = nullptr; p.ce_zlabel = nullptr; p.ce_argkey = argkey;
+        p.ce_classes = G; p.ce_s = 0.f; p.ce_m = 0.f;
+    }
+    return conv_gemm_launch(probe_packed, (long long)P, 1536, 1536, gallery_packed, 1536, p, 1, S_(stream));
+}
+
+FFR_API int ffr_roc_hist(const float* scores, int ld, int P, int G, const int* probe_id, const int* gallery_id,
+                         const double* thresholds, int T, unsigned long long* hist, ffr_stream_t stream) {
+    FFR_CHECK_ARG(hist && thresholds && ((P == 0 || G == 0) || (scores && probe_id && gallery_id)), "ffr_roc_hist: null pointer");
+    return roc_hist_launch(scores, ld, P, G, probe_id, gallery_id, thresholds, T, hist, S_(stream));
+}
+
 FFR_API int ffr_clip_adam(const void* table, const int* chunks, int n_chunks, const float* hyper, float beta1,
                           float beta2, float eps, float weight_decay, float clip, ffr_stream_t stream) {
     FFR_CHECK_ARG(n_chunks == 0 || (table && chunks && hyper), "ffr_clip_adam: null pointer");

@@ -201,7 +201,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
         const uint32_t t_row = tmem_base + (acc * SUB + sub) * BN + chalf * HALF + (static_cast<uint32_t>(quad * 32) << 16);
 
         // EPI_COSFACE per-row running values (one row per thread, HALF classes per tile)
-        const int ce_lab = ((flags & EPI_COSFACE) && m < p.M) ? __ldg(p.ce_label + m) : -1;
+        const int ce_lab = ((flags & EPI_COSFACE) && p.ce_label != nullptr && m < p.M) ? __ldg(p.ce_label + m) : -1;
         float ce_sum = 0.f, ce_zl = 0.f, ce_best = -3.0e38f;
         int ce_bestc = 0;
 
@@ -339,8 +339,8 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
             }
         }
         if ((flags & EPI_COSFACE) && m < p.M) {
-            atomicAdd(p.ce_sumexp + m, ce_sum);
-            if (ce_lab >= nc0 && ce_lab < nc0 + HALF) p.ce_zlabel[m] = ce_zl;
+            if (p.ce_sumexp != nullptr) atomicAdd(p.ce_sumexp + m, ce_sum);
+            if (p.ce_zlabel != nullptr && ce_lab >= nc0 && ce_lab < nc0 + HALF) p.ce_zlabel[m] = ce_zl;
             if (nc0 < p.ce_classes) {
                 uint32_t u = __float_as_uint(ce_best);
                 u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);            // monotone map float -> uint

@@ -36,6 +36,8 @@ int cosface_finish_launch(const float* sumexp, const float* zlabel, const unsign
 int cosface_bwd_launch(const float* cosv, int c_pad, int classes, int n, int n_pad, const int* label, const float* sumexp,
                        const float* gloss, float s, float m, void* dcos, void* dcosT, cudaStream_t stream);
 int normalize_bwd_launch(const float* x, const float* dxh, int rows, float* dx, cudaStream_t stream);
+int roc_hist_launch(const float* scores, int ld, int P, int G, const int* probe_id, const int* gallery_id,
+                    const double* thresholds, int T, unsigned long long* hist, cudaStream_t stream);
 int self_similarity_launch(const float* x, int n, float* ss_space, float* ss_channel, cudaStream_t stream);
 int scale_f32_launch(const float* in, float* out, long long count, float scale, cudaStream_t stream);
 int wgrad_launch(const void* dz, int ld_dz, const void* x, int ld_x, int x_ch0, int P, int Cout, int Cin, int G,

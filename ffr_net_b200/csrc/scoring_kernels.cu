@@ -126,4 +126,54 @@ int threshold_sweep_launch(const float* score, const int* label, const double* t
     return launch_status("threshold_sweep_kernel");
 }
 
+// ----------------------------------------------------------------------------------------------------------
+// 1:N gallery scoring (generalises the paired scoring of lfw_eval.py:246-259 to a full similarity matrix):
+// accept/reject counts of a (P x G) cosine matrix at every threshold of the grid, split into genuine (same identity)
+// and impostor pairs. A score falls into bin b = number of thresholds t with (double)score > t (strict, exactly the
+// comparison of eval_acc, lfw_eval.py:141-147; the grid is ascending so b comes from a binary search); the counts
+// of "accepted at threshold t" are the suffix sums of the two histograms, taken on the host in integers.
+// hist: [2][T+1] unsigned long long (genuine, impostor), zeroed by the launcher.
+// ----------------------------------------------------------------------------------------------------------
+constexpr int ROC_MAX_T = 1024;
+__global__ void __launch_bounds__(256) roc_hist_kernel(const float* __restrict__ scores, int ld, int P, int G,
+                                                       const int* __restrict__ probe_id, const int* __restrict__ gallery_id,
+                                                       const double* __restrict__ thresholds, int T,
+                                                       unsigned long long* __restrict__ hist) {
+    __shared__ double s_thr[ROC_MAX_T];
+    __shared__ unsigned int s_hist[2][ROC_MAX_T + 1];
+    for (int i = threadIdx.x; i < T; i += 256) s_thr[i] = thresholds[i];
+    for (int i = threadIdx.x; i < 2 * (ROC_MAX_T + 1); i += 256) (&s_hist[0][0])[i] = 0u;
+    __syncthreads();
+    for (int p = blockIdx.x; p < P; p += gridDim.x) {
+        const int pid = probe_id[p];
+        const float* row = scores + (long long)p * ld;
+        for (int g = threadIdx.x; g < G; g += 256) {
+            const double sc = (double)__ldg(row + g);
+            int lo = 0, hi = T;                    // b = |{t : sc > thr[t]}| = first index with !(sc > thr[index])
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (sc > s_thr[mid]) lo = mid + 1; else hi = mid;
+            }
+            atomicAdd(&s_hist[(gallery_id[g] == pid) ? 0 : 1][lo], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * (T + 1); i += 256) {
+        const int k = i / (T + 1), b = i - k * (T + 1);
+        const unsigned int c = s_hist[k][b];
+        if (c) atomicAdd(hist + (long long)k * (T + 1) + b, (unsigned long long)c);
+    }
+}
+
+int roc_hist_launch(const float* scores, int ld, int P, int G, const int* probe_id, const int* gallery_id,
+                    const double* thresholds, int T, unsigned long long* hist, cudaStream_t stream) {
+    FFR_CHECK_ARG(T >= 1 && T <= ROC_MAX_T, "roc_hist: T=%d (max %d)", T, ROC_MAX_T);
+    FFR_CHECK_ARG(ld >= G && P >= 0 && G >= 0, "roc_hist: P=%d G=%d ld=%d", P, G, ld);
+    FFR_CUDA(cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * 2 * (size_t)(T + 1), stream));
+    if (P == 0 || G == 0) return 0;
+    const int grid = P < num_sms() * 4 ? P : num_sms() * 4;
+    roc_hist_kernel<<<grid, 256, 0, stream>>>(scores, ld, P, G, probe_id, gallery_id, thresholds, T, hist);
+    return launch_status("roc_hist_kernel");
+}
+
 }  // namespace ffr

@@ -115,3 +115,77 @@ def get_avg_accuracy(encoder, recnet, data_loader, flag=0, verbose=False):
             print("Best threshold: {:.4f}; Test accuracy: {:.4f}".format(t, a))
         print("Average accuracy: {}".format(r["avg_acc"]))
     return r_new["avg_acc"], r["avg_acc"]
+
+
+# ----------------------------------------------------------------------------------------------------------
+# 1:N gallery scoring: the paired cosine of calculate_distance (lfw_eval.py:246-249) generalised
+# to a full probe x gallery similarity matrix on the tcgen05 GEMM, rank-1 identification from its epilogue, and the
+# accept counts for ROC / TAR@FAR with the reference's decision rule ((double)score > threshold on the np.arange grid).
+# ----------------------------------------------------------------------------------------------------------
+def _ceil(a, b):
+    return (a + b - 1) // b * b
+
+
+def gallery_cosine(probe, gallery, want_rank1=True):
+    """probe (P,512), gallery (G,512) fp32 CUDA -> (cos (P,G) fp32 [a view of a padded matrix], rank1 (P,) int64 or None).
+    Rows are L2-normalised as F.normalize does (for non-degenerate embeddings equal to f1.f2/(|f1||f2|+1e-8) of
+    lfw_eval.py:246 to fp32 round-off); operands are split into bf16 hi + lo so the cosines carry ~1e-5 error."""
+    if not (probe.is_cuda and gallery.is_cuda):
+        raise RuntimeError("ffr_net_b200.scoring runs only on CUDA; there is no CPU fallback")
+    probe, gallery = probe.contiguous().float(), gallery.contiguous().float()
+    assert probe.dim() == 2 and gallery.dim() == 2 and probe.shape[1] == 512 and gallery.shape[1] == 512
+    lib, P, dev = _lib.load(), _lib.ptr, probe.device
+    n_p, n_g = probe.shape[0], gallery.shape[0]
+    if n_p == 0 or n_g == 0:
+        return torch.empty(n_p, n_g, dtype=torch.float32, device=dev), (torch.empty(n_p, dtype=torch.int64, device=dev)
+                                                                         if want_rank1 else None)
+    p_pad, g_pad = _ceil(n_p, 64), _ceil(n_g, 256)
+    pp = torch.empty(p_pad, 1536, dtype=torch.bfloat16, device=dev)
+    gp = torch.empty(g_pad, 1536, dtype=torch.bfloat16, device=dev)
+    st = _lib.stream_ptr()
+    _lib.check(lib.ffr_cosface_pack(P(probe), n_p, p_pad, 0, P(pp), None, 0, st), "pack(probe)")
+    _lib.check(lib.ffr_cosface_pack(P(gallery), n_g, g_pad, 1, P(gp), None, 0, st), "pack(gallery)")
+    cos = torch.empty(n_p, g_pad, dtype=torch.float32, device=dev)
+    key = torch.empty(n_p, dtype=torch.int64, device=dev) if want_rank1 else None
+    _lib.check(lib.ffr_gallery_cosine(P(pp), n_p, P(gp), g_pad, n_g, P(cos), P(key), st), "gallery_cosine")
+    rank1 = None
+    if want_rank1:
+        rank1 = 0xFFFFFFFF - (key & 0xFFFFFFFF)
+    return cos[:, :n_g], rank1
+
+
+def roc_counts(scores, probe_ids, gallery_ids, thresholds=None):
+    """Accepted-pair counts at every threshold of the grid: returns dict(thresholds, true_accept, false_accept,
+    n_genuine, n_impostor, tar, far) with integer counts (numpy int64) — TA(t) = #{genuine pairs with score > t}.
+    scores: (P,G) fp32 CUDA (may be a strided view), ids: integer tensors."""
+    if not scores.is_cuda:
+        raise RuntimeError("ffr_net_b200.scoring runs only on CUDA; there is no CPU fallback")
+    thr = thresholds_grid() if thresholds is None else np.asarray(thresholds, dtype=np.float64)
+    assert np.all(np.diff(thr) > 0), "thresholds must be ascending"
+    dev = scores.device
+    if scores.stride(1) != 1:
+        scores = scores.contiguous()
+    n_p, n_g = scores.shape
+    pid = probe_ids.to(device=dev, dtype=torch.int32).contiguous()
+    gid = gallery_ids.to(device=dev, dtype=torch.int32).contiguous()
+    thr_d = torch.from_numpy(thr).to(dev)
+    hist = torch.empty(2, len(thr) + 1, dtype=torch.int64, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.ffr_roc_hist(_lib.ptr(scores), scores.stride(0), n_p, n_g, _lib.ptr(pid), _lib.ptr(gid),
+                                _lib.ptr(thr_d), len(thr), _lib.ptr(hist), _lib.stream_ptr()), "roc_hist")
+    h = hist.cpu().numpy()
+    # bin b = number of thresholds below the score; accepted at threshold index t  <=>  b >= t + 1
+    suffix = np.cumsum(h[:, ::-1], axis=1)[:, ::-1]
+    ta, fa = suffix[0, 1:], suffix[1, 1:]
+    n_gen, n_imp = int(h[0].sum()), int(h[1].sum())
+    return dict(thresholds=thr, true_accept=ta, false_accept=fa, n_genuine=n_gen, n_impostor=n_imp,
+                tar=ta / max(n_gen, 1), far=fa / max(n_imp, 1))
+
+
+def tar_at_far(roc, far_target):
+    """Largest TAR among the grid thresholds whose FAR does not exceed far_target (and that threshold)."""
+    ok = np.nonzero(roc["far"] <= far_target)[0]
+    if len(ok) == 0:
+        return 0.0, None
+    i = ok[np.argmax(roc["tar"][ok])]
+    return float(roc["tar"][i]), float(roc["thresholds"][i])

@@ -195,6 +195,21 @@ FFR_API int ffr_pack_conv3x3(const float* w, int cout, int cin, int cout_p, int 
 FFR_API int ffr_clip_adam(const void* table, const int* chunks, int n_chunks, const float* hyper, float beta1,
                           float beta2, float eps, float weight_decay, float clip, ffr_stream_t stream);
 
+/* ---- 1:N gallery scoring: the paired scoring of lfw/lfw_eval.py:246-259 generalised to a similarity matrix ---- */
+
+/* cos_out[p][g_pad] (fp32) = probe . gallery^T for operands packed by ffr_cosface_pack (probe: mode 0, gallery: mode 1;
+ * L2-normalised, bf16 hi/lo split, K = 1536, cosine error ~1e-5). g_pad multiple of 256; columns >= G are padding.
+ * argkey (may be NULL): per probe the arg-max gallery column as (orderable cosine bits << 32) | (0xFFFFFFFF - g), first
+ * maximum wins — the rank-1 identification. */
+FFR_API int ffr_gallery_cosine(const void* probe_packed, int P, const void* gallery_packed, int g_pad, int G,
+                               float* cos_out, unsigned long long* argkey, ffr_stream_t stream);
+
+/* Histograms for ROC / TAR@FAR: hist[2][T+1] (uint64; genuine = same identity, impostor), bin b of a score = number of
+ * grid thresholds t with (double)score > t (the strict comparison of eval_acc, lfw_eval.py:141-147; thresholds
+ * ascending, T <= 1024). Accepted-at-threshold counts are suffix sums of the bins. scores [P][ld] fp32, ids int32. */
+FFR_API int ffr_roc_hist(const float* scores, int ld, int P, int G, const int* probe_id, const int* gallery_id,
+                         const double* thresholds, int T, unsigned long long* hist, ffr_stream_t stream);
+
 /* ---- CosFace head + CrossEntropy, training path (AddMarginProduct recnet.py:238-270, trainer.py:173-176) ------ */
 
 /* Rows of x (fp32 [rows][512]) -> F.normalize'd (eps 1e-12) bf16 hi/lo split, packed [rows_pad][1536]:

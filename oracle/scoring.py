@@ -96,3 +96,27 @@ def synth_pair_scores(n=6000, seed=0):
         labels[f * per:f * per + per // 2] = 1
     scores = np.where(labels == 1, rng.normal(0.55, 0.18, n), rng.normal(0.05, 0.15, n)).clip(-0.999, 0.999)
     return scores.astype(np.float32), labels
+
+
+# ----------------------------------------------------------------------------------------------------------
+# 1:N gallery scoring: the paired rule of lfw_eval.py:246-249 / eval_acc :141-147 applied to every (probe, gallery)
+# pair. float64 cosines, literal counting loops over the threshold grid.
+# ----------------------------------------------------------------------------------------------------------
+def gallery_cosine(probe, gallery):
+    """(P,D),(G,D) -> (P,G) float64: f1.f2 / (|f1||f2| + 1e-8), the formula of lfw_eval.py:246."""
+    p = np.asarray(probe, dtype=np.float64)
+    g = np.asarray(gallery, dtype=np.float64)
+    num = p @ g.T
+    den = np.linalg.norm(p, axis=1)[:, None] * np.linalg.norm(g, axis=1)[None, :] + 1e-8
+    return num / den
+
+
+def roc_counts(scores_f32, probe_ids, gallery_ids, thresholds=None):
+    """Accepted genuine / impostor pair counts per threshold: predict same iff float(score) > threshold (strict),
+    as eval_acc does (lfw_eval.py:141-147)."""
+    thr = np.arange(-1.0, 1.0, 0.005) if thresholds is None else np.asarray(thresholds, dtype=np.float64)
+    s = np.asarray(scores_f32, dtype=np.float32).astype(np.float64)
+    same = np.asarray(probe_ids)[:, None] == np.asarray(gallery_ids)[None, :]
+    ta = np.array([int(np.count_nonzero((s > t) & same)) for t in thr], dtype=np.int64)
+    fa = np.array([int(np.count_nonzero((s > t) & ~same)) for t in thr], dtype=np.int64)
+    return dict(thresholds=thr, true_accept=ta, false_accept=fa, n_genuine=int(same.sum()), n_impostor=int((~same).sum()))

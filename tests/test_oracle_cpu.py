@@ -115,3 +115,24 @@ def test_preprocess_oracle_matches_reference_golden():
     got2 = opp.preprocess_batch(g["masks"], g["flips"]).numpy()
     assert np.array_equal(got1, g["img1"]) and np.array_equal(got2, g["img2"])
     assert g["flips"].any() and not g["flips"].all()
+
+
+def test_gallery_oracle_consistent_with_paired_scoring():
+    """The 1:N oracle restates the paired rule: its diagonal equals oracle pair_cosine, and its counts at a threshold
+    equal a literal Python loop of eval_acc's comparison (lfw_eval.py:141-147)."""
+    g = torch.Generator().manual_seed(2)
+    a, b = torch.randn(9, 512, generator=g), torch.randn(9, 512, generator=g)
+    m = osc.gallery_cosine(a.numpy(), b.numpy())
+    assert np.abs(np.diag(m) - osc.pair_cosine(a, b).numpy().astype(np.float64)).max() <= 1e-6
+    pid, gid = np.arange(9) % 3, np.arange(9) % 3
+    roc = osc.roc_counts(m.astype(np.float32), pid, gid, thresholds=[-0.05, 0.0, 0.05])
+    for k, t in enumerate([-0.05, 0.0, 0.05]):
+        ta = fa = 0
+        for i in range(9):
+            for j in range(9):
+                same = 1 if float(np.float32(m[i, j])) > t else 0
+                if same and pid[i] == gid[j]:
+                    ta += 1
+                if same and pid[i] != gid[j]:
+                    fa += 1
+        assert roc["true_accept"][k] == ta and roc["false_accept"][k] == fa

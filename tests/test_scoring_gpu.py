@@ -82,3 +82,60 @@ def test_get_avg_accuracy_end_to_end(lib):
     ref_new = osc.sweep(osc.pair_cosine(f1n, f2n).numpy(), labels.numpy(), 10)["avg_acc"]
     ref = osc.sweep(osc.pair_cosine(f1, f2).numpy(), labels.numpy(), 10)["avg_acc"]
     assert abs(acc_new - ref_new) <= 1.0 / 60 and abs(acc - ref) <= 1.0 / 60   # scores differ by fp32 round-off only
+
+
+@pytest.mark.parametrize("n_p,n_g", [(1, 1), (37, 300), (256, 1000), (130, 2049)])
+def test_gallery_cosine_and_rank1(lib, n_p, n_g):
+    """probe x gallery cosine matrix on the tcgen05 GEMM (hi/lo-split bf16 operands) vs the float64 oracle (formula of
+    lfw_eval.py:246): <= 2e-5 absolute; rank-1 index identical wherever the top-2 gap exceeds that error."""
+    g = torch.Generator().manual_seed(n_p * 7 + n_g)
+    gallery = torch.randn(n_g, 512, generator=g)
+    owner = torch.randint(0, n_g, (n_p,), generator=g)
+    probe = gallery[owner] + 0.6 * torch.randn(n_p, 512, generator=g)          # noisy views of gallery entries
+    cos, rank1 = scoring.gallery_cosine(probe.cuda(), gallery.cuda())
+    ref = osc.gallery_cosine(probe.numpy(), gallery.numpy())
+    assert cos.shape == (n_p, n_g)
+    assert np.abs(cos.cpu().numpy().astype(np.float64) - ref).max() <= 2e-5
+    top2 = np.sort(ref, axis=1)[:, -2:] if n_g > 1 else np.concatenate([ref - 1, ref], axis=1)
+    clear = (top2[:, 1] - top2[:, 0]) > 1e-4
+    assert np.array_equal(rank1.cpu().numpy()[clear], ref.argmax(1)[clear])
+    assert clear.mean() > 0.9
+
+
+def test_roc_counts_bit_exact(lib):
+    """ffr_roc_hist + suffix sums vs literal counting with the reference's rule ((double)score > t on the np.arange
+    grid): integer counts identical; scores placed exactly ON grid values exercise the strict comparison."""
+    g = torch.Generator().manual_seed(5)
+    n_p, n_g = 67, 413
+    scores = (torch.rand(n_p, n_g, generator=g) * 2.2 - 1.1)
+    grid = scoring.thresholds_grid()
+    scores[0, :50] = torch.from_numpy(grid[100:150].astype(np.float32))          # fp32 roundings of grid points
+    scores[1, :3] = torch.tensor([-1.0, 0.995, 1.0])
+    pid = torch.randint(0, 20, (n_p,), generator=g)
+    gid = torch.randint(0, 20, (n_g,), generator=g)
+    got = scoring.roc_counts(scores.cuda(), pid.cuda(), gid.cuda())
+    ref = osc.roc_counts(scores.numpy(), pid.numpy(), gid.numpy())
+    assert got["n_genuine"] == ref["n_genuine"] and got["n_impostor"] == ref["n_impostor"]
+    assert np.array_equal(got["true_accept"], ref["true_accept"])
+    assert np.array_equal(got["false_accept"], ref["false_accept"])
+    # strided view input (what gallery_cosine returns) and TAR@FAR helper
+    padded = torch.zeros(n_p, 512)
+    padded[:, :n_g] = scores
+    got2 = scoring.roc_counts(padded.cuda()[:, :n_g], pid.cuda(), gid.cuda())
+    assert np.array_equal(got2["true_accept"], ref["true_accept"])
+    tar, thr = scoring.tar_at_far(got, 0.1)
+    ok = ref["false_accept"] / ref["n_impostor"] <= 0.1
+    assert abs(tar - (ref["true_accept"][ok] / ref["n_genuine"]).max()) < 1e-12 and thr is not None
+
+
+def test_gallery_identification_end_to_end(lib):
+    """Embeddings -> cosine matrix -> rank-1 + ROC on a synthetic gallery of 300 identities with 2 probes each."""
+    g = torch.Generator().manual_seed(9)
+    centers = torch.nn.functional.normalize(torch.randn(300, 512, generator=g))
+    probes = centers.repeat_interleave(2, 0) + 0.03 * torch.randn(600, 512, generator=g)
+    pid = torch.arange(300).repeat_interleave(2)
+    cos, rank1 = scoring.gallery_cosine(probes.cuda(), centers.cuda())
+    assert (rank1.cpu() == pid).float().mean().item() == 1.0
+    roc = scoring.roc_counts(cos, pid.cuda(), torch.arange(300).cuda())
+    tar, thr = scoring.tar_at_far(roc, 1e-3)
+    assert roc["n_genuine"] == 600 and roc["n_impostor"] == 600 * 299 and tar == 1.0
