@@ -6,8 +6,11 @@
 // a 3x3 convolution tap is then nothing but a row offset, so every A tile is a plain 2-D TMA box and the
 // zero padding comes from rows that are stored as zeros (or from TMA out-of-bounds fill at the tensor ends).
 // Wp is the packed K-major weight matrix [Cout, ntaps*Cin]. Accumulators live in TMEM (double buffered, so the
-// epilogue of tile i overlaps the MMAs of tile i+1); one thread issues tcgen05.mma, one thread issues TMA, four
+// epilogue of tile i overlaps the MMAs of tile i+1); one elected lane issues tcgen05.mma, one issues TMA, eight
 // warps run the fused epilogue straight out of TMEM.
+// Three tilings share this parameter block and epilogue: the sliding-window kernel (3x3 / stride 1, the nine taps are
+// descriptor offsets into one TMA window), the tile-per-tap kernel (everything else), and on H9 maps the pixel-major
+// variant of the latter (EPI_PIXMAJOR: an M tile is 128 images at one pixel, A tiles are 4-D TMA boxes).
 #pragma once
 #include <cstdint>
 #include <cuda_bf16.h>
