@@ -59,6 +59,7 @@ _SIGNATURES = {
     "ffr_debug_set_wgrad_splits": (None, [_i]),
     "ffr_pixmajor_profitable": (_i, [_i]),
     "ffr_debug_set_pixmajor": (None, [_i]),
+    "ffr_debug_set_pixmajor_backbone": (None, [_i]),
     "ffr_debug_mma_bench": (_i, [_p, _i, _i, _i, _i, _i, _p]),
     "ffr_debug_rowshift_probe": (_i, [_p, _p, _p, _i, _i, _p]),
 }

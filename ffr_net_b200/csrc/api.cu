@@ -96,7 +96,8 @@ FFR_API int ffr_conv3x3_bnpre_prelu_fwd(const void* x, int n_img, int S, int Cin
     p.Cout = Cout;
     taps_3x3_flat(p, G);
     p.rows_per_img = G * G; p.Wp = G; p.S = S; p.h0 = 0; p.n_img = n_img;
-    p.flags = EPI_GEOM | EPI_BORDER_BIAS | EPI_PRELU | (out_s2d ? EPI_OUT_S2D : 0u);
+    p.flags = EPI_GEOM | EPI_BORDER_BIAS | EPI_PRELU | (out_s2d ? EPI_OUT_S2D : 0u) |
+              (pixmajor_backbone(S, n_img) ? EPI_PIXMAJOR : 0u);
     p.bias = bias9; p.slope = slope;
     p.out = reinterpret_cast<__nv_bfloat16*>(out);
     p.ldo = out_s2d ? 4 * Cout : Cout;
@@ -115,7 +116,8 @@ FFR_API int ffr_conv3x3_bn_pool_fwd(const void* x, int n_img, int S, int C, int 
     p.Cout = Cout;
     if (stride == 1) taps_3x3_flat(p, G); else taps_3x3_s2d(p, G, C);
     p.rows_per_img = G * G; p.Wp = G; p.S = So; p.h0 = 0; p.n_img = n_img;
-    p.flags = EPI_GEOM | EPI_BIAS | (pool ? EPI_POOL : 0u);
+    p.flags = EPI_GEOM | EPI_BIAS | (pool ? EPI_POOL : 0u) |
+              ((stride == 1 && pixmajor_backbone(So, n_img)) ? EPI_PIXMAJOR : 0u);
     p.bias = bias;
     p.out = reinterpret_cast<__nv_bfloat16*>(out);
     p.ldo = Cout;
@@ -236,6 +238,7 @@ FFR_API int ffr_recnet_convlayer_fwd(const void* x, int n, int Cin, const void* 
 
 FFR_API int ffr_pixmajor_profitable(int n) { return pixmajor_profitable(n) ? 1 : 0; }
 FFR_API void ffr_debug_set_pixmajor(int mode) { set_pixmajor_mode(mode); }
+FFR_API void ffr_debug_set_pixmajor_backbone(int max_s) { set_pixmajor_backbone(max_s); }
 
 FFR_API int ffr_self_similarity(const float* x, int n, float* ss_space, float* ss_channel, ffr_stream_t stream) {
     FFR_CHECK_ARG(n == 0 || x, "ffr_self_similarity: null input");

@@ -75,6 +75,7 @@ __device__ __forceinline__ PixTile pix_tile(const ConvGemmParams& p, int m_tile)
     t.ho = qh + p.pix_off;
     t.wo = q - qh * p.pix_side + p.pix_off;
     t.tapmask = 0;
+    if (t.ho >= p.pix_pad_from || t.wo >= p.pix_pad_from) return t;
     for (int tap = 0; tap < p.ntaps; ++tap) {
         const int r = (p.ntaps == 9) ? tap / 3 : 1, s = (p.ntaps == 9) ? tap % 3 : 1;
         const int hs = t.ho + r - 1, ws = t.wo + s - 1;
@@ -142,6 +143,11 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
             h = pt.ho - p.h0;
             w = pt.wo - p.h0;
             if ((flags & EPI_GEOM) && !(flags & EPI_SCATTER)) valid = valid && h >= 0 && h < p.S && w >= 0 && w < p.S;
+            if (border) {
+                const int ch = (h == 0) ? 0 : ((h == p.S - 1) ? 2 : 1);
+                const int cw = (w == 0) ? 0 : ((w == p.S - 1) ? 2 : 1);
+                cls = ch * 3 + cw;
+            }
         } else if (flags & EPI_GEOM) {
             if (small_m) {
                 fast_divmod(m, p.rows_per_img, inv_rpi, n_img, r_local);
@@ -471,6 +477,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BN;
+            if (kb1 <= kb0) {                    // pixel-major pad point: nothing to accumulate, the epilogue stores zeros
+                if (elect_one_sync()) umma_commit(&tfull_bar[acc]);
+                __syncwarp();
+                continue;
+            }
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
@@ -738,7 +749,14 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
 // which 32 are halo) by more than what the sliding-window kernel wins back (~8 %): n >= ~96 except just above a
 // multiple of 128. g_pix_mode: -1 = this rule, 0 / 1 = forced off / on (ffr_debug_set_pixmajor, tests and tuning).
 static int g_pix_mode = -1;
+// Experiment switch (default off): backbone 3x3/s1 convs on maps with S <= this use pixel-major tiles over the
+// halo-shared flat layout. Measured at N=512 (tools/pix_backbone_bench.py, profiles/r01_pix_backbone_bench_512.json):
+// slower than the sliding-window kernel (8.72 ms -> 8.90 ms for S <= 7, 10.1 ms for S <= 14): the 13-23 % fewer MMA
+// rows do not pay for nine A tiles per k-chunk instead of one window and per-row pooling reductions.
+static int g_pix_backbone_max_s = 0;
 void set_pixmajor_mode(int mode) { g_pix_mode = mode; }
+void set_pixmajor_backbone(int max_s) { g_pix_backbone_max_s = max_s; }
+bool pixmajor_backbone(int S, int n_img) { return S <= g_pix_backbone_max_s && n_img >= 1; }
 bool pixmajor_profitable(int n_img) {
     if (g_pix_mode >= 0) return g_pix_mode != 0;
     const long long pix = 49LL * ((n_img + BLOCK_M - 1) / BLOCK_M);
@@ -761,15 +779,26 @@ int conv_gemm_launch(const void* a, long long a_rows, int a_cols, int a_ld, cons
     int BN = (p.Cout % 256 == 0) ? 256 : ((p.Cout % 128 == 0) ? 128 : 64);
     const bool pix = (p.flags & EPI_PIXMAJOR) != 0;
     if (pix) {
-        FFR_CHECK_ARG(p.rows_per_img == 81 && p.Wp == 9 && p.n_img > 0 && (p.ntaps == 9 || p.ntaps == 1) &&
-                      num_splits <= 1 && p.b_rows_per_mtile == 0, "conv_gemm: pixel-major tiles need an H9 map");
+        FFR_CHECK_ARG(p.Wp >= 2 && p.rows_per_img == p.Wp * p.Wp && p.n_img > 0 && (p.ntaps == 9 || p.ntaps == 1) &&
+                      num_splits <= 1 && p.b_rows_per_mtile == 0, "conv_gemm: pixel-major tiles need a square flat map");
         const bool dgrad = (p.flags & EPI_PIX_DGRAD) != 0;
         p.pix_iblocks = (p.n_img + BLOCK_M - 1) / BLOCK_M;
-        p.pix_side = dgrad ? 9 : 7;
-        p.pix_off = dgrad ? 0 : 1;
-        p.pix_src_lo = dgrad ? 1 : 0;
-        p.pix_src_hi = dgrad ? 7 : 8;
-        p.M = p.n_img * 81;
+        if (p.h0 == 0) {          // halo-shared zero-padded map (backbone): outputs S x S from (0,0); taps that leave
+            FFR_CHECK_ARG(!dgrad && p.S == p.Wp - 1, "conv_gemm: pixel-major zero-pad map needs S = Wp - 1");
+            p.pix_side = p.Wp;    // the grid are zero-filled by TMA, the shared pad row/column is stored as zeros.
+            p.pix_off = 0;        // The pad points are output tiles too (no taps: they only store the zeros the
+            p.pix_src_lo = -1;    // next convolution's taps expect there)
+            p.pix_src_hi = p.Wp;
+            p.pix_pad_from = p.S;
+        } else {
+            p.pix_pad_from = 1 << 30;                  // H9 (reflection halo materialised)
+            FFR_CHECK_ARG(p.Wp == 9 && p.S == 7 && p.h0 == 1, "conv_gemm: pixel-major H9 map expected");
+            p.pix_side = dgrad ? 9 : 7;
+            p.pix_off = dgrad ? 0 : 1;
+            p.pix_src_lo = dgrad ? 1 : 0;
+            p.pix_src_hi = dgrad ? 7 : 8;
+        }
+        p.M = p.n_img * p.rows_per_img;
         // N tile: fewest (waves x cycles per MMA) over the SMs; the measured issue rates are 128 / 64 / 48 cycles
         const int m_tiles = p.pix_side * p.pix_side * p.pix_iblocks;
         long long best = -1;
@@ -807,7 +836,7 @@ int conv_gemm_launch(const void* a, long long a_rows, int a_cols, int a_ld, cons
 
     int G = 0;
     if (pix) {
-        rc = make_tmap_h9_pixel_bf16(&tmA, a, (uint64_t)p.n_img, (uint64_t)a_cols, (uint64_t)a_ld, BLOCK_M);
+        rc = make_tmap_pixel_bf16(&tmA, a, (uint64_t)p.n_img, (uint32_t)p.Wp, (uint64_t)a_cols, (uint64_t)a_ld, BLOCK_M);
         if (rc) return rc;
         switch (BN) {
             case 256: return launch_cfg<256>(tmA, tmB, p, grid, stream);

@@ -75,6 +75,7 @@ struct ConvGemmParams {
     int pix_iblocks;                // image blocks of 128 per pixel
     int pix_side, pix_off;          // output pixels: side x side, starting at (off, off) in H9 coordinates
     int pix_src_lo, pix_src_hi;     // a tap is skipped when its source pixel leaves [lo, hi]^2
+    int pix_pad_from;               // output pixels with h or w >= this are pad points: no taps, zeros are stored
     // EPI_COSFACE (AddMarginProduct + CrossEntropy, recnet.py:257-270, trainer.py:173-176)
     const int* ce_label;            // [M]
     float* ce_sumexp;               // [M], zeroed by the caller

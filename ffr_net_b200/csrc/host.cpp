@@ -64,14 +64,21 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 // lands in shared memory as box_imgs rows of 64 channels, i.e. exactly like a 2-D box of consecutive rows.
 int make_tmap_h9_pixel_bf16(CUtensorMap* out, const void* base, uint64_t n_img, uint64_t cols, uint64_t ld_elems,
                             uint32_t box_imgs) {
+    return make_tmap_pixel_bf16(out, base, n_img, 9, cols, ld_elems, box_imgs);
+}
+
+// General form: a flat map with G x G rows per image (H9: G = 9; halo-shared backbone maps: G = S + 1). Coordinates
+// outside [0, G) are filled with zeros by TMA, which is exactly the zero padding of a tap that leaves the image.
+int make_tmap_pixel_bf16(CUtensorMap* out, const void* base, uint64_t n_img, uint32_t G, uint64_t cols,
+                         uint64_t ld_elems, uint32_t box_imgs) {
     encode_tiled_fn enc = get_encode();
     if (!enc) return set_error(-2, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
     if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(-1, "TMA base pointer not 16-B aligned");
     if ((ld_elems * 2) % 16 != 0) return set_error(-1, "TMA row pitch %llu B not a multiple of 16",
                                                    (unsigned long long)(ld_elems * 2));
     if (box_imgs > 256) return set_error(-1, "TMA box of %u images too large", box_imgs);
-    cuuint64_t gdim[4] = {cols, 9, 9, n_img};
-    cuuint64_t gstr[3] = {ld_elems * 2, 9 * ld_elems * 2, 81 * ld_elems * 2};
+    cuuint64_t gdim[4] = {cols, G, G, n_img};
+    cuuint64_t gstr[3] = {ld_elems * 2, (uint64_t)G * ld_elems * 2, (uint64_t)G * G * ld_elems * 2};
     cuuint32_t box[4] = {64, 1, 1, box_imgs};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,

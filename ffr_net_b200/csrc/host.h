@@ -34,6 +34,8 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
                       uint32_t box_rows, uint32_t box_cols = 64);
 int make_tmap_h9_pixel_bf16(CUtensorMap* out, const void* base, uint64_t n_img, uint64_t cols, uint64_t ld_elems,
                             uint32_t box_imgs);
+int make_tmap_pixel_bf16(CUtensorMap* out, const void* base, uint64_t n_img, uint32_t G, uint64_t cols,
+                         uint64_t ld_elems, uint32_t box_imgs);
 
 int num_sms();
 

@@ -45,6 +45,8 @@ int wgrad_launch(const void* dz, int ld_dz, const void* x, int ld_x, int x_ch0, 
 void set_wgrad_splits(int s);
 void set_pixmajor_mode(int mode);
 bool pixmajor_profitable(int n_img);
+void set_pixmajor_backbone(int max_s);
+bool pixmajor_backbone(int S, int n_img);
 bool pixmajor_profitable_k64(int n_img);
 int bn_prelu_fwd_launch(const void* z, int ldz, const float* mean, const float* rstd, const float* gamma,
                         const float* beta, const float* slope, const void* res, int ldres, void* out, int ldo,

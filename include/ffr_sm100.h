@@ -271,6 +271,9 @@ FFR_API int ffr_debug_set_counters(void* counters);
 FFR_API int ffr_pixmajor_profitable(int n);
 /* Tests / tuning: -1 = the rule above, 0 = never, 1 = always. */
 FFR_API void ffr_debug_set_pixmajor(int mode);
+/* Experiment switch: backbone 3x3 stride-1 convolutions on maps with S <= max_s (and >= 96 images) use pixel-major
+ * tiles over the halo-shared flat layout (0 = off, the default; measured no gain). */
+FFR_API void ffr_debug_set_pixmajor_backbone(int max_s);
 
 /* Tuning only: splits > 0 overrides the split-count heuristic of ffr_wgrad3x3 (0 restores it). */
 FFR_API void ffr_debug_set_wgrad_splits(int splits);

@@ -81,9 +81,18 @@ def test_splitk_atomic(lib, splits):
     assert torch.equal(out, a.float() @ w.float().t())   # integer-valued: exact in any order
 
 
+@pytest.fixture(params=["window", "pixmajor"])
+def backbone_tiles(request, lib):
+    """Backbone 3x3/s1 convolutions on the production sliding-window tiles and on the experimental pixel-major tiles
+    over the halo-shared flat layout (zero padding from TMA out-of-bounds fill, pad points stored as zero tiles)."""
+    lib.ffr_debug_set_pixmajor_backbone(1000 if request.param == "pixmajor" else 0)
+    yield request.param
+    lib.ffr_debug_set_pixmajor_backbone(0)
+
+
 @pytest.mark.parametrize("n,S,cin,cout", [(3, 14, 64, 64), (2, 7, 128, 256), (5, 28, 64, 128), (2, 14, 256, 512),
                                             (2, 112, 64, 64), (3, 56, 64, 128)])
-def test_conv3x3_bnpre_prelu(lib, n, S, cin, cout):
+def test_conv3x3_bnpre_prelu(lib, n, S, cin, cout, backbone_tiles):
     """conv(pad0(BN(x))) + PReLU through ffr_conv3x3_bnpre_prelu_fwd vs F.conv2d on the same bf16-rounded operands.
     Tolerance 2e-3 of max|ref| (fp32 accumulation order) + bf16 output rounding (2^-8 relative)."""
     from ffr_net_b200 import packing
@@ -114,7 +123,7 @@ def test_conv3x3_bnpre_prelu(lib, n, S, cin, cout):
 
 @pytest.mark.parametrize("n,S,c,cout,stride", [(3, 14, 64, 64, 1), (2, 14, 128, 128, 2), (4, 28, 64, 64, 2),
                                                 (2, 7, 512, 512, 1)])
-def test_conv3x3_bn_pool(lib, n, S, c, cout, stride):
+def test_conv3x3_bn_pool(lib, n, S, c, cout, stride, backbone_tiles):
     from ffr_net_b200 import packing
     g = torch.Generator(device="cuda").manual_seed(S + c + stride)
     x = torch.randn(n, c, S, S, generator=g, device="cuda")
