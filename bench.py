@@ -183,7 +183,7 @@ def _config(with_recnet, cpu_sample=None):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from oracle import backbone as ob          # synthetic weights/input generator (not on the timed path)
+    from ffr_net_b200 import synth as ob       # synthetic weights / input generators (no oracle on this arm)
     from ffr_net_b200 import _lib
     from ffr_net_b200.backbone import Backbone
 
@@ -204,7 +204,7 @@ def run_ours(args):
     enc = enc.to(dev).eval()
     rec = None
     if with_recnet:
-        from oracle import recnet as orr
+        from ffr_net_b200 import synth as orr
         from ffr_net_b200.recnet import RecNet
         rec = RecNet()
         rec.load_state_dict(orr.synth_recnet_state_dict(0))
@@ -367,8 +367,8 @@ def _bench_train(args, enc, dev, world, rank, timed):
     """Trainer.forward + optimizer_parameters (2 encoder fwd, 2 RecNet fwd with label, losses, backward, gradient
     all-reduce, clip, Adam, LR step) on 256 synthetic pairs per GPU."""
     import torch
-    from oracle import backbone as ob
-    from oracle import recnet as orr
+    from ffr_net_b200 import synth as ob
+    from ffr_net_b200 import synth as orr
     from ffr_net_b200.recnet import RecNet
     from ffr_net_b200.trainer import Trainer, default_opts
     pairs = 256

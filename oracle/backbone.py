@@ -75,59 +75,6 @@ def backbone_forward(sd, x, return_body=False):
     return y, f
 
 
-# ----------------------------------------------------------------------------------------------------------
-# Deterministic synthetic weights (checkpoints are Google-Drive hosted and unavailable offline).
-# ----------------------------------------------------------------------------------------------------------
-def _bn_entries(sd, p, c, g):
-    sd[p + "weight"] = torch.empty(c).uniform_(0.8, 1.2, generator=g)
-    sd[p + "bias"] = torch.empty(c).uniform_(-0.1, 0.1, generator=g)
-    sd[p + "running_mean"] = torch.empty(c).uniform_(-0.1, 0.1, generator=g)
-    sd[p + "running_var"] = torch.empty(c).uniform_(0.8, 1.2, generator=g)
-    sd[p + "num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
-
-
-def _conv_w(shape, g):
-    fan_in = shape[1] * shape[2] * shape[3]
-    b = 1.0 / math.sqrt(fan_in)          # == nn.Conv2d default kaiming_uniform_(a=sqrt(5)) bound
-    return torch.empty(shape).uniform_(-b, b, generator=g)
-
-
-def synth_backbone_state_dict(seed=0):
-    """Random-init state_dict with the reference's 402 keys. BN affine/running stats and PReLU
-    slopes are drawn away from identity so that folding bugs are visible."""
-    g = torch.Generator().manual_seed(seed)
-    sd = {}
-    sd["input_layer.0.weight"] = _conv_w((64, 3, 3, 3), g)
-    _bn_entries(sd, "input_layer.1.", 64, g)
-    sd["input_layer.2.weight"] = torch.empty(64).uniform_(0.1, 0.4, generator=g)
-    for u, (cin, depth, stride) in enumerate(unit_table()):
-        p = "body.%d." % u
-        if cin != depth:
-            sd[p + "shortcut_layer.0.weight"] = _conv_w((depth, cin, 1, 1), g)
-            _bn_entries(sd, p + "shortcut_layer.1.", depth, g)
-        _bn_entries(sd, p + "res_layer.0.", cin, g)
-        sd[p + "res_layer.1.weight"] = _conv_w((depth, cin, 3, 3), g)
-        sd[p + "res_layer.2.weight"] = torch.empty(depth).uniform_(0.1, 0.4, generator=g)
-        sd[p + "res_layer.3.weight"] = _conv_w((depth, depth, 3, 3), g)
-        _bn_entries(sd, p + "res_layer.4.", depth, g)
-        sd[p + "res_layer.5.fc1.weight"] = _conv_w((depth // 16, depth, 1, 1), g)
-        sd[p + "res_layer.5.fc2.weight"] = _conv_w((depth, depth // 16, 1, 1), g)
-    _bn_entries(sd, "output_layer.0.", 512, g)
-    b = 1.0 / math.sqrt(25088)
-    sd["output_layer.3.weight"] = torch.empty(512, 25088).uniform_(-b, b, generator=g)
-    sd["output_layer.3.bias"] = torch.empty(512).uniform_(-b, b, generator=g)
-    _bn_entries(sd, "output_layer.4.", 512, g)
-    _bn_entries(sd, "bn.", 512, g)
-    return sd
-
-
-def synth_faces(n, seed=0, masked=False):
-    """Synthetic 'face' batch in [-1,1] (range of ToTensor+Normalize(.5,.5), data/dataloader.py:15-19).
-    masked=True overwrites rows 56..111 with a per-image, per-channel constant."""
-    g = torch.Generator().manual_seed(seed)
-    x = torch.randn(n, 3, 112, 112, generator=g).mul_(0.5).clamp_(-1, 1)
-    if masked:
-        g2 = torch.Generator().manual_seed(seed + 1)
-        col = torch.empty(n, 3, 1, 1).uniform_(-1, 1, generator=g2)
-        x[:, :, 56:, :] = col
-    return x
+# Deterministic synthetic weights / inputs live in ffr_net_b200/synth.py (shared by tests, bench and tools so that the
+# product benchmark never imports oracle/); re-exported here under their historical names.
+from ffr_net_b200.synth import synth_backbone_state_dict, synth_faces  # noqa: E402,F401

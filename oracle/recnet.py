@@ -157,35 +157,5 @@ def recnet_forward(sd, x, label=None, training=False, return_stats=False, emulat
     return out
 
 
-# ----------------------------------------------------------------------------------------------------------
-# Deterministic synthetic weights: init_weights(recnet, 'kaiming') semantics (recnet.py:13-42, trainer.py:65-66):
-# conv/linear weights kaiming-normal(fan_in), biases 0; BatchNorm weight ~ N(1, 0.02), bias 0; PReLU 0.25;
-# classifier xavier-uniform. `perturb=True` additionally moves BN stats / PReLU slopes / linear biases away from
-# their trivial values so that folding mistakes are visible.
-# ----------------------------------------------------------------------------------------------------------
-def synth_recnet_state_dict(seed=0, perturb=True):
-    g = torch.Generator().manual_seed(seed)
-    sd = {}
-
-    def kaiming(shape, fan_in):
-        return torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_in)
-
-    for p, cin, cout in CONV_LAYERS:
-        sd[p + ".conv2d.weight"] = kaiming((cout, cin, 3, 3), cin * 9)
-        sd[p + ".relu.func.weight"] = (torch.empty(cout).uniform_(0.1, 0.4, generator=g) if perturb
-                                       else torch.full((cout,), 0.25))
-        q = p + ".norm.norm."
-        sd[q + "weight"] = 1.0 + 0.02 * torch.randn(cout, generator=g)
-        sd[q + "bias"] = torch.empty(cout).uniform_(-0.1, 0.1, generator=g) if perturb else torch.zeros(cout)
-        sd[q + "running_mean"] = torch.empty(cout).uniform_(-0.1, 0.1, generator=g) if perturb else torch.zeros(cout)
-        sd[q + "running_var"] = torch.empty(cout).uniform_(0.8, 1.2, generator=g) if perturb else torch.ones(cout)
-        sd[q + "num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
-    for p, cin, cout in LINEARS:
-        sd[p + ".weight"] = kaiming((cout, cin), cin)
-        sd[p + ".bias"] = torch.empty(cout).uniform_(-0.1, 0.1, generator=g) if perturb else torch.zeros(cout)
-    for i in (1, 4, 7):
-        sd["Conv4Channel.%d.func.weight" % i] = (torch.empty(512).uniform_(0.1, 0.4, generator=g) if perturb
-                                                 else torch.full((512,), 0.25))
-    b = math.sqrt(6.0 / (512 + NUM_CLASSES))
-    sd["classifier.weight"] = torch.empty(NUM_CLASSES, 512).uniform_(-b, b, generator=g)
-    return sd
+# Deterministic synthetic weights live in ffr_net_b200/synth.py (see oracle/backbone.py); re-exported here.
+from ffr_net_b200.synth import synth_recnet_state_dict  # noqa: E402,F401

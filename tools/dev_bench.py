@@ -7,7 +7,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import backbone as ob  # weights generator only
+from ffr_net_b200 import synth as ob
 from ffr_net_b200.backbone import Backbone
 
 
@@ -50,7 +50,7 @@ def main():
         out = {"n": n, "ms": ms, "img_s": n / ms * 1e3, "agg": agg, "rows": rows}
         # ---- RecNet stage ----
         try:
-            from oracle import recnet as orr
+            from ffr_net_b200 import synth as orr
             from ffr_net_b200.recnet import RecNet
             rec = RecNet()
             rec.load_state_dict(orr.synth_recnet_state_dict(0))

@@ -10,8 +10,8 @@ import time
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import backbone as ob   # synthetic weights / generators only
-from oracle import recnet as orr
+from ffr_net_b200 import synth as ob   # synthetic weights / generators only
+from ffr_net_b200 import synth as orr
 from ffr_net_b200 import scoring
 from ffr_net_b200.backbone import Backbone
 from ffr_net_b200.recnet import RecNet

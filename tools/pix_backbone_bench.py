@@ -7,7 +7,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import backbone as ob
+from ffr_net_b200 import synth as ob
 from ffr_net_b200 import _lib
 from ffr_net_b200.backbone import Backbone
 

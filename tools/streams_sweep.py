@@ -7,8 +7,8 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import backbone as ob  # weights generators only
-from oracle import recnet as orr
+from ffr_net_b200 import synth as ob
+from ffr_net_b200 import synth as orr
 from ffr_net_b200.backbone import Backbone
 from ffr_net_b200.recnet import RecNet
 

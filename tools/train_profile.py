@@ -6,8 +6,8 @@ import torch
 from torch.profiler import ProfilerActivity, profile
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import backbone as ob
-from oracle import recnet as orr
+from ffr_net_b200 import synth as ob
+from ffr_net_b200 import synth as orr
 from ffr_net_b200.backbone import Backbone
 from ffr_net_b200.recnet import RecNet
 from ffr_net_b200.trainer import Trainer, default_opts
