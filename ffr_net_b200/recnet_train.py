@@ -44,6 +44,50 @@ def _pad1(t, n):
     return out
 
 
+# Running-statistics updates are read-modify-writes of module buffers. When the two RecNet calls of a training step run
+# concurrently on two streams (Trainer, opts.two_streams) they are collected here and applied after the join, first
+# call first, exactly as the sequential reference does (models/trainer.py:144-145).
+_STATS_SINK = None
+
+
+def _update_running_stats(bn, mean, var, cnt):
+    with torch.no_grad():                           # momentum 0.1, unbiased variance (nn.BatchNorm2d in train mode)
+        bn.running_mean.mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * mean)
+        bn.running_var.mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * var * (cnt / max(cnt - 1.0, 1.0)))
+        bn.num_batches_tracked += 1
+
+
+class deferred_running_stats:
+    """Context manager: ConvLayer forwards inside it record their batch statistics in `self.items` instead of
+    updating the BatchNorm buffers; apply() performs the updates in recording order."""
+
+    def __enter__(self):
+        global _STATS_SINK
+        self.items, self._prev = [], _STATS_SINK
+        _STATS_SINK = self.items
+        return self
+
+    def __exit__(self, *exc):
+        global _STATS_SINK
+        _STATS_SINK = self._prev
+        return False
+
+    def apply(self):
+        for bn, mean, var, cnt in self.items:
+            _update_running_stats(bn, mean, var, cnt)
+
+
+def prepack(model):
+    """Pack every ConvLayer weight (forward + dgrad layouts) and the class matrix of the head on the CURRENT stream, so
+    that concurrent forward calls only hit the caches."""
+    from . import head
+    for _, layer in model.conv_layers():
+        w = layer.conv2d.weight
+        _packed_weights(layer, w, _ceil64(w.shape[1]), _ceil64(w.shape[0]))
+    head._packed_classes(_lib.load(), model.classifier.weight)
+    model._train_tables(model.classifier.weight.device)
+
+
 def _packed_weights(layer, weight, cin_p, cout_p):
     """bf16 K-major weights for the forward GEMM and the dgrad GEMM, packed by one kernel and cached until the
     parameter changes (the two RecNet calls of a step and the backward share them)."""
@@ -97,10 +141,10 @@ class _ConvLayerTrain(torch.autograd.Function):
         var = (stats[1] / cnt - mean * mean).clamp_min_(0.0)
         rstd = torch.rsqrt(var + BN_EPS)
         bn = layer.norm.norm
-        with torch.no_grad():                       # running statistics (momentum 0.1, unbiased variance)
-            bn.running_mean.mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * mean[:cout])
-            bn.running_var.mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * var[:cout] * (cnt / max(cnt - 1.0, 1.0)))
-            bn.num_batches_tracked += 1
+        if _STATS_SINK is not None:                 # concurrent forward calls: the caller applies them in call order
+            _STATS_SINK.append((bn, mean[:cout], var[:cout], cnt))
+        else:
+            _update_running_stats(bn, mean[:cout], var[:cout], cnt)
         g_p, b_p, s_p = _pad1(gamma, cout_p), _pad1(beta, cout_p), _pad1(slope, cout_p)
         out = torch.empty(n * 81, cout_p, dtype=torch.bfloat16, device=dev)
         res = res_h9.contiguous() if res_h9 is not None else None

@@ -31,7 +31,7 @@ def default_opts(**kw):
     """The hyper-parameters run.py passes (run.py:10-28)."""
     o = types.SimpleNamespace(phase="train", lr=0.1, beta1=0.9, beta2=0.999, weight_decay=0.0, optimizer="adam",
                               loss_weight=[1.0, 1.0, 1.0, 1.0], device="cuda", continue_train=False,
-                              ckpt_dir="./checkpoints")
+                              ckpt_dir="./checkpoints", fused_head=True, two_streams=True)
     for k, v in kw.items():
         setattr(o, k, v)
     return o
@@ -75,6 +75,9 @@ class Trainer:
         # CosFace head + CrossEntropy as one fused forward/backward (head.py); opts.fused_head=False keeps the
         # reference's op sequence on library kernels (two (N,10575) tensors + nn.CrossEntropyLoss)
         self.fused_head = bool(getattr(opts, "fused_head", True))
+        # run the two RecNet calls of an iteration on two streams (see _forward_two_streams)
+        self.two_streams = bool(getattr(opts, "two_streams", True))
+        self._side = None
         self.mse_loss = nn.MSELoss()
         self.triplet = TripletLoss()
         self.cross_entropy = nn.CrossEntropyLoss()
@@ -180,16 +183,47 @@ class Trainer:
             rec = lambda fmap: forward_train(self.recnet, fmap, self.gt_label, fused_ce=True)
         else:
             rec = lambda fmap: self.recnet(fmap, self.gt_label)
+        if self.two_streams and self.recnet.training:
+            out_non, out_ocl = self._forward_two_streams(rec)
+        else:
+            out_non, out_ocl = rec(self.feat_map_non), rec(self.feat_map_ocl)
         (self.f_non, self.pred_loss_non, self.pred_label_non, self.M_space_non, self.M_channel_non, self.space_non,
-         self.channel_non) = rec(self.feat_map_non)
+         self.channel_non) = out_non
         (self.f_ocl, self.pred_loss_ocl, self.pred_label_ocl, self.M_space_ocl, self.M_channel_ocl, self.space_ocl,
-         self.channel_ocl) = rec(self.feat_map_ocl)
+         self.channel_ocl) = out_ocl
         if isinstance(self.pred_label_ocl, FusedCE):
             pred = self.pred_label_ocl.pred
         else:
             pred = self.pred_label_ocl.detach().argmax(1)
         self.pred_label = pred
         self._correct = pred.eq(self.gt_label).sum()          # no host sync here; .item() in get_current_values
+
+    def _forward_two_streams(self, rec):
+        """The two RecNet calls of an iteration (unmasked, masked; models/trainer.py:144-145) are independent until the
+        losses: the second runs on a side stream forked from the current one, so its many small kernels (and, through
+        autograd, their backward counterparts) overlap the first call's. Shared state is kept race-free: weights are
+        packed before the fork, BatchNorm running statistics are applied after the join in call order."""
+        from . import recnet_train
+        dev = self.feat_map_non.device
+        recnet_train.prepack(self.recnet)
+        main = torch.cuda.current_stream(dev)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=dev)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        self._side.wait_event(fork)
+        with recnet_train.deferred_running_stats() as stats:
+            with torch.cuda.stream(self._side):
+                out_ocl = rec(self.feat_map_ocl)
+                join = torch.cuda.Event()
+                join.record(self._side)
+            n_side = len(stats.items)
+            out_non = rec(self.feat_map_non)
+        main.wait_event(join)
+        # reference order: all layers of the unmasked call, then all layers of the masked call
+        stats.items = stats.items[n_side:] + stats.items[:n_side]
+        stats.apply()
+        return out_non, out_ocl
 
     def backward(self):
         # trainer.py:157-161 calls selfSimilarity five times and discards one of the two Grams in four of them;

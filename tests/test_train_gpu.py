@@ -308,3 +308,54 @@ def test_trainer_checkpoint_roundtrip(lib, tmp_path):
         v1, _ = tr.recnet(y)
         v2, _ = tr2.recnet(y)
     assert (v1 - v2).abs().max().item() <= 1e-5 * v1.abs().max().item() + 1e-6
+
+
+def test_two_stream_recnet_calls_match_sequential(lib):
+    """opts.two_streams: the masked RecNet call on a side stream, concurrent with the unmasked one. Same losses,
+    BatchNorm running statistics applied in the reference's order (two updates per layer), gradients equal up to the
+    run-to-run noise of the sequential step; and the whole thing replays from a CUDA graph."""
+    from ffr_net_b200.trainer import Trainer, default_opts
+    bsd, rsd = ob.synth_backbone_state_dict(0), orr.synth_recnet_state_dict(0)
+    n = 8
+    a, b = ob.synth_faces(n, seed=5).cuda(), ob.synth_faces(n, seed=5, masked=True).cuda()
+    label = torch.randint(0, 10575, (n,), generator=torch.Generator().manual_seed(5)).cuda()
+    res = []
+    for two in (False, False, True):
+        rec = RecNet()
+        rec.load_state_dict(rsd)
+        tr = Trainer(default_opts(lr=1e-3, two_streams=two), recnet=rec, encoder_weights=bsd)
+        tr.set_input(a, b, label)
+        tr.forward()
+        tr.zero_grad()
+        tr.backward()
+        torch.cuda.synchronize()
+        res.append(([float(l.detach()) for l in tr.loss_items], {k: p.grad.clone() for k, p in rec.named_parameters()},
+                    {k: v.clone() for k, v in rec.state_dict().items() if "running" in k or "tracked" in k}))
+    (l0, g0, s0), (l0b, g0b, _), (l1, g1, s1) = res
+    assert all(abs(x - y) <= 1e-3 * max(1.0, abs(x)) for x, y in zip(l0, l1)), (l0, l1)
+    for k in s0:
+        if k.endswith("num_batches_tracked"):
+            assert int(s0[k]) == int(s1[k]) == 2
+        else:
+            assert rel_l2(s1[k], s0[k]) <= 2e-3, k
+    cosd = sorted(torch.nn.functional.cosine_similarity(g1[k].reshape(1, -1), g0[k].reshape(1, -1)).item() for k in g0)
+    cosn = sorted(torch.nn.functional.cosine_similarity(g0b[k].reshape(1, -1), g0[k].reshape(1, -1)).item() for k in g0)
+    print("two-stream vs sequential grad cosine: min %.4f median %.4f | run-to-run: min %.4f median %.4f" %
+          (cosd[0], cosd[len(cosd) // 2], cosn[0], cosn[len(cosn) // 2]))
+    assert cosd[len(cosd) // 2] >= min(0.99, cosn[len(cosn) // 2] - 0.01) and cosd[0] >= cosn[0] - 0.1
+    # graph capture + a few replays with the side stream inside the graph
+    rec = RecNet()
+    rec.load_state_dict(rsd)
+    for split in (False, True):              # one graph, and the data-parallel form (two graphs around the exchange)
+        rec = RecNet()
+        rec.load_state_dict(rsd)
+        tr = Trainer(default_opts(lr=1e-3, two_streams=True), recnet=rec, encoder_weights=bsd)
+        tr.capture_step(a, b, label, warmup=2, split_optimizer=split)
+        for _ in range(3):
+            tr.step(a, b, label)
+        torch.cuda.synchronize()
+        vals = tr.get_current_values()
+        assert all(torch.isfinite(p).all() for p in rec.parameters())
+        assert abs(float(vals["SelfSimilarityLoss"]) - l0[0]) <= 0.1 * max(1.0, abs(l0[0]))
+        # 2 calls per iteration x (2 warm-up iterations + 3 replays); the capture itself executes nothing
+        assert int(rec.state_dict()["Conv4Merge.0.norm.norm.num_batches_tracked"]) == 2 * (2 + 3)
