@@ -31,7 +31,8 @@ def default_opts(**kw):
     """The hyper-parameters run.py passes (run.py:10-28)."""
     o = types.SimpleNamespace(phase="train", lr=0.1, beta1=0.9, beta2=0.999, weight_decay=0.0, optimizer="adam",
                               loss_weight=[1.0, 1.0, 1.0, 1.0], device="cuda", continue_train=False,
-                              ckpt_dir="./checkpoints", fused_head=True, two_streams=True)
+                              ckpt_dir="./checkpoints", fused_head=True, two_streams=True,
+                              merge_encoder_batches=True)
     for k, v in kw.items():
         setattr(o, k, v)
     return o
@@ -77,6 +78,7 @@ class Trainer:
         self.fused_head = bool(getattr(opts, "fused_head", True))
         # run the two RecNet calls of an iteration on two streams (see _forward_two_streams)
         self.two_streams = bool(getattr(opts, "two_streams", True))
+        self.merge_encoder_batches = bool(getattr(opts, "merge_encoder_batches", True))
         self._side = None
         self.mse_loss = nn.MSELoss()
         self.triplet = TripletLoss()
@@ -176,8 +178,16 @@ class Trainer:
 
     def forward(self):
         with torch.no_grad():
-            self.feat_map_non, self.feat_extract_non = self.encoder(self.nonocl)
-            self.feat_map_ocl, self.feat_extract_ocl = self.encoder(self.ocl)
+            if self.merge_encoder_batches and self.nonocl.shape == self.ocl.shape:
+                # the frozen eval-mode backbone is per-image: one forward over both image sets (better tile / wave
+                # occupancy than two half-size ones), then split — same values as the two calls of trainer.py:141-142
+                n = self.nonocl.shape[0]
+                y, f = self.encoder(torch.cat((self.nonocl, self.ocl), 0))
+                self.feat_map_non, self.feat_map_ocl = y[:n], y[n:]
+                self.feat_extract_non, self.feat_extract_ocl = f[:n], f[n:]
+            else:
+                self.feat_map_non, self.feat_extract_non = self.encoder(self.nonocl)
+                self.feat_map_ocl, self.feat_extract_ocl = self.encoder(self.ocl)
         if self.fused_head and self.recnet.training:
             from .recnet_train import forward_train
             rec = lambda fmap: forward_train(self.recnet, fmap, self.gt_label, fused_ce=True)

@@ -94,7 +94,7 @@ def test_trainer_fused_head_matches_library_head(lib):
     for fused in (False, False, True):
         rec = RecNet()
         rec.load_state_dict(rsd)
-        tr = Trainer(default_opts(fused_head=fused), recnet=rec, encoder_weights=bsd)
+        tr = Trainer(default_opts(fused_head=fused, merge_encoder_batches=False), recnet=rec, encoder_weights=bsd)
         if not feats:
             with torch.no_grad():
                 feats.extend([tr.encoder(a), tr.encoder(b)])

@@ -48,7 +48,7 @@ def trainer_grads(fused, feats, rsd, bsd, a, b, label):
 
     rec = RecNet()
     rec.load_state_dict(rsd)
-    tr = Trainer(default_opts(fused_head=fused), recnet=rec, encoder_weights=bsd)
+    tr = Trainer(default_opts(fused_head=fused, merge_encoder_batches=False), recnet=rec, encoder_weights=bsd)
     if not feats:
         with torch.no_grad():
             feats.extend([tuple(t.clone() for t in tr.encoder(a)), tuple(t.clone() for t in tr.encoder(b))])
@@ -69,7 +69,7 @@ def backward_twice(rsd, bsd, a, b, label, fused):
     from ffr_net_b200.trainer import Trainer, default_opts
     rec = RecNet()
     rec.load_state_dict(rsd)
-    tr = Trainer(default_opts(fused_head=fused), recnet=rec, encoder_weights=bsd)
+    tr = Trainer(default_opts(fused_head=fused, merge_encoder_batches=False), recnet=rec, encoder_weights=bsd)
     tr.set_input(a, b, label)
     tr.forward()
     orig = torch.Tensor.backward
