@@ -66,7 +66,8 @@ def test_pair_cosine_and_masked_inputs(models):
 def test_backbone_batch_invariance(models):
     """Images are independent: row i of a batch equals the same image run alone, up to fp32 accumulation order (the
     SE squeeze and the split-K head use atomics whose partial sums depend on how tiles straddle images): the feature
-    map may differ by a bf16 ulp here and there (<= 2^-7 of its range), the embedding by <= 1e-4."""
+    map may differ by a bf16 ulp here and there that then propagates through the remaining units (measured up to
+    6e-3 of its range here, up to 1e-2 over larger batches), the unit-norm embedding by a few 1e-4."""
     sd, m = models
     x = ob.synth_faces(4, seed=9).cuda()
     with torch.no_grad():
@@ -78,7 +79,7 @@ def test_backbone_batch_invariance(models):
         y1b, f1b = m(x[2:3])
     print("batch invariance: featmap rel diff %.3e, embedding abs diff %.3e; run-to-run %.3e" %
           (dy, df, (y1b - y1).abs().max().item()))
-    assert dy <= 1e-2 and df <= 1e-3     # chaotic amplification of single bf16 ulps through 24 units
+    assert dy <= 2e-2 and df <= 2e-3     # chaotic amplification of single bf16 ulps through 24 units (measured <= 5.8e-3 / 3.4e-4)
 
 
 def test_backbone_rejects_training_and_cpu(models):
@@ -124,7 +125,7 @@ def test_empty_and_odd_batches(models):
         y7, f7 = m(x.cuda())
         y3, f3 = m(x[:3].cuda())
     assert torch.isfinite(f7).all()
-    assert (f7[:3] - f3).abs().max().item() <= 1e-3
+    assert (f7[:3] - f3).abs().max().item() <= 2e-3          # batch-invariance bound
     with pytest.raises(ValueError):
         m(torch.zeros(2, 3, 96, 112, device="cuda"))
 
@@ -171,7 +172,7 @@ def test_backbone_forward_u8_matches_fp32_input(models):
         y2, f2 = m.forward_u8(torch.from_numpy(imgs).cuda(), flip=flips.cuda())
         y3, f3 = m(opp.preprocess_batch(imgs, flips.numpy()).cuda())
     # same kernels on bit-identical stem inputs: only the fp32 atomics order of the SE / head sums differs
-    assert (f1 - f0).abs().max().item() <= 1e-3 and (y1 - y0).abs().max().item() <= 1e-2 * y0.abs().max().item()
-    assert (f2 - f3).abs().max().item() <= 1e-3 and (y2 - y3).abs().max().item() <= 1e-2 * y3.abs().max().item()
-    assert (f2[1] - f0[1]).abs().max().item() <= 1e-3          # image 1 is not flipped
-    assert (f2[0] - f0[0]).abs().max().item() > 1e-3            # image 0 is
+    assert (f1 - f0).abs().max().item() <= 2e-3 and (y1 - y0).abs().max().item() <= 2e-2 * y0.abs().max().item()
+    assert (f2 - f3).abs().max().item() <= 2e-3 and (y2 - y3).abs().max().item() <= 2e-2 * y3.abs().max().item()
+    assert (f2[1] - f0[1]).abs().max().item() <= 2e-3          # image 1 is not flipped
+    assert (f2[0] - f0[0]).abs().max().item() > 1e-2            # image 0 is

@@ -39,7 +39,7 @@ def test_embeddings_bs512_properties(lib, nets):
     # feature-map bound doubled because this is the extreme over 12.8 M elements (bf16 ulp flips through 24 units)
     yv, fv, vv = y.view(8, 64, -1), f.view(8, 64, -1), v.view(8, 64, -1)
     assert (yv - yv[:1]).abs().max().item() <= 2e-2 * y.abs().max().item()
-    assert (fv - fv[:1]).abs().max().item() <= 1e-3
+    assert (fv - fv[:1]).abs().max().item() <= 2e-3
     assert (vv - vv[:1]).abs().max().item() <= 1e-2 * v.abs().max().item()
     assert (v2 - v).abs().max().item() <= 1e-2 * v.abs().max().item()
     cos = torch.nn.functional.cosine_similarity(vv[0], vv[5], dim=1)           # same image, different batch slot
