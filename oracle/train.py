@@ -53,3 +53,22 @@ def train_step(bsd, rsd, img1, img2, label, loss_weight=(1.0, 1.0, 1.0, 1.0), em
     acc = (out_ocl[2].argmax(1) == label).float().mean().item()
     grads = {k: p.grad for k, p in params.items()}
     return [float(i.detach()) for i in items], grads, {k: v.detach() for k, v in st2.items()}, acc
+
+
+def clip_adam_step(params, grads, lr, step=1, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, clip=1.0, state=None):
+    """clip_grad_value_(params, 1.0) followed by one torch.optim.Adam step (models/trainer.py:183-187), restated with
+    the textbook update on plain tensors. `state` carries (exp_avg, exp_avg_sq) per name between steps."""
+    state = {} if state is None else state
+    out = {}
+    b1, b2 = betas
+    for k, p in params.items():
+        g = grads[k].clamp(-clip, clip)
+        if weight_decay != 0.0:
+            g = g + weight_decay * p
+        m, v = state.get(k, (torch.zeros_like(p), torch.zeros_like(p)))
+        m = b1 * m + (1 - b1) * g
+        v = b2 * v + (1 - b2) * g * g
+        state[k] = (m, v)
+        denom = (v.sqrt() / (1 - b2 ** step) ** 0.5) + eps
+        out[k] = p - (lr / (1 - b1 ** step)) * m / denom
+    return out, state

@@ -136,3 +136,40 @@ def test_gallery_oracle_consistent_with_paired_scoring():
                 if same and pid[i] != gid[j]:
                     fa += 1
         assert roc["true_accept"][k] == ta and roc["false_accept"][k] == fa
+
+
+def test_train_oracle_matches_reference_trainer_golden():
+    """oracle.train.train_step + clip_adam_step against the REAL models/trainer.py Trainer (set_input / forward /
+    backward / clip_grad_value_ / Adam.step on a hand-built instance, tools/make_golden.py golden_trainer): the four
+    weighted loss items, accuracy, the norm of every one of the 76 gradients, gradient and post-step parameter slices,
+    BatchNorm running statistics after the two forward calls."""
+    from oracle import train as otr
+    g = _load("trainer_ref.npz")
+    bsd, rsd = ob.synth_backbone_state_dict(0), orr.synth_recnet_state_dict(0)
+    img1, img2 = ob.synth_faces(2, seed=3), ob.synth_faces(2, seed=3, masked=True)
+    label = torch.tensor([5, 4242])
+    items, grads, stats, acc = otr.train_step(bsd, rsd, img1, img2, label)
+    assert np.allclose(items, g["losses"], rtol=1e-5, atol=1e-7), (items, g["losses"])     # measured 9e-8
+    assert acc == float(g["accuracy"])
+    keys = [str(k) for k in g["grad_norm_keys"]]
+    assert sorted(grads) == keys and len(keys) == 76
+    norms = np.array([float(grads[k].norm()) for k in keys])
+    assert np.allclose(norms, g["grad_norms"], rtol=1e-4, atol=1e-9), np.abs(norms / g["grad_norms"] - 1).max()   # 8e-7
+
+    def sl(t):
+        f = t.detach().reshape(-1)
+        return f if f.numel() <= 2048 else f[::997]
+    params = {k: rsd[k] for k in grads}
+    after, _ = otr.clip_adam_step(params, grads, lr=1e-3)
+    for name in [k[5:] for k in g.files if k.startswith("grad:")]:
+        ref = g["grad:" + name]
+        got = sl(grads[name]).numpy()
+        assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max() + 1e-9, name
+        ref_p, got_p = g["after:" + name], sl(after[name]).numpy()
+        # Adam's first step moves every element by ~lr * sign(g): compare the step, not just the value
+        ref_0 = sl(rsd[name]).numpy()
+        flip = np.abs((got_p - ref_0) - (ref_p - ref_0)) > 2e-4 * 1e-3
+        assert flip.mean() <= 0.02, (name, flip.mean())     # only elements whose gradient is ~0 may disagree
+    assert np.allclose(stats["Conv4Merge.0.norm.norm.running_mean"].numpy(), g["run_mean_merge0"], rtol=1e-4, atol=1e-6)
+    assert np.allclose(stats["Conv4Space.0.norm.norm.running_var"].numpy(), g["run_var_space0"], rtol=1e-4, atol=1e-6)
+    assert int(stats["Conv4Merge.0.norm.norm.num_batches_tracked"]) == int(g["nbt"]) == 2

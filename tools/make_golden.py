@@ -100,6 +100,91 @@ def golden_preprocess():
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+GOLD_TRAIN_TENSORS = ["classifier.weight", "Conv4Merge.0.conv2d.weight", "Conv4Merge.1.conv2.norm.norm.bias",
+                      "ChannelFlipMerge.0.conv2d.weight", "Conv4Space.0.conv2d.weight", "Conv4Space.0.norm.norm.weight",
+                      "Conv4Space.5.conv2.relu.func.weight", "Conv4Channel.0.weight", "Conv4Channel.8.bias",
+                      "Conv4Channel.4.func.weight"]
+
+
+def gold_slice(t):
+    """Deterministic thinning that keeps fixtures small: every 997th element of the flattened tensor (all if small)."""
+    f = t.detach().reshape(-1)
+    return f.clone() if f.numel() <= 2048 else f[::997].clone()
+
+
+def golden_trainer():
+    """The REAL models/trainer.py Trainer (set_input / forward / backward / optimizer_parameters, :129-187) on a
+    hand-built instance (its __init__ wants the Google-Drive checkpoint and GPU ids), CPU fp32, 2 pairs:
+    losses, accuracy, gradient slices before clipping, parameters after clip + Adam, BN running statistics
+    -> tests/golden/trainer_ref.npz. recnet.py:262 hard-codes device='cuda' for the one-hot; torch.zeros is patched to
+    drop that keyword (no other change)."""
+    stub_missing()
+    try:
+        import cv2  # noqa: F401
+    except Exception:
+        sys.modules["cv2"] = _Stub("cv2")
+    import types as _types
+    from pretrain.model_ir_se50 import Backbone
+    import models.recnet as mr
+    import models.trainer as mt
+    from ffr_net_b200 import synth
+    real_zeros = torch.zeros
+
+    def zeros_cpu(*a, **k):
+        k.pop("device", None)
+        return real_zeros(*a, **k)
+
+    bsd, rsd = synth.synth_backbone_state_dict(0), synth.synth_recnet_state_dict(0)
+    img1, img2 = synth.synth_faces(2, seed=3), synth.synth_faces(2, seed=3, masked=True)
+    label = torch.tensor([5, 4242])
+    tr = mt.Trainer.__new__(mt.Trainer)
+    tr.opts = _types.SimpleNamespace(phase="train", lr=1e-3, beta1=0.9, beta2=0.999, weight_decay=0.0, optimizer="adam",
+                                     loss_weight=[1.0, 1.0, 1.0, 1.0])
+    tr.isTrain, tr.lr = True, tr.opts.lr
+    tr.encoder = Backbone(50, 0.6, "ir_se")
+    tr.encoder.load_state_dict(bsd, strict=True)
+    tr.recnet = mr.RecNet(norm_type="bn", relu_type="prelu")
+    tr.recnet.load_state_dict(rsd, strict=True)
+    for p in tr.encoder.parameters():
+        p.requires_grad = False
+    tr.forward_encoder = lambda x: tr.encoder(x)
+    tr.forward_recnet = lambda x, l: tr.recnet(x, l)
+    tr.encoder.eval()
+    tr.recnet.train()
+    tr.config_optimizer()
+    tr.config_criterion()
+    mr.torch.zeros = zeros_cpu
+    try:
+        tr.set_input(img1, img2, label)
+        with torch.no_grad():
+            pass
+        tr.forward()
+        tr.optim.zero_grad()
+        tr.backward()
+        named = dict(tr.recnet.named_parameters())
+        grads = {k: gold_slice(named[k].grad) for k in GOLD_TRAIN_TENSORS}
+        gnorm = {k: float(named[k].grad.norm()) for k in named}
+        losses = [float(l.detach()) for l in tr.loss_items]
+        # the optimizer half of optimizer_parameters (:183-187) on the gradients just computed
+        mt.clip_grad_value_(tr.recnet.parameters(), 1.0)
+        tr.optim.step()
+        after = {k: gold_slice(named[k]) for k in GOLD_TRAIN_TENSORS}
+    finally:
+        mr.torch.zeros = real_zeros
+    sd = tr.recnet.state_dict()
+    out = {"losses": np.array(losses), "accuracy": np.float64(tr.accuracy), "pos_loss": np.float64(float(tr.pos_loss)),
+           "neg_loss": np.float64(float(tr.neg_loss)),
+           "grad_norm_keys": np.array(sorted(gnorm)), "grad_norms": np.array([gnorm[k] for k in sorted(gnorm)]),
+           "run_mean_merge0": sd["Conv4Merge.0.norm.norm.running_mean"].numpy(),
+           "run_var_space0": sd["Conv4Space.0.norm.norm.running_var"].numpy(),
+           "nbt": np.int64(int(sd["Conv4Merge.0.norm.norm.num_batches_tracked"]))}
+    for k in GOLD_TRAIN_TENSORS:
+        out["grad:" + k] = grads[k].numpy()
+        out["after:" + k] = after[k].numpy()
+    np.savez_compressed(os.path.join(OUT, "trainer_ref.npz"), **out)
+    print("trainer_ref.npz: losses", losses, "acc", tr.accuracy)
+
+
 def golden_checkpoint():
     """A tiny checkpoint written by the REAL utils.save (utils/utils.py:110-115) with the container layout of
     Trainer.save_model (models/trainer.py:216-224) -> tests/golden/tiny_ckpt_ref.pth.gzip."""
@@ -122,6 +207,8 @@ def main():
         return golden_preprocess()
     if len(sys.argv) > 1 and sys.argv[1] == "checkpoint":
         return golden_checkpoint()
+    if len(sys.argv) > 1 and sys.argv[1] == "trainer":
+        return golden_trainer()
     torch.set_num_threads(os.cpu_count() or 1)
     from pretrain.model_ir_se50 import Backbone
     import models.recnet as mr
@@ -173,6 +260,7 @@ def main():
     # ---- preprocessing, checkpoint container ----
     golden_preprocess()
     golden_checkpoint()
+    golden_trainer()
 
     # ---- scoring: the real lfw_eval functions on 6000 synthetic pairs ----
     stub_missing()
