@@ -11,6 +11,7 @@ synthetic 112x112 faces, random-init weights. A "step" is one forward pass over 
 import argparse
 import json
 import os
+import re
 import statistics
 import subprocess
 import sys
@@ -314,11 +315,18 @@ def run_ours(args):
         step(x_dev)
         torch.cuda.synchronize()
         prev, durs, total = e_first, [], 0.0
+        conv_ms, conv_flop, conv_n = 0.0, 0.0, 0
         for what, ev in enc._profile:
             dt = prev.elapsed_time(ev)
             total += dt
             if what.startswith("conv") and "256>256@14s1" in what:
                 durs.append(dt)
+            m = re.match(r"conv[12] (\d+)>(\d+)@(\d+)s(\d)$", what)     # every 3x3 conv of the backbone body
+            if m:
+                cin, cout, S, st = (int(v) for v in m.groups())
+                conv_ms += dt
+                conv_flop += 2.0 * BATCH * (S // st) ** 2 * cin * cout * 9
+                conv_n += 1
             prev = ev
         enc._profile = None
         if durs:
@@ -331,6 +339,10 @@ def run_ours(args):
                     "unit": "TFLOP/s", "frac": achieved / peak, "avg_launch_ms": avg_ms,
                     "share_of_step": sum(durs) / (ms / args.steps),
                     "traffic": _ncu_traffic()}
+            if conv_n:      # all 48 3x3 convolutions of the backbone body together (un-padded FLOPs / their summed time)
+                agg = conv_flop / (conv_ms * 1e-3) / 1e12
+                roof["all_backbone_conv_gemms"] = {"launches": conv_n, "achieved": agg, "frac": agg / peak,
+                                                   "ms_per_step": conv_ms, "share_of_step": conv_ms / (ms / args.steps)}
         if world == 1:
             cpu = cpu_baseline(with_recnet)
 
