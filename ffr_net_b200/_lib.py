@@ -15,7 +15,74 @@ _i = ctypes.c_int
 _u32 = ctypes.c_uint32
 _i64 = ctypes.c_int64
 
+_f = ctypes.c_float
+
+
+class EPI:
+    """Epilogue flags of ffr_conv_gemm / ffr_conv_gemm_ex (FFR_EPI_* in include/ffr_sm100.h)."""
+    BIAS, BORDER_BIAS, PRELU, GEOM = 1 << 0, 1 << 1, 1 << 2, 1 << 3
+    POOL, OUT_S2D, OUT_F32_ATOMIC, SIGMOID = 1 << 4, 1 << 5, 1 << 6, 1 << 7
+    SCATTER, RESIDUAL, STATS, OUT_F32 = 1 << 8, 1 << 9, 1 << 10, 1 << 11
+    COSFACE, PIXMAJOR, PIX_DGRAD = 1 << 12, 1 << 13, 1 << 14
+    MUL_DSIG, RES_F16, OUT_F16 = 1 << 15, 1 << 16, 1 << 17
+
+
+class ConvGemmDesc(ctypes.Structure):
+    """ffr_conv_gemm_desc (include/ffr_sm100.h)."""
+    _fields_ = [("a", _p), ("a_rows", _i64), ("a_cols", _i), ("a_ld", _i),
+                ("wp", _p), ("Cin", _i), ("Cout", _i), ("ntaps", _i),
+                ("tap_row_shift", _p), ("tap_ch_off", _p),
+                ("M", _i), ("rows_per_img", _i), ("Wp", _i), ("S", _i), ("h0", _i), ("n_img", _i),
+                ("flags", _u32),
+                ("bias", _p), ("slope", _p),
+                ("out", _p), ("ldo", _i), ("s2d_So", _i),
+                ("pool", _p), ("out_f32", _p),
+                ("res", _p), ("ldres", _i),
+                ("stats", _p), ("stats_part", _p),
+                ("num_splits", _i),
+                ("scatter", _p), ("scatter_n", _i), ("out_rows_per_img", _i),
+                ("b_rows_per_mtile", _i), ("b_mtile_div", _i),
+                ("a_hilo", _i), ("a_lo_off", _i),
+                ("f16", _i)]
+
+
+class PrepTrainDesc(ctypes.Structure):
+    """ffr_prep_train_desc (include/ffr_sm100.h)."""
+    _fields_ = ([(k, _p) for k in ("x", "w0", "b0", "slope1", "slope4", "slope7", "A1", "c1", "A2", "c2", "w8", "b8")] +
+                [("s0_h", _p), ("s0_ld", _i), ("s0_lo", _i), ("s0_b", _p), ("s0_ldb", _i),
+                 ("cm_h", _p), ("cm_ld", _i), ("cm_lo", _i), ("cm_b", _p), ("cm_ldb", _i),
+                 ("fm_h", _p), ("fm_ld", _i), ("fm_lo", _i), ("fm_b", _p), ("fm_ldb", _i)] +
+                [(k, _p) for k in ("g0", "g1", "g2", "h7b", "xk", "mch", "inv_c", "tmat", "ss_space")])
+
+
 _SIGNATURES = {
+    "ffr_conv_gemm_ex": (_i, [ctypes.POINTER(ConvGemmDesc), _p]),
+    "ffr_bn_finalize": (_i, [_p, _i, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p]),
+    "ffr_bn_act_fwd": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _i, _p, _i, _p, _i, _i, _p, _i, _i, _i, _i, _i, _p]),
+    "ffr_nchw_to_h9_f32": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "ffr_bn_act_bwd_partial_rows": (_i, [_i, _i]),
+    "ffr_bn_act_bwd": (_i, [_p, _i, _i, _p, _i, _p, _i, _i, _p, _i, _f, _p, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p,
+                            _i, _i, _p, _i, _i, _i, _i, _p]),
+    "ffr_h9_avgpool": (_i, [_p, _i, _p, _i, _i, _i, _p]),
+    "ffr_wgrad_workspace_floats": (_i64, [_i, _i, _i, _i, _i]),
+    "ffr_wgrad": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "ffr_pack_conv3x3_f16": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
+    "ffr_recnet_prep_train": (_i, [ctypes.POINTER(PrepTrainDesc), _i, _p]),
+    "ffr_chan_compose": (_i, [_p] * 14 + [_p]),
+    "ffr_chan_compose_bwd": (_i, [_p] * 18 + [_i, _p]),
+    "ffr_feat_space_train": (_i, [_p, _p, _p, _i, _i, _p, _i, _p, _i, _i, _p]),
+    "ffr_feat_space_bwd": (_i, [_p, _p, _p, _i, _p, _i, _p, _i, _p]),
+    "ffr_fc_bwd_gather": (_i, [_p, _i, _p, _i, _p]),
+    "ffr_chan_bwd_part_floats": (_i, []),
+    "ffr_chan_bwd": (_i, [_p] * 20 + [_i, _i, _p]),
+    "ffr_selfsim_channel_pack": (_i, [_p, _i, _p, _i, _i, _p, _p, _p, _p, _p]),
+    "ffr_selfsim_channel_bwd": (_i, [_p, _p, _i, _p, _f, _p, _i, _i, _p]),
+    "ffr_sumsq_reduce": (_i, [_p, _i, _i, _i, _p, _p]),
+    "ffr_selfsim_space_loss": (_i, [_p, _i, _p, _i, _i, _f, _p, _p, _i, _p]),
+    "ffr_triplet_identity": (_i, [_p, _p, _p, _p, _i, _f, _f, _f, _p, _p, _p, _p]),
+    "ffr_loss_finalize": (_i, [_p, _p, _p, _p, _i, _i, _f, _f, _f, _f, _p, _p]),
+    "ffr_add3_f32": (_i, [_p, _p, _p, _p, _i64, _p]),
+    "ffr_cosface_ce_bwd_grouped": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _i, _f, _f, _p, _p, _p]),
     "ffr_version": (_i, []),
     "ffr_last_error": (ctypes.c_char_p, []),
     "ffr_launch_count": (ctypes.c_longlong, []),

@@ -79,6 +79,32 @@ class _Packed:
     pass
 
 
+class _CpuModules:
+    pass
+
+
+def _cpu_view(model):
+    """The module tree with every parameter / buffer copied to the host (ONE device->host transfer per tensor; a model
+    that still lives on the CPU is used as is)."""
+    import copy
+    if all(not t.is_cuda for t in list(model.parameters()) + list(model.buffers())):
+        return model
+    packed, ws, prof = model._packed, model._ws, model._profile
+    model._packed, model._ws, model._profile = None, {}, None
+    try:
+        clone = copy.deepcopy(model).cpu()
+    finally:
+        model._packed, model._ws, model._profile = packed, ws, prof
+    return clone
+
+
+def _to_device(pk, device):
+    for obj in [pk] + list(getattr(pk, "units", [])):
+        for k, v in list(vars(obj).items()):
+            if torch.is_tensor(v):
+                setattr(obj, k, v.to(device).contiguous())
+
+
 class Backbone(nn.Module):
     IMG = 112
 
@@ -113,12 +139,15 @@ class Backbone(nn.Module):
             return self._packed
         pk = _Packed()
         pk.key = key
+        # The backbone is frozen: folding / packing happens once per load, on the HOST (plain torch CPU ops on copies of
+        # the parameters), and only the packed tensors are uploaded — no device kernels are spent on weight preparation.
+        cpu = _cpu_view(self)
         with torch.no_grad():
-            conv, bn, prelu = self.input_layer[0], self.input_layer[1], self.input_layer[2]
+            conv, bn, prelu = cpu.input_layer[0], cpu.input_layer[1], cpu.input_layer[2]
             pk.stem_w, pk.stem_b = packing.pack_stem(conv.weight.detach(), _bn_fold(bn))
             pk.stem_a = prelu.weight.detach().float().contiguous()
             pk.units = []
-            for unit in self.body:
+            for unit in cpu.body:
                 u = _Packed()
                 u.cin, u.depth, u.stride = unit.in_channel, unit.depth, unit.stride
                 bn0, conv1, pr, conv2, bn1, se = unit.res_layer
@@ -136,10 +165,11 @@ class Backbone(nn.Module):
                     u.wsc = packing.pack_conv(unit.shortcut_layer[0].weight.detach(), out_scale=ss)
                     u.bsc = sb.contiguous()
                 pk.units.append(u)
-            pk.bn_scale, pk.bn_shift = [t.contiguous() for t in _bn_fold(self.bn)]
-            lin, bn1d = self.output_layer[3], self.output_layer[4]
+            pk.bn_scale, pk.bn_shift = [t.contiguous() for t in _bn_fold(cpu.bn)]
+            lin, bn1d = cpu.output_layer[3], cpu.output_layer[4]
             pk.head_w, pk.head_b = packing.pack_head(lin.weight.detach(), lin.bias.detach(),
-                                                     _bn_fold(self.output_layer[0]), _bn_fold(bn1d))
+                                                     _bn_fold(cpu.output_layer[0]), _bn_fold(bn1d))
+        _to_device(pk, device)
         self._packed = pk
         return pk
 

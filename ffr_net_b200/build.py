@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libffr_sm100.so")
 
-SOURCES = ["api.cu", "conv_gemm.cu", "backbone_kernels.cu", "recnet_kernels.cu", "train_kernels.cu", "head_kernels.cu", "scoring_kernels.cu", "probe.cu", "host.cpp"]
+SOURCES = ["api.cu", "conv_gemm.cu", "backbone_kernels.cu", "recnet_kernels.cu", "train_kernels.cu", "bn_train_kernels.cu", "recnet_train_kernels.cu", "loss_kernels.cu", "head_kernels.cu", "scoring_kernels.cu", "probe.cu", "host.cpp"]
 HEADERS = ["ptx.cuh", "conv_gemm.cuh", "host.h", "kernels.h", os.path.join("..", "..", "include", "ffr_sm100.h")]
 
 NVCC_FLAGS = [

@@ -85,6 +85,40 @@ FFR_API int ffr_conv_gemm(const void* a, int64_t a_rows, int a_cols, int a_ld, c
     return conv_gemm_launch(a, a_rows, a_cols, a_ld, wp, Cin, p, num_splits, S_(stream));
 }
 
+FFR_API int ffr_conv_gemm_ex(const ffr_conv_gemm_desc* d, ffr_stream_t stream) {
+    FFR_CHECK_ARG(d && d->a && d->wp, "ffr_conv_gemm_ex: null operand");
+    FFR_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= 9, "ffr_conv_gemm_ex: ntaps=%d", d->ntaps);
+    ConvGemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = d->M;
+    p.Cout = d->Cout;
+    p.ntaps = d->ntaps;
+    for (int t = 0; t < d->ntaps; ++t) {
+        p.tap_row_shift[t] = d->tap_row_shift ? d->tap_row_shift[t] : 0;
+        p.tap_ch_off[t] = d->tap_ch_off ? d->tap_ch_off[t] : 0;
+    }
+    p.rows_per_img = d->rows_per_img; p.Wp = d->Wp; p.S = d->S; p.h0 = d->h0; p.n_img = d->n_img;
+    p.flags = d->flags;
+    p.bias = d->bias; p.slope = d->slope;
+    p.out = reinterpret_cast<__nv_bfloat16*>(d->out); p.ldo = d->ldo; p.s2d_So = d->s2d_So;
+    p.pool = d->pool; p.out_f32 = d->out_f32;
+    p.res = reinterpret_cast<const __nv_bfloat16*>(d->res); p.ldres = d->ldres;
+    p.stats = d->stats; p.stats_part = d->stats_part;
+    p.scatter = reinterpret_cast<const int2*>(d->scatter); p.scatter_n = d->scatter_n;
+    p.out_rows_per_img = d->out_rows_per_img;
+    p.b_rows_per_mtile = d->b_rows_per_mtile; p.b_mtile_div = d->b_mtile_div;
+    p.a_hilo = d->a_hilo; p.a_lo_off = d->a_lo_off;
+    p.idesc_xor = d->f16 ? ((1u << 7) | (1u << 10)) : 0u;     // a_format / b_format: BF16 (1) -> F16 (0)
+    const uint32_t flags = d->flags;
+    if (flags & (EPI_BIAS | EPI_BORDER_BIAS)) FFR_CHECK_ARG(d->bias, "ffr_conv_gemm_ex: bias flag without bias");
+    if (flags & EPI_PRELU) FFR_CHECK_ARG(d->slope, "ffr_conv_gemm_ex: PReLU flag without slopes");
+    if (flags & EPI_POOL) FFR_CHECK_ARG(d->pool, "ffr_conv_gemm_ex: pool flag without buffer");
+    if (flags & (EPI_OUT_F32_ATOMIC | EPI_OUT_F32)) FFR_CHECK_ARG(d->out_f32, "ffr_conv_gemm_ex: fp32 output missing");
+    if (flags & (EPI_RESIDUAL | EPI_MUL_DSIG)) FFR_CHECK_ARG(d->res, "ffr_conv_gemm_ex: residual operand missing");
+    if (flags & EPI_STATS) FFR_CHECK_ARG(d->stats || d->stats_part, "ffr_conv_gemm_ex: stats buffer missing");
+    return conv_gemm_launch(d->a, d->a_rows, d->a_cols, d->a_ld, d->wp, d->Cin, p, d->num_splits, S_(stream));
+}
+
 FFR_API int ffr_conv3x3_bnpre_prelu_fwd(const void* x, int n_img, int S, int Cin, const void* wp, int Cout,
                                 const float* bias9, const float* slope, void* out, int out_s2d, ffr_stream_t stream) {
     FFR_CHECK_ARG(x && wp && bias9 && slope && out, "ffr_conv3x3_bnpre_prelu_fwd: null pointer");
@@ -271,6 +305,27 @@ FFR_API int ffr_wgrad3x3(const void* dz, int ld_dz, const void* x, int ld_x, int
 
 FFR_API void ffr_debug_set_wgrad_splits(int splits) { set_wgrad_splits(splits); }
 
+FFR_API int64_t ffr_wgrad_workspace_floats(int P, int Cout, int Cin, int ntaps, int deterministic) {
+    return wgrad_workspace_floats(P, Cout, Cin, ntaps, 9, deterministic, nullptr);
+}
+
+FFR_API int ffr_wgrad(const void* dz, int ld_dz, const void* x, int ld_x, int x_ch0, int P, int Cout, int Cin, int ntaps,
+                      int f16, int deterministic, int accumulate, int ld_w, int bias_col, float* dw, float* db,
+                      float* workspace, ffr_stream_t stream) {
+    FFR_CHECK_ARG(dz && x && dw && workspace, "ffr_wgrad: null pointer");
+    FFR_CHECK_ARG(ntaps == 9 || ntaps == 1, "ffr_wgrad: ntaps=%d", ntaps);
+    FFR_CHECK_ARG(ld_dz % 64 == 0 && ld_x % 8 == 0 && x_ch0 % 8 == 0, "ffr_wgrad: bad pitches");
+    FFR_CHECK_ARG(bias_col < 0 || db, "ffr_wgrad: bias column without db");
+    return wgrad_launch_ex(dz, ld_dz, x, ld_x, x_ch0, P, Cout, Cin, 9, ntaps, f16, deterministic, accumulate, ld_w, bias_col,
+                           dw, db, workspace, S_(stream));
+}
+
+FFR_API int ffr_pack_conv3x3_f16(const float* w, int cout, int cin, int cout_p, int cin_p, void* fwd_f16, void* dgrad_bf16,
+                                 ffr_stream_t stream) {
+    FFR_CHECK_ARG(w && fwd_f16, "ffr_pack_conv3x3_f16: null pointer");
+    return pack_conv3x3_launch_ex(w, cout, cin, cout_p, cin_p, fwd_f16, dgrad_bf16, 1, S_(stream));
+}
+
 FFR_API int ffr_bn_prelu_fwd(const void* z, int ldz, const float* mean, const float* rstd, const float* gamma,
                              const float* beta, const float* slope, const void* res, int ldres, void* out, int ldo,
                              const int* scatter, int scatter_n, int n, int C, ffr_stream_t stream) {
@@ -335,6 +390,16 @@ FFR_API int ffr_cosface_ce_bwd(const float* cos_in, int c_pad, int classes, int 
     FFR_CHECK_ARG(cos_in && label && sumexp && gloss && dcos && dcosT, "ffr_cosface_ce_bwd: null pointer");
     FFR_CHECK_ARG(c_pad % 64 == 0 && n_pad % 64 == 0 && n_pad >= n && classes <= c_pad, "ffr_cosface_ce_bwd: bad shape");
     return cosface_bwd_launch(cos_in, c_pad, classes, n, n_pad, label, sumexp, gloss, s, m, dcos, dcosT, S_(stream));
+}
+
+FFR_API int ffr_cosface_ce_bwd_grouped(const float* cos_in, int c_pad, int classes, int n, int n_pad, const int* label,
+                                       const float* sumexp, const float* gloss, int n_per_group, float s, float m, void* dcos,
+                                       void* dcosT, ffr_stream_t stream) {
+    FFR_CHECK_ARG(cos_in && label && sumexp && gloss && dcos && dcosT, "ffr_cosface_ce_bwd_grouped: null pointer");
+    FFR_CHECK_ARG(c_pad % 64 == 0 && n_pad % 64 == 0 && n_pad >= n && classes <= c_pad && n_per_group > 0 &&
+                  n % n_per_group == 0, "ffr_cosface_ce_bwd_grouped: bad shape");
+    return cosface_bwd_launch_ex(cos_in, c_pad, classes, n, n_pad, label, sumexp, gloss, s, m, dcos, dcosT, n_per_group,
+                                 S_(stream));
 }
 
 FFR_API int ffr_normalize_bwd(const float* x, const float* dxh, int rows, float* dx, ffr_stream_t stream) {

@@ -3,6 +3,8 @@
 #include "kernels.h"
 #include "ptx.cuh"
 
+#include <cuda_fp16.h>
+
 namespace ffr {
 
 constexpr int BLOCK_M = 128;
@@ -82,6 +84,19 @@ __device__ __forceinline__ PixTile pix_tile(const ConvGemmParams& p, int m_tile)
         if (hs >= p.pix_src_lo && hs <= p.pix_src_hi && ws >= p.pix_src_lo && ws <= p.pix_src_hi) t.tapmask |= 1u << tap;
     }
     return t;
+}
+
+// 16-bit pair -> fp32 (bf16 by default, fp16 when f16 is set) and back
+__device__ __forceinline__ float cvt16_lo(uint32_t u, bool f16) {
+    return f16 ? __half2float(__ushort_as_half(static_cast<unsigned short>(u & 0xFFFFu))) : bf16lo(u);
+}
+__device__ __forceinline__ float cvt16_hi(uint32_t u, bool f16) {
+    return f16 ? __half2float(__ushort_as_half(static_cast<unsigned short>(u >> 16))) : bf16hi(u);
+}
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi, bool f16) {
+    if (!f16) return pack_bf16x2(lo, hi);
+    const __half2 t = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&t);
 }
 
 __device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float c, float d) {
@@ -238,16 +253,20 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
                     x[q * 4 + 3] = fmaxf(x[q * 4 + 3], 0.f) + s4.w * fminf(x[q * 4 + 3], 0.f);
                 }
             }
-            if (flags & EPI_RESIDUAL) {
+            if (flags & (EPI_RESIDUAL | EPI_MUL_DSIG)) {
                 if (valid) {
+                    const bool rf16 = (flags & EPI_RES_F16) != 0;
                     const uint4* rp = reinterpret_cast<const uint4*>(p.res + (long long)m * p.ldres + nc0 + c0);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const uint4 r = __ldg(rp + q);
-                        x[q * 8 + 0] += bf16lo(r.x); x[q * 8 + 1] += bf16hi(r.x);
-                        x[q * 8 + 2] += bf16lo(r.y); x[q * 8 + 3] += bf16hi(r.y);
-                        x[q * 8 + 4] += bf16lo(r.z); x[q * 8 + 5] += bf16hi(r.z);
-                        x[q * 8 + 6] += bf16lo(r.w); x[q * 8 + 7] += bf16hi(r.w);
+                        const float rv[8] = {cvt16_lo(r.x, rf16), cvt16_hi(r.x, rf16), cvt16_lo(r.y, rf16), cvt16_hi(r.y, rf16),
+                                             cvt16_lo(r.z, rf16), cvt16_hi(r.z, rf16), cvt16_lo(r.w, rf16), cvt16_hi(r.w, rf16)};
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            if (flags & EPI_MUL_DSIG) x[q * 8 + e] *= rv[e] * (1.0f - rv[e]);
+                            else                      x[q * 8 + e] += rv[e];
+                        }
                     }
                 }
             }
@@ -288,12 +307,13 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
             }
             if (do_store || (flags & EPI_SCATTER)) {
                 uint4 pk[4];
+                const bool of16 = (flags & EPI_OUT_F16) != 0;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    pk[q].x = pack_bf16x2(x[q * 8 + 0], x[q * 8 + 1]);
-                    pk[q].y = pack_bf16x2(x[q * 8 + 2], x[q * 8 + 3]);
-                    pk[q].z = pack_bf16x2(x[q * 8 + 4], x[q * 8 + 5]);
-                    pk[q].w = pack_bf16x2(x[q * 8 + 6], x[q * 8 + 7]);
+                    pk[q].x = pack16x2(x[q * 8 + 0], x[q * 8 + 1], of16);
+                    pk[q].y = pack16x2(x[q * 8 + 2], x[q * 8 + 3], of16);
+                    pk[q].z = pack16x2(x[q * 8 + 4], x[q * 8 + 5], of16);
+                    pk[q].w = pack16x2(x[q * 8 + 6], x[q * 8 + 7], of16);
                 }
                 if (do_store) {
                     uint4* o = reinterpret_cast<uint4*>(orow + c0);
@@ -317,8 +337,14 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
                 for (int j = 0; j < 32; ++j) { sq[j] = x[j] * x[j]; xs[j] = x[j]; }
                 const float s1 = warp_colsum32(xs, lane);
                 const float s2 = warp_colsum32(sq, lane);
-                atomicAdd(p.stats + nc0 + c0 + lane, s1);
-                atomicAdd(p.stats + p.Cout + nc0 + c0 + lane, s2);
+                if (p.stats_part != nullptr) {     // one plain store per (M tile, quadrant, channel): deterministic
+                    float* o = p.stats_part + ((long long)((m_group * SUB + sub) * 4 + quad) * 2) * p.Cout + nc0 + c0 + lane;
+                    o[0] = s1;
+                    o[p.Cout] = s2;
+                } else {
+                    atomicAdd(p.stats + nc0 + c0 + lane, s1);
+                    atomicAdd(p.stats + p.Cout + nc0 + c0 + lane, s2);
+                }
             }
             if ((flags & EPI_POOL) && (flags & EPI_PIXMAJOR)) {   // every row is a different image
                 if (valid) {
@@ -407,7 +433,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
 
     const int num_work = p.num_m_tiles * p.num_n_tiles * p.num_splits;
-    const int kb_total = p.ntaps * p.kb_per_tap;
+    const int kb_total = p.ntaps * p.kpt_a;
 
     if (warp == WARP_TMA) {
         // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
@@ -419,20 +445,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int n_tile = t % p.num_n_tiles;
             const int m_tile = t / p.num_n_tiles;
             const int m0 = m_tile * BLOCK_M;
-            const int b_row = n_tile * BN + m_tile * p.b_rows_per_mtile;
+            const int b_row = n_tile * BN + (m_tile / p.b_mtile_div) * p.b_rows_per_mtile;
             if (p.flags & EPI_PIXMAJOR) {        // A tile = 128 images at the tap's source pixel; taps outside are skipped
                 const PixTile pt = pix_tile(p, m_tile);
                 for (int tap = 0; tap < p.ntaps; ++tap) {
                     if (!((pt.tapmask >> tap) & 1u)) continue;
                     const int r = (p.ntaps == 9) ? tap / 3 : 1, s = (p.ntaps == 9) ? tap % 3 : 1;
-                    for (int c = 0; c < p.kb_per_tap; ++c) {
+                    for (int c = 0; c < p.kpt_a; ++c) {          // hi chunks, then (a_hilo) the lo chunks on the same weights
                         mbar_wait(&empty_bar[stage], phase ^ 1);
+                        const int cb = (c < p.kb_per_tap) ? c : c - p.kb_per_tap;
+                        const int a_col = p.tap_ch_off[tap] + cb * BLOCK_K + ((c < p.kb_per_tap) ? 0 : p.a_lo_off);
                         if (elect_one_sync()) {
                             mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                            tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], p.tap_ch_off[tap] + c * BLOCK_K,
+                            tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], a_col,
                                         pt.wo + s - 1, pt.ho + r - 1, pt.img0);
                             tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage],
-                                        (tap * p.kb_per_tap + c) * BLOCK_K, b_row);
+                                        (tap * p.kb_per_tap + cb) * BLOCK_K, b_row);
                         }
                         __syncwarp();
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -442,25 +470,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             const int kb0 = split * p.kb_per_split;
             const int kb1 = min(kb0 + p.kb_per_split, kb_total);
-            int tap = kb0 / p.kb_per_tap;
-            int c = kb0 - tap * p.kb_per_tap;
+            int tap = kb0 / p.kpt_a;
+            int c = kb0 - tap * p.kpt_a;
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
-                const int a_col = p.tap_ch_off[tap] + c * BLOCK_K;
+                const int cb = (c < p.kb_per_tap) ? c : c - p.kb_per_tap;
+                const int a_col = p.tap_ch_off[tap] + cb * BLOCK_K + ((c < p.kb_per_tap) ? 0 : p.a_lo_off);
                 const int a_row = m0 + p.tap_row_shift[tap];
                 if (elect_one_sync()) {
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                     tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], a_col, a_row);
-                    tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, b_row);
+                    tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage],
+                                (tap * p.kb_per_tap + cb) * BLOCK_K, b_row);
                 }
                 __syncwarp();
-                if (++c == p.kb_per_tap) { c = 0; ++tap; }
+                if (++c == p.kpt_a) { c = 0; ++tap; }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == WARP_MMA) {
         // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
-        constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN);
+        const uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN) ^ p.idesc_xor;
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
@@ -470,7 +500,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int kb1 = min(kb0 + p.kb_per_split, kb_total);
             if (p.flags & EPI_PIXMAJOR) {        // the producer streams only the taps whose source pixel exists
                 kb0 = 0;
-                kb1 = __popc(pix_tile(p, (work / p.num_splits) / p.num_n_tiles).tapmask) * p.kb_per_tap;
+                kb1 = __popc(pix_tile(p, (work / p.num_splits) / p.num_n_tiles).tapmask) * p.kpt_a;
             }
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
@@ -624,7 +654,7 @@ conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             atomicAdd(p.dbg + DBG_TMA_TOTAL, (unsigned long long)(clock64() - t_begin));
         }
     } else if (warp == WARP_MMA) {
-        constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN);
+        const uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN) ^ p.idesc_xor;
         int sa = 0, sb = 0;
         uint32_t pa = 0, pb = 0;
         int it = 0;
@@ -718,7 +748,7 @@ void set_debug_counters(unsigned long long* dptr) { g_dbg = dptr; }
 
 // Is this launch a plain 3x3/stride-1 flat convolution (taps (r-1)*G + (s-1), no channel offsets)?
 static bool window_eligible(const ConvGemmParams& p, int* G_out) {
-    if (!g_use_window || p.ntaps != 9 || p.num_splits != 1 || p.b_rows_per_mtile != 0) return false;
+    if (!g_use_window || p.ntaps != 9 || p.num_splits != 1 || p.b_rows_per_mtile != 0 || p.a_hilo) return false;
     const int G = p.tap_row_shift[7] - p.tap_row_shift[4];
     if (G < 4) return false;
     for (int r = 0; r < 3; ++r)
@@ -811,7 +841,11 @@ int conv_gemm_launch(const void* a, long long a_rows, int a_cols, int a_ld, cons
         }
     }
     p.kb_per_tap = Cin / BLOCK_K;
-    const int kb_total = p.ntaps * p.kb_per_tap;
+    p.a_hilo = p.a_hilo ? 1 : 0;
+    p.kpt_a = p.kb_per_tap * (1 + p.a_hilo);
+    if (p.b_mtile_div < 1) p.b_mtile_div = 1;
+    FFR_CHECK_ARG(!p.a_hilo || (p.a_lo_off % 8 == 0 && p.a_lo_off + Cin <= a_cols), "conv_gemm: bad hi/lo layout");
+    const int kb_total = p.ntaps * p.kpt_a;
     if (num_splits < 1) num_splits = 1;
     p.kb_per_split = (kb_total + num_splits - 1) / num_splits;
     p.num_splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
@@ -830,7 +864,7 @@ int conv_gemm_launch(const void* a, long long a_rows, int a_cols, int a_ld, cons
     if (grid == 0) return 0;
 
     CUtensorMap tmA, tmB;
-    const uint64_t b_rows = (uint64_t)p.Cout + (uint64_t)(p.num_m_tiles - 1) * (uint64_t)p.b_rows_per_mtile;
+    const uint64_t b_rows = (uint64_t)p.Cout + (uint64_t)((p.num_m_tiles - 1) / p.b_mtile_div) * (uint64_t)p.b_rows_per_mtile;
     int rc = make_tmap_2d_bf16(&tmB, wp, b_rows, (uint64_t)p.ntaps * Cin, (uint64_t)p.ntaps * Cin, BN);
     if (rc) return rc;
 

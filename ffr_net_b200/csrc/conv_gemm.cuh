@@ -40,6 +40,9 @@ enum EpiFlags : uint32_t {
                                  // are 40 % of a row-major tile). A taps are 4-D TMA boxes (channel, w, h, image).
     EPI_PIX_DGRAD   = 1u << 14,  // with EPI_PIXMAJOR: outputs cover all 81 grid points, and a tap is skipped when its
                                  // source pixel is a halo point (the operand is zero there: dz of a reflection-padded conv)
+    EPI_MUL_DSIG    = 1u << 15,  // x *= r * (1 - r) with r = res[m, co]: backward of a sigmoid whose OUTPUT r is stored
+    EPI_RES_F16     = 1u << 16,  // res holds fp16 (default bf16)
+    EPI_OUT_F16     = 1u << 17,  // 16-bit outputs (out / scatter) are fp16 (default bf16)
 };
 
 struct ConvGemmParams {
@@ -66,11 +69,18 @@ struct ConvGemmParams {
     float* out_f32;        // [M, Cout]
     const __nv_bfloat16* res;  // residual, row pitch ldres
     int ldres;
-    float* stats;          // [2, Cout] : sum, sum of squares
+    float* stats;          // [2, Cout] : sum, sum of squares (atomic accumulation), used when stats_part == nullptr
+    float* stats_part;     // deterministic alternative: [4 * num_m_tiles][2][Cout] per-(M tile, TMEM quadrant) partial
+                           // sums, every entry written exactly once (plain stores); reduced by bn_finalize in a fixed order
     const int2* scatter;   // [rows_per_img][scatter_n] : (destination row within the image, channel offset) or (-1, *)
     int scatter_n;         // 1..8
     int out_rows_per_img;  // rows per image of the destination matrix
-    int b_rows_per_mtile;  // batched B: weight-matrix row offset added per M tile (0 = shared weights)
+    int b_rows_per_mtile;  // batched B: weight-matrix row offset added per group of b_mtile_div M tiles (0 = shared weights)
+    int b_mtile_div;       // M tiles per B batch (>= 1)
+    int a_hilo;            // 1: the A matrix holds [hi | lo] halves (lo at column a_lo_off); every tap / k-chunk is
+    int a_lo_off;          //    accumulated twice, hi then lo, against the SAME weight tile (fp16 hi + lo activations)
+    int kpt_a;             // A k-blocks per tap = kb_per_tap * (1 + a_hilo)  (filled in by conv_gemm_launch)
+    uint32_t idesc_xor;    // XOR-ed into the bf16 instruction descriptor: selects fp16 operands (both A and B)
     // EPI_PIXMAJOR (filled in by conv_gemm_launch)
     int pix_iblocks;                // image blocks of 128 per pixel
     int pix_side, pix_off;          // output pixels: side x side, starting at (off, off) in H9 coordinates

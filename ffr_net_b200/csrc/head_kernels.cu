@@ -137,15 +137,19 @@ int cosface_finish_launch(const float* sumexp, const float* zlabel, const unsign
 __global__ void __launch_bounds__(256) cosface_bwd_kernel(const float* __restrict__ cosv, int c_pad, int classes, int n, int n_pad,
                                                           const int* __restrict__ label, const float* __restrict__ sumexp,
                                                           const float* __restrict__ gloss, float s, float mrg,
-                                                          __nv_bfloat16* __restrict__ dcos, __nv_bfloat16* __restrict__ dcosT) {
+                                                          __nv_bfloat16* __restrict__ dcos, __nv_bfloat16* __restrict__ dcosT,
+                                                          int n_per_group) {
     __shared__ __nv_bfloat16 t[64][66];
     const int c0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;      // tx: class within tile, ty: 4 row groups
-    const float gs = __ldg(gloss) * s / (float)n;
+    // n_per_group > 0: the rows are several batches (RecNet calls) of n_per_group samples, each with its own mean CE
+    // loss and upstream gradient gloss[group]
     for (int i = ty; i < 64; i += 4) {
         const int r = n0 + i, c = c0 + tx;
         float d = 0.f;
         if (r < n && c < classes) {
+            const float gs = (n_per_group > 0) ? __ldg(gloss + r / n_per_group) * s / (float)n_per_group
+                                               : __ldg(gloss) * s / (float)n;
             const int lab = __ldg(label + r);
             const float z = s * (__ldg(cosv + (long long)r * c_pad + c) - ((c == lab) ? mrg : 0.f));
             const float pr = __expf(z - s) / __ldg(sumexp + r);
@@ -162,13 +166,18 @@ __global__ void __launch_bounds__(256) cosface_bwd_kernel(const float* __restric
     }
 }
 
-int cosface_bwd_launch(const float* cosv, int c_pad, int classes, int n, int n_pad, const int* label, const float* sumexp,
-                       const float* gloss, float s, float m, void* dcos, void* dcosT, cudaStream_t stream) {
+int cosface_bwd_launch_ex(const float* cosv, int c_pad, int classes, int n, int n_pad, const int* label, const float* sumexp,
+                          const float* gloss, float s, float m, void* dcos, void* dcosT, int n_per_group, cudaStream_t stream) {
     if (n == 0) return 0;
     cosface_bwd_kernel<<<dim3(c_pad / 64, (n_pad + 63) / 64), 256, 0, stream>>>(
         cosv, c_pad, classes, n, n_pad, label, sumexp, gloss, s, m, reinterpret_cast<__nv_bfloat16*>(dcos),
-        reinterpret_cast<__nv_bfloat16*>(dcosT));
+        reinterpret_cast<__nv_bfloat16*>(dcosT), n_per_group);
     return launch_status("cosface_bwd_kernel");
+}
+
+int cosface_bwd_launch(const float* cosv, int c_pad, int classes, int n, int n_pad, const int* label, const float* sumexp,
+                       const float* gloss, float s, float m, void* dcos, void* dcosT, cudaStream_t stream) {
+    return cosface_bwd_launch_ex(cosv, c_pad, classes, n, n_pad, label, sumexp, gloss, s, m, dcos, dcosT, 0, stream);
 }
 
 // ---- Jacobian of F.normalize over rows of 512: dx = (dxh - xh (xh . dxh)) / max(||x||, eps) ---------------------------

@@ -35,6 +35,8 @@ int cosface_finish_launch(const float* sumexp, const float* zlabel, const unsign
                           float* loss, long long* pred, cudaStream_t stream);
 int cosface_bwd_launch(const float* cosv, int c_pad, int classes, int n, int n_pad, const int* label, const float* sumexp,
                        const float* gloss, float s, float m, void* dcos, void* dcosT, cudaStream_t stream);
+int cosface_bwd_launch_ex(const float* cosv, int c_pad, int classes, int n, int n_pad, const int* label, const float* sumexp,
+                          const float* gloss, float s, float m, void* dcos, void* dcosT, int n_per_group, cudaStream_t stream);
 int normalize_bwd_launch(const float* x, const float* dxh, int rows, float* dx, cudaStream_t stream);
 int roc_hist_launch(const float* scores, int ld, int P, int G, const int* probe_id, const int* gallery_id,
                     const double* thresholds, int T, unsigned long long* hist, cudaStream_t stream);
@@ -42,6 +44,10 @@ int self_similarity_launch(const float* x, int n, float* ss_space, float* ss_cha
 int scale_f32_launch(const float* in, float* out, long long count, float scale, cudaStream_t stream);
 int wgrad_launch(const void* dz, int ld_dz, const void* x, int ld_x, int x_ch0, int P, int Cout, int Cin, int G,
                  float* dw, float* ws, cudaStream_t stream);
+long long wgrad_workspace_floats(int P, int Cout, int Cin, int ntaps, int G, int deterministic, int* splits_out);
+int wgrad_launch_ex(const void* dz, int ld_dz, const void* x, int ld_x, int x_ch0, int P, int Cout, int Cin, int G,
+                    int ntaps, int f16, int deterministic, int accumulate, int ld_w, int bias_col, float* dw, float* db,
+                    float* ws, cudaStream_t stream);
 void set_wgrad_splits(int s);
 void set_pixmajor_mode(int mode);
 bool pixmajor_profitable(int n_img);
@@ -58,6 +64,8 @@ int bn_prelu_bwd_launch(const void* da, int ldda, const int* scatter, int scatte
 int nchw_to_h9_launch(const float* x, void* out, int ld, int ch0, int n_img, int C, int mirror, cudaStream_t stream);
 int pack_conv3x3_launch(const float* w, int cout, int cin, int cout_p, int cin_p, void* fwd, void* dgrad,
                         cudaStream_t stream);
+int pack_conv3x3_launch_ex(const float* w, int cout, int cin, int cout_p, int cin_p, void* fwd, void* dgrad, int fwd_f16,
+                           cudaStream_t stream);
 int h9_to_nchw_launch(const void* in, int ld, int ch0, float* y, int n_img, int C, int fold, cudaStream_t stream);
 int clip_adam_launch(const void* table, const int* chunks, int n_chunks, const float* hyper, float b1, float b2,
                      float eps, float wd, float clip, cudaStream_t stream);

@@ -186,7 +186,11 @@ mn_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(bar, 0);
         tc_fence_after();
         // instruction descriptor with both operands MN-major
-        const uint32_t idesc = umma_idesc_bf16(128, 64) | (1u << 15) | (1u << 16);
+        // variant bit 1: A holds fp16 (a_format = F16), bit 2: B holds fp16 — mixed fp16 x bf16 operands in one MMA
+        uint32_t idesc = umma_idesc_bf16(128, 64) | (1u << 15) | (1u << 16);
+        if (variant & 2) idesc &= ~(7u << 7);
+        if (variant & 4) idesc &= ~(7u << 10);
+        variant &= 1;
         const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB) + r0 * 128;
         if (elect_one_sync()) {
             for (int ks = 0; ks < 4; ++ks) {

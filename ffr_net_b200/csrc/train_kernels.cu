@@ -10,6 +10,7 @@
 #include "ptx.cuh"
 
 #include <cmath>
+#include <cuda_fp16.h>
 
 namespace ffr {
 
@@ -29,8 +30,13 @@ struct WgradParams {
     int splits, kb_per_split, kb_total;
     int tap_shift[9];
     int pix_iblocks;       // > 0: pixel-major contraction (k-block = 64 images at one interior pixel, 4-D TMA boxes)
-    float* ws;             // staging, fp32 [9][cout_p][cin_p] (tap-major so that a thread's 32 columns are contiguous)
+    float* ws;             // staging, fp32 [slabs][ntaps][cout_p][cin_p] (tap-major so that a thread's 32 columns are contiguous)
     int cout_p, cin_p;     // m_tiles * 128, n_tiles * WG_BN
+    int ntaps;             // 9 (3x3 on the H9 grid) or 1 (plain X^T Y contraction over rows)
+    int slabs;             // 1: splits of the pixel axis meet in one staging slab (vector reductions, atomics);
+                           // == splits: every split owns a slab (plain stores) and the finish kernel adds the slabs
+                           // in a fixed order — deterministic
+    uint32_t idesc_xor;    // fp16 operands instead of bf16
 };
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
@@ -65,7 +71,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant__ C
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int num_work = 9 * p.m_tiles * p.n_tiles * p.splits;
+    const int num_work = p.ntaps * p.m_tiles * p.n_tiles * p.splits;
 
     // work -> (split, n_tile, m_tile, tap); tap slowest so concurrently running CTAs share the dz / x tiles in L2
     if (warp == 9) {
@@ -106,7 +112,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant__ C
             }
         }
     } else if (warp == 10) {
-        const uint32_t idesc = umma_idesc_bf16(128, WG_BN) | (1u << 15) | (1u << 16);   // both operands MN-major
+        const uint32_t idesc = (umma_idesc_bf16(128, WG_BN) | (1u << 15) | (1u << 16)) ^ p.idesc_xor;   // both operands MN-major
         int stage = 0; uint32_t phase = 0; int it = 0;
         for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++it) {
             const int split = work % p.splits;
@@ -137,6 +143,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant__ C
         int it = 0;
         for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++it) {
             int w = work / p.splits;
+            const int split = work - w * p.splits;
             const int n_tile = w % p.n_tiles; w /= p.n_tiles;
             const int m_tile = w % p.m_tiles; w /= p.m_tiles;
             const int tap = w;
@@ -153,8 +160,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant__ C
                 const int ci0 = n_tile * WG_BN + chalf * (WG_BN / 2) + c0;
                 // one 128-byte run per thread: plain vector stores when the tile is complete, vector reductions
                 // (REDG.ADD.F32x4) when the pixel axis is split over several CTAs
-                float* o = p.ws + ((long long)tap * p.cout_p + co) * p.cin_p + ci0;
-                if (p.splits == 1) {
+                const int slab = (p.slabs > 1) ? split : 0;
+                float* o = p.ws + (((long long)slab * p.ntaps + tap) * p.cout_p + co) * p.cin_p + ci0;
+                if (p.splits == 1 || p.slabs > 1) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
                         reinterpret_cast<float4*>(o)[q] =
@@ -176,17 +184,28 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant__ C
     if (warp == 8) { tc_fence_after(); tmem_dealloc<2 * WG_BN>(tmem_base); }
 }
 
-// staging [9][cout_p][cin_p] -> dw [Cout][Cin][3][3] (OIHW); one CTA per output channel
-__global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restrict__ ws, int cout_p, int cin_p, int Cout, int Cin,
-                                                           float* __restrict__ dw) {
+// staging [slabs][ntaps][cout_p][cin_p] -> dw [Cout][Cin][ntaps] (OIHW for 3x3); one CTA per output channel. The slabs are
+// added in a fixed order; accumulate != 0 adds to dw instead of overwriting it. bias_col >= 0: that input column is
+// not part of dw but goes to db[co] (a ones-column appended to the activation operand yields the bias gradient).
+__global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restrict__ ws, int slabs, int ntaps, int cout_p,
+                                                           int cin_p, int Cout, int Cin, int ld_w, int bias_col,
+                                                           float* __restrict__ dw, float* __restrict__ db, int accumulate) {
     const int co = blockIdx.x;
+    const long long slab_stride = (long long)ntaps * cout_p * cin_p;
     for (int ci = threadIdx.x; ci < Cin; ci += blockDim.x) {
         float v[9];
-#pragma unroll
-        for (int t = 0; t < 9; ++t) v[t] = __ldg(ws + ((long long)t * cout_p + co) * cin_p + ci);
-        float* o = dw + ((long long)co * Cin + ci) * 9;
-#pragma unroll
-        for (int t = 0; t < 9; ++t) o[t] = v[t];
+        for (int t = 0; t < ntaps; ++t) {
+            const float* q = ws + ((long long)t * cout_p + co) * cin_p + ci;
+            float a = 0.f;
+            for (int sl = 0; sl < slabs; ++sl) a += __ldg(q + sl * slab_stride);
+            v[t] = a;
+        }
+        if (ci == bias_col) {
+            if (accumulate) db[co] += v[0]; else db[co] = v[0];
+            continue;
+        }
+        float* o = dw + ((long long)co * ld_w + ci) * ntaps;
+        for (int t = 0; t < ntaps; ++t) { if (accumulate) o[t] += v[t]; else o[t] = v[t]; }
     }
 }
 
@@ -206,27 +225,47 @@ static int wgrad_pick_splits(int base_work, int kb_total, int sms) {
     return best;
 }
 
-// dz: [P][ld_dz] bf16 (zeros on halo rows), x: [P][ld_x] bf16 H9 (with halo), dw: fp32 [Cout][Cin][3][3] (overwritten),
-// ws: fp32 staging of 9 * ceil128(Cout) * ceil256(Cin) elements.
-int wgrad_launch(const void* dz, int ld_dz, const void* x, int ld_x, int x_ch0, int P, int Cout, int Cin, int G,
-                 float* dw, float* ws, cudaStream_t stream) {
+// dz: [P][ld_dz] (zeros on halo rows), x: [P][ld_x] H9 (with halo) — both bf16, or both fp16 (f16 != 0);
+// dw: fp32 [Cout][Cin][ntaps]; ws: fp32 staging of wgrad_workspace_floats() elements.
+// deterministic != 0: one staging slab per split of the pixel axis, added in a fixed order by the finish kernel.
+long long wgrad_workspace_floats(int P, int Cout, int Cin, int ntaps, int G, int deterministic, int* splits_out) {
+    const int m_tiles = (Cout + 127) / 128, n_tiles = (Cin + WG_BN - 1) / WG_BN;
+    const int n_img = P / 81;
+    const bool pix = (ntaps == 9) && (G == 9) && (P % 81 == 0) && pixmajor_profitable_k64(n_img);
+    const int kb_total = pix ? 49 * ((n_img + 63) / 64) : (P + 63) / 64;
+    int splits = wgrad_pick_splits(ntaps * m_tiles * n_tiles, kb_total, num_sms());
+    if (g_wgrad_splits > 0) splits = g_wgrad_splits;
+    const int kps = (kb_total + splits - 1) / splits;
+    splits = (kb_total + kps - 1) / kps;
+    if (splits_out) *splits_out = splits;
+    return (long long)(deterministic ? splits : 1) * ntaps * (m_tiles * 128) * (n_tiles * WG_BN);
+}
+
+int wgrad_launch_ex(const void* dz, int ld_dz, const void* x, int ld_x, int x_ch0, int P, int Cout, int Cin, int G,
+                    int ntaps, int f16, int deterministic, int accumulate, int ld_w, int bias_col, float* dw, float* db,
+                    float* ws, cudaStream_t stream) {
     WgradParams p;
     p.P = P; p.Cout = Cout; p.Cin = Cin; p.ws = ws;
+    p.ntaps = ntaps;
+    p.idesc_xor = f16 ? ((1u << 7) | (1u << 10)) : 0u;
     p.m_tiles = (Cout + 127) / 128;
     p.n_tiles = (Cin + WG_BN - 1) / WG_BN;
     p.cout_p = p.m_tiles * 128;
     p.cin_p = p.n_tiles * WG_BN;
     const int n_img = P / 81;
-    const bool pix = (G == 9) && (P % 81 == 0) && pixmajor_profitable_k64(n_img);
+    const bool pix = (ntaps == 9) && (G == 9) && (P % 81 == 0) && pixmajor_profitable_k64(n_img);
     p.pix_iblocks = pix ? (n_img + 63) / 64 : 0;
     p.kb_total = pix ? 49 * p.pix_iblocks : (P + 63) / 64;
-    const int base_work = 9 * p.m_tiles * p.n_tiles;
-    int splits = wgrad_pick_splits(base_work, p.kb_total, num_sms());
-    if (g_wgrad_splits > 0) splits = g_wgrad_splits;
+    const int base_work = ntaps * p.m_tiles * p.n_tiles;
+    int splits = 1;
+    wgrad_workspace_floats(P, Cout, Cin, ntaps, G, deterministic, &splits);
     p.kb_per_split = (p.kb_total + splits - 1) / splits;
     p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
-    for (int r = 0; r < 3; ++r)
-        for (int s = 0; s < 3; ++s) p.tap_shift[r * 3 + s] = (r - 1) * G + (s - 1);
+    p.slabs = deterministic ? p.splits : 1;
+    for (int t = 0; t < 9; ++t) p.tap_shift[t] = 0;
+    if (ntaps == 9)
+        for (int r = 0; r < 3; ++r)
+            for (int s = 0; s < 3; ++s) p.tap_shift[r * 3 + s] = (r - 1) * G + (s - 1);
     CUtensorMap tmDZ, tmX;
     // the x map starts at channel x_ch0 of a possibly wider (concatenated) matrix and exposes Cin padded to 64 columns
     const int cin_cols = (Cin + 63) / 64 * 64;
@@ -248,15 +287,21 @@ int wgrad_launch(const void* dz, int ld_dz, const void* x, int ld_x, int x_ch0, 
         FFR_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr = true;
     }
-    if (p.splits > 1)
-        FFR_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 9ull * p.cout_p * p.cin_p, stream));
+    if (p.splits > 1 && p.slabs == 1)
+        FFR_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)ntaps * p.cout_p * p.cin_p, stream));
     const int num_work = base_work * p.splits;
     const int grid = num_work < num_sms() ? num_work : num_sms();
     wgrad_kernel<<<grid, WG_THREADS, smem, stream>>>(tmDZ, tmX, p);
     rc = launch_status("wgrad_kernel");
     if (rc) return rc;
-    wgrad_finish_kernel<<<Cout, 256, 0, stream>>>(ws, p.cout_p, p.cin_p, Cout, Cin, dw);
+    wgrad_finish_kernel<<<Cout, 256, 0, stream>>>(ws, p.slabs, ntaps, p.cout_p, p.cin_p, Cout, Cin, ld_w, bias_col, dw, db,
+                                                  accumulate);
     return launch_status("wgrad_finish_kernel");
+}
+
+int wgrad_launch(const void* dz, int ld_dz, const void* x, int ld_x, int x_ch0, int P, int Cout, int Cin, int G,
+                 float* dw, float* ws, cudaStream_t stream) {
+    return wgrad_launch_ex(dz, ld_dz, x, ld_x, x_ch0, P, Cout, Cin, G, 9, 0, 0, 0, Cin, -1, dw, nullptr, ws, stream);
 }
 
 void set_wgrad_splits(int s) { g_wgrad_splits = s; }
@@ -520,7 +565,7 @@ h9_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, int ld, int ch0, float* 
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 pack_conv3x3_kernel(const float* __restrict__ w, int cout, int cin, int cout_p, int cin_p,
-                    __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ dgrad) {
+                    __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ dgrad, int fwd_f16) {
     const long long total = (long long)cout_p * cin_p * 9;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int ci = (int)(i % cin_p);
@@ -528,19 +573,25 @@ pack_conv3x3_kernel(const float* __restrict__ w, int cout, int cin, int cout_p, 
         const int co = (int)(i / ((long long)cin_p * 9));
         const float v = (co < cout && ci < cin) ? w[((long long)co * cin + ci) * 9 + t] : 0.f;
         const __nv_bfloat16 b = __float2bfloat16(v);
-        fwd[i] = b;                                                      // i == (co*9 + t)*cin_p + ci
+        if (fwd_f16) reinterpret_cast<__half*>(fwd)[i] = __float2half_rn(v);
+        else fwd[i] = b;                                                 // i == (co*9 + t)*cin_p + ci
         if (dgrad) dgrad[((long long)ci * 9 + (8 - t)) * cout_p + co] = b;
     }
 }
 
-int pack_conv3x3_launch(const float* w, int cout, int cin, int cout_p, int cin_p, void* fwd, void* dgrad,
-                        cudaStream_t stream) {
+int pack_conv3x3_launch_ex(const float* w, int cout, int cin, int cout_p, int cin_p, void* fwd, void* dgrad, int fwd_f16,
+                           cudaStream_t stream) {
     const long long total = (long long)cout_p * cin_p * 9;
     int grid = (int)((total + 255) / 256);
     if (grid > num_sms() * 16) grid = num_sms() * 16;
     pack_conv3x3_kernel<<<grid, 256, 0, stream>>>(w, cout, cin, cout_p, cin_p, reinterpret_cast<__nv_bfloat16*>(fwd),
-                                                  reinterpret_cast<__nv_bfloat16*>(dgrad));
+                                                  reinterpret_cast<__nv_bfloat16*>(dgrad), fwd_f16);
     return launch_status("pack_conv3x3_kernel");
+}
+
+int pack_conv3x3_launch(const float* w, int cout, int cin, int cout_p, int cin_p, void* fwd, void* dgrad,
+                        cudaStream_t stream) {
+    return pack_conv3x3_launch_ex(w, cout, cin, cout_p, cin_p, fwd, dgrad, 0, stream);
 }
 
 int nchw_to_h9_launch(const float* x, void* out, int ld, int ch0, int n_img, int C, int mirror, cudaStream_t stream) {

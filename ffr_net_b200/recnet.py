@@ -8,6 +8,7 @@ expressed as scatter tables) and for the two per-sample GEMMs of the channel rec
 
 The torch sub-modules only hold parameters under the reference's names. There is no CPU / PyTorch fallback.
 """
+import ctypes
 import math
 
 import torch
@@ -261,12 +262,6 @@ class RecNet(nn.Module):
         self._packed = pk
         return pk
 
-    def _train_tables(self, device):
-        key = str(device)
-        if getattr(self, "_ttab", None) is None or self._ttab[0] != key:
-            self._ttab = (key, (_h9_scatter(0, device),))
-        return self._ttab[1]
-
     def _workspace(self, n, device, slot=0):
         key = (n, str(device))
         held = self._ws.get(slot)
@@ -300,12 +295,16 @@ class RecNet(nn.Module):
             raise RuntimeError("ffr_net_b200.RecNet runs only on CUDA (sm_100a); there is no CPU fallback")
         if input.dim() != 4 or tuple(input.shape[1:]) != (512, 7, 7):
             raise ValueError("expected input (N,512,7,7), got %s" % (tuple(input.shape),))
-        if self.training or label is not None or (torch.is_grad_enabled() and input.requires_grad):
+        if self.training:
             from . import recnet_train
             return recnet_train.forward_train(self, input, label)
+        if torch.is_grad_enabled() and input.requires_grad:
+            raise NotImplementedError("RecNet in eval mode is forward-only; a gradient w.r.t. its input is not implemented")
         if input.shape[0] == 0:                      # empty batch: nothing to launch
             return (torch.empty(0, 512, dtype=torch.float32, device=input.device),
                     torch.empty(0, 512, 7, 7, dtype=torch.float32, device=input.device))
+        if label is not None:
+            return self._forward_eval_label(input, label)
         n = input.shape[0]
         x = input.contiguous().float()
         v = torch.empty(n, 512, dtype=torch.float32, device=x.device)
@@ -314,6 +313,30 @@ class RecNet(nn.Module):
                           lambda i, lo, hi: self._forward_eval(x[lo:hi], True, slot=i, out_v=v[lo:hi],
                                                                out_map=feat_new[lo:hi]))
         return v, feat_new
+
+    def _forward_eval_label(self, input, label):
+        """Eval-mode call WITH a label: the reference returns the 7-tuple in any mode (recnet.py:425-429). Folded-BN
+        forward as without label; M_space / M_channel / feat_space / feat_channel are exported from the workspace, the
+        two (N,10575) head outputs are the literal AddMarginProduct expressions."""
+        from . import recnet_train
+        lib = _lib.load()
+        P, st = _lib.ptr, _lib.stream_ptr()
+        x = input.contiguous().float()
+        n, dev = x.shape[0], x.device
+        aux = {}
+        v, _ = self._forward_eval(x, want_map=False, slot=0, aux=aux)
+        ws = self._workspace(n, dev, 0)
+        m_space = torch.empty(n, 64, 7, 7, dtype=torch.float32, device=dev)
+        _lib.check(lib.ffr_rows_to_nchw(P(ws.mspace), 1, 64, 0, None, None, P(m_space), n, 7, 9, 1, 81, 64, st), "M_space")
+        m_space = m_space[:, :49].reshape(n, 49, 49).contiguous()
+        m_channel = ws.mch.view(n, 512, 512).float()
+        feat_channel = torch.empty(n, 512, 7, 7, dtype=torch.float32, device=dev)
+        _lib.check(lib.ffr_rows_to_nchw(P(ws.cm), 0, 1536, 512, None, None, P(feat_channel), n, 7, 9, 1, 81, 512, st),
+                   "feat_channel")
+        with torch.no_grad():
+            pred_loss, pred_label = recnet_train.add_margin_product(self.classifier.weight, v, label, self.classifier.s,
+                                                                    self.classifier.m)
+        return v, pred_loss, pred_label, m_space, m_channel, aux["feat_space"], feat_channel
 
     def embed_from_images(self, encoder, x):
         """encoder(x) -> RecNet -> rectified embedding, the per-image path of lfw_eval.calculate_distance:241-242.
@@ -332,7 +355,7 @@ class RecNet(nn.Module):
         streams.fork_join(streams.chunk_bounds(n), x.device, chunk)
         return v
 
-    def _forward_eval(self, x, want_map=True, slot=0, out_v=None, out_map=None):
+    def _forward_eval(self, x, want_map=True, slot=0, out_v=None, out_map=None, aux=None):
         lib = _lib.load()
         P = _lib.ptr
         prof = self._profile
@@ -372,15 +395,32 @@ class RecNet(nn.Module):
         conv("Conv4Space.4", ws.b128[2], ws.b64[0])
         conv("Conv4Space.5.conv1", ws.b64[0], ws.b64[1])
         conv("Conv4Space.5.conv2", ws.b64[1], None, res=ws.b64[0], sigmoid=True, out_f32=ws.mspace)
-        chk(lib.ffr_feat_space(P(x), P(ws.mspace), P(ws.cm), None, n, st), "feat_space")
+        fs_nchw = None
+        if aux is not None:
+            fs_nchw = torch.empty(n, 512, 7, 7, dtype=torch.float32, device=dev)
+            aux["feat_space"] = fs_nchw
+        chk(lib.ffr_feat_space(P(x), P(ws.mspace), P(ws.cm), P(fs_nchw), n, st), "feat_space")
 
         # ---- channel rectifier (recnet.py:372-386, 406, 410): M_channel = sigmoid(h5 W8^T + b8); M_channel @ X ----
-        chk(lib.ffr_conv_gemm(P(ws.h5), n * 512, 64, 64, P(pk.w8), 64, 512, 1, None, None, n * 512, 64, 1, 1, 0, n,
-                              0x1 | 0x80, P(pk.b8), None, P(ws.mch), 512, 0, None, None, None, 0, None, 1,
-                              None, 0, 0, 0, st), "M_channel")
-        chk(lib.ffr_conv_gemm(P(ws.xt), n * 128, 512, 512, P(ws.mch), 512, 512, 1, None, None, n * 128, 128, 128, 0, 0,
-                              n, 0x8 | 0x100, None, None, P(ws.fm), 1024, 0, None, None, None, 0, None, 1,
-                              P(pk.t_flip), 8, 81, 512, st), "feat_channel")
+        EPI = _lib.EPI
+        d = _lib.ConvGemmDesc()                      # M_channel rows (sample, c) = sigmoid(h5 W8^T + b8), K = 64 (32 valid)
+        d.a, d.a_rows, d.a_cols, d.a_ld = P(ws.h5), n * 512, 64, 64
+        d.wp, d.Cin, d.Cout, d.ntaps = P(pk.w8), 64, 512, 1
+        d.M, d.n_img = n * 512, n
+        d.flags = EPI.BIAS | EPI.SIGMOID
+        d.bias = P(pk.b8)
+        d.out, d.ldo = P(ws.mch), 512
+        d.num_splits = 1
+        chk(lib.ffr_conv_gemm_ex(ctypes.byref(d), st), "M_channel")
+        d = _lib.ConvGemmDesc()                      # feat_channel = M_channel @ X per sample: batched weight operand
+        d.a, d.a_rows, d.a_cols, d.a_ld = P(ws.xt), n * 128, 512, 512
+        d.wp, d.Cin, d.Cout, d.ntaps = P(ws.mch), 512, 512, 1
+        d.M, d.rows_per_img, d.Wp, d.n_img = n * 128, 128, 128, n
+        d.flags = EPI.GEOM | EPI.SCATTER             # rows (h*7+w) -> flip / cat slots + reflection mirrors (t_flip)
+        d.out, d.ldo = P(ws.fm), 1024
+        d.scatter, d.scatter_n, d.out_rows_per_img = P(pk.t_flip), 8, 81
+        d.num_splits, d.b_rows_per_mtile, d.b_mtile_div = 1, 512, 1
+        chk(lib.ffr_conv_gemm_ex(ctypes.byref(d), st), "feat_channel")
 
         # ---- flip merge (recnet.py:415-418) and final merge (:420-423) ----
         conv("ChannelFlipMerge.0", ws.fm, ws.c512[0])

@@ -75,6 +75,34 @@ FFR_API int ffr_conv_gemm(const void* a, int64_t a_rows, int a_cols, int a_ld, c
  *   (FFR_EPI_SCATTER); b_rows_per_mtile != 0 makes the weight operand batched: M tile i reads weight rows starting at
  *   i*b_rows_per_mtile (per-sample matrices such as M_channel). */
 
+/* Extended form of ffr_conv_gemm (same kernel): operands may be fp16, the A matrix may carry fp16 hi + lo halves
+ * (training forward: x = hi + lo keeps ~21 mantissa bits at twice the MMA count), BatchNorm statistics can be written
+ * as deterministic per-tile partial sums, the weight operand can be batched per group of M tiles, and the epilogue can
+ * apply the backward of a stored sigmoid. Fields not listed here mean what the ffr_conv_gemm arguments mean. */
+#define FFR_EPI_MUL_DSIG       (1u << 15) /* x *= r*(1-r), r = res[m][co] (sigmoid backward from its stored output) */
+#define FFR_EPI_RES_F16        (1u << 16) /* res is fp16 (default bf16) */
+#define FFR_EPI_OUT_F16        (1u << 17) /* 16-bit outputs are fp16 (default bf16) */
+typedef struct ffr_conv_gemm_desc {
+    const void* a; int64_t a_rows; int a_cols; int a_ld;
+    const void* wp; int Cin; int Cout; int ntaps;
+    const int* tap_row_shift; const int* tap_ch_off;      /* host arrays [ntaps] or NULL (zeros) */
+    int M, rows_per_img, Wp, S, h0, n_img;
+    uint32_t flags;
+    const float* bias; const float* slope;
+    void* out; int ldo; int s2d_So;
+    float* pool; float* out_f32;
+    const void* res; int ldres;
+    float* stats;                 /* [2][Cout], atomically accumulated (caller zeroes) when stats_part is NULL */
+    float* stats_part;            /* [4*ceil(M/128) (row-major) or 4*49*ceil(n_img/128) (pixel-major)][2][Cout] partial sums,
+                                     row = (M tile)*4 + 32-row quadrant; written, not accumulated */
+    int num_splits;
+    const int* scatter; int scatter_n; int out_rows_per_img;
+    int b_rows_per_mtile; int b_mtile_div;                /* B rows advance by b_rows_per_mtile every b_mtile_div M tiles */
+    int a_hilo; int a_lo_off;                             /* A = [hi | lo], lo at column a_lo_off */
+    int f16;                                              /* 1: A and B hold fp16 (tcgen05 kind::f16 needs equal formats) */
+} ffr_conv_gemm_desc;
+FFR_API int ffr_conv_gemm_ex(const ffr_conv_gemm_desc* d, ffr_stream_t stream);
+
 /* Conv2d(Cin,Cout,3,stride 1,pad 1) on a flat SxS map (model_ir_se50.py:67 with the BatchNorm of :66 folded:
  * scale into wp, shift into the 9-class border bias table `bias9` [9][Cout]) + PReLU (:68).
  * out_s2d != 0 writes the space-to-depth layout consumed by ffr_conv3x3_bn_pool_fwd(stride = 2). */
@@ -195,6 +223,136 @@ FFR_API int ffr_pack_conv3x3(const float* w, int cout, int cin, int cout_p, int 
 FFR_API int ffr_clip_adam(const void* table, const int* chunks, int n_chunks, const float* hyper, float beta1,
                           float beta2, float eps, float weight_decay, float clip, ffr_stream_t stream);
 
+/* ---- RecNet training, batched over the two calls of an iteration (models/trainer.py:144-145) ----------------------
+ * G = n_img / n_per_group "groups" (RecNet calls) run in one launch; BatchNorm statistics stay per group. Activations are
+ * fp16 hi + lo halves ([rows][2*C]: hi at column c, lo at lo_off + c; lo_off 0 = hi only) for the forward GEMMs plus a
+ * bf16 copy for the weight-gradient GEMMs; raw conv outputs z and all activation gradients are fp32; dz is bf16.
+ * Every reduction is a fixed-order two-stage sum (no floating-point atomics): results are run-to-run deterministic. */
+
+/* BatchNorm2d batch statistics (recnet.py:83 in training mode) from the per-tile partial sums the conv epilogue wrote
+ * (ffr_conv_gemm_desc.stats_part, part_rows rows): mean_rstd [G][2][C] <- (mean, 1/sqrt(var + eps)) per group, and the
+ * running statistics (momentum update, unbiased variance) applied group after group; num_batches_tracked += G. */
+FFR_API int ffr_bn_finalize(const float* part, int part_rows, int pixmajor, int n_img, int n_per_group, int C, int C_real,
+                            float momentum, float eps, float* running_mean, float* running_var,
+                            long long* num_batches_tracked, float* mean_rstd, ffr_stream_t stream);
+
+/* a = prelu(gamma (z - mean_g) rstd_g + beta) (+ res) (recnet.py:83-84, :217) from the fp32 conv output z [n_img*81][ldz]:
+ * out_h / out_b receive a at every destination of the H9 scatter table (own row + reflection mirrors, recnet.py:64) as
+ * fp16 hi/lo resp. bf16; out_f (optional) the fp32 value on the own row (sigmoid != 0: sigmoid(a), recnet.py:370). */
+FFR_API int ffr_bn_act_fwd(const float* z, int ldz, const float* mean_rstd, const float* gamma, const float* beta,
+                           const float* slope, const void* res, int ldres, int res_lo_off, void* out_h, int ldo,
+                           int lo_off, void* out_b, int ldb, float* out_f, int ldf, int sigmoid, const int* scatter,
+                           int scatter_n, int n_img, int n_per_group, int C, int C_real, ffr_stream_t stream);
+
+/* Backward of the above. Output-gradient sources (fp32, any subset): da on the H9 grid (folded over the scatter table),
+ * dadd on own rows, dv [n_img][lddv] * dv_scale broadcast over the pixels (AvgPool2d(7), recnet.py:423).
+ * afold [n_img*81][ldaf] receives the folded gradient (own rows; it is also the residual-branch gradient of a
+ * ResidualBlock); dgamma / dbeta / dslope the parameter gradients (overwritten, or += when accumulate);
+ * dz [n_img*81][lddz] bf16 the gradient of the conv output (zeros on halo rows).
+ * partial: fp32 workspace [ffr_bn_act_bwd_partial_rows(G, C)][3][C]; gsum: [G][2][C]. */
+FFR_API int ffr_bn_act_bwd_partial_rows(int n_groups, int C);
+FFR_API int ffr_bn_act_bwd(const float* da, int ldda, int da_ch0, const int* scatter, int scatter_n, const float* dadd,
+                           int ldadd, int dadd_ch0, const float* dv, int lddv, float dv_scale, const float* z, int ldz,
+                           const float* mean_rstd, const float* gamma, const float* beta, const float* slope,
+                           float* afold, int ldaf, float* partial, float* gsum, float* dgamma, float* dbeta,
+                           float* dslope, int accumulate, int C_real, void* dz, int lddz, int n_img, int n_per_group,
+                           int C, ffr_stream_t stream);
+
+/* fp32 NCHW (n,C,7,7) -> own rows of an fp32 H9 matrix [n*81][ld], channel slot ch0 (layout of the `dadd` source). */
+FFR_API int ffr_nchw_to_h9_f32(const float* x, float* out, int ld, int ch0, int n, int C, ffr_stream_t stream);
+
+/* v[n][c] = mean over the 49 valid rows of an fp32 H9 matrix (AvgPool2d(7), recnet.py:423). */
+FFR_API int ffr_h9_avgpool(const float* a, int lda, float* v, int ldv, int n_img, int C, ffr_stream_t stream);
+
+/* Weight gradient, general form of ffr_wgrad3x3: dw[co][ci][t] (+)= sum_p dz[p][co] x[p + shift_t][x_ch0 + ci] over P rows;
+ * ntaps 9 (3x3 on the H9 grid, P = n*81) or 1 (plain Y^T X, e.g. Linear weights); operands both bf16 (f16 = 0) or both
+ * fp16; deterministic != 0: one staging slab per split of the row axis, added in a fixed order; bias_col >= 0: that
+ * column of x is a column of ones and its result goes to db[co] instead of dw. ld_w = row pitch of dw in ci units.
+ * workspace: ffr_wgrad_workspace_floats(...) fp32 elements. */
+FFR_API int64_t ffr_wgrad_workspace_floats(int P, int Cout, int Cin, int ntaps, int deterministic);
+FFR_API int ffr_wgrad(const void* dz, int ld_dz, const void* x, int ld_x, int x_ch0, int P, int Cout, int Cin, int ntaps,
+                      int f16, int deterministic, int accumulate, int ld_w, int bias_col, float* dw, float* db,
+                      float* workspace, ffr_stream_t stream);
+
+/* Packs a 3x3 conv weight like ffr_pack_conv3x3 with the forward operand in fp16 (dgrad operand stays bf16). */
+FFR_API int ffr_pack_conv3x3_f16(const float* w, int cout, int cin, int cout_p, int cin_p, void* fwd_f16, void* dgrad_bf16,
+                                 ffr_stream_t stream);
+
+/* RecNet.forward up to the convolution stacks for a training batch (recnet.py:399-402, :406, :410-417, Conv4Channel
+ * :372-386): selfSimilarity, the cat() fan-outs, the whole channel rectifier in fp32 and feat_channel with its flip / cat
+ * fan-out. Saves what the backward needs (pre-PReLU activations g0/g1/g2, h7 | 1, X rows, M_channel in bf16, 1/|X_c|). */
+typedef struct ffr_prep_train_desc {
+    const float* x;                                  /* (n,512,7,7) fp32 NCHW */
+    const float* w0; const float* b0;                /* Conv4Channel.0 [32][561], [32] */
+    const float* slope1; const float* slope4; const float* slope7;    /* Conv4Channel.{1,4,7}.func.weight [512] */
+    const float* A1; const float* c1; const float* A2; const float* c2;   /* ffr_chan_compose outputs */
+    const float* w8; const float* b8;                /* Conv4Channel.8 [512][32], [512] */
+    void* s0_h; int s0_ld; int s0_lo; void* s0_b; int s0_ldb;     /* Conv4Space input [n*81][..], 576 channels */
+    void* cm_h; int cm_ld; int cm_lo; void* cm_b; int cm_ldb;     /* Conv4Merge input, 1536 channels (slot 1024.. <- X) */
+    void* fm_h; int fm_ld; int fm_lo; void* fm_b; int fm_ldb;     /* ChannelFlipMerge input, 1024 channels */
+    float* g0; float* g1; float* g2;                 /* [n*512][32] each */
+    void* h7b; void* xk; void* mch;                  /* bf16 [n*512][64], [n*512][64], [n*512][512] */
+    float* inv_c; float* tmat; float* ss_space;      /* [n*512], [n][49][32], optional [n][49][49] */
+} ffr_prep_train_desc;
+FFR_API int ffr_recnet_prep_train(const ffr_prep_train_desc* d, int n, ffr_stream_t stream);
+
+/* Linear(32->512) directly followed by Linear(512->32) (recnet.py:375-376, :378-379) composed into 32x32 maps:
+ * A1 = W3 W2, c1 = W3 b2 + b3, A2 = W6 W5, c2 = W6 b5 + b6; and the backward of the composition. */
+FFR_API int ffr_chan_compose(const float* w2, const float* b2, const float* w3, const float* b3, const float* w5,
+                             const float* b5, const float* w6, const float* b6, float* A1, float* c1, float* A2,
+                             float* c2, const float* w8, void* w8t, ffr_stream_t stream);
+/*   w8t (optional): bf16 [64][512] <- W8^T (Conv4Channel.8.weight [512][32]), rows 32..63 zero: K-major operand of the
+ *   backward GEMM dh7 = dM_pre @ W8. */
+FFR_API int ffr_chan_compose_bwd(const float* w2, const float* b2, const float* w3, const float* w5, const float* b5,
+                                 const float* w6, const float* dA1, const float* dc1, const float* dA2, const float* dc2,
+                                 float* dw2, float* db2, float* dw3, float* db3, float* dw5, float* db5, float* dw6,
+                                 float* db6, int accumulate, ffr_stream_t stream);
+
+/* feat_space = X @ M_space (recnet.py:409) into slot [0,512) of the Conv4Merge input (+ fp32 copy on own rows), and the
+ * backward w.r.t. M_space through its sigmoid: dmsp [n*81][64] (own row of pixel j, column i). */
+FFR_API int ffr_feat_space_train(const float* x, const float* mspace, void* cm_h, int cm_ld, int cm_lo, void* cm_b,
+                                 int cm_ldb, float* fs_f32, int ldfs, int n, ffr_stream_t stream);
+FFR_API int ffr_feat_space_bwd(const float* x, const float* mspace, const float* dcm, int lddcm, const float* dfs,
+                               int lddfs, float* dmsp, int n, ffr_stream_t stream);
+
+/* Gradient of the flip / cat / reflection fan-out of feat_channel (recnet.py:416-417): dfm fp32 [n*81][lddfm] on the H9
+ * grid -> dfc bf16 [n*512][64] (row = channel, 49 valid columns). */
+FFR_API int ffr_fc_bwd_gather(const float* dfm, int lddfm, void* dfc, int n, ffr_stream_t stream);
+
+/* Backward of the thin Conv4Channel chain (recnet.py:373-384) given dh7 [n*512][64] fp32: gradients of
+ * Conv4Channel.0 (dW0 [32][561], db0), the three PReLUs, and of the composed maps (tmp [2112] = dA2, dc2, dA1, dc1 for
+ * ffr_chan_compose_bwd). part: workspace [n][ffr_chan_bwd_part_floats()], dslope_part [n][3][512]. */
+FFR_API int ffr_chan_bwd_part_floats(void);
+FFR_API int ffr_chan_bwd(const float* x, const float* dh7, const float* g0, const float* g1, const float* g2,
+                         const float* inv_c, const float* tmat, const float* A1, const float* A2, const float* slope1,
+                         const float* slope4, const float* slope7, float* part, float* dslope_part, float* tmp,
+                         float* db0, float* dW0, float* dslope1, float* dslope4, float* dslope7, int accumulate, int n,
+                         ffr_stream_t stream);
+
+/* ---- losses of Trainer.backward (models/trainer.py:31-43, :154-178), forward + gradient ------------------------- */
+
+/* Channel self-similarity (recnet.py:232 + trainer.py:158-165): operands of D = F^F^T - X^X^T as one K = 384 GEMM
+ * (bf16 hi/lo splits, see csrc/loss_kernels.cu), F^T for the gradient GEMM and 1/|F_c|. f: fp32 H9 [n_img*81][ldf]. */
+FFR_API int ffr_selfsim_channel_pack(const float* f, int ldf, const float* x, int n_img, int n_per_group, void* A6,
+                                     void* B6, void* FhT, float* inv_f, ffr_stream_t stream);
+/* e = D F^ [n_img*512][64] -> df (fp32 H9 own rows): normalisation Jacobian, coef = 4 w / (n * 512 * 512). */
+FFR_API int ffr_selfsim_channel_bwd(const float* e, const float* f, int ldf, const float* inv_f, float coef, float* df,
+                                    int lddf, int n_img, ffr_stream_t stream);
+/* Partial sums of the sum-of-squares half of a stats_part buffer: out[g*64 + k]. */
+FFR_API int ffr_sumsq_reduce(const float* part, int rows_per_group, int C, int groups, float* out, ffr_stream_t stream);
+/* Spatial self-similarity (recnet.py:231 + trainer.py:158-164): loss_part[s] = sum (G - T)^2, dfs = gradient (optional). */
+FFR_API int ffr_selfsim_space_loss(const float* fs, int ldfs, const float* x, int n_img, int n_per_group, float coef,
+                                   float* loss_part, float* dfs, int lddfs, ffr_stream_t stream);
+/* TripletLoss (trainer.py:38-43, :167-169) and the identity MSE (:171): row_part [n][5], gradients w.r.t. the pooled
+ * RecNet features of the two calls. */
+FFR_API int ffr_triplet_identity(const float* f_non, const float* f_ocl, const float* e_non, const float* e_ocl, int n,
+                                 float w_trip, float w_id, float margin, float* row_part, float* df_non, float* df_ocl,
+                                 ffr_stream_t stream);
+/* out[0..3] weighted loss items (trainer.py:178), out[4] / out[5] mean pos / neg distance, out[6] total. */
+FFR_API int ffr_loss_finalize(const float* space_part, const float* chan_sums, const float* row_part, const float* ce, int n,
+                              int groups, float w0, float w1, float w2, float w3, float* out, ffr_stream_t stream);
+FFR_API int ffr_add3_f32(const float* a, const float* b, const float* c, float* out, int64_t count, ffr_stream_t stream);
+
 /* ---- 1:N gallery scoring: the paired scoring of lfw/lfw_eval.py:246-259 generalised to a similarity matrix ---- */
 
 /* cos_out[p][g_pad] (fp32) = probe . gallery^T for operands packed by ffr_cosface_pack (probe: mode 0, gallery: mode 1;
@@ -236,6 +394,12 @@ FFR_API int ffr_cosface_ce_finish(const float* sumexp, const float* zlabel, cons
 FFR_API int ffr_cosface_ce_bwd(const float* cos_in, int c_pad, int classes, int n, int n_pad, const int* label,
                                const float* sumexp, const float* gloss, float s, float m, void* dcos, void* dcosT,
                                ffr_stream_t stream);
+
+/* The same for several batches of n_per_group rows each (the two RecNet calls of an iteration share one GEMM): row r uses
+ * the upstream gradient gloss[r / n_per_group] and the mean over n_per_group rows. */
+FFR_API int ffr_cosface_ce_bwd_grouped(const float* cos_in, int c_pad, int classes, int n, int n_pad, const int* label,
+                                       const float* sumexp, const float* gloss, int n_per_group, float s, float m, void* dcos,
+                                       void* dcosT, ffr_stream_t stream);
 
 /* Jacobian of F.normalize(x, dim=1) on rows of 512: dx = (dxh - xh (xh . dxh)) / max(|x|, 1e-12). */
 FFR_API int ffr_normalize_bwd(const float* x, const float* dxh, int rows, float* dx, ffr_stream_t stream);

@@ -29,7 +29,7 @@ def _worker(rank, world, port, ret):
         p.grad = torch.randn(p.shape, generator=g)
     local = [p.grad.clone() for p in net.parameters()]
     t = Trainer.__new__(Trainer)          # only the all-reduce helper is under test (no GPU needed)
-    t.recnet, t._flat = net, None
+    t.recnet, t._flat, t._flat_bound, t._ar_events = net, None, False, []
     t.allreduce_gradients()
     # expected: mean over ranks of the per-rank gradients
     exp = []
@@ -43,7 +43,8 @@ def _worker(rank, world, port, ret):
     t2 = Trainer.__new__(Trainer)
     net2 = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.PReLU(5), torch.nn.Linear(5, 3))
     net2.load_state_dict(net.state_dict())
-    t2.recnet, t2._flat, t2._flat_bound = net2, None, False
+    t2.recnet, t2._flat, t2._flat_bound, t2._ar_events = net2, None, False, []
+    t2._order_parameters()
     t2.bind_flat_gradients()
     x = torch.randn(4, 7, generator=g)
     net2(x).square().sum().backward()
@@ -57,6 +58,28 @@ def _worker(rank, world, port, ret):
         parts = [torch.zeros_like(local2[i]) for _ in range(world)]
         dist.all_gather(parts, local2[i])
         ok = ok and torch.allclose(p.grad, sum(parts) / world, atol=1e-6)
+    # bucketed exchange (what backward() triggers bucket by bucket under DP): every bucket is averaged exactly once and
+    # allreduce_gradients() afterwards only joins
+    t3 = Trainer.__new__(Trainer)
+    net3 = torch.nn.ModuleDict({"classifier": torch.nn.Linear(4, 3), "Conv4Merge": torch.nn.Linear(3, 2),
+                                "Conv4Space": torch.nn.PReLU(2)})
+    t3.recnet, t3._flat, t3._flat_bound, t3._ar_events, t3._comm_stream = net3, None, False, [], None
+    t3.overlap_allreduce = True
+    t3._order_parameters()
+    t3.bind_flat_gradients()
+    names = [b[0] for b in t3._buckets]
+    ok = ok and names == ["classifier", "Conv4Merge", "Conv4Space"]
+    ok = ok and t3._buckets[0][1] == 0 and t3._buckets[-1][2] == t3._flat.numel()
+    with torch.no_grad():
+        t3._flat.copy_(torch.randn(t3._flat.numel(), generator=g))
+    local3 = t3._flat.clone()
+    for nme in names:
+        t3._bucket_ready(nme)
+    ok = ok and len(t3._ar_events) == 3
+    t3.allreduce_gradients()
+    parts = [torch.zeros_like(local3) for _ in range(world)]
+    dist.all_gather(parts, local3)
+    ok = ok and torch.allclose(t3._flat, sum(parts) / world, atol=1e-6) and t3._ar_events == []
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 

@@ -54,34 +54,37 @@ def test_embeddings_bs512_properties(lib, nets):
 
 def test_training_step_256_pairs_tiling_property(lib, nets):
     """Under batch-statistics BatchNorm a batch made of 4 copies of 64 pairs has the same statistics, the same mean
-    losses and the same gradients as the 64 pairs alone. 256 pairs run on pixel-major tiles, 64 on row-major ones, so
-    this also cross-checks the two tilings (forward, dgrad with tap skipping, wgrad) at the benchmark size."""
+    losses and the same gradients as the 64 pairs alone. The 256-pair step (BASELINE configs[2]) runs on pixel-major
+    tiles, the 64-pair step is forced onto row-major tiles, so this also cross-checks the two tilings (forward, dgrad with
+    tap skipping, wgrad) at the benchmark size; and the 256-pair step is reproducible bit for bit."""
     from ffr_net_b200.trainer import Trainer, default_opts
-    bsd, rsd, _, _ = nets
-    assert lib.ffr_pixmajor_profitable(256) == 1 and lib.ffr_pixmajor_profitable(64) == 0
+    bsd, rsd, enc, _ = nets
+    assert lib.ffr_pixmajor_profitable(512) == 1
     a, b = ob.synth_faces(64, seed=41).cuda(), ob.synth_faces(64, seed=41, masked=True).cuda()
     label = torch.randint(0, 10575, (64,), generator=torch.Generator().manual_seed(41)).cuda()
+    with torch.no_grad():
+        y64, f64 = enc(torch.cat((a, b)))
     res = []
-    for reps in (1, 4, 1):
+    for reps, mode in ((1, 0), (4, -1), (4, -1)):
+        lib.ffr_debug_set_pixmajor(mode)
         rec = RecNet()
         rec.load_state_dict(rsd)
         tr = Trainer(default_opts(lr=1e-3), recnet=rec, encoder_weights=bsd)
+        yy = torch.cat((y64[:64].repeat(reps, 1, 1, 1), y64[64:].repeat(reps, 1, 1, 1)))
+        ff = torch.cat((f64[:64].repeat(reps, 1), f64[64:].repeat(reps, 1)))
+        tr.encoder = lambda x, yy=yy, ff=ff: (yy, ff)
         tr.set_input(a.repeat(reps, 1, 1, 1), b.repeat(reps, 1, 1, 1), label.repeat(reps))
         tr.forward()
-        tr.zero_grad()
         tr.backward()
         torch.cuda.synchronize()
-        res.append(([float(l.detach()) for l in tr.loss_items], {k: p.grad.clone() for k, p in rec.named_parameters()},
+        res.append(([float(l) for l in tr.loss_items], {k: p.grad.clone() for k, p in rec.named_parameters()},
                     float(tr._correct) / (64 * reps)))
-    (l64, g64, acc64), (l256, g256, acc256), (l64b, g64b, _) = res
+    lib.ffr_debug_set_pixmajor(-1)
+    (l64, g64, acc64), (l256, g256, acc256), (l256b, g256b, _) = res
     assert all(torch.isfinite(g).all() for g in g256.values())
-    assert all(abs(x - y) <= 2e-3 * max(1.0, abs(x)) for x, y in zip(l64, l256)), (l64, l256)
-    assert abs(acc64 - acc256) <= 2.0 / 64
-
-    def cosines(ga, gb):
-        return sorted(torch.nn.functional.cosine_similarity(ga[k].reshape(1, -1), gb[k].reshape(1, -1)).item() for k in ga)
-    c_tiled, c_noise = cosines(g256, g64), cosines(g64b, g64)
-    print("grad cosine 256-tiled vs 64: min %.4f median %.4f | run-to-run at 64: min %.4f median %.4f" %
-          (c_tiled[0], c_tiled[len(c_tiled) // 2], c_noise[0], c_noise[len(c_noise) // 2]))
-    # gradients agree up to the bf16 rounding-noise level of the step itself (DESIGN.md section 4)
-    assert c_tiled[len(c_tiled) // 2] >= 0.99 and c_tiled[0] >= min(0.9, c_noise[0] - 0.05)
+    assert all(abs(x - y) <= 1e-4 * max(1.0, abs(x)) for x, y in zip(l64, l256)), (l64, l256)
+    assert abs(acc64 - acc256) <= 1e-9
+    errs = sorted(((g256[k].double() - g64[k].double()).norm() / (g64[k].double().norm() + 1e-30)).item() for k in g64)
+    print("256-pair (4 x 64, pixel-major) vs 64-pair (row-major) gradients: worst %.3e median %.3e" % (errs[-1], errs[len(errs) // 2]))
+    assert errs[-1] <= 2e-2 and errs[len(errs) // 2] <= 5e-3
+    assert l256 == l256b and all(torch.equal(g256[k], g256b[k]) for k in g256)

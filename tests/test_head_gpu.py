@@ -70,54 +70,3 @@ def test_cosface_pack_hi_lo_split(lib):
         assert torch.equal(hi[:70], ref.bfloat16().float())
         assert p[70:].abs().max().item() == 0.0
         assert torch.equal(tr.float().cpu().t(), hi)
-
-
-def test_trainer_fused_head_matches_library_head(lib):
-    """Trainer with the fused head vs the same step with the reference op sequence on library kernels: same losses
-    and the same head / trunk gradients within the bf16-operand tolerance of the fused backward GEMMs."""
-    from oracle import backbone as ob
-    from ffr_net_b200.recnet import RecNet
-    from ffr_net_b200.trainer import Trainer, default_opts
-    bsd, rsd = ob.synth_backbone_state_dict(0), orr.synth_recnet_state_dict(0)
-    a, b = ob.synth_faces(4, seed=3).cuda(), ob.synth_faces(4, seed=3, masked=True).cuda()
-    label = torch.tensor([5, 17, 10000, 3], device="cuda")
-    res, feats = [], []
-
-    class _FixedEncoder:                       # same backbone outputs for every trainer: isolates the RecNet/head path
-        def __init__(self):
-            self.i = 0
-
-        def __call__(self, x):
-            self.i += 1
-            return feats[(self.i - 1) % 2]
-
-    for fused in (False, False, True):
-        rec = RecNet()
-        rec.load_state_dict(rsd)
-        tr = Trainer(default_opts(fused_head=fused, merge_encoder_batches=False), recnet=rec, encoder_weights=bsd)
-        if not feats:
-            with torch.no_grad():
-                feats.extend([tr.encoder(a), tr.encoder(b)])
-        tr.encoder = _FixedEncoder()
-        tr.set_input(a, b, label)
-        tr.forward()
-        tr.zero_grad()
-        tr.backward()
-        torch.cuda.synchronize()
-        res.append(([float(l.detach()) for l in tr.loss_items], {k: p.grad.clone() for k, p in rec.named_parameters()},
-                    tr.pred_label.clone()))
-    (l0, g0, p0), (l0b, g0b, _), (l1, g1, p1) = res
-    assert all(abs(x - y) <= 1e-3 * max(1.0, abs(x)) for x, y in zip(l0, l1)), (l0, l1)
-    assert torch.equal(p0, p1)
-    noise = sorted(rel_l2(g0b[k], g0[k]) for k in g0)
-    devs = sorted((rel_l2(g1[k], g0[k]), k) for k in g0)
-    n_med, n_worst = noise[len(noise) // 2], noise[-1]
-    d_med, d_worst = devs[len(devs) // 2][0], devs[-1][0]
-    print("library head run-to-run (same feature maps): worst %.3e median %.3e" % (n_worst, n_med))
-    print("fused vs library head: losses", l0, l1, "| worst %.3e (%s) median %.3e" % (d_worst, devs[-1][1], d_med))
-    assert rel_l2(g1["classifier.weight"], g0["classifier.weight"]) <= 1e-2
-    # The trunk sees dL/dv with ~2e-3 relative noise (bf16 operands of the fused backward GEMMs, TF32 in the library
-    # head). At batch 4 the train-mode BatchNorm chain is very sensitive (DESIGN.md section 7), and the step itself is
-    # not bit-reproducible (fp32 atomics in the BN statistics / split-K wgrad): bound the deviation by the larger of
-    # a fixed tolerance and twice the measured run-to-run noise of the unchanged path.
-    assert d_med <= max(3e-2, 2 * n_med) and d_worst <= max(0.1, 2 * n_worst)

@@ -54,3 +54,24 @@ def test_mn_major_descriptor_semantics(lib):
         json.dump(result, f)
     print("mn-major probe:", result)
     assert all(result["variant0"]), result
+
+
+def test_fp16_operands(lib):
+    """tcgen05.mma kind::f16 with fp16 operands (a_format = b_format = F16): the training forward GEMMs use fp16
+    activations (hi + lo) and fp16 weights. MIXED formats (fp16 x bf16 in one instruction) raise an illegal-instruction
+    fault on B200 (measured once, profiles/r02_probe_mixed_formats.json) — which is why the weight-gradient GEMM contracts
+    the bf16 dz with a bf16 COPY of the activations."""
+    g = torch.Generator(device="cuda").manual_seed(2)
+    a = torch.randint(-3, 4, (96, 128), generator=g, device="cuda").float()
+    b = torch.randint(-3, 4, (96, 64), generator=g, device="cuda").float()
+    a = a + 0.0009765625 * torch.randint(0, 2, (96, 128), generator=g, device="cuda")   # 2^-10: exact in fp16, not in bf16
+    aa, bb = a.half(), b.half()
+    out = torch.zeros(128, 64, dtype=torch.float32, device="cuda")
+    _lib.check(lib.ffr_debug_mn_probe(_lib.ptr(aa), _lib.ptr(bb), _lib.ptr(out), 0, 6, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = aa[:64].float().t() @ bb[:64].float()
+    err = float((out - ref).abs().max())
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/probe_f16.json", "w") as f:
+        json.dump({"f16xf16_max_abs_err": err}, f)
+    assert err == 0.0
