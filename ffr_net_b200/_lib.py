@@ -100,7 +100,7 @@ _SIGNATURES = {
     "ffr_gallery_cosine": (_i, [_p, _i, _p, _i, _i, _p, _p, _p]),
     "ffr_roc_hist": (_i, [_p, _i, _i, _i, _p, _p, _p, _i, _p, _p]),
     "ffr_cosface_pack": (_i, [_p, _i, _i, _i, _p, _p, _i, _p]),
-    "ffr_cosface_ce_fwd": (_i, [_p, _i, _p, _i, _i, _p, ctypes.c_float, ctypes.c_float, _p, _p, _p, _p, _p]),
+    "ffr_cosface_ce_fwd": (_i, [_p, _i, _p, _i, _i, _p, ctypes.c_float, ctypes.c_float, _p, _p, _p, _p, _p, _p]),
     "ffr_cosface_ce_finish": (_i, [_p, _p, _p, _i, ctypes.c_float, _p, _p, _p]),
     "ffr_cosface_ce_bwd": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, ctypes.c_float, ctypes.c_float, _p, _p, _p]),
     "ffr_normalize_bwd": (_i, [_p, _p, _i, _p, _p]),

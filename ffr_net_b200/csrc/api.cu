@@ -360,11 +360,11 @@ FFR_API int ffr_cosface_pack(const float* x, int rows, int rows_pad, int mode, v
 
 FFR_API int ffr_cosface_ce_fwd(const void* v_packed, int n, const void* w_packed, int c_pad, int classes, const int* label,
                                float s, float m, float* cos_out, float* sumexp, float* zlabel,
-                               unsigned long long* argkey, ffr_stream_t stream) {
+                               unsigned long long* argkey, float* sumexp_part, ffr_stream_t stream) {
     FFR_CHECK_ARG(v_packed && w_packed && label && cos_out && sumexp && zlabel && argkey, "ffr_cosface_ce_fwd: null pointer");
     FFR_CHECK_ARG(n > 0 && c_pad % 256 == 0 && classes > 0 && classes <= c_pad, "ffr_cosface_ce_fwd: n=%d c_pad=%d classes=%d",
                   n, c_pad, classes);
-    FFR_CUDA(cudaMemsetAsync(sumexp, 0, sizeof(float) * (size_t)n, S_(stream)));
+    if (!sumexp_part) FFR_CUDA(cudaMemsetAsync(sumexp, 0, sizeof(float) * (size_t)n, S_(stream)));
     FFR_CUDA(cudaMemsetAsync(argkey, 0, sizeof(unsigned long long) * (size_t)n, S_(stream)));
     ConvGemmParams p;
     memset(&p, 0, sizeof(p));
@@ -374,8 +374,11 @@ FFR_API int ffr_cosface_ce_fwd(const void* v_packed, int n, const void* w_packed
     p.flags = EPI_OUT_F32 | EPI_COSFACE;
     p.out_f32 = cos_out;
     p.ce_label = label; p.ce_sumexp = sumexp; p.ce_zlabel = zlabel; p.ce_argkey = argkey;
+    p.ce_sumexp_part = sumexp_part;
     p.ce_classes = classes; p.ce_s = s; p.ce_m = m;
-    return conv_gemm_launch(v_packed, (long long)n, 1536, 1536, w_packed, 1536, p, 1, S_(stream));
+    int rc = conv_gemm_launch(v_packed, (long long)n, 1536, 1536, w_packed, 1536, p, 1, S_(stream));
+    if (rc || !sumexp_part) return rc;
+    return sumexp_reduce_launch(sumexp_part, n, c_pad / 128, sumexp, S_(stream));   // N tile 256, two column halves each
 }
 
 FFR_API int ffr_cosface_ce_finish(const float* sumexp, const float* zlabel, const unsigned long long* argkey, int n, float s,

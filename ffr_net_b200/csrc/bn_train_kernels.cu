@@ -46,28 +46,43 @@ __device__ __forceinline__ int h9_row_of_pixel(int pix) { return (pix / 7 + 1) *
 //   mode 1: pixel-major tiles, r = ((pixel * iblocks + ib) * 4 + quad) -> images [ib*128 + quad*32, +32).
 //   Partial rows beyond the data hold zeros (invalid rows are zeroed by the epilogue), so any group they map to is fine.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+constexpr int BN_MAX_GROUPS = 4;
+
+// block = 32 channels x 8 row slices; every slice adds its rows (r = slice, slice + 8, ...) per group in double, the
+// eight slices are then added in a fixed order.
+__global__ void __launch_bounds__(256)
 bn_finalize_kernel(const float* __restrict__ part, int R, int mode, int iblocks, int n_per_group, int G, int C,
                    int C_real, float momentum, float eps, float* __restrict__ running_mean,
                    float* __restrict__ running_var, long long* __restrict__ nbt, float* __restrict__ mr) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c == 0 && nbt != nullptr) *nbt += G;
-    if (c >= C) return;
-    const double cnt = (double)n_per_group * 49.0;
-    for (int g = 0; g < G; ++g) {
-        double s = 0.0, ss = 0.0;
-        for (int r = 0; r < R; ++r) {
-            int img;
-            if (mode == 0) img = (r * 32) / 81;
-            else img = ((r >> 2) % iblocks) * 128 + (r & 3) * 32;
+    __shared__ double red[8][BN_MAX_GROUPS][2][33];
+    const int cl = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && nbt != nullptr) *nbt += G;
+    double s[BN_MAX_GROUPS], ss[BN_MAX_GROUPS];
+#pragma unroll
+    for (int g = 0; g < BN_MAX_GROUPS; ++g) { s[g] = 0.0; ss[g] = 0.0; }
+    if (c < C) {
+        for (int r = slice; r < R; r += 8) {
+            const int img = (mode == 0) ? (r * 32) / 81 : ((r >> 2) % iblocks) * 128 + (r & 3) * 32;
             int rg = img / n_per_group;
             if (rg >= G) rg = G - 1;
-            if (rg != g) continue;
-            s += (double)part[((long long)r * 2) * C + c];
-            ss += (double)part[((long long)r * 2 + 1) * C + c];
+            const double a = (double)part[((long long)r * 2) * C + c], b = (double)part[((long long)r * 2 + 1) * C + c];
+#pragma unroll
+            for (int g = 0; g < BN_MAX_GROUPS; ++g)
+                if (g == rg) { s[g] += a; ss[g] += b; }
         }
-        const double mean = s / cnt;
-        double var = ss / cnt - mean * mean;
+    }
+#pragma unroll
+    for (int g = 0; g < BN_MAX_GROUPS; ++g) { red[slice][g][0][cl] = s[g]; red[slice][g][1][cl] = ss[g]; }
+    __syncthreads();
+    if (slice != 0 || c >= C) return;
+    const double cnt = (double)n_per_group * 49.0;
+    for (int g = 0; g < G; ++g) {
+        double ts = 0.0, tss = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { ts += red[k][g][0][cl]; tss += red[k][g][1][cl]; }
+        const double mean = ts / cnt;
+        double var = tss / cnt - mean * mean;
         if (var < 0.0) var = 0.0;
         mr[((long long)g * 2) * C + c] = (float)mean;
         mr[((long long)g * 2 + 1) * C + c] = (float)(1.0 / sqrt(var + (double)eps));
@@ -264,21 +279,32 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(const BnActBwd p
     }
 }
 
-__global__ void __launch_bounds__(128) bn_act_bwd_finalize_kernel(const BnActBwd p) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= p.C) return;
+__global__ void __launch_bounds__(256) bn_act_bwd_finalize_kernel(const BnActBwd p) {
+    __shared__ float red[8][3][33];
+    const int cl = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
     float tg = 0.f, tb = 0.f, ts = 0.f;
     for (int g = 0; g < p.G; ++g) {
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-        for (int k = 0; k < p.ctas_per_group; ++k) {
-            const float* q = p.partial + ((long long)(g * p.ctas_per_group + k) * 3) * p.C + c;
-            s0 += q[0]; s1 += q[p.C]; s2 += q[2 * p.C];
+        if (c < p.C) {
+            for (int k = slice; k < p.ctas_per_group; k += 8) {
+                const float* q = p.partial + ((long long)(g * p.ctas_per_group + k) * 3) * p.C + c;
+                s0 += q[0]; s1 += q[p.C]; s2 += q[2 * p.C];
+            }
         }
-        p.gsum[((long long)g * 2) * p.C + c] = s0;
-        p.gsum[((long long)g * 2 + 1) * p.C + c] = s1;
-        tb += s0; tg += s1; ts += s2;
+        __syncthreads();
+        red[slice][0][cl] = s0; red[slice][1][cl] = s1; red[slice][2][cl] = s2;
+        __syncthreads();
+        if (slice == 0 && c < p.C) {
+            s0 = s1 = s2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { s0 += red[k][0][cl]; s1 += red[k][1][cl]; s2 += red[k][2][cl]; }
+            p.gsum[((long long)g * 2) * p.C + c] = s0;
+            p.gsum[((long long)g * 2 + 1) * p.C + c] = s1;
+            tb += s0; tg += s1; ts += s2;
+        }
     }
-    if (c < p.C_real) {
+    if (slice == 0 && c < p.C_real) {
         if (p.accumulate) { p.dgamma[c] += tg; p.dbeta[c] += tb; p.dslope[c] += ts; }
         else              { p.dgamma[c] = tg;  p.dbeta[c] = tb;  p.dslope[c] = ts; }
     }
@@ -373,9 +399,10 @@ FFR_API int ffr_bn_finalize(const float* part, int part_rows, int pixmajor, int 
                   "ffr_bn_finalize: bad arguments");
     const int G = n_img / n_per_group;
     FFR_CHECK_ARG(G == 1 || n_per_group % 32 == 0, "ffr_bn_finalize: batched groups need n_per_group %% 32 == 0");
+    FFR_CHECK_ARG(G <= BN_MAX_GROUPS, "ffr_bn_finalize: at most %d groups", BN_MAX_GROUPS);
     FFR_CHECK_ARG(!running_mean == !running_var, "ffr_bn_finalize: running_mean / running_var go together");
     const int iblocks = (n_img + 127) / 128;
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, S_(stream)>>>(part, part_rows, pixmajor, iblocks, n_per_group, G, C,
+    bn_finalize_kernel<<<(C + 31) / 32, 256, 0, S_(stream)>>>(part, part_rows, pixmajor, iblocks, n_per_group, G, C,
                                                                C_real, momentum, eps, running_mean, running_var,
                                                                num_batches_tracked, mean_rstd);
     return launch_status("bn_finalize_kernel");
@@ -441,7 +468,7 @@ FFR_API int ffr_bn_act_bwd(const float* da, int ldda, int da_ch0, const int* sca
     bn_act_bwd_reduce_kernel<<<grid, 256, 0, S_(stream)>>>(p);
     int rc = launch_status("bn_act_bwd_reduce_kernel");
     if (rc) return rc;
-    bn_act_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, S_(stream)>>>(p);
+    bn_act_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, S_(stream)>>>(p);
     rc = launch_status("bn_act_bwd_finalize_kernel");
     if (rc) return rc;
     const long long total = (long long)n_img * 81 * (C / 8);

@@ -371,7 +371,9 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
             }
         }
         if ((flags & EPI_COSFACE) && m < p.M) {
-            if (p.ce_sumexp != nullptr) atomicAdd(p.ce_sumexp + m, ce_sum);
+            if (p.ce_sumexp_part != nullptr)
+                p.ce_sumexp_part[(long long)m * (2 * p.num_n_tiles) + n_tile * 2 + chalf] = ce_sum;
+            else if (p.ce_sumexp != nullptr) atomicAdd(p.ce_sumexp + m, ce_sum);
             if (p.ce_zlabel != nullptr && ce_lab >= nc0 && ce_lab < nc0 + HALF) p.ce_zlabel[m] = ce_zl;
             if (nc0 < p.ce_classes) {
                 uint32_t u = __float_as_uint(ce_best);

@@ -88,7 +88,8 @@ struct ConvGemmParams {
     int pix_pad_from;               // output pixels with h or w >= this are pad points: no taps, zeros are stored
     // EPI_COSFACE (AddMarginProduct + CrossEntropy, recnet.py:257-270, trainer.py:173-176)
     const int* ce_label;            // [M]
-    float* ce_sumexp;               // [M], zeroed by the caller
+    float* ce_sumexp;               // [M], zeroed by the caller (atomic accumulation), used when ce_sumexp_part == nullptr
+    float* ce_sumexp_part;          // deterministic alternative: [M][2 * num_n_tiles] partial sums, plain stores
     float* ce_zlabel;               // [M]
     unsigned long long* ce_argkey;  // [M], zeroed by the caller: (orderable cos bits << 32) | (0xFFFFFFFF - class)
     int ce_classes;                 // real class count (columns >= ce_classes are padding)

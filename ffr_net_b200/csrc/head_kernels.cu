@@ -106,6 +106,22 @@ int cosface_pack_launch(const float* x, int rows, int rows_pad, int mode, void* 
     return launch_status("cosface_pack_kernel");
 }
 
+// ---- fixed-order sum of the per-(row, column tile) partial softmax denominators -------------------------------------
+__global__ void __launch_bounds__(256) sumexp_reduce_kernel(const float* __restrict__ part, int n, int parts,
+                                                            float* __restrict__ sumexp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.f;
+    for (int k = 0; k < parts; ++k) s += part[(long long)i * parts + k];
+    sumexp[i] = s;
+}
+
+int sumexp_reduce_launch(const float* part, int n, int parts, float* sumexp, cudaStream_t stream) {
+    if (n == 0) return 0;
+    sumexp_reduce_kernel<<<(n + 255) / 256, 256, 0, stream>>>(part, n, parts, sumexp);
+    return launch_status("sumexp_reduce_kernel");
+}
+
 // ---- finish: loss = mean(log(sumexp) + s - z_label); pred = arg-max class ---------------------------------------------
 __global__ void __launch_bounds__(1024) cosface_finish_kernel(const float* __restrict__ sumexp, const float* __restrict__ zlabel,
                                                               const unsigned long long* __restrict__ argkey, int n, float s,

@@ -31,6 +31,7 @@ int rows_to_nchw_launch(const void* rows, int is_f32, int ld, int ch0, const flo
                         int n, int S, int G, int off, int rows_per_img, int C, cudaStream_t stream);
 int cosface_pack_launch(const float* x, int rows, int rows_pad, int mode, void* packed, void* transposed, int t_ld,
                         cudaStream_t stream);
+int sumexp_reduce_launch(const float* part, int n, int parts, float* sumexp, cudaStream_t stream);
 int cosface_finish_launch(const float* sumexp, const float* zlabel, const unsigned long long* argkey, int n, float s,
                           float* loss, long long* pred, cudaStream_t stream);
 int cosface_bwd_launch(const float* cosv, int c_pad, int classes, int n, int n_pad, const int* label, const float* sumexp,

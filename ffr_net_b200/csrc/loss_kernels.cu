@@ -44,7 +44,9 @@ __device__ __forceinline__ float block_sum(float v, float* scratch /*[32]*/) {
 }
 
 // ----------------------------------------------------------------------------------------------------------
-// Channel self-similarity: pack. One CTA per sample, thread = channel row c.
+// Channel self-similarity: pack. CTA = (sample, 64-channel chunk); the chunk of F and of the target X goes through
+// shared memory so that every global access is coalesced (rows of A6 / B6 are 768 bytes each, consecutive rows are
+// contiguous).
 //   f: fp32 H9 matrix [n_img*81][ldf], own rows valid (feat_channel of the RecNet call); x: [n][512][49] targets.
 // ----------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) selfsim_channel_pack_kernel(const float* __restrict__ f, int ldf,
@@ -53,42 +55,56 @@ __global__ void __launch_bounds__(256) selfsim_channel_pack_kernel(const float* 
                                                                    __nv_bfloat16* __restrict__ B6,
                                                                    __nv_bfloat16* __restrict__ FhT,
                                                                    float* __restrict__ inv_f) {
-    const int s = blockIdx.x, c = blockIdx.y * 256 + threadIdx.x;
+    __shared__ float fs[64][50], xs[64][50];     // [channel][pixel] (+1 pad column: conflict-free row walks)
+    __shared__ float invf[64], invx[64];
+    const int s = blockIdx.x, c0 = blockIdx.y * 64, tid = threadIdx.x;
     const int t = s % n_per_group;
-    float fv[49], xv[49];
-    float sf = 0.f, sx = 0.f;
-#pragma unroll
-    for (int hw = 0; hw < 49; ++hw) {
-        fv[hw] = f[((long long)s * 81 + h9_row_l(hw)) * ldf + c];
-        xv[hw] = __ldg(x + ((long long)t * 512 + c) * 49 + hw);
-        sf = fmaf(fv[hw], fv[hw], sf);
-        sx = fmaf(xv[hw], xv[hw], sx);
+    for (int i = tid; i < 49 * 64; i += 256) {
+        const int hw = i >> 6, c = i & 63;
+        fs[c][hw] = f[((long long)s * 81 + h9_row_l(hw)) * ldf + c0 + c];
     }
-    const float inf_ = 1.0f / fmaxf(sqrtf(sf), 1e-12f), inx = 1.0f / fmaxf(sqrtf(sx), 1e-12f);
-    inv_f[(long long)s * 512 + c] = inf_;
-    const long long row = (long long)s * 512 + c;
-    uint32_t* a = reinterpret_cast<uint32_t*>(A6 + row * 384);
-    uint32_t* b = reinterpret_cast<uint32_t*>(B6 + row * 384);
-#pragma unroll
-    for (int w = 0; w < 32; ++w) {              // 32 words = 64 columns per chunk
-        float f0 = 0.f, f1 = 0.f, x0 = 0.f, x1 = 0.f;
-        if (2 * w < 49) { f0 = fv[2 * w] * inf_; x0 = xv[2 * w] * inx; }
-        if (2 * w + 1 < 49) { f1 = fv[2 * w + 1] * inf_; x1 = xv[2 * w + 1] * inx; }
-        const __nv_bfloat16 fh0 = __float2bfloat16_rn(f0), fh1 = __float2bfloat16_rn(f1);
-        const __nv_bfloat16 xh0 = __float2bfloat16_rn(x0), xh1 = __float2bfloat16_rn(x1);
-        const float fl0 = f0 - __bfloat162float(fh0), fl1 = f1 - __bfloat162float(fh1);
-        const float xl0 = x0 - __bfloat162float(xh0), xl1 = x1 - __bfloat162float(xh1);
-        const uint32_t FH = (uint32_t)__bfloat16_as_ushort(fh0) | ((uint32_t)__bfloat16_as_ushort(fh1) << 16);
-        const uint32_t XH = (uint32_t)__bfloat16_as_ushort(xh0) | ((uint32_t)__bfloat16_as_ushort(xh1) << 16);
-        const uint32_t FL = pack_bf16x2(fl0, fl1), XL = pack_bf16x2(xl0, xl1);
-        const uint32_t NXH = XH ^ 0x80008000u, NXL = XL ^ 0x80008000u;     // sign flip of both halves
-        a[w] = FH; a[32 + w] = FL; a[64 + w] = FH; a[96 + w] = NXH; a[128 + w] = NXL; a[160 + w] = NXH;
-        b[w] = FH; b[32 + w] = FH; b[64 + w] = FL; b[96 + w] = XH;  b[128 + w] = XH;  b[160 + w] = XL;
+    const float* xc = x + ((long long)t * 512 + c0) * 49;
+    for (int i = tid; i < 64 * 49; i += 256) xs[i / 49][i % 49] = __ldg(xc + i);
+    __syncthreads();
+    {   // row norms: 4 threads per channel row
+        const int c = tid >> 2, q = tid & 3;
+        float sf = 0.f, sx = 0.f;
+        for (int hw = q; hw < 49; hw += 4) { sf = fmaf(fs[c][hw], fs[c][hw], sf); sx = fmaf(xs[c][hw], xs[c][hw], sx); }
+        sf += __shfl_xor_sync(0xffffffffu, sf, 1); sf += __shfl_xor_sync(0xffffffffu, sf, 2);
+        sx += __shfl_xor_sync(0xffffffffu, sx, 1); sx += __shfl_xor_sync(0xffffffffu, sx, 2);
+        if (q == 0) {
+            const float a = 1.0f / fmaxf(sqrtf(sf), 1e-12f);
+            invf[c] = a;
+            invx[c] = 1.0f / fmaxf(sqrtf(sx), 1e-12f);
+            inv_f[(long long)s * 512 + c0 + c] = a;
+        }
     }
-    // F^T (hi part): [s*64 + hw][c], rows 49..63 zero
-#pragma unroll
-    for (int hw = 0; hw < 64; ++hw)
-        FhT[((long long)s * 64 + hw) * 512 + c] = __float2bfloat16_rn(hw < 49 ? fv[hw < 49 ? hw : 0] * inf_ : 0.f);
+    __syncthreads();
+    uint32_t* a = reinterpret_cast<uint32_t*>(A6 + ((long long)s * 512 + c0) * 384);
+    uint32_t* b = reinterpret_cast<uint32_t*>(B6 + ((long long)s * 512 + c0) * 384);
+    for (int w = tid; w < 64 * 192; w += 256) {            // 192 words per row = 6 chunks x 32 words (64 columns each)
+        const int c = w / 192, cw = w - c * 192;
+        const int chunk = cw >> 5, k2 = (cw & 31) * 2;
+        const bool is_x = chunk >= 3;
+        const float iv = is_x ? invx[c] : invf[c];
+        const float* src = is_x ? xs[c] : fs[c];
+        const float v0 = (k2 < 49) ? src[k2] * iv : 0.f, v1 = (k2 + 1 < 49) ? src[k2 + 1] * iv : 0.f;
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+        const uint32_t HI = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        const uint32_t LO = pack_bf16x2(v0 - __bfloat162float(h0), v1 - __bfloat162float(h1));
+        // A = [Fh | Fl | Fh | -Xh | -Xl | -Xh],  B = [Fh | Fh | Fl | Xh | Xh | Xl]
+        const int sub = is_x ? chunk - 3 : chunk;
+        uint32_t av = (sub == 1) ? LO : HI;
+        const uint32_t bv = (sub == 2) ? LO : HI;
+        if (is_x) av ^= 0x80008000u;                        // sign flip of both halves
+        a[w] = av;
+        b[w] = bv;
+    }
+    // F^T (hi part): [s*64 + hw][c0 + c], rows 49..63 zero
+    for (int i = tid; i < 64 * 64; i += 256) {
+        const int hw = i >> 6, c = i & 63;
+        FhT[((long long)s * 64 + hw) * 512 + c0 + c] = __float2bfloat16_rn(hw < 49 ? fs[c][hw] * invf[c] : 0.f);
+    }
 }
 
 // Gradient finish: e = D F^ (fp32 [n_img*512][64], columns 0..48) ->
@@ -337,7 +353,7 @@ FFR_API int ffr_selfsim_channel_pack(const float* f, int ldf, const float* x, in
                                      void* B6, void* FhT, float* inv_f, ffr_stream_t stream) {
     FFR_CHECK_ARG(f && x && A6 && B6 && FhT && inv_f && n_per_group > 0, "ffr_selfsim_channel_pack: bad arguments");
     if (n_img == 0) return 0;
-    selfsim_channel_pack_kernel<<<dim3(n_img, 2), 256, 0, S_(stream)>>>(f, ldf, x, n_per_group,
+    selfsim_channel_pack_kernel<<<dim3(n_img, 8), 256, 0, S_(stream)>>>(f, ldf, x, n_per_group,
                                                               reinterpret_cast<__nv_bfloat16*>(A6),
                                                               reinterpret_cast<__nv_bfloat16*>(B6),
                                                               reinterpret_cast<__nv_bfloat16*>(FhT), inv_f);

@@ -17,7 +17,7 @@ EPI_OUT_F32_ATOMIC, EPI_OUT_F32 = 0x40, 0x800
 
 import weakref
 
-_wcache = weakref.WeakKeyDictionary()      # parameter -> (key, packed, transposed): dies with the parameter
+_wcache = {}      # id(parameter) -> (key, packed, transposed, weakref to the parameter); dead entries are evicted
 
 
 def _ceil(a, b):
@@ -28,7 +28,9 @@ def _packed_classes(lib, weight):
     """hi/lo-split normalised class matrix [c_pad x 1536] and its bf16 transpose [512 x c_pad]; repacked (into the same
     buffers) whenever the weights change (torch version counter, or the fused optimizer's generation counter)."""
     key = (weight.data_ptr(), weight._version, _lib.weights_generation(), str(weight.device))
-    held = _wcache.get(weight)
+    held = _wcache.get(id(weight))
+    if held is not None and held[3]() is not weight:      # id reused by another tensor
+        held = None
     if held is not None and held[0] == key:
         return held[1], held[2]
     classes = weight.shape[0]
@@ -40,7 +42,9 @@ def _packed_classes(lib, weight):
         wt = torch.empty(512, c_pad, dtype=torch.bfloat16, device=weight.device)
     _lib.check(lib.ffr_cosface_pack(_lib.ptr(weight.detach()), classes, c_pad, 1, _lib.ptr(wp), _lib.ptr(wt), c_pad,
                                     _lib.stream_ptr()), "cosface_pack(classes)")
-    _wcache[weight] = (key, wp, wt)
+    for k in [k for k, v in _wcache.items() if v[3]() is None]:
+        del _wcache[k]
+    _wcache[id(weight)] = (key, wp, wt, weakref.ref(weight))
     return wp, wt
 
 
@@ -65,8 +69,9 @@ class _CosFaceCE(torch.autograd.Function):
         sumexp = torch.empty(n, dtype=torch.float32, device=dev)
         zlabel = torch.empty(n, dtype=torch.float32, device=dev)
         argkey = torch.empty(n, dtype=torch.int64, device=dev)
+        part = torch.empty(n, c_pad // 128, dtype=torch.float32, device=dev)
         _lib.check(lib.ffr_cosface_ce_fwd(P(vp), n, P(wp), c_pad, classes, P(lab), s, m, P(cos), P(sumexp), P(zlabel),
-                                          P(argkey), st), "cosface_ce_fwd")
+                                          P(argkey), P(part), st), "cosface_ce_fwd")
         loss = torch.empty((), dtype=torch.float32, device=dev)
         pred = torch.empty(n, dtype=torch.int64, device=dev)
         _lib.check(lib.ffr_cosface_ce_finish(P(sumexp), P(zlabel), P(argkey), n, s, P(loss), P(pred), st),
@@ -143,6 +148,7 @@ class GroupedHead:
         self.vt = torch.zeros(512, self.n_pad, **bf)
         self.cos = torch.zeros(n_total, self.c_pad, **f32)
         self.sumexp = torch.zeros(n_total, **f32)
+        self.sumexp_part = torch.zeros(n_total, self.c_pad // 128, **f32)
         self.zlabel = torch.zeros(n_total, **f32)
         self.argkey = torch.zeros(n_total, dtype=torch.int64, device=dev)
         self.pred = torch.zeros(n_total, dtype=torch.int64, device=dev)
@@ -169,7 +175,8 @@ class GroupedHead:
         _lib.check(lib.ffr_cosface_pack(P(v), self.NT, self.n_pad, 0, P(self.vp), P(self.vt), self.n_pad, st),
                    "cosface_pack(samples)")
         _lib.check(lib.ffr_cosface_ce_fwd(P(self.vp), self.NT, P(self.wp), self.c_pad, self.classes, P(self.lab), s, m,
-                                          P(self.cos), P(self.sumexp), P(self.zlabel), P(self.argkey), st), "cosface_ce_fwd")
+                                          P(self.cos), P(self.sumexp), P(self.zlabel), P(self.argkey), P(self.sumexp_part),
+                                          st), "cosface_ce_fwd")
         for g in range(G):
             lo = g * self.n
             _lib.check(lib.ffr_cosface_ce_finish(P(self.sumexp[lo:]), P(self.zlabel[lo:]), P(self.argkey[lo:]), self.n, s,

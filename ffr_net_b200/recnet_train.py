@@ -78,6 +78,7 @@ class TrainEngine:
         self.deterministic = bool(deterministic)
         self._ws = {}
         self._pack = None
+        self.trace = None          # debugging: set to a list to record (name, tensor clone) after every stage
         self.layers = []
         for name, cin, cout in _CONVS:
             m = model
@@ -87,6 +88,10 @@ class TrainEngine:
             L.name, L.mod, L.cin, L.cout = name, m, cin, cout
             L.cin_p, L.cout_p = _ceil64(cin), _ceil64(cout)
             self.layers.append(L)
+
+    def _tr(self, name, t):
+        if self.trace is not None and t is not None:
+            self.trace.append((name, t.detach().clone()))
 
     # ------------------------------------------------------------------------------------------------------
     def _packed(self, dev):
@@ -197,6 +202,8 @@ class TrainEngine:
         bn = L.mod.norm.norm
         z, mr = ws.z[i], ws.mr[i]
         self._conv_fwd(lib, ws, L, packs[i][0], src, z, st)
+        self._tr("fwd.%s.z" % L.name, z)
+        self._tr("fwd.%s.part" % L.name, ws.part[: ws.part_rows * 2 * L.cout_p])
         _lib.check(lib.ffr_bn_finalize(_P(ws.part), ws.part_rows, 1 if ws.pix else 0, ws.NT, ws.n, L.cout_p, L.cout,
                                        BN_MOMENTUM, BN_EPS, _P(bn.running_mean), _P(bn.running_var),
                                        _P(bn.num_batches_tracked), _P(mr), st), "bn_finalize " + L.name)
@@ -210,6 +217,11 @@ class TrainEngine:
             _P(dst.b) if dst is not None else None, dst.b.shape[1] if dst is not None else 0,
             _P(out_f), out_f.shape[1] if out_f is not None else 0, 1 if sigmoid else 0,
             _P(tab), 4, ws.NT, ws.n, L.cout_p, L.cout, st), "bn_act_fwd " + L.name)
+        self._tr("fwd.%s.mr" % L.name, mr)
+        if dst is not None:
+            self._tr("fwd.%s.out_h" % L.name, dst.h)
+            self._tr("fwd.%s.out_b" % L.name, dst.b)
+        self._tr("fwd.%s.out_f" % L.name, out_f)
 
     def forward(self, x, n_groups, slot=0, v_out=None):
         """x: (G*n,512,7,7) fp32 CUDA, the G calls concatenated. Returns the workspace holding every result:
@@ -250,6 +262,10 @@ class TrainEngine:
         d.h7b, d.xk, d.mch = _P(ws.h7b), _P(ws.xk), _P(ws.mch)
         d.inv_c, d.tmat, d.ss_space = _P(ws.inv_c), _P(ws.tmat), None
         _lib.check(lib.ffr_recnet_prep_train(ctypes.byref(d), NT, st), "recnet_prep_train")
+        for nm in ("s0", "cm", "fm"):
+            self._tr("fwd.prep.%s" % nm, getattr(ws, nm).h)
+        self._tr("fwd.prep.g2", ws.g[2])
+        self._tr("fwd.prep.mch", ws.mch)
 
         f = lambda *a, **k: self._layer_fwd(lib, ws, *a, st=st, **k)
         # spatial rectifier (recnet.py:362-371, :404-405)
@@ -303,11 +319,16 @@ class TrainEngine:
             _P(ws.z[i]), C, _P(ws.mr[i]), _P(bn.weight), _P(bn.bias), _P(L.mod.relu.func.weight),
             _P(af), C, _P(ws.bwd_part), _P(ws.gsum), _P(gw), _P(gb), _P(gs), 1 if accumulate else 0, L.cout,
             _P(dz), C, ws.NT, ws.n, C, st), "bn_act_bwd " + L.name)
+        self._tr("bwd.%s.afold" % L.name, af)
+        self._tr("bwd.%s.dz" % L.name, dz)
+        self._tr("bwd.%s.dgamma" % L.name, gw)
         _lib.check(lib.ffr_wgrad(_P(dz), C, _P(src.b), src.b.shape[1], 0, ws.R, L.cout, L.cin, 9, 0,
                                  1 if self.deterministic else 0, 1 if accumulate else 0, L.cin, -1,
                                  _P(grads[L.name + ".conv2d.weight"]), None, _P(ws.wgrad_ws), st), "wgrad " + L.name)
+        self._tr("bwd.%s.dw" % L.name, grads[L.name + ".conv2d.weight"])
         if dgrad_out is not None:
             self._dgrad(lib, ws, L, packs[i][1], dz, dgrad_out, dgrad_cols if dgrad_cols is not None else L.cin_p, st)
+            self._tr("bwd.%s.dgrad" % L.name, dgrad_out)
         return af
 
     def backward(self, ws, grads, dv=None, dfs=None, dfc=None, dfnew=None, accumulate=False, on_stage=None):
@@ -347,6 +368,8 @@ class TrainEngine:
         d.res, d.ldres = _P(ws.mch), 512
         d.num_splits, d.b_rows_per_mtile, d.b_mtile_div = 1, 512, 4
         _lib.check(lib.ffr_conv_gemm_ex(ctypes.byref(d), st), "dM_pre GEMM")
+        self._tr("bwd.chan.dfc_op", ws.dfc_op)
+        self._tr("bwd.chan.dmpre", ws.dmpre)
         d = _lib.ConvGemmDesc()            # dh7[c][k] = sum_j dM_pre[c][j] W8[j][k]  (W8^T packed by ffr_chan_compose)
         d.a, d.a_rows, d.a_cols, d.a_ld = _P(ws.dmpre), NT * 512, 512, 512
         d.wp, d.Cin, d.Cout, d.ntaps = _P(ws.w8t), 512, 64, 1
@@ -355,6 +378,7 @@ class TrainEngine:
         d.out_f32 = _P(ws.dh7)
         d.num_splits = 1
         _lib.check(lib.ffr_conv_gemm_ex(ctypes.byref(d), st), "dh7 GEMM")
+        self._tr("bwd.chan.dh7", ws.dh7)
         # dW8[j][k] = sum_rows dM_pre[row][j] h7[row][k]; the ones column of h7b gives db8[j]
         _lib.check(lib.ffr_wgrad(_P(ws.dmpre), 512, _P(ws.h7b), 64, 0, NT * 512, 512, 33, 1, 0,
                                  1 if self.deterministic else 0, 1 if accumulate else 0, 32, 32,
@@ -379,6 +403,7 @@ class TrainEngine:
         # ---- spatial rectifier: feat_space = X @ M_space (slot [0,512) of the Conv4Merge input) ----
         _lib.check(lib.ffr_feat_space_bwd(_P(ws.x), _P(ws.mspace), _P(ws.dcm), 1024, _P(dfs), 512 if dfs is not None else 0,
                                           _P(ws.dmsp), NT, st), "feat_space_bwd")
+        self._tr("bwd.space.dmsp", ws.dmsp)
         af8 = b(8, ws.a64[1], dadd=ws.dmsp, afold=ws.af[0], dgrad_out=view(ws.da[0], 64))
         b(7, ws.a64[0], da=view(ws.da[0], 64), afold=ws.af[1], dgrad_out=view(ws.da[1], 64))
         b(6, ws.a128[2], da=view(ws.da[1], 64), dadd=af8, afold=ws.af[2], dgrad_out=view(ws.da[0], 128))

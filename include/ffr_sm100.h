@@ -382,7 +382,9 @@ FFR_API int ffr_cosface_pack(const float* x, int rows, int rows_pad, int mode, v
  * torch.argmax). c_pad must be a multiple of 256; label is int32. sumexp and argkey are zeroed here. */
 FFR_API int ffr_cosface_ce_fwd(const void* v_packed, int n, const void* w_packed, int c_pad, int classes, const int* label,
                                float s, float m, float* cos_out, float* sumexp, float* zlabel,
-                               unsigned long long* argkey, ffr_stream_t stream);
+                               unsigned long long* argkey, float* sumexp_part, ffr_stream_t stream);
+/*   sumexp_part (optional): fp32 workspace [n][c_pad / 128]; when given, the softmax denominators are accumulated as
+ *   per-tile partial sums added in a fixed order (bit-reproducible) instead of with fp32 atomics. */
 
 /* loss = mean_i(log(sumexp[i]) + s - zlabel[i]) (device scalar); pred[i] = arg-max class (int64, may be NULL). */
 FFR_API int ffr_cosface_ce_finish(const float* sumexp, const float* zlabel, const unsigned long long* argkey, int n, float s,

@@ -82,6 +82,7 @@ def test_training_step_256_pairs_tiling_property(lib, nets):
     lib.ffr_debug_set_pixmajor(-1)
     (l64, g64, acc64), (l256, g256, acc256), (l256b, g256b, _) = res
     assert all(torch.isfinite(g).all() for g in g256.values())
+    print("losses 64 pairs", l64, "256 pairs", l256)
     assert all(abs(x - y) <= 1e-4 * max(1.0, abs(x)) for x, y in zip(l64, l256)), (l64, l256)
     assert abs(acc64 - acc256) <= 1e-9
     errs = sorted(((g256[k].double() - g64[k].double()).norm() / (g64[k].double().norm() + 1e-30)).item() for k in g64)

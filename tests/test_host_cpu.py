@@ -46,7 +46,7 @@ def test_argument_errors_are_reported_without_a_gpu():
                            0, None, None, None, 0, None, 1, None, 0, 0, 0, None), b"pixel-major"),
         (lambda: lib.ffr_conv3x3_bnpre_prelu_fwd(one, 1, 13, 64, one, 64, one, one, one, 1, None), b"even S"),
         (lambda: lib.ffr_cosface_pack(one, 5, 70, 0, one, None, 0, None), b"rows_pad"),
-        (lambda: lib.ffr_cosface_ce_fwd(one, 4, one, 300, 300, one, 30.0, 0.4, one, one, one, one, None), b"c_pad"),
+        (lambda: lib.ffr_cosface_ce_fwd(one, 4, one, 300, 300, one, 30.0, 0.4, one, one, one, one, None, None), b"c_pad"),
         (lambda: lib.ffr_cosface_ce_bwd(one, 320, 300, 4, 60, one, one, one, 30.0, 0.4, one, one, None), b"bad shape"),
         (lambda: lib.ffr_wgrad3x3(one, 60, one, 64, 0, 1, 64, 64, one, one, None), b"pitches"),
         (lambda: lib.ffr_self_similarity(one, 1, None, None, None), b"no output"),

@@ -61,7 +61,8 @@ def test_fused_clip_adam_state_dict_roundtrip(lib):
         for p, gr in zip(pa, grads[it]):
             p.grad = gr.clone()
         oa.step()
-    sd = oa.state_dict()
+    import copy
+    sd = copy.deepcopy(oa.state_dict())         # as a checkpoint round trip would (load_state_dict shares tensors)
     assert "_lr_on_device" not in sd["param_groups"][0]
     assert all(float(st["step"]) == 3.0 for st in sd["state"].values())
     with torch.no_grad():
@@ -70,9 +71,9 @@ def test_fused_clip_adam_state_dict_roundtrip(lib):
         for q, p in zip(pc, pa):
             q.copy_(p)
     ob_ = FusedClipAdam(pb, lr=0.05, clip_value=1.0)
-    ob_.load_state_dict(sd)
+    ob_.load_state_dict(copy.deepcopy(sd))
     oc = torch.optim.Adam(pc, lr=0.05)
-    oc.load_state_dict(sd)
+    oc.load_state_dict(copy.deepcopy(sd))
     for it in range(3, 5):
         for x, y, z, gr in zip(pa, pb, pc, grads[it]):
             x.grad, y.grad, z.grad = gr.clone(), gr.clone(), gr.clone()
