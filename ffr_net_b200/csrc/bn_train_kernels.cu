@@ -46,15 +46,16 @@ __device__ __forceinline__ int h9_row_of_pixel(int pix) { return (pix / 7 + 1) *
 //   mode 1: pixel-major tiles, r = ((pixel * iblocks + ib) * 4 + quad) -> images [ib*128 + quad*32, +32).
 //   Partial rows beyond the data hold zeros (invalid rows are zeroed by the epilogue), so any group they map to is fine.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int BN_MAX_GROUPS = 4;
+constexpr int BN_MAX_GROUPS = 2;
 
-// block = 32 channels x 8 row slices; every slice adds its rows (r = slice, slice + 8, ...) per group in double, the
-// eight slices are then added in a fixed order.
-__global__ void __launch_bounds__(256)
+// block = 32 channels x 32 row slices; every slice adds its rows (r = slice, slice + 32, ...) per group in double, the
+// slices are then added in a fixed order (latency-bound otherwise: few channels, hundreds of partial rows).
+constexpr int BNF_SLICES = 32;
+__global__ void __launch_bounds__(1024)
 bn_finalize_kernel(const float* __restrict__ part, int R, int mode, int iblocks, int n_per_group, int G, int C,
                    int C_real, float momentum, float eps, float* __restrict__ running_mean,
                    float* __restrict__ running_var, long long* __restrict__ nbt, float* __restrict__ mr) {
-    __shared__ double red[8][BN_MAX_GROUPS][2][33];
+    __shared__ double red[BNF_SLICES][BN_MAX_GROUPS][2][33];
     const int cl = threadIdx.x & 31, slice = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
     if (blockIdx.x == 0 && threadIdx.x == 0 && nbt != nullptr) *nbt += G;
@@ -62,11 +63,13 @@ bn_finalize_kernel(const float* __restrict__ part, int R, int mode, int iblocks,
 #pragma unroll
     for (int g = 0; g < BN_MAX_GROUPS; ++g) { s[g] = 0.0; ss[g] = 0.0; }
     if (c < C) {
-        for (int r = slice; r < R; r += 8) {
+#pragma unroll 4
+        for (int r = slice; r < R; r += BNF_SLICES) {
             const int img = (mode == 0) ? (r * 32) / 81 : ((r >> 2) % iblocks) * 128 + (r & 3) * 32;
             int rg = img / n_per_group;
             if (rg >= G) rg = G - 1;
-            const double a = (double)part[((long long)r * 2) * C + c], b = (double)part[((long long)r * 2 + 1) * C + c];
+            const double a = (double)__ldg(part + ((long long)r * 2) * C + c);
+            const double b = (double)__ldg(part + ((long long)r * 2 + 1) * C + c);
 #pragma unroll
             for (int g = 0; g < BN_MAX_GROUPS; ++g)
                 if (g == rg) { s[g] += a; ss[g] += b; }
@@ -80,7 +83,7 @@ bn_finalize_kernel(const float* __restrict__ part, int R, int mode, int iblocks,
     for (int g = 0; g < G; ++g) {
         double ts = 0.0, tss = 0.0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { ts += red[k][g][0][cl]; tss += red[k][g][1][cl]; }
+        for (int k = 0; k < BNF_SLICES; ++k) { ts += red[k][g][0][cl]; tss += red[k][g][1][cl]; }
         const double mean = ts / cnt;
         double var = tss / cnt - mean * mean;
         if (var < 0.0) var = 0.0;
@@ -402,7 +405,7 @@ FFR_API int ffr_bn_finalize(const float* part, int part_rows, int pixmajor, int 
     FFR_CHECK_ARG(G <= BN_MAX_GROUPS, "ffr_bn_finalize: at most %d groups", BN_MAX_GROUPS);
     FFR_CHECK_ARG(!running_mean == !running_var, "ffr_bn_finalize: running_mean / running_var go together");
     const int iblocks = (n_img + 127) / 128;
-    bn_finalize_kernel<<<(C + 31) / 32, 256, 0, S_(stream)>>>(part, part_rows, pixmajor, iblocks, n_per_group, G, C,
+    bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, S_(stream)>>>(part, part_rows, pixmajor, iblocks, n_per_group, G, C,
                                                                C_real, momentum, eps, running_mean, running_var,
                                                                num_batches_tracked, mean_rstd);
     return launch_status("bn_finalize_kernel");

@@ -94,7 +94,10 @@ def get_fold_accuracy(fold, predicts, new=0):
     n = predicts.shape[0]
     test = fold[1]
     n_folds = max(1, round(n / max(1, len(test))))
-    f = test[0] * n_folds // n
+    bounds = [i * n // n_folds for i in range(n_folds + 1)]     # KFold's contiguous test ranges (lfw_eval.py:113-117)
+    if test[0] not in bounds[:-1]:
+        raise ValueError("fold does not start at a KFold boundary of %d folds over %d pairs" % (n_folds, n))
+    f = bounds.index(test[0])
     res = _sweep_np(predicts, n_folds)
     return res["best_thr"][f], res["test_acc"][f]
 

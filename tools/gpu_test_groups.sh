@@ -21,7 +21,8 @@ G[graph]="tests/test_train_gpu.py -k cuda_graph"
 G[step]="tests/test_train_gpu.py -k full_step"
 G[ckpt]="tests/test_train_gpu.py -k checkpoint"
 G[fullsize]="tests/test_fullsize_gpu.py"
-ORDER="probe conv bnact wgrad prep chanbwd fspace losses triplet head adam fwd grads literal graph step ckpt fullsize"
+G[lfw]="tests/test_lfw_gpu.py"
+ORDER="probe conv bnact wgrad prep chanbwd fspace losses triplet head adam fwd grads literal graph step ckpt fullsize lfw"
 [ $# -gt 0 ] && ORDER="$*"
 for name in $ORDER; do
   timeout 900 python -m pytest ${G[$name]} -m gpu -q -s > gpurun_out/t_$name.log 2>&1
