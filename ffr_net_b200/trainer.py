@@ -44,7 +44,7 @@ def default_opts(**kw):
     o = types.SimpleNamespace(phase="train", lr=0.1, beta1=0.9, beta2=0.999, weight_decay=0.0, optimizer="adam",
                               loss_weight=[1.0, 1.0, 1.0, 1.0], device="cuda", continue_train=False,
                               which_file="latest", ckpt_dir="./checkpoints", literal=False, merge_encoder_batches=True,
-                              overlap_allreduce=True)
+                              overlap_allreduce=True, data_parallel=True)
     for k, v in kw.items():
         setattr(o, k, v)
     return o
@@ -334,6 +334,8 @@ class Trainer:
     # ------------------------------------------------------------------------------------------------------
     def _dp(self):
         import torch.distributed as dist
+        if not getattr(self.opts, "data_parallel", True) if hasattr(self, "opts") else False:
+            return False
         return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
     @staticmethod
