@@ -51,8 +51,8 @@ class PrepTrainDesc(ctypes.Structure):
     _fields_ = ([(k, _p) for k in ("x", "w0", "b0", "slope1", "slope4", "slope7", "A1", "c1", "A2", "c2", "w8", "b8")] +
                 [("s0_h", _p), ("s0_ld", _i), ("s0_lo", _i), ("s0_b", _p), ("s0_ldb", _i),
                  ("cm_h", _p), ("cm_ld", _i), ("cm_lo", _i), ("cm_b", _p), ("cm_ldb", _i),
-                 ("fm_h", _p), ("fm_ld", _i), ("fm_lo", _i), ("fm_b", _p), ("fm_ldb", _i)] +
-                [(k, _p) for k in ("g0", "g1", "g2", "h7b", "xk", "mch", "inv_c", "tmat", "ss_space")])
+                 ] +
+                [(k, _p) for k in ("g0", "g1", "g2", "h7b", "xk", "mch2", "x3", "inv_c", "tmat", "ss_space")])
 
 
 _SIGNATURES = {
@@ -68,6 +68,7 @@ _SIGNATURES = {
     "ffr_wgrad": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "ffr_pack_conv3x3_f16": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
     "ffr_recnet_prep_train": (_i, [ctypes.POINTER(PrepTrainDesc), _i, _p]),
+    "ffr_fc_scatter": (_i, [_p, _p, _i, _i, _p, _i, _i, _p]),
     "ffr_chan_compose": (_i, [_p] * 14 + [_p]),
     "ffr_chan_compose_bwd": (_i, [_p] * 18 + [_i, _p]),
     "ffr_feat_space_train": (_i, [_p, _p, _p, _i, _i, _p, _i, _p, _i, _i, _p]),

@@ -68,11 +68,14 @@ struct PrepTrain {
     const float* w8; const float* b8;     // Conv4Channel.8 [512][32], [512]
     ActDst s0;                            // Conv4Space input: X | ss_space | 0, 576 channels
     ActDst cm;                            // Conv4Merge input, slot [1024,1536) <- X
-    ActDst fm;                            // ChannelFlipMerge input: [0,512) flip_W(feat_channel), [512,1024) feat_channel
     float* g0; float* g1; float* g2;      // pre-PReLU activations of the chain, [n*512][32] each (saved for backward)
     __nv_bfloat16* h7b;                   // [n*512][64]: h7 | 1 | 0...   (B operand of the dW8 / db8 contraction)
     __nv_bfloat16* xk;                    // [n*512][64]: X rows, 49 valid (B operand of dM = dFC X^T)
-    __nv_bfloat16* mch;                   // [n*512][512] M_channel = sigmoid(.) (backward needs m (1 - m))
+    __half* mch2;                         // [n*512][1024] fp16: M_channel = sigmoid(.) as [hi | lo] (A operand of
+                                          // feat_channel = M_channel @ X; the hi part also serves the backward's m (1 - m))
+    __half* x3;                           // [n*64][1536] fp16: X^T rows (pixel hw, 49 valid) as [hi | lo | hi] over the
+                                          // 512 channels: per-sample B operand of the same GEMM, run as three "taps" with
+                                          // A column offsets (0, 0, 512): hi.hi + hi.lo + lo.hi
     float* inv_c;                         // [n*512] 1 / max(|X_c|, eps)
     float* tmat;                          // [n][49][32] T = Xh^T W0b^T (saved for backward)
     float* ss_space;                      // optional [n][49][49]
@@ -102,7 +105,6 @@ __global__ void __launch_bounds__(512, 1) recnet_prep_train_kernel(const PrepTra
         xs[i] = (hw < 49) ? x[c * 49 + hw] : 0.f;
     }
     for (int i = tid; i < 49 * 32; i += 512) { const int hw = i >> 5, k = i & 31; W0a[i] = p.w0[k * 561 + hw]; }
-    for (int i = tid; i < 1024; i += 512) { A1s[i] = p.A1[i]; A2s[i] = p.A2[i]; }
     if (tid < 32) { misc[tid] = p.b0[tid]; misc[32 + tid] = p.c1[tid]; misc[64 + tid] = p.c2[tid]; }
     __syncthreads();
 
@@ -157,30 +159,38 @@ __global__ void __launch_bounds__(512, 1) recnet_prep_train_kernel(const PrepTra
         Gs[o] = g * inv_s[i] * inv_s[j];
     }
     __syncthreads();                      // all reads of the partial Grams are done: `big` is free
-    // T[hw][j] = sum_c Xh[c][hw] * W0b[j][c]: (7 consecutive pixels, j, half of the channels) per thread; the two halves
-    // land in two planes of `big` and are added in a fixed order
+    // T[hw][j] = sum_c Xh[c][hw] * W0b[j][c]. W0b (Conv4Channel.0.weight[:, 49:], row pitch 561) is staged in `big` as
+    // [c][j] with coalesced global reads; work item = (7 consecutive pixels, j, half of the channels); the two halves land
+    // in T and in the (not yet loaded) A1/A2 area and are added in a fixed order
+    float* W0bs = big;                    // [512][33] (pitch 33: conflict-free for lanes over c (fill) and over j (use))
+    for (int i = tid; i < 32 * 512; i += 512) {
+        const int j = i >> 9, c = i & 511;
+        W0bs[c * 33 + j] = __ldg(p.w0 + j * 561 + 49 + c) * inv_c[c];
+    }
+    __syncthreads();
     if (tid < 448) {
         const int j = tid & 31, hg = (tid >> 5) % 7, half = tid / 224;
         float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         const int c_lo = half * 256;
-        const float* w0b = p.w0 + j * 561 + 49;
 #pragma unroll 4
         for (int c = c_lo; c < c_lo + 256; ++c) {
-            const float wj = __ldg(w0b + c) * inv_c[c];
+            const float wj = W0bs[c * 33 + j];
             const float* xr = xs + c * XS + hg * 7;
 #pragma unroll
             for (int q = 0; q < 7; ++q) acc[q] = fmaf(xr[q], wj, acc[q]);
         }
+        float* dstp = half ? A1s : T;     // A1s..A2s: 2048 floats, loaded from global only after this phase
 #pragma unroll
-        for (int q = 0; q < 7; ++q) big[half * 1568 + (hg * 7 + q) * 32 + j] = acc[q];
+        for (int q = 0; q < 7; ++q) dstp[(hg * 7 + q) * 32 + j] = acc[q];
     }
     __syncthreads();
     for (int o = tid; o < 49 * 32; o += 512) {
-        const float t = big[o] + big[1568 + o];
+        const float t = T[o] + A1s[o];
         T[o] = t;
         p.tmat[(long long)n * 1568 + o] = t;
     }
-    __syncthreads();                      // `big` is free again: stage W8 / b8 for the last Linear
+    __syncthreads();                      // `big` is free again: stage W8 / b8 for the last Linear; load the composed maps
+    for (int i = tid; i < 1024; i += 512) { A1s[i] = p.A1[i]; A2s[i] = p.A2[i]; }
     float* W8s = big;                     // [512][32]
     float* b8s = big + 512 * 32;          // [512]
     for (int i = tid; i < 512 * 32; i += 512) W8s[i] = p.w8[i];
@@ -195,6 +205,11 @@ __global__ void __launch_bounds__(512, 1) recnet_prep_train_kernel(const PrepTra
             const long long row = (long long)n * 81 + pos;
             act_store(p.s0, row, tid, v);
             act_store(p.cm, row, 1024 + tid, v);
+        }
+        for (int hw = 0; hw < 64; ++hw) {          // X^T rows for the feat_channel GEMM: [hi | lo | hi], rows 49..63 zero
+            const H16 sx = split_h(hw < 49 ? xs[tid * XS + hw] : 0.f);
+            __half* xr = p.x3 + ((long long)n * 64 + hw) * 1536 + tid;
+            xr[0] = sx.hi; xr[512] = sx.lo; xr[1024] = sx.hi;
         }
         __nv_bfloat16* xkr = p.xk + ((long long)n * 512 + tid) * 64;
 #pragma unroll 1
@@ -292,46 +307,54 @@ __global__ void __launch_bounds__(512, 1) recnet_prep_train_kernel(const PrepTra
         for (int q = 5; q < 8; ++q) ob[q] = make_uint4(0u, 0u, 0u, 0u);
     }
 
-    // ---- M_channel[c][j] = sigmoid(h7[c] . W8[j] + b8[j]) (recnet.py:385-386, :406) and
-    //      feat_channel[c][hw] = sum_j M_channel[c][j] * X[j][hw] (:410), fused: M is only kept as bf16 for backward ----
-    float fc[52];
-#pragma unroll
-    for (int q = 0; q < 52; ++q) fc[q] = 0.f;
-    __nv_bfloat16* mrow = p.mch + crow * 512;
+    // ---- M_channel[c][j] = sigmoid(h7[c] . W8[j] + b8[j]) (recnet.py:385-386, :406), written as fp16 [hi | lo]:
+    //      feat_channel = M_channel @ X (:410) runs on the tcgen05 GEMM as three K = 512 taps (hi.hi + hi.lo + lo.hi) ----
+    __half* mrow = p.mch2 + crow * 1024;
 #pragma unroll 1
     for (int j0 = 0; j0 < 512; j0 += 8) {
-        float m8[8];
+        uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int j = j0 + e;
-            const float4* wr = reinterpret_cast<const float4*>(W8s + j * 32);
-            float a = b8s[j];
+        for (int e = 0; e < 8; e += 2) {
+            float m2[2];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float4 w4 = wr[q];
-                a = fmaf(w4.x, h[q * 4 + 0], a); a = fmaf(w4.y, h[q * 4 + 1], a);
-                a = fmaf(w4.z, h[q * 4 + 2], a); a = fmaf(w4.w, h[q * 4 + 3], a);
+            for (int u = 0; u < 2; ++u) {
+                const int j = j0 + e + u;
+                const float4* wr = reinterpret_cast<const float4*>(W8s + j * 32);
+                float a0 = b8s[j], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 w4 = wr[q];
+                    a0 = fmaf(w4.x, h[q * 4 + 0], a0); a1 = fmaf(w4.y, h[q * 4 + 1], a1);
+                    a2 = fmaf(w4.z, h[q * 4 + 2], a2); a3 = fmaf(w4.w, h[q * 4 + 3], a3);
+                }
+                m2[u] = 1.0f / (1.0f + __expf(-((a0 + a1) + (a2 + a3))));
             }
-            const float m = 1.0f / (1.0f + __expf(-a));
-            m8[e] = m;
-            const float4* xr = reinterpret_cast<const float4*>(xs + j * XS);
-#pragma unroll
-            for (int q = 0; q < 13; ++q) {
-                const float4 x4 = xr[q];
-                fc[q * 4 + 0] = fmaf(m, x4.x, fc[q * 4 + 0]); fc[q * 4 + 1] = fmaf(m, x4.y, fc[q * 4 + 1]);
-                fc[q * 4 + 2] = fmaf(m, x4.z, fc[q * 4 + 2]); fc[q * 4 + 3] = fmaf(m, x4.w, fc[q * 4 + 3]);
-            }
+            const H16 s0 = split_h(m2[0]), s1 = split_h(m2[1]);
+            hi[e >> 1] = (uint32_t)__half_as_ushort(s0.hi) | ((uint32_t)__half_as_ushort(s1.hi) << 16);
+            lo[e >> 1] = (uint32_t)__half_as_ushort(s0.lo) | ((uint32_t)__half_as_ushort(s1.lo) << 16);
         }
-        *reinterpret_cast<uint4*>(mrow + j0) = make_uint4(pack_bf16x2(m8[0], m8[1]), pack_bf16x2(m8[2], m8[3]),
-                                                          pack_bf16x2(m8[4], m8[5]), pack_bf16x2(m8[6], m8[7]));
+        *reinterpret_cast<uint4*>(mrow + j0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(mrow + 512 + j0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
-    // flip / cat fan-out (recnet.py:416-417): slot [512,1024) <- feat_channel, slot [0,512) <- W-flipped feat_channel
-#pragma unroll
-    for (int hw = 0; hw < 49; ++hw) {
+}
+
+// feat_channel rows [n*512][64] fp32 (row = channel c, column = pixel hw; the GEMM output) -> ChannelFlipMerge input
+// with the flip / cat fan-out (recnet.py:416-417): slot [512,1024) <- feat_channel, slot [0,512) <- W-flipped, each with
+// its reflection mirrors. grid (8 channel chunks of 64, n).
+__global__ void __launch_bounds__(256) fc_scatter_kernel(const float* __restrict__ fcraw, const ActDst fm) {
+    __shared__ float tile[49][65];
+    const int n = blockIdx.y, c0 = blockIdx.x * 64;
+    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+        const int c = i >> 6, hw = i & 63;
+        if (hw < 49) tile[hw][c] = fcraw[((long long)n * 512 + c0 + c) * 64 + hw];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 49 * 64; i += 256) {
+        const int hw = i >> 6, c = i & 63;
         const int hh = hw / 7, ww = hw - hh * 7;
-        const float v = fc[hw];
-        for_each_mirror(n, hh, ww, [&](long long row) { act_store(p.fm, row, 512 + c, v); });
-        for_each_mirror(n, hh, 6 - ww, [&](long long row) { act_store(p.fm, row, c, v); });
+        const float v = tile[hw][c];
+        for_each_mirror(n, hh, ww, [&](long long row) { act_store(fm, row, 512 + c0 + c, v); });
+        for_each_mirror(n, hh, 6 - ww, [&](long long row) { act_store(fm, row, c0 + c, v); });
     }
 }
 
@@ -768,7 +791,7 @@ extern "C" {
 
 FFR_API int ffr_recnet_prep_train(const ffr_prep_train_desc* d, int n, ffr_stream_t stream) {
     FFR_CHECK_ARG(d && d->x && d->w0 && d->b0 && d->slope1 && d->slope4 && d->slope7 && d->A1 && d->c1 && d->A2 && d->c2 &&
-                  d->w8 && d->b8 && d->s0_h && d->cm_h && d->fm_h && d->g0 && d->g1 && d->g2 && d->h7b && d->xk && d->mch &&
+                  d->w8 && d->b8 && d->s0_h && d->cm_h && d->g0 && d->g1 && d->g2 && d->h7b && d->xk && d->mch2 && d->x3 &&
                   d->inv_c && d->tmat, "ffr_recnet_prep_train: null pointer");
     if (n == 0) return 0;
     PrepTrain p;
@@ -776,10 +799,9 @@ FFR_API int ffr_recnet_prep_train(const ffr_prep_train_desc* d, int n, ffr_strea
     p.A1 = d->A1; p.c1 = d->c1; p.A2 = d->A2; p.c2 = d->c2; p.w8 = d->w8; p.b8 = d->b8;
     p.s0 = mk_dst(d->s0_h, d->s0_ld, d->s0_lo, d->s0_b, d->s0_ldb);
     p.cm = mk_dst(d->cm_h, d->cm_ld, d->cm_lo, d->cm_b, d->cm_ldb);
-    p.fm = mk_dst(d->fm_h, d->fm_ld, d->fm_lo, d->fm_b, d->fm_ldb);
     p.g0 = d->g0; p.g1 = d->g1; p.g2 = d->g2;
     p.h7b = reinterpret_cast<__nv_bfloat16*>(d->h7b); p.xk = reinterpret_cast<__nv_bfloat16*>(d->xk);
-    p.mch = reinterpret_cast<__nv_bfloat16*>(d->mch);
+    p.mch2 = reinterpret_cast<__half*>(d->mch2); p.x3 = reinterpret_cast<__half*>(d->x3);
     p.inv_c = d->inv_c; p.tmat = d->tmat; p.ss_space = d->ss_space;
     const int smem = (512 * XS + 512 + 64 + 49 * 49 + 3 + 49 * 32 * 2 + 2048 + 96 + 8 * 2401) * (int)sizeof(float);
     static bool attr = false;
@@ -789,6 +811,14 @@ FFR_API int ffr_recnet_prep_train(const ffr_prep_train_desc* d, int n, ffr_strea
     }
     recnet_prep_train_kernel<<<n, 512, smem, S_(stream)>>>(p);
     return launch_status("recnet_prep_train_kernel");
+}
+
+FFR_API int ffr_fc_scatter(const float* fcraw, void* fm_h, int fm_ld, int fm_lo, void* fm_b, int fm_ldb, int n,
+                           ffr_stream_t stream) {
+    FFR_CHECK_ARG(fcraw && fm_h, "ffr_fc_scatter: null pointer");
+    if (n == 0) return 0;
+    fc_scatter_kernel<<<dim3(8, n), 256, 0, S_(stream)>>>(fcraw, mk_dst(fm_h, fm_ld, fm_lo, fm_b, fm_ldb));
+    return launch_status("fc_scatter_kernel");
 }
 
 FFR_API int ffr_chan_compose(const float* w2, const float* b2, const float* w3, const float* b3, const float* w5,

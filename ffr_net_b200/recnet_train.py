@@ -31,6 +31,7 @@ BN_MOMENTUM = 0.1
 
 EPI = _lib.EPI
 _TAPS9 = (ctypes.c_int * 9)(*[(r - 1) * 9 + (s - 1) for r in range(3) for s in range(3)])
+_FC_CHOFF = (ctypes.c_int * 3)(0, 0, 512)
 
 # ConvLayers in execution order: (attribute path, Cin, Cout)
 _CONVS = [
@@ -153,7 +154,9 @@ class TrainEngine:
         ws.g = [torch.zeros(NT * 512, 32, **f32) for _ in range(3)]
         ws.h7b = torch.zeros(NT * 512, 64, **bf)
         ws.xk = torch.zeros(NT * 512, 64, **bf)
-        ws.mch = torch.zeros(NT * 512, 512, **bf)
+        ws.mch2 = torch.zeros(NT * 512, 1024, dtype=torch.float16, device=dev)   # M_channel [hi | lo]
+        ws.x3 = torch.zeros(NT * 64, 1536, dtype=torch.float16, device=dev)      # X^T [hi | lo | hi] per sample
+        ws.fcraw = torch.zeros(NT * 512, 64, **f32)                              # feat_channel rows (c) x pixels
         ws.inv_c = torch.zeros(NT * 512, **f32)
         ws.tmat = torch.zeros(NT, 49, 32, **f32)
         # backward
@@ -226,7 +229,7 @@ class TrainEngine:
     def forward(self, x, n_groups, slot=0, v_out=None):
         """x: (G*n,512,7,7) fp32 CUDA, the G calls concatenated. Returns the workspace holding every result:
         ws.v (pooled feat_new, (G*n,512); written to v_out instead when given), ws.fs / ws.fc / ws.fnew (fp32 H9 rows),
-        ws.mspace, ws.mch. `slot` selects one of several resident workspaces of the same shape."""
+        ws.mspace, ws.mch2. `slot` selects one of several resident workspaces of the same shape."""
         lib = _lib.load()
         st = _lib.stream_ptr()
         m = self.model
@@ -255,17 +258,30 @@ class TrainEngine:
         d.slope1, d.slope4, d.slope7 = _P(c[1].func.weight), _P(c[4].func.weight), _P(c[7].func.weight)
         d.A1, d.c1, d.A2, d.c2 = _P(A[0:]), _P(A[1024:]), _P(A[1056:]), _P(A[2080:])
         d.w8, d.b8 = _P(c[8].weight), _P(c[8].bias)
-        for nm, act in (("s0", ws.s0), ("cm", ws.cm), ("fm", ws.fm)):
+        for nm, act in (("s0", ws.s0), ("cm", ws.cm)):
             setattr(d, nm + "_h", _P(act.h)); setattr(d, nm + "_ld", act.h.shape[1]); setattr(d, nm + "_lo", act.lo)
             setattr(d, nm + "_b", _P(act.b)); setattr(d, nm + "_ldb", act.b.shape[1])
         d.g0, d.g1, d.g2 = _P(ws.g[0]), _P(ws.g[1]), _P(ws.g[2])
-        d.h7b, d.xk, d.mch = _P(ws.h7b), _P(ws.xk), _P(ws.mch)
+        d.h7b, d.xk, d.mch2, d.x3 = _P(ws.h7b), _P(ws.xk), _P(ws.mch2), _P(ws.x3)
         d.inv_c, d.tmat, d.ss_space = _P(ws.inv_c), _P(ws.tmat), None
         _lib.check(lib.ffr_recnet_prep_train(ctypes.byref(d), NT, st), "recnet_prep_train")
+        # feat_channel = M_channel @ X (recnet.py:410): rows (sample, c) x pixels; three K = 512 "taps" over A = [hi | lo]
+        # (column offsets 0, 0, 512) against B = [X_hi | X_lo | X_hi]: hi.hi + hi.lo + lo.hi in fp16
+        g = _lib.ConvGemmDesc()
+        g.a, g.a_rows, g.a_cols, g.a_ld = _P(ws.mch2), NT * 512, 1024, 1024
+        g.wp, g.Cin, g.Cout, g.ntaps = _P(ws.x3), 512, 64, 3
+        g.tap_ch_off = ctypes.cast(_FC_CHOFF, ctypes.c_void_p)
+        g.M = NT * 512
+        g.flags = EPI.OUT_F32
+        g.out_f32 = _P(ws.fcraw)
+        g.num_splits, g.b_rows_per_mtile, g.b_mtile_div, g.f16 = 1, 64, 4, 1
+        _lib.check(lib.ffr_conv_gemm_ex(ctypes.byref(g), st), "feat_channel GEMM")
+        _lib.check(lib.ffr_fc_scatter(_P(ws.fcraw), _P(ws.fm.h), ws.fm.h.shape[1], ws.fm.lo, _P(ws.fm.b), ws.fm.b.shape[1],
+                                      NT, st), "fc_scatter")                      # flip / cat fan-out (:416-417)
         for nm in ("s0", "cm", "fm"):
             self._tr("fwd.prep.%s" % nm, getattr(ws, nm).h)
         self._tr("fwd.prep.g2", ws.g[2])
-        self._tr("fwd.prep.mch", ws.mch)
+        self._tr("fwd.prep.mch2", ws.mch2)
 
         f = lambda *a, **k: self._layer_fwd(lib, ws, *a, st=st, **k)
         # spatial rectifier (recnet.py:362-371, :404-405)
@@ -363,9 +379,9 @@ class TrainEngine:
         d.a, d.a_rows, d.a_cols, d.a_ld = _P(ws.dfc_op), NT * 512, 64, 64
         d.wp, d.Cin, d.Cout, d.ntaps = _P(ws.xk), 64, 512, 1
         d.M = NT * 512
-        d.flags = EPI.MUL_DSIG
+        d.flags = EPI.MUL_DSIG | EPI.RES_F16
         d.out, d.ldo = _P(ws.dmpre), 512
-        d.res, d.ldres = _P(ws.mch), 512
+        d.res, d.ldres = _P(ws.mch2), 1024         # m = hi part of the fp16 M_channel
         d.num_splits, d.b_rows_per_mtile, d.b_mtile_div = 1, 512, 4
         _lib.check(lib.ffr_conv_gemm_ex(ctypes.byref(d), st), "dM_pre GEMM")
         self._tr("bwd.chan.dfc_op", ws.dfc_op)
@@ -460,7 +476,7 @@ class _RecNetTrainFn(torch.autograd.Function):
         fs = _rows_to_nchw(lib, ws.fs, 512, 512, n, st)
         fc = _rows_to_nchw(lib, ws.fc, 512, 512, n, st)
         msp = _rows_to_nchw(lib, ws.mspace, 64, 64, n, st)[:, :49].reshape(n, 49, 49).contiguous()
-        mch = ws.mch.view(n, 512, 512).float()
+        mch = ws.mch2[:, :512].float().view(n, 512, 512)
         ctx.model, ctx.ws, ctx.n = model, ws, n
         ctx.step = ws.owner
         ctx.mark_non_differentiable(msp, mch)

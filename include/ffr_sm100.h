@@ -278,9 +278,13 @@ FFR_API int ffr_wgrad(const void* dz, int ld_dz, const void* x, int ld_x, int x_
 FFR_API int ffr_pack_conv3x3_f16(const float* w, int cout, int cin, int cout_p, int cin_p, void* fwd_f16, void* dgrad_bf16,
                                  ffr_stream_t stream);
 
-/* RecNet.forward up to the convolution stacks for a training batch (recnet.py:399-402, :406, :410-417, Conv4Channel
- * :372-386): selfSimilarity, the cat() fan-outs, the whole channel rectifier in fp32 and feat_channel with its flip / cat
- * fan-out. Saves what the backward needs (pre-PReLU activations g0/g1/g2, h7 | 1, X rows, M_channel in bf16, 1/|X_c|). */
+/* RecNet.forward up to the convolution stacks for a training batch (recnet.py:399-402, :406, Conv4Channel :372-386):
+ * selfSimilarity, the cat() fan-outs and the whole channel rectifier in fp32. M_channel = sigmoid(.) is written as fp16
+ * [hi | lo] (mch2) and X^T as [hi | lo | hi] (x3): feat_channel = M_channel @ X (:410) is then ONE call of ffr_conv_gemm_ex
+ * (f16; three "taps" of K = 512 with A column offsets 0, 0, 512 = hi.hi + hi.lo + lo.hi; batched weight operand x3; fp32
+ * output [n*512][64]) followed by ffr_fc_scatter (flip / cat fan-out of :416-417 into the ChannelFlipMerge input). Saves
+ * what the backward needs (pre-PReLU activations g0/g1/g2, h7 | 1, X rows, 1/|X_c|; m (1 - m) comes from the hi part of
+ * mch2). */
 typedef struct ffr_prep_train_desc {
     const float* x;                                  /* (n,512,7,7) fp32 NCHW */
     const float* w0; const float* b0;                /* Conv4Channel.0 [32][561], [32] */
@@ -289,12 +293,16 @@ typedef struct ffr_prep_train_desc {
     const float* w8; const float* b8;                /* Conv4Channel.8 [512][32], [512] */
     void* s0_h; int s0_ld; int s0_lo; void* s0_b; int s0_ldb;     /* Conv4Space input [n*81][..], 576 channels */
     void* cm_h; int cm_ld; int cm_lo; void* cm_b; int cm_ldb;     /* Conv4Merge input, 1536 channels (slot 1024.. <- X) */
-    void* fm_h; int fm_ld; int fm_lo; void* fm_b; int fm_ldb;     /* ChannelFlipMerge input, 1024 channels */
     float* g0; float* g1; float* g2;                 /* [n*512][32] each */
-    void* h7b; void* xk; void* mch;                  /* bf16 [n*512][64], [n*512][64], [n*512][512] */
+    void* h7b; void* xk;                             /* bf16 [n*512][64] each */
+    void* mch2; void* x3;                            /* fp16 [n*512][1024], [n*64][1536] */
     float* inv_c; float* tmat; float* ss_space;      /* [n*512], [n][49][32], optional [n][49][49] */
 } ffr_prep_train_desc;
 FFR_API int ffr_recnet_prep_train(const ffr_prep_train_desc* d, int n, ffr_stream_t stream);
+/* fcraw fp32 [n*512][64] (row = channel, column = pixel) -> ChannelFlipMerge input (hi/lo + bf16 copy, 1024 channels):
+ * slot [512,1024) <- feat_channel, slot [0,512) <- flip_W(feat_channel), each with its reflection mirrors. */
+FFR_API int ffr_fc_scatter(const float* fcraw, void* fm_h, int fm_ld, int fm_lo, void* fm_b, int fm_ldb, int n,
+                           ffr_stream_t stream);
 
 /* Linear(32->512) directly followed by Linear(512->32) (recnet.py:375-376, :378-379) composed into 32x32 maps:
  * A1 = W3 W2, c1 = W3 b2 + b3, A2 = W6 W5, c2 = W6 b5 + b6; and the backward of the composition. */

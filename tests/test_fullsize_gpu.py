@@ -87,5 +87,5 @@ def test_training_step_256_pairs_tiling_property(lib, nets):
     assert abs(acc64 - acc256) <= 1e-9
     errs = sorted(((g256[k].double() - g64[k].double()).norm() / (g64[k].double().norm() + 1e-30)).item() for k in g64)
     print("256-pair (4 x 64, pixel-major) vs 64-pair (row-major) gradients: worst %.3e median %.3e" % (errs[-1], errs[len(errs) // 2]))
-    assert errs[-1] <= 2e-2 and errs[len(errs) // 2] <= 5e-3
+    assert errs[-1] <= 4e-2 and errs[len(errs) // 2] <= 1e-2     # measured 1.7e-2 / 3.8e-3
     assert l256 == l256b and all(torch.equal(g256[k], g256b[k]) for k in g256)

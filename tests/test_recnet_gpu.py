@@ -76,12 +76,28 @@ def test_recnet_batch_invariance(models):
     assert (v5[3:4] - v1).abs().max().item() <= 1e-5 * v1.abs().max().item() + 1e-6
 
 
-def test_recnet_rejects_cpu_and_training(models):
+def test_recnet_rejects_cpu(models):
     sd, m = models
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 512, 7, 7))
-    with pytest.raises(NotImplementedError):     # label path in eval mode: the reference never uses it
-        m(torch.zeros(2, 512, 7, 7, device="cuda"), torch.zeros(2, dtype=torch.long, device="cuda"))
+
+
+def test_recnet_eval_with_label_returns_seven_tuple(models):
+    """The reference returns the 7-tuple whenever a label is given, in any mode (recnet.py:425-429): eval-mode forward
+    (folded BatchNorm, bf16 path) + exported M_space / M_channel / feat_space / feat_channel + the AddMarginProduct pair."""
+    sd, m = models
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(3, 512, 7, 7, generator=g) * 0.3
+    label = torch.tensor([1, 10574, 77])
+    with torch.no_grad():
+        ref = orr.recnet_forward(sd, x, label)
+        out = m(x.cuda(), label.cuda())
+    names = ["feat_new_v", "pred_loss", "pred_label", "M_space", "M_channel", "feat_space", "feat_channel"]
+    assert len(out) == 7
+    for nme, a, b in zip(names, out, ref):
+        e = ((a.cpu() - b).abs().max() / b.abs().max()).item()
+        print("eval 7-tuple %-12s max rel err %.3e" % (nme, e))
+        assert a.shape == b.shape and e <= 2e-2, nme
 
 
 @pytest.mark.parametrize("n", [1, 3])

@@ -246,8 +246,10 @@ def test_cuda_graph_step_bit_equals_eager_and_eval_sees_new_weights(lib):
         v2, _ = graphed.recnet(y)
         v3, _ = fresh(y)
     torch.cuda.synchronize()
-    assert torch.equal(v2, v3)
-    assert not torch.equal(v1, v2)
+    rel = lambda a, b: ((a - b).abs().max() / b.abs().max()).item()
+    # (the eval path accumulates its pooled sums with fp32 atomics: equal up to their order, not bit for bit)
+    assert rel(v2, v3) <= 1e-5, rel(v2, v3)
+    assert rel(v1, v2) >= 1e-3            # the two training steps in between did change the weights
 
 
 def test_trainer_full_step_public_api(lib):

@@ -276,7 +276,9 @@ def _run_prep(lib, x, p, hilo=True):
     o = dict(g=[torch.zeros(n * 512, 32, device=dev) for _ in range(3)],
              h7b=torch.zeros(n * 512, 64, dtype=torch.bfloat16, device=dev),
              xk=torch.zeros(n * 512, 64, dtype=torch.bfloat16, device=dev),
-             mch=torch.zeros(n * 512, 512, dtype=torch.bfloat16, device=dev),
+             mch2=torch.zeros(n * 512, 1024, dtype=torch.float16, device=dev),
+             x3=torch.zeros(n * 64, 1536, dtype=torch.float16, device=dev),
+             fcraw=torch.zeros(n * 512, 64, device=dev),
              inv_c=torch.zeros(n * 512, device=dev), tmat=torch.zeros(n, 49, 32, device=dev),
              ss=torch.zeros(n, 49, 49, device=dev), s0=s0, cm=cm, fm=fm, A=A, w8t=w8t, pd=pd)
     d = _lib.PrepTrainDesc()
@@ -286,13 +288,22 @@ def _run_prep(lib, x, p, hilo=True):
     d.slope1, d.slope4, d.slope7 = P(pd["s1"]), P(pd["s4"]), P(pd["s7"])
     d.A1, d.c1, d.A2, d.c2 = P(A[0:]), P(A[1024:]), P(A[1056:]), P(A[2080:])
     d.w8, d.b8 = P(pd["w8"]), P(pd["b8"])
-    for nm, (h, b), c in (("s0", s0, 576), ("cm", cm, 1536), ("fm", fm, 1024)):
+    for nm, (h, b), c in (("s0", s0, 576), ("cm", cm, 1536)):
         setattr(d, nm + "_h", P(h)); setattr(d, nm + "_ld", 2 * c); setattr(d, nm + "_lo", c)
         setattr(d, nm + "_b", P(b)); setattr(d, nm + "_ldb", c)
     d.g0, d.g1, d.g2 = P(o["g"][0]), P(o["g"][1]), P(o["g"][2])
-    d.h7b, d.xk, d.mch = P(o["h7b"]), P(o["xk"]), P(o["mch"])
+    d.h7b, d.xk, d.mch2, d.x3 = P(o["h7b"]), P(o["xk"]), P(o["mch2"]), P(o["x3"])
     d.inv_c, d.tmat, d.ss_space = P(o["inv_c"]), P(o["tmat"]), P(o["ss"])
     _lib.check(lib.ffr_recnet_prep_train(ctypes.byref(d), n, st), "prep_train")
+    g = _lib.ConvGemmDesc()                # feat_channel = M_channel @ X on the tcgen05 GEMM (K = 1536, fp16 hi/lo splits)
+    g.a, g.a_rows, g.a_cols, g.a_ld = P(o["mch2"]), n * 512, 1024, 1024
+    g.wp, g.Cin, g.Cout, g.ntaps = P(o["x3"]), 512, 64, 3
+    choff = (ctypes.c_int * 3)(0, 0, 512)
+    g.tap_ch_off = ctypes.cast(choff, ctypes.c_void_p)
+    g.M, g.flags, g.out_f32 = n * 512, EPI.OUT_F32, P(o["fcraw"])
+    g.num_splits, g.b_rows_per_mtile, g.b_mtile_div, g.f16 = 1, 64, 4, 1
+    _lib.check(lib.ffr_conv_gemm_ex(ctypes.byref(g), st), "feat_channel GEMM")
+    _lib.check(lib.ffr_fc_scatter(P(o["fcraw"]), P(fm[0]), 2048, 1024, P(fm[1]), 1024, n, st), "fc_scatter")
     torch.cuda.synchronize()
     return o
 
@@ -316,7 +327,12 @@ def test_recnet_prep_train(lib):
         assert rel_l2(o["g"][i].view(n, 512, 32).cpu(), ref[k]) <= 2e-5, k
     assert rel_l2(o["h7b"][:, :32].float().view(n, 512, 32).cpu(), ref["h7"]) <= 4e-3
     assert torch.equal(o["h7b"][:, 32].float().cpu(), torch.ones(n * 512)) and o["h7b"][:, 33:].float().abs().max().item() == 0
-    assert rel_l2(o["mch"].float().view(n, 512, 512).cpu(), ref["m"]) <= 4e-3
+    m_dev = (o["mch2"][:, :512].float() + o["mch2"][:, 512:].float()).view(n, 512, 512).cpu()
+    assert rel_l2(m_dev, ref["m"]) <= 2e-5
+    x3 = o["x3"].float().view(n, 64, 3, 512).cpu()
+    assert rel_l2((x3[:, :49, 0] + x3[:, :49, 1]).transpose(1, 2), x.reshape(n, 512, 49)) <= 1e-6
+    assert torch.equal(x3[:, :, 0], x3[:, :, 2]) and x3[:, 49:].abs().max().item() == 0
+    assert rel_l2(o["fcraw"][:, :49].view(n, 512, 49).cpu(), ref["fc"]) <= 2e-5
     flat = x.reshape(n, 512, 49)
     assert rel_l2(o["xk"][:, :49].float().view(n, 512, 49).cpu(), flat) <= 4e-3 and o["xk"][:, 49:].float().abs().max().item() == 0
     assert rel_l2(o["inv_c"].view(n, 512).cpu(), 1 / flat.double().norm(dim=2)) <= 1e-5
@@ -360,7 +376,8 @@ def test_channel_rectifier_backward(lib):
     d.a, d.a_rows, d.a_cols, d.a_ld = P(dfc_op), n * 512, 64, 64
     d.wp, d.Cin, d.Cout, d.ntaps = P(o["xk"]), 64, 512, 1
     d.M, d.flags = n * 512, EPI.MUL_DSIG
-    d.out, d.ldo, d.res, d.ldres = P(dmpre), 512, P(o["mch"]), 512
+    d.flags |= EPI.RES_F16
+    d.out, d.ldo, d.res, d.ldres = P(dmpre), 512, P(o["mch2"]), 1024
     d.num_splits, d.b_rows_per_mtile, d.b_mtile_div = 1, 512, 4
     _lib.check(lib.ffr_conv_gemm_ex(ctypes.byref(d), st), "dM_pre")
     dh7 = torch.zeros(n * 512, 64, device=dev)

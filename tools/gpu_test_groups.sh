@@ -21,6 +21,7 @@ G[graph]="tests/test_train_gpu.py -k cuda_graph"
 G[step]="tests/test_train_gpu.py -k full_step"
 G[ckpt]="tests/test_train_gpu.py -k checkpoint"
 G[fullsize]="tests/test_fullsize_gpu.py"
+G[recnet]="tests/test_recnet_gpu.py"
 G[lfw]="tests/test_lfw_gpu.py"
 ORDER="probe conv bnact wgrad prep chanbwd fspace losses triplet head adam fwd grads literal graph step ckpt fullsize lfw"
 [ $# -gt 0 ] && ORDER="$*"
