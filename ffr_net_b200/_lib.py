@@ -7,6 +7,8 @@ import re
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libffr_sm100.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "ffr_sm100.h")
+PROBE_LIB_PATH = os.path.join(_HERE, "lib", "libffr_sm100_probe.so")
+PROBE_HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "ffr_sm100_probe.h")
 
 _lib = None
 
@@ -94,9 +96,6 @@ _SIGNATURES = {
     "ffr_self_similarity": (_i, [_p, _i, _p, _p, _p]),
     "ffr_feat_space": (_i, [_p, _p, _p, _p, _i, _p]),
     "ffr_rows_to_nchw": (_i, [_p, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
-    "ffr_wgrad3x3": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
-    "ffr_bn_prelu_fwd": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _p]),
-    "ffr_bn_prelu_bwd": (_i, [_p, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _i, _p, _p, _i, _i, _i, _p]),
     "ffr_pack_conv3x3": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
     "ffr_gallery_cosine": (_i, [_p, _i, _p, _i, _i, _p, _p, _p]),
     "ffr_roc_hist": (_i, [_p, _i, _i, _i, _p, _p, _p, _i, _p, _p]),
@@ -107,8 +106,6 @@ _SIGNATURES = {
     "ffr_normalize_bwd": (_i, [_p, _p, _i, _p, _p]),
     "ffr_clip_adam": (_i, [_p, _p, _i, _p, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                            ctypes.c_float, _p]),
-    "ffr_nchw_to_h9": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
-    "ffr_h9_to_nchw": (_i, [_p, _i, _i, _p, _i, _i, _i, _p]),
     "ffr_pair_cosine": (_i, [_p, _p, _p, _i, _i, _p]),
     "ffr_threshold_sweep": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "ffr_scale_f32": (_i, [_p, _p, _i64, ctypes.c_float, _p]),
@@ -133,11 +130,29 @@ _SIGNATURES = {
 }
 
 
-def declared_symbols():
-    """Names of every function include/ffr_sm100.h declares (used by the CPU-side export test)."""
-    with open(HEADER_PATH) as f:
+def declared_symbols(header=None):
+    """Names of every function a header under include/ declares (used by the CPU-side export test)."""
+    with open(header or HEADER_PATH) as f:
         text = f.read()
     return sorted(set(re.findall(r"FFR_API\s+[\w\s\*]+?\b(ffr_\w+)\s*\(", text)))
+
+
+_probe = None
+
+
+def load_probe():
+    """The separate debug library with the hardware probes / micro-benchmarks (csrc/probe.cu)."""
+    global _probe
+    if _probe is None:
+        if not os.path.exists(PROBE_LIB_PATH):
+            raise RuntimeError("libffr_sm100_probe.so not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        lib = ctypes.CDLL(PROBE_LIB_PATH)
+        for name in declared_symbols(PROBE_HEADER_PATH):
+            fn = getattr(lib, name)
+            if name in _SIGNATURES:
+                fn.restype, fn.argtypes = _SIGNATURES[name]
+        _probe = lib
+    return _probe
 
 
 def load():

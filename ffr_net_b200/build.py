@@ -12,9 +12,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libffr_sm100.so")
+PROBE_LIB_PATH = os.path.join(LIB_DIR, "libffr_sm100_probe.so")     # debug probes / micro-benchmarks, not the product
 
-SOURCES = ["api.cu", "conv_gemm.cu", "backbone_kernels.cu", "recnet_kernels.cu", "train_kernels.cu", "bn_train_kernels.cu", "recnet_train_kernels.cu", "loss_kernels.cu", "head_kernels.cu", "scoring_kernels.cu", "probe.cu", "host.cpp"]
-HEADERS = ["ptx.cuh", "conv_gemm.cuh", "host.h", "kernels.h", os.path.join("..", "..", "include", "ffr_sm100.h")]
+SOURCES = ["api.cu", "conv_gemm.cu", "backbone_kernels.cu", "recnet_kernels.cu", "train_kernels.cu", "bn_train_kernels.cu", "recnet_train_kernels.cu", "loss_kernels.cu", "head_kernels.cu", "scoring_kernels.cu", "host.cpp"]
+PROBE_SOURCES = ["probe.cu", "host.cpp"]
+HEADERS = ["ptx.cuh", "conv_gemm.cuh", "host.h", "kernels.h", os.path.join("..", "..", "include", "ffr_sm100.h"),
+           os.path.join("..", "..", "include", "ffr_sm100_probe.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -33,10 +36,10 @@ def _nvcc():
 
 
 def _stale():
-    if not os.path.exists(LIB_PATH):
+    if not (os.path.exists(LIB_PATH) and os.path.exists(PROBE_LIB_PATH)):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    t = min(os.path.getmtime(LIB_PATH), os.path.getmtime(PROBE_LIB_PATH))
+    deps = [os.path.join(CSRC, s) for s in SOURCES + PROBE_SOURCES + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
@@ -50,7 +53,7 @@ def build(force=False, verbose=False):
     nvcc = _nvcc()
     procs = []
     objs = []
-    for src in SOURCES:
+    for src in SOURCES + [p for p in PROBE_SOURCES if p not in SOURCES]:
         path = os.path.join(CSRC, src)
         if not os.path.exists(path):
             continue
@@ -68,9 +71,12 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed")
     # cudart is linked statically (nvcc default); no -lcuda: the driver entry point is looked up at run time
-    cmd = [nvcc, "-shared", "-o", LIB_PATH + ".tmp"] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
-    subprocess.check_call(cmd)
-    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    def obj(src):
+        return os.path.join(obj_dir, os.path.splitext(src)[0] + ".o")
+    for lib_path, srcs in ((LIB_PATH, SOURCES), (PROBE_LIB_PATH, PROBE_SOURCES)):
+        cmd = [nvcc, "-shared", "-o", lib_path + ".tmp"] + [obj(s_) for s_ in srcs] + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        subprocess.check_call(cmd)
+        os.replace(lib_path + ".tmp", lib_path)
     return LIB_PATH
 
 

@@ -296,13 +296,6 @@ FFR_API int ffr_scale_f32(const float* in, float* out, int64_t count, float scal
     return scale_f32_launch(in, out, count, scale, S_(stream));
 }
 
-FFR_API int ffr_wgrad3x3(const void* dz, int ld_dz, const void* x, int ld_x, int x_ch0, int n, int Cout, int Cin,
-                         float* dw, float* workspace, ffr_stream_t stream) {
-    FFR_CHECK_ARG(dz && x && dw && workspace, "ffr_wgrad3x3: null pointer");
-    FFR_CHECK_ARG(ld_dz % 64 == 0 && ld_x % 8 == 0 && x_ch0 % 8 == 0, "ffr_wgrad3x3: bad pitches");
-    return wgrad_launch(dz, ld_dz, x, ld_x, x_ch0, n * 81, Cout, Cin, 9, dw, workspace, S_(stream));
-}
-
 FFR_API void ffr_debug_set_wgrad_splits(int splits) { set_wgrad_splits(splits); }
 
 FFR_API int64_t ffr_wgrad_workspace_floats(int P, int Cout, int Cin, int ntaps, int deterministic) {
@@ -324,24 +317,6 @@ FFR_API int ffr_pack_conv3x3_f16(const float* w, int cout, int cin, int cout_p, 
                                  ffr_stream_t stream) {
     FFR_CHECK_ARG(w && fwd_f16, "ffr_pack_conv3x3_f16: null pointer");
     return pack_conv3x3_launch_ex(w, cout, cin, cout_p, cin_p, fwd_f16, dgrad_bf16, 1, S_(stream));
-}
-
-FFR_API int ffr_bn_prelu_fwd(const void* z, int ldz, const float* mean, const float* rstd, const float* gamma,
-                             const float* beta, const float* slope, const void* res, int ldres, void* out, int ldo,
-                             const int* scatter, int scatter_n, int n, int C, ffr_stream_t stream) {
-    FFR_CHECK_ARG(z && mean && rstd && gamma && beta && slope && out && scatter, "ffr_bn_prelu_fwd: null pointer");
-    return bn_prelu_fwd_launch(z, ldz, mean, rstd, gamma, beta, slope, res, ldres, out, ldo, scatter, scatter_n, n, C,
-                               S_(stream));
-}
-
-FFR_API int ffr_bn_prelu_bwd(const void* da, int ldda, const int* scatter, int scatter_n, const void* z, int ldz,
-                             const float* mean, const float* rstd, const float* gamma, const float* beta,
-                             const float* slope, void* dy, int lddy, void* dres, int lddres, float* sums, void* dz,
-                             int lddz, int n, int C, ffr_stream_t stream) {
-    FFR_CHECK_ARG(da && scatter && z && mean && rstd && gamma && beta && slope && dy && sums && dz,
-                  "ffr_bn_prelu_bwd: null pointer");
-    return bn_prelu_bwd_launch(da, ldda, scatter, scatter_n, z, ldz, mean, rstd, gamma, beta, slope, dy, lddy, dres,
-                               lddres, sums, dz, lddz, n, C, S_(stream));
 }
 
 FFR_API int ffr_pack_conv3x3(const float* w, int cout, int cin, int cout_p, int cin_p, void* fwd, void* dgrad,
@@ -440,16 +415,6 @@ FFR_API int ffr_clip_adam(const void* table, const int* chunks, int n_chunks, co
                           float beta2, float eps, float weight_decay, float clip, ffr_stream_t stream) {
     FFR_CHECK_ARG(n_chunks == 0 || (table && chunks && hyper), "ffr_clip_adam: null pointer");
     return clip_adam_launch(table, chunks, n_chunks, hyper, beta1, beta2, eps, weight_decay, clip, S_(stream));
-}
-
-FFR_API int ffr_nchw_to_h9(const float* x, void* out, int ld, int ch0, int n, int C, int mirror, ffr_stream_t stream) {
-    FFR_CHECK_ARG(x && out, "ffr_nchw_to_h9: null pointer");
-    return nchw_to_h9_launch(x, out, ld, ch0, n, C, mirror, S_(stream));
-}
-
-FFR_API int ffr_h9_to_nchw(const void* in, int ld, int ch0, float* y, int n, int C, int fold, ffr_stream_t stream) {
-    FFR_CHECK_ARG(in && y, "ffr_h9_to_nchw: null pointer");
-    return h9_to_nchw_launch(in, ld, ch0, y, n, C, fold, S_(stream));
 }
 
 FFR_API int ffr_pair_cosine(const float* f1, const float* f2, float* score, int pairs, int D, ffr_stream_t stream) {

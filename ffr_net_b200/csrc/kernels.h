@@ -43,8 +43,6 @@ int roc_hist_launch(const float* scores, int ld, int P, int G, const int* probe_
                     const double* thresholds, int T, unsigned long long* hist, cudaStream_t stream);
 int self_similarity_launch(const float* x, int n, float* ss_space, float* ss_channel, cudaStream_t stream);
 int scale_f32_launch(const float* in, float* out, long long count, float scale, cudaStream_t stream);
-int wgrad_launch(const void* dz, int ld_dz, const void* x, int ld_x, int x_ch0, int P, int Cout, int Cin, int G,
-                 float* dw, float* ws, cudaStream_t stream);
 long long wgrad_workspace_floats(int P, int Cout, int Cin, int ntaps, int G, int deterministic, int* splits_out);
 int wgrad_launch_ex(const void* dz, int ld_dz, const void* x, int ld_x, int x_ch0, int P, int Cout, int Cin, int G,
                     int ntaps, int f16, int deterministic, int accumulate, int ld_w, int bias_col, float* dw, float* db,
@@ -55,19 +53,10 @@ bool pixmajor_profitable(int n_img);
 void set_pixmajor_backbone(int max_s);
 bool pixmajor_backbone(int S, int n_img);
 bool pixmajor_profitable_k64(int n_img);
-int bn_prelu_fwd_launch(const void* z, int ldz, const float* mean, const float* rstd, const float* gamma,
-                        const float* beta, const float* slope, const void* res, int ldres, void* out, int ldo,
-                        const int* scatter, int scatter_n, int n_img, int C, cudaStream_t stream);
-int bn_prelu_bwd_launch(const void* da, int ldda, const int* scatter, int scatter_n, const void* z, int ldz,
-                        const float* mean, const float* rstd, const float* gamma, const float* beta, const float* slope,
-                        void* dy, int lddy, void* dres, int lddres, float* sums, void* dz, int lddz, int n_img, int C,
-                        cudaStream_t stream);
-int nchw_to_h9_launch(const float* x, void* out, int ld, int ch0, int n_img, int C, int mirror, cudaStream_t stream);
 int pack_conv3x3_launch(const float* w, int cout, int cin, int cout_p, int cin_p, void* fwd, void* dgrad,
                         cudaStream_t stream);
 int pack_conv3x3_launch_ex(const float* w, int cout, int cin, int cout_p, int cin_p, void* fwd, void* dgrad, int fwd_f16,
                            cudaStream_t stream);
-int h9_to_nchw_launch(const void* in, int ld, int ch0, float* y, int n_img, int C, int fold, cudaStream_t stream);
 int clip_adam_launch(const void* table, const int* chunks, int n_chunks, const float* hyper, float b1, float b2,
                      float eps, float wd, float clip, cudaStream_t stream);
 int pair_cosine_launch(const float* f1, const float* f2, float* score, int pairs, int D, cudaStream_t stream);

@@ -3,7 +3,7 @@
 // (not a multiple of the 1024-byte swizzle atom) read rows [r0, r0+128) of a TMA-written tile?
 // variant 0: base_offset field = 0; variant 1: base_offset = (start_address >> 7) & 7.
 // The answer decides how the sliding-window convolution kernel addresses its taps.
-#include "../../include/ffr_sm100.h"
+#include "../../include/ffr_sm100_probe.h"
 #include "host.h"
 #include "ptx.cuh"
 

@@ -2,9 +2,8 @@
 //   - wgrad_kernel: weight gradient of a reflection-padded 3x3 conv as a tcgen05 GEMM that contracts over PIXELS.
 //     Both operands are read straight from their row-major (pixel-major) H9 matrices as MN-major UMMA operands
 //     (profiles/r01_probe_mn_major.json); a tap is a TMA row-coordinate shift of the x operand.
-//   - bn_prelu_fwd_kernel: batch-statistics BatchNorm + PReLU (+ residual) on the raw conv output, scattered into H9.
-//   - bn_prelu_bwd_reduce_kernel / bn_prelu_bwd_dz_kernel: gradient fold of the reflection mirrors, PReLU and
-//     BatchNorm backward (per-channel reductions, then dz).
+//   - pack_conv3x3_kernel: fp16 (forward) / bf16 (dgrad) K-major packings of a conv weight; clip_adam_kernel.
+//   (BatchNorm / PReLU forward and backward live in bn_train_kernels.cu.)
 #include "host.h"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -299,263 +298,7 @@ int wgrad_launch_ex(const void* dz, int ld_dz, const void* x, int ld_x, int x_ch
     return launch_status("wgrad_finish_kernel");
 }
 
-int wgrad_launch(const void* dz, int ld_dz, const void* x, int ld_x, int x_ch0, int P, int Cout, int Cin, int G,
-                 float* dw, float* ws, cudaStream_t stream) {
-    return wgrad_launch_ex(dz, ld_dz, x, ld_x, x_ch0, P, Cout, Cin, G, 9, 0, 0, 0, Cin, -1, dw, nullptr, ws, stream);
-}
-
 void set_wgrad_splits(int s) { g_wgrad_splits = s; }
-
-// ------------------------------------------------------------------------------------------------------------
-// BatchNorm(batch statistics) + PReLU (+ residual) forward on the raw conv output z (rows of the H9 grid).
-// stats: [2][C] = per-channel sum and sum of squares over the n*49 valid rows (accumulated by the conv epilogue).
-// Writes a = prelu(gamma*(z-mean)*rstd + beta) (+ res) to every destination of the scatter table (self + mirrors).
-// grid.x covers rows*C/8 work items of 8 channels.
-// ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-bn_prelu_fwd_kernel(const __nv_bfloat16* __restrict__ z, int ldz, const float* __restrict__ mean,
-                    const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                    const float* __restrict__ slope, const __nv_bfloat16* __restrict__ res, int ldres,
-                    __nv_bfloat16* __restrict__ out, int ldo, const int2* __restrict__ scatter, int scatter_n,
-                    int n_img, int C) {
-    const int c8n = C / 8;
-    const long long total = (long long)n_img * 49 * c8n;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c8 = (int)(i % c8n);
-        const long long pr = i / c8n;
-        const int n = (int)(pr / 49), pix = (int)(pr - (long long)n * 49);
-        const int r_local = (pix / 7 + 1) * 9 + (pix % 7 + 1);
-        const long long row = (long long)n * 81 + r_local;
-        const uint4 zv = __ldg(reinterpret_cast<const uint4*>(z + row * ldz) + c8);
-        float v[8] = {bf16lo(zv.x), bf16hi(zv.x), bf16lo(zv.y), bf16hi(zv.y), bf16lo(zv.z), bf16hi(zv.z), bf16lo(zv.w), bf16hi(zv.w)};
-        float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (res) {
-            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(res + row * ldres) + c8);
-            r[0] = bf16lo(rv.x); r[1] = bf16hi(rv.x); r[2] = bf16lo(rv.y); r[3] = bf16hi(rv.y);
-            r[4] = bf16lo(rv.z); r[5] = bf16hi(rv.z); r[6] = bf16lo(rv.w); r[7] = bf16hi(rv.w);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = c8 * 8 + j;
-            float y = (v[j] - mean[c]) * rstd[c] * gamma[c] + beta[c];
-            y = fmaxf(y, 0.f) + slope[c] * fminf(y, 0.f);
-            v[j] = y + r[j];
-        }
-        const uint4 o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-        for (int k = 0; k < scatter_n; ++k) {
-            const int2 e = __ldg(scatter + r_local * scatter_n + k);
-            if (e.x >= 0) *(reinterpret_cast<uint4*>(out + ((long long)n * 81 + e.x) * ldo + e.y) + c8) = o;
-        }
-    }
-}
-
-int bn_prelu_fwd_launch(const void* z, int ldz, const float* mean, const float* rstd, const float* gamma,
-                        const float* beta, const float* slope, const void* res, int ldres, void* out, int ldo,
-                        const int* scatter, int scatter_n, int n_img, int C, cudaStream_t stream) {
-    FFR_CHECK_ARG(C % 8 == 0, "bn_prelu_fwd: C=%d", C);
-    const long long total = (long long)n_img * 49 * (C / 8);
-    int grid = (int)((total + 255) / 256);
-    if (grid > num_sms() * 8) grid = num_sms() * 8;
-    bn_prelu_fwd_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(z), ldz, mean, rstd, gamma, beta,
-                                                  slope, reinterpret_cast<const __nv_bfloat16*>(res), ldres,
-                                                  reinterpret_cast<__nv_bfloat16*>(out), ldo,
-                                                  reinterpret_cast<const int2*>(scatter), scatter_n, n_img, C);
-    return launch_status("bn_prelu_fwd_kernel");
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// Backward, pass 1. da_h9 is the gradient w.r.t. the H9 OUTPUT tensor (own row + mirror rows, possibly a channel
-// slot of a wider matrix): fold it (sum over the scatter destinations), then
-//   dy = da * prelu'(y);   sums[0][c] += dy;  sums[1][c] += dy * zhat;  sums[2][c] += da * min(y, 0)
-// and store dy (bf16, plain rows) for pass 2; optionally store the folded da as the residual-branch gradient.
-// One CTA handles a slab of valid rows for 64 channels; per-channel partial sums are reduced in shared memory.
-// ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-bn_prelu_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, int ldda, const int2* __restrict__ scatter, int scatter_n,
-                           const __nv_bfloat16* __restrict__ z, int ldz, const float* __restrict__ mean,
-                           const float* __restrict__ rstd, const float* __restrict__ gamma,
-                           const float* __restrict__ beta, const float* __restrict__ slope,
-                           __nv_bfloat16* __restrict__ dy, int lddy, __nv_bfloat16* __restrict__ dres, int lddres,
-                           float* __restrict__ sums, int n_img, int C) {
-    // 256 threads = 32 row lanes x 8 channel groups of 8 (16-byte accesses; a row's 64-channel slab is one 128-byte line)
-    __shared__ float red[3][32][65];
-    const int c0 = blockIdx.y * 64;
-    const int cg = (threadIdx.x & 7) * 8;            // first channel of this thread's group within the slab
-    const int rlane = threadIdx.x >> 3;              // 32 row lanes
-    const long long rows = (long long)n_img * 49;
-    float s0[8], s1[8], s2[8], m[8], rs[8], g[8], b[8], sl[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int c = c0 + cg + j;
-        s0[j] = s1[j] = s2[j] = 0.f;
-        m[j] = mean[c]; rs[j] = rstd[c]; g[j] = gamma[c]; b[j] = beta[c]; sl[j] = slope[c];
-    }
-    for (long long pr = (long long)blockIdx.x * 32 + rlane; pr < rows; pr += (long long)gridDim.x * 32) {
-        const int n = (int)(pr / 49), pix = (int)(pr - (long long)n * 49);
-        const int r_local = (pix / 7 + 1) * 9 + (pix % 7 + 1);
-        const long long row = (long long)n * 81 + r_local;
-        const uint4 zv = __ldg(reinterpret_cast<const uint4*>(z + row * ldz + c0 + cg));
-        float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int k = 0; k < scatter_n; ++k) {
-            const int2 e = __ldg(scatter + r_local * scatter_n + k);
-            if (e.x >= 0) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(da + ((long long)n * 81 + e.x) * ldda + e.y + c0 + cg));
-                a[0] += bf16lo(u.x); a[1] += bf16hi(u.x); a[2] += bf16lo(u.y); a[3] += bf16hi(u.y);
-                a[4] += bf16lo(u.z); a[5] += bf16hi(u.z); a[6] += bf16lo(u.w); a[7] += bf16hi(u.w);
-            }
-        }
-        const float zz[8] = {bf16lo(zv.x), bf16hi(zv.x), bf16lo(zv.y), bf16hi(zv.y),
-                             bf16lo(zv.z), bf16hi(zv.z), bf16lo(zv.w), bf16hi(zv.w)};
-        float d[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float zh = (zz[j] - m[j]) * rs[j];
-            const float y = zh * g[j] + b[j];
-            d[j] = a[j] * (y > 0.f ? 1.f : sl[j]);
-            s0[j] += d[j];
-            s1[j] += d[j] * zh;
-            s2[j] += a[j] * fminf(y, 0.f);
-        }
-        *reinterpret_cast<uint4*>(dy + row * lddy + c0 + cg) =
-            make_uint4(pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]), pack_bf16x2(d[4], d[5]), pack_bf16x2(d[6], d[7]));
-        if (dres)
-            *reinterpret_cast<uint4*>(dres + row * lddres + c0 + cg) =
-                make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        red[0][rlane][cg + j] = s0[j]; red[1][rlane][cg + j] = s1[j]; red[2][rlane][cg + j] = s2[j];
-    }
-    __syncthreads();
-    if (threadIdx.x < 192) {
-        const int q = threadIdx.x / 64, c = threadIdx.x % 64;
-        float t = 0.f;
-#pragma unroll
-        for (int r = 0; r < 32; ++r) t += red[q][r][c];
-        atomicAdd(sums + q * C + c0 + c, t);
-    }
-}
-
-// Pass 2: dz = gamma * rstd * (dy - sum(dy)/cnt - zhat * sum(dy*zhat)/cnt) on the valid rows of dz_h9 and ZERO on its
-// halo rows (the dgrad / wgrad GEMMs read dz as a zero-padded map); the residual-branch gradient buffer gets its
-// halo rows zeroed here as well (its valid rows were written by pass 1).
-__global__ void __launch_bounds__(256)
-bn_prelu_bwd_dz_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, const __nv_bfloat16* __restrict__ z, int ldz,
-                       const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
-                       const float* __restrict__ sums, __nv_bfloat16* __restrict__ dz, int lddz,
-                       __nv_bfloat16* __restrict__ dres, int lddres, int n_img, int C) {
-    const int c8n = C / 8;
-    const float inv_cnt = 1.0f / (float)(n_img * 49);
-    const long long total = (long long)n_img * 81 * c8n;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c8 = (int)(i % c8n);
-        const long long row = i / c8n;
-        const int pos = (int)(row % 81);
-        const int hp = pos / 9, wp = pos - hp * 9;
-        if (hp == 0 || hp == 8 || wp == 0 || wp == 8) {
-            *(reinterpret_cast<uint4*>(dz + row * lddz) + c8) = make_uint4(0, 0, 0, 0);
-            if (dres) *(reinterpret_cast<uint4*>(dres + row * lddres) + c8) = make_uint4(0, 0, 0, 0);
-            continue;
-        }
-        const uint4 dv = __ldg(reinterpret_cast<const uint4*>(dy + row * lddy) + c8);
-        const uint4 zv = __ldg(reinterpret_cast<const uint4*>(z + row * ldz) + c8);
-        const float d[8] = {bf16lo(dv.x), bf16hi(dv.x), bf16lo(dv.y), bf16hi(dv.y), bf16lo(dv.z), bf16hi(dv.z), bf16lo(dv.w), bf16hi(dv.w)};
-        const float zz[8] = {bf16lo(zv.x), bf16hi(zv.x), bf16lo(zv.y), bf16hi(zv.y), bf16lo(zv.z), bf16hi(zv.z), bf16lo(zv.w), bf16hi(zv.w)};
-        float o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = c8 * 8 + j;
-            const float zh = (zz[j] - mean[c]) * rstd[c];
-            o[j] = gamma[c] * rstd[c] * (d[j] - sums[c] * inv_cnt - zh * sums[C + c] * inv_cnt);
-        }
-        *(reinterpret_cast<uint4*>(dz + row * lddz) + c8) =
-            make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-    }
-}
-
-int bn_prelu_bwd_launch(const void* da, int ldda, const int* scatter, int scatter_n, const void* z, int ldz,
-                        const float* mean, const float* rstd, const float* gamma, const float* beta, const float* slope,
-                        void* dy, int lddy, void* dres, int lddres, float* sums, void* dz, int lddz, int n_img, int C,
-                        cudaStream_t stream) {
-    FFR_CHECK_ARG(C % 64 == 0, "bn_prelu_bwd: C=%d", C);
-    FFR_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 3 * C, stream));
-    const long long rows = (long long)n_img * 49;
-    // ~8 CTAs per SM in total: enough rows in flight to cover the HBM latency, few enough atomics at the end
-    int gx = (int)((rows + 63) / 64);
-    const int cap = (num_sms() * 8 + C / 64 - 1) / (C / 64);
-    if (gx > cap) gx = cap;
-    if (gx < 1) gx = 1;
-    dim3 grid(gx, C / 64);
-    bn_prelu_bwd_reduce_kernel<<<grid, 256, 0, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(da), ldda, reinterpret_cast<const int2*>(scatter), scatter_n,
-        reinterpret_cast<const __nv_bfloat16*>(z), ldz, mean, rstd, gamma, beta, slope,
-        reinterpret_cast<__nv_bfloat16*>(dy), lddy, reinterpret_cast<__nv_bfloat16*>(dres), lddres, sums, n_img, C);
-    int rc = launch_status("bn_prelu_bwd_reduce_kernel");
-    if (rc) return rc;
-    const long long total = (long long)n_img * 81 * (C / 8);
-    int g2 = (int)((total + 255) / 256);
-    if (g2 > num_sms() * 8) g2 = num_sms() * 8;
-    bn_prelu_bwd_dz_kernel<<<g2, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy), lddy,
-                                                   reinterpret_cast<const __nv_bfloat16*>(z), ldz, mean, rstd, gamma, sums,
-                                                   reinterpret_cast<__nv_bfloat16*>(dz), lddz,
-                                                   reinterpret_cast<__nv_bfloat16*>(dres), lddres, n_img, C);
-    return launch_status("bn_prelu_bwd_dz_kernel");
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// Layout converters with gradients: fp32 NCHW (n,C,7,7) <-> bf16 H9.
-//   nchw_to_h9: scatter each pixel to its own row and mirrors, channel slot ch0 of a matrix with row pitch ld.
-//   h9_to_nchw_fold: out[n][c][pix] = sum over the scatter destinations of pix (gradient fold), or just the own row.
-// ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-nchw_to_h9_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int ld, int ch0, int n_img, int C,
-                  int mirror) {
-    __shared__ float tile[49][65];
-    const int n = blockIdx.y, c0 = blockIdx.x * 64;
-    for (int i = threadIdx.x; i < 64 * 49; i += 256) {
-        const int c = i / 49, pix = i - c * 49;
-        tile[pix][c] = (c0 + c < C) ? x[((long long)n * C + c0 + c) * 49 + pix] : 0.f;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 81 * 32; i += 256) {
-        const int pos = i >> 5, cp = (i & 31) * 2;
-        const int hp = pos / 9, wp = pos - hp * 9;
-        const int sh = hp == 0 ? 1 : (hp == 8 ? 5 : hp - 1), sw = wp == 0 ? 1 : (wp == 8 ? 5 : wp - 1);
-        const int pix = sh * 7 + sw;
-        const bool halo = (hp == 0 || hp == 8 || wp == 0 || wp == 8);
-        *reinterpret_cast<uint32_t*>(out + ((long long)n * 81 + pos) * ld + ch0 + c0 + cp) =
-            (halo && !mirror) ? 0u : pack_bf16x2(tile[pix][cp], tile[pix][cp + 1]);
-    }
-}
-
-__global__ void __launch_bounds__(256)
-h9_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, int ld, int ch0, float* __restrict__ y, int n_img, int C,
-                  int fold) {
-    __shared__ float tile[49][65];
-    const int n = blockIdx.y, c0 = blockIdx.x * 64;
-    for (int i = threadIdx.x; i < 49 * 32; i += 256) {
-        const int pix = i >> 5, cp = (i & 31) * 2;
-        const int h = pix / 7, w = pix - h * 7;
-        const int mh = fold ? ((h == 1) ? -2 : ((h == 5) ? 2 : 0)) : 0;
-        const int mw = fold ? ((w == 1) ? -2 : ((w == 5) ? 2 : 0)) : 0;
-        const long long base = (long long)n * 81 + (h + 1) * 9 + (w + 1);
-        float a = 0.f, b = 0.f;
-        auto add = [&](long long row) {
-            const uint32_t u = *reinterpret_cast<const uint32_t*>(in + row * ld + ch0 + c0 + cp);
-            a += bf16lo(u); b += bf16hi(u);
-        };
-        add(base);
-        if (mh) add(base + mh * 9);
-        if (mw) add(base + mw);
-        if (mh && mw) add(base + mh * 9 + mw);
-        tile[pix][cp] = a; tile[pix][cp + 1] = b;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 64 * 49; i += 256) {
-        const int c = i / 49, pix = i - c * 49;
-        if (c0 + c < C) y[((long long)n * C + c0 + c) * 49 + pix] = tile[pix][c];
-    }
-}
 
 // ------------------------------------------------------------------------------------------------------------
 // Weight packing for one ConvLayer in a single launch (done once per optimizer step, cached by the host):
@@ -592,18 +335,6 @@ int pack_conv3x3_launch_ex(const float* w, int cout, int cin, int cout_p, int ci
 int pack_conv3x3_launch(const float* w, int cout, int cin, int cout_p, int cin_p, void* fwd, void* dgrad,
                         cudaStream_t stream) {
     return pack_conv3x3_launch_ex(w, cout, cin, cout_p, cin_p, fwd, dgrad, 0, stream);
-}
-
-int nchw_to_h9_launch(const float* x, void* out, int ld, int ch0, int n_img, int C, int mirror, cudaStream_t stream) {
-    dim3 grid((C + 63) / 64, n_img);
-    nchw_to_h9_kernel<<<grid, 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out), ld, ch0, n_img, C, mirror);
-    return launch_status("nchw_to_h9_kernel");
-}
-
-int h9_to_nchw_launch(const void* in, int ld, int ch0, float* y, int n_img, int C, int fold, cudaStream_t stream) {
-    dim3 grid((C + 63) / 64, n_img);
-    h9_to_nchw_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), ld, ch0, y, n_img, C, fold);
-    return launch_status("h9_to_nchw_kernel");
 }
 
 }  // namespace ffr

@@ -187,30 +187,6 @@ FFR_API int ffr_rows_to_nchw(const void* rows, int is_f32, int ld, int ch0, cons
 /* out = in * scale (AvgPool2d(7) finish, recnet.py:423). */
 FFR_API int ffr_scale_f32(const float* in, float* out, int64_t count, float scale, ffr_stream_t stream);
 
-/* ---- RecNet training (models/recnet.py ConvLayer in train mode, models/trainer.py:154-187) ------------------- */
-
-/* Weight gradient of ReflectionPad2d(1)+Conv2d(3x3) (autograd of recnet.py:82): dw[co][ci][r][s] =
- * sum_p dz[p][co] * x[p + (r-1)*9 + (s-1)][x_ch0 + ci] over the P = n*81 rows of the H9 grid (dz is zero on halo rows).
- * dz [P][ld_dz] bf16, x [P][ld_x] bf16, dw fp32 [Cout][Cin][3][3] (OVERWRITTEN). workspace: fp32 staging of
- * 9 * ceil128(Cout) * ceil256(Cin) elements (tap-major partial sums; vector reductions when the pixel axis is split). */
-FFR_API int ffr_wgrad3x3(const void* dz, int ld_dz, const void* x, int ld_x, int x_ch0, int n, int Cout, int Cin,
-                         float* dw, float* workspace, ffr_stream_t stream);
-
-/* Train-mode BatchNorm2d (batch statistics) + PReLU (+ residual) on the raw conv output z (recnet.py:83-84,217):
- * a = prelu(gamma*(z-mean)*rstd+beta) (+res), scattered to H9 rows (own row + reflection mirrors / concat slot). */
-FFR_API int ffr_bn_prelu_fwd(const void* z, int ldz, const float* mean, const float* rstd, const float* gamma,
-                             const float* beta, const float* slope, const void* res, int ldres, void* out, int ldo,
-                             const int* scatter, int scatter_n, int n, int C, ffr_stream_t stream);
-
-/* Backward of the above: folds the gradient of the H9 output (own row + mirrors), PReLU and BatchNorm backward.
- * sums [3][C] fp32 receives sum(dy) (= dbeta), sum(dy*zhat) (= dgamma), sum(da*min(y,0)) (= dslope);
- * dy [n*81][lddy] bf16 scratch; dres (optional) folded output gradient for the residual branch; dz [n*81][lddz] bf16
- * gradient of the raw conv output on valid rows (the buffer's halo rows must be, and stay, zero). */
-FFR_API int ffr_bn_prelu_bwd(const void* da, int ldda, const int* scatter, int scatter_n, const void* z, int ldz,
-                             const float* mean, const float* rstd, const float* gamma, const float* beta,
-                             const float* slope, void* dy, int lddy, void* dres, int lddres, float* sums, void* dz,
-                             int lddz, int n, int C, ffr_stream_t stream);
-
 /* Packs one 3x3 conv weight (fp32 OIHW) for the forward GEMM and (optionally) for its dgrad in a single launch:
  * fwd [cout_p][9*cin_p], dgrad [cin_p][9*cout_p] (spatially flipped + transposed), zero padded. */
 FFR_API int ffr_pack_conv3x3(const float* w, int cout, int cin, int cout_p, int cin_p, void* fwd, void* dgrad,
@@ -414,11 +390,6 @@ FFR_API int ffr_cosface_ce_bwd_grouped(const float* cos_in, int c_pad, int class
 /* Jacobian of F.normalize(x, dim=1) on rows of 512: dx = (dxh - xh (xh . dxh)) / max(|x|, 1e-12). */
 FFR_API int ffr_normalize_bwd(const float* x, const float* dxh, int rows, float* dx, ffr_stream_t stream);
 
-/* fp32 NCHW (n,C,7,7) -> bf16 H9 channel slot (mirror != 0: reflection halo filled, else halo zero) and back
- * (fold != 0: sums the mirror rows into the pixel, i.e. the gradient of the mirrored scatter). */
-FFR_API int ffr_nchw_to_h9(const float* x, void* out, int ld, int ch0, int n, int C, int mirror, ffr_stream_t stream);
-FFR_API int ffr_h9_to_nchw(const void* in, int ld, int ch0, float* y, int n, int C, int fold, ffr_stream_t stream);
-
 /* ---- LFW-style verification scoring (lfw/lfw_eval.py) ------------------------------------------------------ */
 
 /* score[i] = sum(f1[i]*f2[i]) / (|f1[i]|*|f2[i]| + 1e-8)  (lfw_eval.py:246,248); f1, f2 fp32 [pairs][D]. */
@@ -451,20 +422,6 @@ FFR_API void ffr_debug_set_pixmajor_backbone(int max_s);
 
 /* Tuning only: splits > 0 overrides the split-count heuristic of ffr_wgrad3x3 (0 restores it). */
 FFR_API void ffr_debug_set_wgrad_splits(int splits);
-
-/* Debug: hardware-semantics probe for row-offset UMMA descriptors (csrc/probe.cu); not on the product path.
- * a [256][64] bf16, w [64][64] bf16, out [128][64] fp32 = a[row_off : row_off+128] @ w^T. */
-FFR_API int ffr_debug_rowshift_probe(const void* a, const void* w, float* out, int row_off, int variant,
-                                     ffr_stream_t stream);
-
-/* Debug: MN-major UMMA operand probe (csrc/probe.cu): a [96][128], b [96][64] bf16 (k rows);
- * out[128][64] = sum_{k<64} a[k][m] * b[r0+k][n]. */
-FFR_API int ffr_debug_mn_probe(const void* a, const void* b, float* out, int r0, int variant, ffr_stream_t stream);
-
-/* Debug: tcgen05.mma issue-rate micro-benchmark (csrc/probe.cu). out_cycles[grid] = cycles for `iters` MMAs of shape
- * M x N x 16 alternating between n_acc accumulators. */
-FFR_API int ffr_debug_mma_bench(long long* out_cycles, int M, int N, int n_acc, int iters, int grid,
-                                ffr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -27,6 +27,44 @@ def test_library_exports_every_declared_symbol():
     assert set(names) <= set(_lib._SIGNATURES), set(names) - set(_lib._SIGNATURES)
 
 
+def test_probe_library_is_separate_and_exports_its_header():
+    """The hardware probes / micro-benchmarks (csrc/probe.cu) are NOT in the product library."""
+    names = _lib.declared_symbols(_lib.PROBE_HEADER_PATH)
+    assert set(names) == {"ffr_debug_rowshift_probe", "ffr_debug_mn_probe", "ffr_debug_mma_bench"}
+    probe, main = ctypes.CDLL(_lib.PROBE_LIB_PATH), ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(probe, n) and not hasattr(main, n), n
+
+
+def test_ctypes_signatures_match_the_headers():
+    """Every ctypes signature in _lib._SIGNATURES has the arity and the argument kinds (pointer / int / int64 / float / u32)
+    of its declaration in include/*.h — a float passed as an int would silently corrupt a call."""
+    import re
+    kinds = {ctypes.c_int: "i", ctypes.c_float: "f", ctypes.c_int64: "q", ctypes.c_uint32: "I", ctypes.c_longlong: "q"}
+
+    def kind_of(c):
+        if c in (ctypes.c_void_p, ctypes.c_char_p) or (isinstance(c, type) and issubclass(c, ctypes._Pointer)):
+            return "P"
+        return kinds.get(c, "?")
+
+    def kind_of_decl(a):
+        a = a.strip()
+        if "*" in a or "ffr_stream_t" in a:
+            return "P"
+        t = re.sub(r"\b\w+$", "", a).replace("const ", "").strip()
+        return {"int": "i", "float": "f", "int64_t": "q", "uint32_t": "I", "long long": "q"}.get(t, "?" + t)
+    checked = 0
+    for header in (_lib.HEADER_PATH, _lib.PROBE_HEADER_PATH):
+        text = re.sub(r"/\*.*?\*/", "", open(header).read(), flags=re.S)
+        for _, name, args in re.findall(r"FFR_API\s+([\w\s\*]+?)\b(ffr_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+            args = args.strip()
+            exp = [] if args in ("", "void") else [kind_of_decl(a) for a in args.split(",")]
+            got = [kind_of(c) for c in _lib._SIGNATURES[name][1]]
+            assert exp == got, (name, "".join(exp), "".join(got))
+            checked += 1
+    assert checked >= 60
+
+
 def test_argument_errors_are_reported_without_a_gpu():
     lib = _lib.load()
     rc = lib.ffr_conv3x3_bnpre_prelu_fwd(None, 1, 14, 64, None, 64, None, None, None, 0, None)
@@ -48,7 +86,7 @@ def test_argument_errors_are_reported_without_a_gpu():
         (lambda: lib.ffr_cosface_pack(one, 5, 70, 0, one, None, 0, None), b"rows_pad"),
         (lambda: lib.ffr_cosface_ce_fwd(one, 4, one, 300, 300, one, 30.0, 0.4, one, one, one, one, None, None), b"c_pad"),
         (lambda: lib.ffr_cosface_ce_bwd(one, 320, 300, 4, 60, one, one, one, 30.0, 0.4, one, one, None), b"bad shape"),
-        (lambda: lib.ffr_wgrad3x3(one, 60, one, 64, 0, 1, 64, 64, one, one, None), b"pitches"),
+        (lambda: lib.ffr_wgrad(one, 60, one, 64, 0, 81, 64, 64, 9, 0, 1, 0, 64, -1, one, None, one, None), b"pitches"),
         (lambda: lib.ffr_self_similarity(one, 1, None, None, None), b"no output"),
         (lambda: lib.ffr_stem_u8_fwd(None, None, 1, one, one, one, one, 1, 112, None), b"null pointer"),
     ]

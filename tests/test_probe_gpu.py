@@ -20,7 +20,7 @@ def test_rowshift_descriptor_semantics(lib):
         ok = []
         for r0 in (0, 1, 3, 7, 8, 15, 16, 17, 29, 64, 100, 128):
             out = torch.zeros(128, 64, dtype=torch.float32, device="cuda")
-            _lib.check(lib.ffr_debug_rowshift_probe(_lib.ptr(a), _lib.ptr(w), _lib.ptr(out), r0, variant,
+            _lib.check(_lib.load_probe().ffr_debug_rowshift_probe(_lib.ptr(a), _lib.ptr(w), _lib.ptr(out), r0, variant,
                                                     _lib.stream_ptr()))
             torch.cuda.synchronize()
             ref = a[r0:r0 + 128].float() @ w.float().t()
@@ -44,7 +44,7 @@ def test_mn_major_descriptor_semantics(lib):
         ok = []
         for r0 in (0, 8, 16, 1, 3, 9, 10, 19, 32):
             out = torch.zeros(128, 64, dtype=torch.float32, device="cuda")
-            _lib.check(lib.ffr_debug_mn_probe(_lib.ptr(a), _lib.ptr(b), _lib.ptr(out), r0, variant, _lib.stream_ptr()))
+            _lib.check(_lib.load_probe().ffr_debug_mn_probe(_lib.ptr(a), _lib.ptr(b), _lib.ptr(out), r0, variant, _lib.stream_ptr()))
             torch.cuda.synchronize()
             ref = a[:64].float().t() @ b[r0:r0 + 64].float()
             ok.append(bool(torch.equal(out, ref)))
@@ -67,7 +67,7 @@ def test_fp16_operands(lib):
     a = a + 0.0009765625 * torch.randint(0, 2, (96, 128), generator=g, device="cuda")   # 2^-10: exact in fp16, not in bf16
     aa, bb = a.half(), b.half()
     out = torch.zeros(128, 64, dtype=torch.float32, device="cuda")
-    _lib.check(lib.ffr_debug_mn_probe(_lib.ptr(aa), _lib.ptr(bb), _lib.ptr(out), 0, 6, _lib.stream_ptr()))
+    _lib.check(_lib.load_probe().ffr_debug_mn_probe(_lib.ptr(aa), _lib.ptr(bb), _lib.ptr(out), 0, 6, _lib.stream_ptr()))
     torch.cuda.synchronize()
     ref = aa[:64].float().t() @ bb[:64].float()
     err = float((out - ref).abs().max())

@@ -18,7 +18,7 @@ for grid in (1, 148):
                 if n_acc * N > 512:
                     continue
                 out = torch.zeros(grid, dtype=torch.int64, device="cuda")
-                _lib.check(lib.ffr_debug_mma_bench(_lib.ptr(out), M, N, n_acc, iters, grid, _lib.stream_ptr()))
+                _lib.check(_lib.load_probe().ffr_debug_mma_bench(_lib.ptr(out), M, N, n_acc, iters, grid, _lib.stream_ptr()))
                 torch.cuda.synchronize()
                 cyc = out.float().mean().item() / iters
                 res.append(dict(grid=grid, M=M, N=N, n_acc=n_acc, cycles_per_mma=cyc))
