@@ -66,6 +66,7 @@ _SIGNATURES = {
     "ffr_bn_act_bwd": (_i, [_p, _i, _i, _p, _i, _p, _i, _i, _p, _i, _f, _p, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p,
                             _i, _i, _p, _i, _i, _i, _i, _p]),
     "ffr_h9_avgpool": (_i, [_p, _i, _p, _i, _i, _i, _p]),
+    "ffr_h9_avgpool_bf16": (_i, [_p, _i, _p, _i, _i, _i, _p]),
     "ffr_wgrad_workspace_floats": (_i64, [_i, _i, _i, _i, _i]),
     "ffr_wgrad": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "ffr_pack_conv3x3_f16": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
@@ -115,7 +116,10 @@ _SIGNATURES = {
     "ffr_subsample2": (_i, [_p, _p, _i, _i, _i, _p]),
     "ffr_stem_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _p]),
     "ffr_stem_u8_fwd": (_i, [_p, _p, _i, _p, _p, _p, _p, _i, _i, _p]),
-    "ffr_se_residual_fwd": (_i, [_p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _p]),
+    "ffr_se_pool_part_floats": (_i64, [_i, _i, _i]),
+    "ffr_se_gate_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "ffr_se_residual_fwd": (_i, [_p, _p, _p, _i, _p, _i, _i, _i, _p]),
+    "ffr_head_workspace_floats": (_i64, [_i, _i, _i]),
     "ffr_export_nchw_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "ffr_head_fwd": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "ffr_debug_set_window": (_i, [_i]),

@@ -196,8 +196,14 @@ class Backbone(nn.Module):
                 so = res // 2
                 ws.s2d[i] = torch.zeros(n * (so + 1) * (so + 1) * 4 * unit.depth, **bf)
                 res = so
-        ws.pool = torch.empty(n * 512, dtype=torch.float32, device=device)
-        ws.acc = torch.empty(n * 512, dtype=torch.float32, device=device)
+        lib = _lib.load()
+        res, part = S, 0
+        for unit in self.body:                                # SE squeeze partial sums: the largest layer's need
+            res //= unit.stride
+            part = max(part, lib.ffr_se_pool_part_floats(n, res, unit.depth))
+        ws.pool_part = torch.empty(part, dtype=torch.float32, device=device)
+        ws.gate = torch.empty(n * 512, dtype=torch.float32, device=device)
+        ws.acc = torch.empty(lib.ffr_head_workspace_floats(n, res, 512), dtype=torch.float32, device=device)
         self._ws[slot] = (key, ws)                            # keep one batch size resident per stream slot
         return ws
 
@@ -289,7 +295,8 @@ class Backbone(nn.Module):
                 L.check(lib.ffr_conv3x3_bnpre_prelu_fwd(P(cur), n, S, u.cin, P(u.w1), u.depth, P(u.bias9), P(u.slope),
                                                         P(t), 0, st), "conv1 %d>%d@%ds1" % (u.cin, u.depth, S))
             L.check(lib.ffr_conv3x3_bn_pool_fwd(P(t), n, S, u.depth, u.stride, P(u.w2), u.depth, P(u.b2), P(ws.u),
-                                                P(ws.pool), st), "conv2 %d>%d@%ds%d" % (u.depth, u.depth, S, u.stride))
+                                                P(ws.pool_part), st), "conv2 %d>%d@%ds%d" % (u.depth, u.depth, S, u.stride))
+            L.check(lib.ffr_se_gate_fwd(P(ws.pool_part), P(u.fc1), P(u.fc2), P(ws.gate), None, n, so, u.depth, st), "se_gate")
             if u.cin == u.depth:
                 sc, mode = cur, (1 if u.stride == 2 else 0)
             else:
@@ -297,8 +304,7 @@ class Backbone(nn.Module):
                 L.check(lib.ffr_conv1x1_bn_fwd(P(ws.xs), n, so, u.cin, P(u.wsc), u.depth, P(u.bsc), P(ws.sc), st),
                         "shortcut")
                 sc, mode = ws.sc, 2
-            L.check(lib.ffr_se_residual_fwd(P(ws.u), P(ws.pool), P(u.fc1), P(u.fc2), P(sc), mode, P(nxt), n, so,
-                                            u.depth, st), "se_residual")
+            L.check(lib.ffr_se_residual_fwd(P(ws.u), P(ws.gate), P(sc), mode, P(nxt), n, so, u.depth, st), "se_residual")
             cur, nxt = nxt, cur
             S = so
         y = None

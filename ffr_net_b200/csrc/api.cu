@@ -139,8 +139,13 @@ FFR_API int ffr_conv3x3_bnpre_prelu_fwd(const void* x, int n_img, int S, int Cin
     return conv_gemm_launch(x, (long long)p.M, Cin, Cin, wp, Cin, p, 1, S_(stream));
 }
 
+FFR_API long long ffr_se_pool_part_floats(int n_img, int So, int Cout) {
+    const long long M = (long long)n_img * (So + 1) * (So + 1);
+    return ((M + 127) / 128) * 4 * 2 * Cout;
+}
+
 FFR_API int ffr_conv3x3_bn_pool_fwd(const void* x, int n_img, int S, int C, int stride, const void* wp, int Cout,
-                            const float* bias, void* out, float* pool, ffr_stream_t stream) {
+                            const float* bias, void* out, float* pool_part, ffr_stream_t stream) {
     FFR_CHECK_ARG(x && wp && bias && out, "ffr_conv3x3_bn_pool_fwd: null pointer");
     FFR_CHECK_ARG(stride == 1 || (stride == 2 && S % 2 == 0), "ffr_conv3x3_bn_pool_fwd: stride=%d S=%d", stride, S);
     const int So = S / stride, G = So + 1;
@@ -150,13 +155,18 @@ FFR_API int ffr_conv3x3_bn_pool_fwd(const void* x, int n_img, int S, int C, int 
     p.Cout = Cout;
     if (stride == 1) taps_3x3_flat(p, G); else taps_3x3_s2d(p, G, C);
     p.rows_per_img = G * G; p.Wp = G; p.S = So; p.h0 = 0; p.n_img = n_img;
-    p.flags = EPI_GEOM | EPI_BIAS | (pool ? EPI_POOL : 0u) |
-              ((stride == 1 && pixmajor_backbone(So, n_img)) ? EPI_PIXMAJOR : 0u);
+    const bool pix = stride == 1 && pixmajor_backbone(So, n_img);
+    p.flags = EPI_GEOM | EPI_BIAS | (pool_part ? EPI_POOL : 0u) | (pix ? EPI_PIXMAJOR : 0u);
     p.bias = bias;
     p.out = reinterpret_cast<__nv_bfloat16*>(out);
     p.ldo = Cout;
-    p.pool = pool;
-    if (pool) FFR_CUDA(cudaMemsetAsync(pool, 0, sizeof(float) * (size_t)n_img * Cout, S_(stream)));
+    if (pixmajor_backbone(So, n_img)) {   // experiment switch (all strides, so that ffr_se_gate_fwd can tell from S and
+                                          // n_img alone): atomics into dense [n_img][Cout] sums
+        p.pool = pool_part;
+        if (pool_part) FFR_CUDA(cudaMemsetAsync(pool_part, 0, sizeof(float) * (size_t)n_img * Cout, S_(stream)));
+    } else {
+        p.pool_part = pool_part;
+    }
     const int a_cols = (stride == 1) ? C : 4 * C;
     return conv_gemm_launch(x, (long long)p.M, a_cols, a_cols, wp, C, p, 1, S_(stream));
 }
@@ -195,10 +205,16 @@ FFR_API int ffr_stem_u8_fwd(const unsigned char* img, const unsigned char* flip,
     return stem_u8_launch(img, flip, swap_rb, w, b, a, out, n_img, S, S_(stream));
 }
 
-FFR_API int ffr_se_residual_fwd(const void* u, const float* pool, const float* w1, const float* w2, const void* shortcut,
-                        int shortcut_mode, void* y, int n_img, int S, int C, ffr_stream_t stream) {
-    FFR_CHECK_ARG(u && pool && w1 && w2 && shortcut && y, "ffr_se_residual_fwd: null pointer");
-    return se_residual_launch(u, pool, w1, w2, shortcut, shortcut_mode, y, n_img, S, C, S_(stream));
+FFR_API int ffr_se_gate_fwd(const float* pool_part, const float* w1, const float* w2, float* gate, float* sums, int n_img,
+                            int S, int C, ffr_stream_t stream) {
+    FFR_CHECK_ARG(pool_part && w1 && w2 && gate, "ffr_se_gate_fwd: null pointer");
+    return se_gate_launch(pool_part, pixmajor_backbone(S, n_img) ? 1 : 0, w1, w2, gate, sums, n_img, S, C, S_(stream));
+}
+
+FFR_API int ffr_se_residual_fwd(const void* u, const float* gate, const void* shortcut, int shortcut_mode, void* y,
+                                int n_img, int S, int C, ffr_stream_t stream) {
+    FFR_CHECK_ARG(u && gate && shortcut && y, "ffr_se_residual_fwd: null pointer");
+    return se_residual_launch(u, gate, shortcut, shortcut_mode, y, n_img, S, C, S_(stream));
 }
 
 FFR_API int ffr_export_nchw_fwd(const void* h, const float* scale, const float* shift, float* y, int n_img, int S, int C,
@@ -207,29 +223,39 @@ FFR_API int ffr_export_nchw_fwd(const void* h, const float* scale, const float* 
     return export_nchw_launch(h, scale, shift, y, n_img, S, C, S_(stream));
 }
 
+// split count of the head GEMM: enough to put ~one wave of CTAs on the machine
+static int head_splits(int n_img, int K) {
+    const int tiles = ((n_img + 127) / 128) * (512 / 256);
+    int splits = (num_sms() + tiles - 1) / tiles;
+    const int kb = K / 64;
+    if (splits > kb / 4) splits = kb / 4;
+    if (splits < 1) splits = 1;
+    const int per = (kb + splits - 1) / splits;
+    return (kb + per - 1) / per;
+}
+
+FFR_API long long ffr_head_workspace_floats(int n_img, int S, int C) {
+    return (long long)head_splits(n_img, (S + 1) * (S + 1) * C) * n_img * 512;
+}
+
 FFR_API int ffr_head_fwd(const void* h, int n_img, int S, int C, const void* wp, const float* bias, float* acc, float* f,
                  ffr_stream_t stream) {
     FFR_CHECK_ARG(h && wp && bias && acc && f, "ffr_head_fwd: null pointer");
     const int D = 512;
     const int K = (S + 1) * (S + 1) * C;       // one image's flat rows, viewed as a single GEMM row
     FFR_CHECK_ARG(K % 64 == 0, "ffr_head_fwd: K=%d", K);
-    FFR_CUDA(cudaMemsetAsync(acc, 0, sizeof(float) * (size_t)n_img * D, S_(stream)));
     ConvGemmParams p;
     memset(&p, 0, sizeof(p));
     p.M = n_img;
     p.Cout = D;
     p.ntaps = 1;
-    p.flags = EPI_OUT_F32_ATOMIC;
+    p.flags = EPI_OUT_F32;                     // deterministic split-K: one fp32 partial product per split, plain stores
     p.out_f32 = acc;
-    // enough splits to put ~one wave of CTAs on the machine
-    const int tiles = ((n_img + 127) / 128) * (D / 256);
-    int splits = (num_sms() + tiles - 1) / tiles;
-    const int kb = K / 64;
-    if (splits > kb / 4) splits = kb / 4;
-    if (splits < 1) splits = 1;
+    p.out_f32_split_stride = (long long)n_img * D;
+    const int splits = head_splits(n_img, K);
     int rc = conv_gemm_launch(h, n_img, K, K, wp, K, p, splits, S_(stream));
     if (rc) return rc;
-    return bias_l2norm_launch(acc, bias, f, n_img, D, S_(stream));
+    return bias_l2norm_launch(acc, splits, p.out_f32_split_stride, bias, f, n_img, D, S_(stream));
 }
 
 FFR_API int ffr_recnet_prep(const float* x, int n, const float* w0aT, const float* w0bT, const float* b0,

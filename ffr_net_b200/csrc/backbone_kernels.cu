@@ -236,33 +236,52 @@ int stem_u8_launch(const unsigned char* img, const unsigned char* flip, int swap
 }
 
 // ----------------------------------------------------------------------------------------------
-// SE gate + residual  (model_ir_se50.py:29-36, 73-76):
-//   s = sigmoid(W2 relu(W1 mean_hw(u)));  y = u * s + shortcut
-// pool holds per-(image, channel) SUMS of u over the SxS valid pixels (accumulated by the conv2 epilogue).
-// shortcut_mode 0: x on the same grid (identity MaxPool(1,1)); 1: x on the (2S)x(2S) grid, subsampled
-// (MaxPool(1,2)); 2: sc on the same grid (Conv1x1+BN shortcut, computed by a GEMM).
-// grid = (chunks, n_img); every CTA recomputes the (tiny) gate of its image.
+// SE gate (model_ir_se50.py:29-36):  s = sigmoid(W2 relu(W1 mean_hw(u)))  per image, from the per-32-row-block partial
+// sums the conv2 epilogue stored (ConvGemmParams::pool_part). Image n owns rows [n*rpi, (n+1)*rpi) of the flat map; a
+// block b covers rows [32b, 32b+31] and holds the sum of the rows of image floor(32b / rpi) in slot 0 and - when it
+// straddles an image boundary (rpi >= 64 > 32: at most two images) - of the next image in slot 1. The blocks are added
+// in a fixed order: no atomics, bit-reproducible. dense != 0: pool_part is [n_img][C] finished sums instead (the
+// pixel-major experiment, whose epilogue adds per row with atomics). One CTA per image.
 // ----------------------------------------------------------------------------------------------
 template <int C>
-__global__ void __launch_bounds__(256) se_residual_kernel(const __nv_bfloat16* __restrict__ u,
-                                                          const float* __restrict__ pool,
-                                                          const float* __restrict__ w1, const float* __restrict__ w2,
-                                                          const __nv_bfloat16* __restrict__ sc, int shortcut_mode,
-                                                          __nv_bfloat16* __restrict__ y, int S) {
+__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ pool_part, int dense,
+                                                      const float* __restrict__ w1, const float* __restrict__ w2,
+                                                      float* __restrict__ gate, float* __restrict__ sums, int rpi, float inv) {
     constexpr int R = C / 16;
-    constexpr int TPR = C / 8;          // threads per row (8 channels = 16 B each)
-    constexpr int RPI = 256 / TPR;      // rows per iteration
+    constexpr int PARTS = (C >= 256) ? 1 : 256 / C;      // threads (c, part): part strides over the blocks
+    __shared__ float s_part[PARTS][C];
     __shared__ float s_mean[C];
     __shared__ float s_hid[R];
-    __shared__ float s_gate[C];
-    const int n = blockIdx.y;
+    const int n = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float inv = 1.0f / (float)(S * S);
-    for (int c = tid; c < C; c += 256) s_mean[c] = pool[(long long)n * C + c] * inv;
+    if (dense) {
+        for (int c = tid; c < C; c += 256) s_mean[c] = pool_part[(long long)n * C + c];
+    } else {
+        const long long r0 = (long long)n * rpi, r1 = r0 + rpi - 1;
+        const int b0 = (int)(r0 >> 5), b1 = (int)(r1 >> 5);
+        for (int i = tid; i < PARTS * C; i += 256) {
+            const int c = i % C, part = i / C;
+            float a = 0.f;
+            for (int b = b0 + part; b <= b1; b += PARTS) {
+                const int slot = (((long long)b << 5) >= r0) ? 0 : 1;      // first row of the block belongs to image n?
+                a += pool_part[((long long)b * 2 + slot) * C + c];
+            }
+            s_part[part][c] = a;
+        }
+        __syncthreads();
+        for (int c = tid; c < C; c += 256) {
+            float a = s_part[0][c];
+#pragma unroll
+            for (int q = 1; q < PARTS; ++q) a += s_part[q][c];
+            s_mean[c] = a;
+        }
+    }
     __syncthreads();
+    if (sums != nullptr)
+        for (int c = tid; c < C; c += 256) sums[(long long)n * C + c] = s_mean[c];
     for (int j = warp; j < R; j += 8) {
         float a = 0.f;
-        for (int c = lane; c < C; c += 32) a = fmaf(__ldg(w1 + j * C + c), s_mean[c], a);
+        for (int c = lane; c < C; c += 32) a = fmaf(__ldg(w1 + j * C + c), s_mean[c] * inv, a);
         a = warp_sum(a);
         if (lane == 0) s_hid[j] = fmaxf(a, 0.f);
     }
@@ -271,55 +290,95 @@ __global__ void __launch_bounds__(256) se_residual_kernel(const __nv_bfloat16* _
         float a = 0.f;
 #pragma unroll
         for (int j = 0; j < R; ++j) a = fmaf(__ldg(w2 + c * R + j), s_hid[j], a);
-        s_gate[c] = 1.0f / (1.0f + __expf(-a));
-    }
-    __syncthreads();
-
-    const int c8 = tid % TPR;
-    float g[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] = s_gate[c8 * 8 + j];
-    const int G = S + 1;
-    const int rows = G * G;
-    const int per = (rows + gridDim.x - 1) / gridDim.x;
-    const int r0 = blockIdx.x * per;
-    const int r1 = min(rows, r0 + per);
-    const long long base = (long long)n * rows;
-    const int G2 = 2 * S + 1;
-    for (int r = r0 + tid / TPR; r < r1; r += RPI) {
-        const uint4 uv = __ldg(reinterpret_cast<const uint4*>(u + (base + r) * C) + c8);
-        long long srow = base + r;
-        if (shortcut_mode == 1) {
-            const int h = r / G, wq = r - h * G;
-            srow = (long long)n * G2 * G2 + (long long)(2 * h) * G2 + 2 * wq;
-        }
-        const uint4 sv = __ldg(reinterpret_cast<const uint4*>(sc + srow * C) + c8);
-        uint4 o;
-        o.x = pack_bf16x2(fmaf(bf16lo(uv.x), g[0], bf16lo(sv.x)), fmaf(bf16hi(uv.x), g[1], bf16hi(sv.x)));
-        o.y = pack_bf16x2(fmaf(bf16lo(uv.y), g[2], bf16lo(sv.y)), fmaf(bf16hi(uv.y), g[3], bf16hi(sv.y)));
-        o.z = pack_bf16x2(fmaf(bf16lo(uv.z), g[4], bf16lo(sv.z)), fmaf(bf16hi(uv.z), g[5], bf16hi(sv.z)));
-        o.w = pack_bf16x2(fmaf(bf16lo(uv.w), g[6], bf16lo(sv.w)), fmaf(bf16hi(uv.w), g[7], bf16hi(sv.w)));
-        reinterpret_cast<uint4*>(y + (base + r) * C)[c8] = o;
+        gate[(long long)n * C + c] = 1.0f / (1.0f + __expf(-a));
     }
 }
 
-int se_residual_launch(const void* u, const float* pool, const float* w1, const float* w2, const void* sc,
-                       int shortcut_mode, void* y, int n_img, int S, int C, cudaStream_t stream) {
+int se_gate_launch(const float* pool_part, int dense, const float* w1, const float* w2, float* gate, float* sums,
+                   int n_img, int S, int C, cudaStream_t stream) {
+    const int rpi = (S + 1) * (S + 1);
+    const float inv = 1.0f / (float)(S * S);
+    FFR_CHECK_ARG(rpi >= 64, "se_gate: map %dx%d too small for the 32-row block scheme", S, S);
+    switch (C) {
+        case 64:  se_gate_kernel<64><<<n_img, 256, 0, stream>>>(pool_part, dense, w1, w2, gate, sums, rpi, inv); break;
+        case 128: se_gate_kernel<128><<<n_img, 256, 0, stream>>>(pool_part, dense, w1, w2, gate, sums, rpi, inv); break;
+        case 256: se_gate_kernel<256><<<n_img, 256, 0, stream>>>(pool_part, dense, w1, w2, gate, sums, rpi, inv); break;
+        case 512: se_gate_kernel<512><<<n_img, 256, 0, stream>>>(pool_part, dense, w1, w2, gate, sums, rpi, inv); break;
+        default: return set_error(-1, "se_gate: unsupported C=%d", C);
+    }
+    return launch_status("se_gate_kernel");
+}
+
+// ----------------------------------------------------------------------------------------------
+// SE scale + residual (model_ir_se50.py:36, 73-76):  y = u * gate[n] + shortcut, one pass over the flat map.
+// shortcut_mode 0: x on the same grid (identity MaxPool(1,1)); 1: x on the (2S)x(2S) grid, subsampled
+// (MaxPool(1,2)); 2: sc on the same grid (Conv1x1+BN shortcut, computed by a GEMM).
+// A thread owns 8 channels (16 B) of a row; UNR rows are in flight per thread (2 x UNR 16-byte loads).
+// ----------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) se_residual_kernel(const __nv_bfloat16* __restrict__ u,
+                                                          const float* __restrict__ gate,
+                                                          const __nv_bfloat16* __restrict__ sc, int shortcut_mode,
+                                                          __nv_bfloat16* __restrict__ y, int S, long long total_rows) {
+    constexpr int TPR = C / 8;          // threads per row
+    constexpr int RPB = 256 / TPR;      // rows per CTA pass
+    constexpr int UNR = 4;
+    const int c8 = threadIdx.x % TPR;
+    const int rsub = threadIdx.x / TPR;
+    const int G = S + 1, rows = G * G, G2 = 2 * S + 1;
+    for (long long rb = (long long)blockIdx.x * (RPB * UNR); rb < total_rows; rb += (long long)gridDim.x * (RPB * UNR)) {
+        uint4 uv[UNR], sv[UNR];
+        float4 g0[UNR], g1[UNR];
+        long long row[UNR];
+#pragma unroll
+        for (int k = 0; k < UNR; ++k) {
+            row[k] = rb + k * RPB + rsub;
+            if (row[k] < total_rows) {
+                const int n = (int)(row[k] / rows);
+                long long srow = row[k];
+                if (shortcut_mode == 1) {
+                    const int r = (int)(row[k] - (long long)n * rows);
+                    const int h = r / G, wq = r - h * G;
+                    srow = (long long)n * G2 * G2 + (long long)(2 * h) * G2 + 2 * wq;
+                }
+                uv[k] = __ldg(reinterpret_cast<const uint4*>(u + row[k] * C) + c8);
+                sv[k] = __ldg(reinterpret_cast<const uint4*>(sc + srow * C) + c8);
+                const float4* gp = reinterpret_cast<const float4*>(gate + (long long)n * C + c8 * 8);
+                g0[k] = __ldg(gp);
+                g1[k] = __ldg(gp + 1);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < UNR; ++k) {
+            if (row[k] < total_rows) {
+                uint4 o;
+                o.x = pack_bf16x2(fmaf(bf16lo(uv[k].x), g0[k].x, bf16lo(sv[k].x)), fmaf(bf16hi(uv[k].x), g0[k].y, bf16hi(sv[k].x)));
+                o.y = pack_bf16x2(fmaf(bf16lo(uv[k].y), g0[k].z, bf16lo(sv[k].y)), fmaf(bf16hi(uv[k].y), g0[k].w, bf16hi(sv[k].y)));
+                o.z = pack_bf16x2(fmaf(bf16lo(uv[k].z), g1[k].x, bf16lo(sv[k].z)), fmaf(bf16hi(uv[k].z), g1[k].y, bf16hi(sv[k].z)));
+                o.w = pack_bf16x2(fmaf(bf16lo(uv[k].w), g1[k].z, bf16lo(sv[k].w)), fmaf(bf16hi(uv[k].w), g1[k].w, bf16hi(sv[k].w)));
+                reinterpret_cast<uint4*>(y + row[k] * C)[c8] = o;
+            }
+        }
+    }
+}
+
+int se_residual_launch(const void* u, const float* gate, const void* sc, int shortcut_mode, void* y, int n_img, int S,
+                       int C, cudaStream_t stream) {
     FFR_CHECK_ARG(shortcut_mode >= 0 && shortcut_mode <= 2, "se_residual: shortcut_mode=%d", shortcut_mode);
-    const int rows = (S + 1) * (S + 1);
-    int chunks = (num_sms() * 4 + n_img - 1) / n_img;
-    const int max_chunks = (rows + 63) / 64;
-    if (chunks > max_chunks) chunks = max_chunks;
-    if (chunks < 1) chunks = 1;
-    dim3 grid(chunks, n_img);
+    const long long total_rows = (long long)n_img * (S + 1) * (S + 1);
+    const int rows_per_pass = (256 / (C / 8)) * 4;
+    long long grid = (total_rows + rows_per_pass - 1) / rows_per_pass;
+    const long long cap = (long long)num_sms() * 8;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
     const __nv_bfloat16* up = reinterpret_cast<const __nv_bfloat16*>(u);
     const __nv_bfloat16* sp = reinterpret_cast<const __nv_bfloat16*>(sc);
     __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
     switch (C) {
-        case 64:  se_residual_kernel<64><<<grid, 256, 0, stream>>>(up, pool, w1, w2, sp, shortcut_mode, yp, S); break;
-        case 128: se_residual_kernel<128><<<grid, 256, 0, stream>>>(up, pool, w1, w2, sp, shortcut_mode, yp, S); break;
-        case 256: se_residual_kernel<256><<<grid, 256, 0, stream>>>(up, pool, w1, w2, sp, shortcut_mode, yp, S); break;
-        case 512: se_residual_kernel<512><<<grid, 256, 0, stream>>>(up, pool, w1, w2, sp, shortcut_mode, yp, S); break;
+        case 64:  se_residual_kernel<64><<<(int)grid, 256, 0, stream>>>(up, gate, sp, shortcut_mode, yp, S, total_rows); break;
+        case 128: se_residual_kernel<128><<<(int)grid, 256, 0, stream>>>(up, gate, sp, shortcut_mode, yp, S, total_rows); break;
+        case 256: se_residual_kernel<256><<<(int)grid, 256, 0, stream>>>(up, gate, sp, shortcut_mode, yp, S, total_rows); break;
+        case 512: se_residual_kernel<512><<<(int)grid, 256, 0, stream>>>(up, gate, sp, shortcut_mode, yp, S, total_rows); break;
         default: return set_error(-1, "se_residual: unsupported C=%d", C);
     }
     return launch_status("se_residual_kernel");
@@ -388,26 +447,36 @@ int export_nchw_launch(const void* h, const float* scale, const float* shift, fl
 }
 
 // ----------------------------------------------------------------------------------------------
-// Embedding finish: f = l2_norm(acc + bias)  (model_ir_se50.py:13-16,141). One warp per row; D multiple of 32.
-// `acc` is the split-K fp32 accumulator of the folded head GEMM (BN2d, Linear, BN1d folded into W', b').
+// Embedding finish: f = l2_norm(sum_s acc[s] + bias)  (model_ir_se50.py:13-16,141). One warp per row; D = 512.
+// `acc` holds the per-split fp32 partial products of the folded head GEMM (BN2d, Linear, BN1d folded into W', b'),
+// [splits][rows][D], added here in split order (deterministic split-K).
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bias_l2norm_kernel(const float* __restrict__ acc, const float* __restrict__ bias,
-                                                          float* __restrict__ f, int rows, int D) {
+__global__ void __launch_bounds__(256) bias_l2norm_kernel(const float* __restrict__ acc, int splits, long long split_stride,
+                                                          const float* __restrict__ bias, float* __restrict__ f, int rows) {
+    constexpr int D = 512;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
+    float v[D / 32];
     float ss = 0.f;
-    for (int c = lane; c < D; c += 32) {
-        const float v = acc[(long long)row * D + c] + bias[c];
-        ss = fmaf(v, v, ss);
+#pragma unroll
+    for (int i = 0; i < D / 32; ++i) {
+        const int c = lane + 32 * i;
+        float a = acc[(long long)row * D + c];
+        for (int s = 1; s < splits; ++s) a += acc[(long long)s * split_stride + (long long)row * D + c];
+        v[i] = a + bias[c];
+        ss = fmaf(v[i], v[i], ss);
     }
     ss = warp_sum(ss);
     const float inv = 1.0f / sqrtf(ss);
-    for (int c = lane; c < D; c += 32) f[(long long)row * D + c] = (acc[(long long)row * D + c] + bias[c]) * inv;
+#pragma unroll
+    for (int i = 0; i < D / 32; ++i) f[(long long)row * D + lane + 32 * i] = v[i] * inv;
 }
 
-int bias_l2norm_launch(const float* acc, const float* bias, float* f, int rows, int D, cudaStream_t stream) {
-    bias_l2norm_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(acc, bias, f, rows, D);
+int bias_l2norm_launch(const float* acc, int splits, long long split_stride, const float* bias, float* f, int rows, int D,
+                       cudaStream_t stream) {
+    FFR_CHECK_ARG(D == 512, "bias_l2norm: D=%d", D);
+    bias_l2norm_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(acc, splits, split_stride, bias, f, rows);
     return launch_status("bias_l2norm_kernel");
 }
 

@@ -372,6 +372,25 @@ __global__ void __launch_bounds__(256) h9_avgpool_kernel(const float* __restrict
     *reinterpret_cast<float4*>(v + (long long)n * ldv + c0) = make_float4(s.x * k, s.y * k, s.z * k, s.w * k);
 }
 
+// the same over a bf16 H9 matrix (the eval path's stored feature map), 8 channels per thread
+__global__ void __launch_bounds__(256) h9_avgpool_bf16_kernel(const __nv_bfloat16* __restrict__ a, int lda,
+                                                              float* __restrict__ v, int ldv, int n_img, int C) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c8n = C / 8;
+    if (i >= (long long)n_img * c8n) return;
+    const int n = (int)(i / c8n), c0 = (int)(i % c8n) * 8;
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int pix = 0; pix < 49; ++pix) {
+        const uint4 t = __ldg(reinterpret_cast<const uint4*>(a + ((long long)n * 81 + h9_row_of_pixel(pix)) * lda + c0));
+        s[0] += bf16lo(t.x); s[1] += bf16hi(t.x); s[2] += bf16lo(t.y); s[3] += bf16hi(t.y);
+        s[4] += bf16lo(t.z); s[5] += bf16hi(t.z); s[6] += bf16lo(t.w); s[7] += bf16hi(t.w);
+    }
+    const float k = 1.0f / 49.0f;
+    float4* o = reinterpret_cast<float4*>(v + (long long)n * ldv + c0);
+    o[0] = make_float4(s[0] * k, s[1] * k, s[2] * k, s[3] * k);
+    o[1] = make_float4(s[4] * k, s[5] * k, s[6] * k, s[7] * k);
+}
+
 // fp32 NCHW (n,C,7,7) -> own rows of an fp32 H9 matrix (channel slot ch0, pitch ld): layout of the `dadd` gradient source
 __global__ void __launch_bounds__(256) nchw_to_h9_f32_kernel(const float* __restrict__ x, float* __restrict__ out, int ld,
                                                              int ch0, int C) {
@@ -494,6 +513,15 @@ FFR_API int ffr_h9_avgpool(const float* a, int lda, float* v, int ldv, int n_img
     if (total == 0) return 0;
     h9_avgpool_kernel<<<(int)((total + 255) / 256), 256, 0, S_(stream)>>>(a, lda, v, ldv, n_img, C);
     return launch_status("h9_avgpool_kernel");
+}
+
+FFR_API int ffr_h9_avgpool_bf16(const void* a, int lda, float* v, int ldv, int n_img, int C, ffr_stream_t stream) {
+    FFR_CHECK_ARG(a && v && C % 8 == 0 && lda % 8 == 0 && ldv % 4 == 0, "ffr_h9_avgpool_bf16: bad arguments");
+    const long long total = (long long)n_img * (C / 8);
+    if (total == 0) return 0;
+    h9_avgpool_bf16_kernel<<<(int)((total + 255) / 256), 256, 0, S_(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(a), lda, v, ldv, n_img, C);
+    return launch_status("h9_avgpool_bf16_kernel");
 }
 
 }  // extern "C"

@@ -125,6 +125,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
     const long long t_begin = clock64();
     for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++it) {
         const int t = work / p.num_splits;
+        const int split = work - t * p.num_splits;
         const int n_tile = t % p.num_n_tiles;
         const int m_group = t / p.num_n_tiles;
         const int n0 = n_tile * BN;
@@ -300,7 +301,8 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
             }
             if (flags & EPI_OUT_F32) {
                 if (m < p.M) {
-                    float4* o = reinterpret_cast<float4*>(p.out_f32 + (long long)m * p.Cout + nc0 + c0);
+                    float4* o = reinterpret_cast<float4*>(p.out_f32 + (long long)split * p.out_f32_split_stride +
+                                                          (long long)m * p.Cout + nc0 + c0);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) o[q] = make_float4(x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
                 }
@@ -353,9 +355,15 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
                     for (int q = 0; q < 8; ++q) red_add_f32x4(o + q * 4, x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
                 }
             } else if (flags & EPI_POOL) {    // x is already zero on invalid rows
+                // deterministic: one plain store per (32-row block, image slot, channel); else atomics into pool
+                float* part = (p.pool_part != nullptr)
+                    ? p.pool_part + ((long long)((m_group * SUB + sub) * 4 + quad) * 2) * p.Cout + nc0 + c0 + lane : nullptr;
                 if (n_lo == n_hi) {
                     const float s = warp_colsum32(x, lane);
-                    if (n_lo < p.n_img) atomicAdd(p.pool + (long long)n_lo * p.Cout + nc0 + c0 + lane, s);
+                    if (n_lo < p.n_img) {
+                        if (part) part[0] = s;
+                        else atomicAdd(p.pool + (long long)n_lo * p.Cout + nc0 + c0 + lane, s);
+                    }
                 } else {               // the warp's 32 rows straddle two images
                     float xb[32];
 #pragma unroll
@@ -365,8 +373,14 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
                     }
                     const float sa = warp_colsum32(x, lane);
                     const float sb = warp_colsum32(xb, lane);
-                    if (n_lo < p.n_img) atomicAdd(p.pool + (long long)n_lo * p.Cout + nc0 + c0 + lane, sa);
-                    if (n_hi < p.n_img) atomicAdd(p.pool + (long long)n_hi * p.Cout + nc0 + c0 + lane, sb);
+                    if (n_lo < p.n_img) {
+                        if (part) part[0] = sa;
+                        else atomicAdd(p.pool + (long long)n_lo * p.Cout + nc0 + c0 + lane, sa);
+                    }
+                    if (n_hi < p.n_img) {
+                        if (part) part[p.Cout] = sb;
+                        else atomicAdd(p.pool + (long long)n_hi * p.Cout + nc0 + c0 + lane, sb);
+                    }
                 }
             }
         }
@@ -853,7 +867,9 @@ int conv_gemm_launch(const void* a, long long a_rows, int a_cols, int a_ld, cons
     p.num_splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
     p.num_m_tiles = pix ? p.pix_side * p.pix_side * p.pix_iblocks : (p.M + BLOCK_M - 1) / BLOCK_M;
     p.num_n_tiles = p.Cout / BN;
-    FFR_CHECK_ARG(p.num_splits == 1 || (p.flags & EPI_OUT_F32_ATOMIC), "conv_gemm: split-K needs the atomic epilogue");
+    FFR_CHECK_ARG(p.num_splits == 1 || (p.flags & EPI_OUT_F32_ATOMIC) ||
+                  ((p.flags & EPI_OUT_F32) && p.out_f32_split_stride >= (long long)p.M * p.Cout),
+                  "conv_gemm: split-K needs the atomic epilogue or per-split fp32 outputs");
     if (p.flags & EPI_SCATTER)
         FFR_CHECK_ARG(p.scatter && p.scatter_n >= 1 && p.scatter_n <= 8 && p.out && p.out_rows_per_img > 0,
                       "conv_gemm: bad scatter table");

@@ -65,8 +65,13 @@ struct ConvGemmParams {
     __nv_bfloat16* out;    // bf16 output, row pitch ldo elements
     int ldo;
     int s2d_So;            // EPI_OUT_S2D: output grid is (So+1)x(So+1) rows per image, 4*Cout channels
-    float* pool;           // [n_img, Cout]
+    float* pool;           // [n_img, Cout] sums, atomic accumulation (pixel-major tiles, or pool_part == nullptr)
+    float* pool_part;      // deterministic alternative for row-major tiles: [ceil(M/32)][2][Cout] per-32-row-block sums
+                           // (slot 0: the image of the block's first row, slot 1: the next image when the block straddles
+                           // two), plain stores; reduced per image in a fixed order by se_gate_kernel
     float* out_f32;        // [M, Cout]
+    long long out_f32_split_stride;   // EPI_OUT_F32 with split-K: split s stores its partial product at
+                                      // out_f32 + s * stride (plain stores, summed in a fixed order by the consumer)
     const __nv_bfloat16* res;  // residual, row pitch ldres
     int ldres;
     float* stats;          // [2, Cout] : sum, sum of squares (atomic accumulation), used when stats_part == nullptr

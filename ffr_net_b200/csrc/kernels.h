@@ -12,12 +12,15 @@ int stem_launch(const float* x, const float* w, const float* b, const float* a, 
                 cudaStream_t stream);
 int stem_u8_launch(const unsigned char* img, const unsigned char* flip, int swap_rb, const float* w, const float* b,
                    const float* a, void* out, int n_img, int S, cudaStream_t stream);
-int se_residual_launch(const void* u, const float* pool, const float* w1, const float* w2, const void* sc,
-                       int shortcut_mode, void* y, int n_img, int S, int C, cudaStream_t stream);
+int se_gate_launch(const float* pool_part, int dense, const float* w1, const float* w2, float* gate, float* sums,
+                   int n_img, int S, int C, cudaStream_t stream);
+int se_residual_launch(const void* u, const float* gate, const void* sc, int shortcut_mode, void* y, int n_img, int S,
+                       int C, cudaStream_t stream);
 int subsample2_launch(const void* x, void* out, int n_img, int So, int C, cudaStream_t stream);
 int export_nchw_launch(const void* h, const float* scale, const float* shift, float* y, int n_img, int S, int C,
                        cudaStream_t stream);
-int bias_l2norm_launch(const float* acc, const float* bias, float* f, int rows, int D, cudaStream_t stream);
+int bias_l2norm_launch(const float* acc, int splits, long long split_stride, const float* bias, float* f, int rows, int D,
+                       cudaStream_t stream);
 void set_use_window(bool on);
 void set_debug_counters(unsigned long long* dptr);
 struct PrepParams {

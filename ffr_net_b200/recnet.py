@@ -284,7 +284,6 @@ class RecNet(nn.Module):
         ws.cm = h9(1536)
         ws.c512 = [h9(512) for _ in range(2)]
         ws.d512 = [h9(512) for _ in range(3)]
-        ws.pool = torch.empty(n, 512, dtype=torch.float32, device=device)
         self._ws[slot] = (key, ws)
         return ws
 
@@ -428,10 +427,12 @@ class RecNet(nn.Module):
         conv("ChannelFlipMerge.1.conv2", ws.c512[1], ws.cm, res=ws.c512[0], scatter=pk.t_h9[512])
         conv("Conv4Merge.0", ws.cm, ws.d512[0])
         conv("Conv4Merge.1.conv1", ws.d512[0], ws.d512[1])
-        conv("Conv4Merge.1.conv2", ws.d512[1], ws.d512[2], res=ws.d512[0], pool=ws.pool)
+        conv("Conv4Merge.1.conv2", ws.d512[1], ws.d512[2], res=ws.d512[0])
 
+        # pool5_7x7 (:424) over the stored map in a fixed order (an epilogue reduction would need atomics: the pooled
+        # embedding is bit-reproducible this way)
         v = out_v if out_v is not None else torch.empty(n, 512, dtype=torch.float32, device=dev)
-        chk(lib.ffr_scale_f32(P(ws.pool), P(v), n * 512, 1.0 / 49.0, st), "avgpool")
+        chk(lib.ffr_h9_avgpool_bf16(P(ws.d512[2]), ws.d512[2].shape[1], P(v), 512, n, 512, st), "avgpool")
         feat_new = None
         if want_map:
             feat_new = out_map if out_map is not None else torch.empty(n, 512, 7, 7, dtype=torch.float32, device=dev)

@@ -42,7 +42,7 @@ typedef void* ffr_stream_t; /* cudaStream_t */
 #define FFR_EPI_PRELU          (1u << 2)  /* max(x,0) + slope[co]*min(x,0) */
 #define FFR_EPI_GEOM           (1u << 3)  /* rows carry (image, h, w): row = n*rows_per_img + h*Wp + w; a row is valid iff
                                              h0 <= h < h0+S and h0 <= w < h0+S (or, with SCATTER, iff it has a destination) */
-#define FFR_EPI_POOL           (1u << 4)  /* atomically add per-(image,co) sums of the valid rows into pool[n_img][Cout] */
+#define FFR_EPI_POOL           (1u << 4)  /* per-(image,co) sums of the valid rows: atomically into pool[n_img][Cout] */
 #define FFR_EPI_OUT_S2D        (1u << 5)  /* bf16 rows go to the space-to-depth map of the following stride-2 conv */
 #define FFR_EPI_OUT_F32_ATOMIC (1u << 6)  /* split-K: atomicAdd fp32 into out_f32[M][Cout] */
 #define FFR_EPI_SIGMOID        (1u << 7)
@@ -110,12 +110,14 @@ FFR_API int ffr_conv3x3_bnpre_prelu_fwd(const void* x, int n_img, int S, int Cin
                                 const float* bias9, const float* slope, void* out, int out_s2d, ffr_stream_t stream);
 
 /* Conv2d(C,Cout,3,stride,pad 1) + BatchNorm (model_ir_se50.py:69-70; scale folded into wp, shift = bias) and the
- * SE squeeze: per-(image,channel) sums of the result land in pool[n_img][Cout] (:31; the call zeroes it, then the
- * epilogue adds atomically).
+ * SE squeeze (:31): the epilogue stores the column sums of every 32-row block of the output map into pool_part
+ * (ffr_se_pool_part_floats(n_img, S/stride, Cout) floats, every used entry written exactly once - no zeroing, no
+ * atomics); ffr_se_gate_fwd adds them per image. pool_part may be NULL (no squeeze).
  * stride 1: x is flat SxS. stride 2: x is the space-to-depth map written by ffr_conv3x3_bnpre_prelu_fwd
  * (rows of the (S/2+1)^2 grid, 4*C channels); S is the INPUT size. Output is flat (S/stride)x(S/stride). */
+FFR_API long long ffr_se_pool_part_floats(int n_img, int So, int Cout);
 FFR_API int ffr_conv3x3_bn_pool_fwd(const void* x, int n_img, int S, int C, int stride, const void* wp, int Cout,
-                            const float* bias, void* out, float* pool, ffr_stream_t stream);
+                            const float* bias, void* out, float* pool_part, ffr_stream_t stream);
 
 /* Conv2d(Cin,Cout,1,stride 2)+BatchNorm shortcut (model_ir_se50.py:62-64) on an already subsampled flat map. */
 FFR_API int ffr_conv1x1_bn_fwd(const void* xs, int n_img, int S, int Cin, const void* wp, int Cout, const float* bias,
@@ -136,11 +138,15 @@ FFR_API int ffr_stem_fwd(const float* x, const float* w, const float* b, const f
 FFR_API int ffr_stem_u8_fwd(const unsigned char* img, const unsigned char* flip, int swap_rb, const float* w,
                             const float* b, const float* a, void* out, int n_img, int S, ffr_stream_t stream);
 
-/* SEModule gate + residual add (model_ir_se50.py:29-36,73-76): y = u*sigmoid(W2 relu(W1 mean(u))) + shortcut.
- * pool = per-(image,channel) sums of u; shortcut_mode 0: same-grid x, 1: x on the 2Sx2S grid (MaxPool2d(1,2)),
- * 2: same-grid conv shortcut. w1 [C/16][C], w2 [C][C/16] fp32. */
-FFR_API int ffr_se_residual_fwd(const void* u, const float* pool, const float* w1, const float* w2, const void* shortcut,
-                        int shortcut_mode, void* y, int n_img, int S, int C, ffr_stream_t stream);
+/* SEModule (model_ir_se50.py:29-36,73-76): y = u*sigmoid(W2 relu(W1 mean(u))) + shortcut, in two launches.
+ * ffr_se_gate_fwd: gate [n_img][C] fp32 from the partial sums ffr_conv3x3_bn_pool_fwd stored (added per image in a
+ * fixed order: bit-reproducible); sums (optional) receives the per-(image,channel) sums of u. w1 [C/16][C], w2 [C][C/16].
+ * ffr_se_residual_fwd: one pass over the map; shortcut_mode 0: same-grid x, 1: x on the 2Sx2S grid (MaxPool2d(1,2)),
+ * 2: same-grid conv shortcut. */
+FFR_API int ffr_se_gate_fwd(const float* pool_part, const float* w1, const float* w2, float* gate, float* sums, int n_img,
+                            int S, int C, ffr_stream_t stream);
+FFR_API int ffr_se_residual_fwd(const void* u, const float* gate, const void* shortcut, int shortcut_mode, void* y,
+                                int n_img, int S, int C, ffr_stream_t stream);
 
 /* y = bn(h) exported as fp32 NCHW (model_ir_se50.py:126,139). */
 FFR_API int ffr_export_nchw_fwd(const void* h, const float* scale, const float* shift, float* y, int n_img, int S, int C,
@@ -148,7 +154,9 @@ FFR_API int ffr_export_nchw_fwd(const void* h, const float* scale, const float* 
 
 /* output_layer (BatchNorm2d -> Dropout(eval) -> Flatten -> Linear(25088,512) -> BatchNorm1d) + l2_norm
  * (model_ir_se50.py:121-125,13-16,141). wp: folded bf16 weights [512][(S+1)^2*C] over the flat rows of one image
- * (zero columns at pad pixels), bias [512] folded; acc [n_img][512] fp32 scratch; f [n_img][512] fp32. */
+ * (zero columns at pad pixels), bias [512] folded; acc: fp32 scratch of ffr_head_workspace_floats() elements (one partial
+ * product per K split, added in split order: bit-reproducible); f [n_img][512] fp32. */
+FFR_API long long ffr_head_workspace_floats(int n_img, int S, int C);
 FFR_API int ffr_head_fwd(const void* h, int n_img, int S, int C, const void* wp, const float* bias, float* acc, float* f,
                  ffr_stream_t stream);
 
@@ -239,6 +247,8 @@ FFR_API int ffr_nchw_to_h9_f32(const float* x, float* out, int ld, int ch0, int 
 
 /* v[n][c] = mean over the 49 valid rows of an fp32 H9 matrix (AvgPool2d(7), recnet.py:423). */
 FFR_API int ffr_h9_avgpool(const float* a, int lda, float* v, int ldv, int n_img, int C, ffr_stream_t stream);
+/* the same over a bf16 H9 matrix (the eval path pools its stored feature map: fixed order, bit-reproducible) */
+FFR_API int ffr_h9_avgpool_bf16(const void* a, int lda, float* v, int ldv, int n_img, int C, ffr_stream_t stream);
 
 /* Weight gradient, general form of ffr_wgrad3x3: dw[co][ci][t] (+)= sum_p dz[p][co] x[p + shift_t][x_ch0 + ci] over P rows;
  * ntaps 9 (3x3 on the H9 grid, P = n*81) or 1 (plain Y^T X, e.g. Linear weights); operands both bf16 (f16 = 0) or both

@@ -2,9 +2,11 @@
 Every rank computes the gradients of its own shard (BatchNorm statistics per rank, like the reference's per-replica
 data_parallel), the bucketed all-reduce averages them during backward; the result must equal the average of the per-shard
 gradients computed on ONE GPU, and after clip + Adam every rank must hold identical parameters."""
+import faulthandler
 import json
 import os
 import sys
+import time
 
 import torch
 import torch.distributed as dist
@@ -33,8 +35,16 @@ def grads_of(tr, data):
     return {k: p.grad.clone() for k, p in tr.recnet.named_parameters()}
 
 
+T0 = time.time()
+
+
+def note(rank, msg):
+    print("[dp_worker rank %d %6.1fs] %s" % (rank, time.time() - T0, msg), file=sys.stderr, flush=True)
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    faulthandler.dump_traceback_later(int(os.environ.get("DP_WORKER_DUMP_AFTER", "150")), exit=True)   # a hang names its line
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = 32
@@ -46,17 +56,29 @@ def main():
         return Trainer(default_opts(lr=1e-3, **kw), recnet=rec, encoder_weights=bsd)
     out = {}
     # (1) data-parallel gradients: bucketed / overlapped exchange, and the single flat all-reduce
+    note(rank, "process group up")
     g_overlap = grads_of(make(overlap_allreduce=True), shard(rank, n))
+    note(rank, "overlapped exchange done")
     g_flat = grads_of(make(overlap_allreduce=False), shard(rank, n))
+    note(rank, "flat exchange done")
     out["overlap_equals_flat"] = all(torch.equal(g_overlap[k], g_flat[k]) for k in g_flat)
     # (2) expected: average of the per-shard gradients, all computed on this GPU without any exchange
     per_shard = [grads_of(make(data_parallel=False), shard(r, n)) for r in range(world)]
-    worst = 0.0
-    for k in g_flat:
-        exp = sum(g[k].double() for g in per_shard) / world
-        err = ((g_flat[k].double() - exp).norm() / (exp.norm() + 1e-30)).item()
-        worst = max(worst, err)
-    out["worst_rel_err_vs_single_gpu_average"] = worst
+    def errors(got):
+        e = {}
+        for k in got:
+            exp = sum(g[k].double() for g in per_shard) / world
+            e[k] = ((got[k].double() - exp).norm() / (exp.norm() + 1e-30)).item()
+        return e
+    e_flat, e_overlap = errors(g_flat), errors(g_overlap)
+    out["worst_rel_err_vs_single_gpu_average"] = max(e_flat.values())
+    out["worst_rel_err_overlap_vs_single_gpu_average"] = max(e_overlap.values())
+    out["worst_params_flat"] = sorted(e_flat.items(), key=lambda kv: -kv[1])[:4]
+    out["worst_params_overlap"] = sorted(e_overlap.items(), key=lambda kv: -kv[1])[:4]
+    # the rank's own shard, computed twice by two trainer instances, must be bit-identical (deterministic engine)
+    again = grads_of(make(data_parallel=False), shard(rank, n))
+    out["own_shard_reproducible"] = all(torch.equal(again[k], per_shard[rank][k]) for k in again)
+    note(rank, "single-GPU shard gradients done")
     # (3) a captured step under DP: every rank ends with identical parameters
     tr = make()
     data = shard(rank, n)
@@ -64,6 +86,7 @@ def main():
     for _ in range(3):
         tr.step(*data)
     torch.cuda.synchronize()
+    note(rank, "captured steps done")
     flat = torch.cat([p.detach().reshape(-1) for p in tr.recnet.parameters()])
     parts = [torch.empty_like(flat) for _ in range(world)]
     dist.all_gather(parts, flat)
@@ -71,7 +94,12 @@ def main():
     out["finite"] = bool(torch.isfinite(flat).all())
     if rank == 0:
         print("DP_RESULT " + json.dumps(out), flush=True)
-    dist.destroy_process_group()
+    dist.barrier()
+    torch.cuda.synchronize()
+    del tr                        # the captured graph holds NCCL kernels: destroying the process group under it hangs
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":

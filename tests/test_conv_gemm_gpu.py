@@ -135,9 +135,15 @@ def test_conv3x3_bn_pool(lib, n, S, c, cout, stride, backbone_tiles):
     so = S // stride
     rows = n * (so + 1) * (so + 1)
     out = torch.full((rows, cout), 3.0, dtype=torch.bfloat16, device="cuda")
-    pool = torch.full((n, cout), 5.0, dtype=torch.float32, device="cuda")
-    rc = lib.ffr_conv3x3_bn_pool_fwd(P(xin), n, S, c, stride, P(wp), cout, P(b1), P(out), P(pool), _stream())
+    # squeeze partial sums: never zeroed by the caller (garbage-filled here); ffr_se_gate_fwd adds them per image
+    part = torch.full((max(lib.ffr_se_pool_part_floats(n, so, cout), n * cout),), 7.0e3, dtype=torch.float32, device="cuda")
+    rc = lib.ffr_conv3x3_bn_pool_fwd(P(xin), n, S, c, stride, P(wp), cout, P(b1), P(out), P(part), _stream())
     _lib.check(rc)
+    fc1 = torch.randn(cout // 16, cout, generator=g, device="cuda") / cout ** 0.5
+    fc2 = torch.randn(cout, cout // 16, generator=g, device="cuda") / 2
+    gate = torch.empty(n, cout, device="cuda")
+    pool = torch.empty(n, cout, device="cuda")
+    _lib.check(lib.ffr_se_gate_fwd(P(part), P(fc1), P(fc2), P(gate), P(pool), n, so, cout, _stream()))
     torch.cuda.synchronize()
     xb = x.to(torch.bfloat16).float()
     wb = wp.float().reshape(cout, 3, 3, c).permute(0, 3, 1, 2)
@@ -148,6 +154,40 @@ def test_conv3x3_bn_pool(lib, n, S, c, cout, stride, backbone_tiles):
     assert layout.flat_pad_rows(out, n, so, cout).abs().max().item() == 0.0
     ref_pool = ref.sum(dim=(2, 3))
     assert (pool - ref_pool).abs().max().item() <= 2e-3 * scale * so * so ** 0.5 + 1e-3
+    # gate = sigmoid(W2 relu(W1 mean)) (model_ir_se50.py:29-36) on the kernel's own sums: fp32, 1e-5
+    ref_gate = torch.sigmoid(torch.relu((pool / (so * so)) @ fc1.t()) @ fc2.t())
+    assert (gate - ref_gate).abs().max().item() <= 1e-5
+    if backbone_tiles != "pixmajor":       # row-major tiles: plain stores, fixed order -> bit-reproducible
+        out2, pool2, gate2 = torch.empty_like(out), torch.empty_like(pool), torch.empty_like(gate)
+        part.fill_(-3.0)
+        _lib.check(lib.ffr_conv3x3_bn_pool_fwd(P(xin), n, S, c, stride, P(wp), cout, P(b1), P(out2), P(part), _stream()))
+        _lib.check(lib.ffr_se_gate_fwd(P(part), P(fc1), P(fc2), P(gate2), P(pool2), n, so, cout, _stream()))
+        torch.cuda.synchronize()
+        assert torch.equal(out, out2) and torch.equal(pool, pool2) and torch.equal(gate, gate2)
+
+
+@pytest.mark.parametrize("n,S,C,mode", [(3, 14, 256, 0), (2, 7, 512, 0), (5, 28, 64, 1), (2, 56, 64, 2), (1, 7, 128, 2)])
+def test_se_residual_isolated(lib, n, S, C, mode):
+    """ffr_se_residual_fwd alone: y = u * gate[n] + shortcut on the flat map (model_ir_se50.py:36,73-76), against torch on
+    the same bf16 inputs; bound: one bf16 rounding of the result. mode 1 reads the shortcut from the (2S)x(2S) grid
+    (MaxPool2d(1, 2) = subsampling), mode 0 / 2 from the same grid."""
+    g = torch.Generator(device="cuda").manual_seed(S * C + mode)
+    u = torch.randn(n, C, S, S, generator=g, device="cuda")
+    gate = torch.rand(n, C, generator=g, device="cuda")
+    S_sc = 2 * S if mode == 1 else S
+    sc = torch.randn(n, C, S_sc, S_sc, generator=g, device="cuda")
+    uf, scf = layout.to_flat(u), layout.to_flat(sc)
+    y = torch.full_like(uf, 9.0)
+    _lib.check(lib.ffr_se_residual_fwd(P(uf), P(gate), P(scf), mode, P(y), n, S, C, _stream()))
+    torch.cuda.synchronize()
+    ub = layout.from_flat(uf, n, S, C)
+    sb = layout.from_flat(scf, n, S_sc, C)
+    if mode == 1:
+        sb = sb[:, :, ::2, ::2]
+    ref = ub * gate.view(n, C, 1, 1) + sb
+    got = layout.from_flat(y, n, S, C)
+    assert (got - ref).abs().max().item() <= 2 ** -8 * ref.abs().max().item()
+    assert layout.flat_pad_rows(y, n, S, C).abs().max().item() == 0.0          # pad rows: 0 * gate + 0
 
 
 def test_conv3x3_s2d_output_roundtrip(lib):

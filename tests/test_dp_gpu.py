@@ -19,7 +19,7 @@ def test_data_parallel_step_two_ranks(lib):
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29611", os.path.join(ROOT, "tests", "dp_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     lines = [l for l in r.stdout.splitlines() if l.startswith("DP_RESULT ")]
     assert r.returncode == 0 and lines, (r.stdout[-2000:], r.stderr[-3000:])
     out = json.loads(lines[-1][len("DP_RESULT "):])

@@ -76,6 +76,20 @@ def test_recnet_batch_invariance(models):
     assert (v5[3:4] - v1).abs().max().item() <= 1e-5 * v1.abs().max().item() + 1e-6
 
 
+@pytest.mark.parametrize("n", [3, 130])
+def test_recnet_eval_bit_reproducible(models, n):
+    """No atomics on the eval path (the pooled embedding is a fixed-order sum over the stored map): same bits run after run,
+    on row-major (n=3) and pixel-major (n=130) tiles."""
+    sd, m = models
+    x = (torch.randn(n, 512, 7, 7, generator=torch.Generator().manual_seed(n)) * 0.3).cuda()
+    with torch.no_grad():
+        v0, m0 = m(x)
+        v0, m0 = v0.clone(), m0.clone()
+        for _ in range(3):
+            v1, m1 = m(x)
+            assert torch.equal(v1, v0) and torch.equal(m1, m0)
+
+
 def test_recnet_rejects_cpu(models):
     sd, m = models
     with pytest.raises(RuntimeError):
