@@ -23,9 +23,11 @@ struct GemmCfg {
     static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int STAGES_PAIR = (BN == 256) ? 6 : 8;       // CTA pairs: half of the weight tile per CTA
     static constexpr int TMEM_COLS = 2 * BN;      // double-buffered fp32 accumulator, 128 lanes x BN columns each
     static constexpr int PARAM_FLOATS = 10 * BN;  // 9 border-class biases (or 1) + PReLU slopes
     static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 256 /*barriers*/ + PARAM_FLOATS * 4;
+    static constexpr int SMEM_BYTES_PAIR = 1024 + STAGES_PAIR * (A_STAGE_BYTES + B_STAGE_BYTES / 2) + 256 + PARAM_FLOATS * 4;
 };
 
 // mbarrier wait that adds the time spent to a counter when profiling counters are enabled
@@ -69,10 +71,10 @@ __device__ __forceinline__ void fast_divmod(int m, int d, float inv_d, int& q, i
 // A work item is SUB consecutive 128-row tiles (SUB accumulators side by side in the TMEM buffer).
 // EPI_PIXMAJOR: M tile -> (output pixel, first image, mask of taps whose source pixel exists)
 struct PixTile { int ho, wo, img0; uint32_t tapmask; };
-__device__ __forceinline__ PixTile pix_tile(const ConvGemmParams& p, int m_tile) {
+// tile = (output pixel q, block ib of 128 images); ib >= pix_iblocks is an empty tile (CTA pairs with an odd block count)
+__device__ __forceinline__ PixTile pix_tile_qi(const ConvGemmParams& p, int q, int ib) {
     PixTile t;
-    const int q = m_tile / p.pix_iblocks;
-    t.img0 = (m_tile - q * p.pix_iblocks) * BLOCK_M;
+    t.img0 = ib * BLOCK_M;
     const int qh = q / p.pix_side;
     t.ho = qh + p.pix_off;
     t.wo = q - qh * p.pix_side + p.pix_off;
@@ -84,6 +86,10 @@ __device__ __forceinline__ PixTile pix_tile(const ConvGemmParams& p, int m_tile)
         if (hs >= p.pix_src_lo && hs <= p.pix_src_hi && ws >= p.pix_src_lo && ws <= p.pix_src_hi) t.tapmask |= 1u << tap;
     }
     return t;
+}
+__device__ __forceinline__ PixTile pix_tile(const ConvGemmParams& p, int m_tile) {
+    const int q = m_tile / p.pix_iblocks;
+    return pix_tile_qi(p, q, m_tile - q * p.pix_iblocks);
 }
 
 // 16-bit pair -> fp32 (bf16 by default, fp16 when f16 is set) and back
@@ -103,11 +109,37 @@ __device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Which work items this CTA's epilogue walks and which M tile a (work item, sub-tile) is. Single CTAs: items
+// blockIdx.x, +gridDim.x, ... and tile = m_group * SUB + sub. CTA pairs (conv_win2_kernel): the pair walks items
+// cluster_id, +num_clusters, ...; an item is two M tiles, CTA rank r owns tile 2 * m_group + r; the non-leader CTA
+// returns its accumulator buffers to the LEADER's tempty barrier (the MMA issuer lives there).
+struct EpiSched {
+    int work0, work_stride, num_work;
+    int tile_mul, tile_add;
+    int pix_ibp;                 // > 0 (pixel-major CTA pairs): image-block PAIRS per pixel; m_group = q * pix_ibp + pair,
+                                 // this CTA owns image block 2 * pair + tile_add of pixel q
+    uint32_t tempty_remote;      // 0, or the shared::cluster address of the leader's tempty_bar[0]
+};
+
+template <int BN, int SUB>
+__device__ __forceinline__ EpiSched epi_sched_single(const ConvGemmParams& p) {
+    EpiSched es;
+    es.work0 = blockIdx.x;
+    es.work_stride = gridDim.x;
+    es.num_work = ((p.num_m_tiles + SUB - 1) / SUB) * p.num_n_tiles * p.num_splits;
+    es.tile_mul = 1;
+    es.tile_add = 0;
+    es.pix_ibp = 0;
+    es.tempty_remote = 0;
+    return es;
+}
+
 template <int BN, int SUB>
 __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uint32_t tmem_base, uint64_t* tfull_bar,
-                                              uint64_t* tempty_bar, float* sparam, const int warp, const int lane) {
+                                              uint64_t* tempty_bar, float* sparam, const int warp, const int lane,
+                                              const EpiSched es) {
     constexpr int HALF = BN / 2;                 // columns per epilogue warp
-    const int num_work = ((p.num_m_tiles + SUB - 1) / SUB) * p.num_n_tiles * p.num_splits;
+    const int num_work = es.num_work;
     const int quad = warp & 3;                   // TMEM lane quadrant == warp % 4
     const int chalf = warp >> 2;                    // which half of the accumulator columns
     const int row_in_tile = quad * 32 + lane;
@@ -123,7 +155,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
     const bool timed = p.dbg != nullptr;
     long long w_e = 0;
     const long long t_begin = clock64();
-    for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++it) {
+    for (int work = es.work0; work < num_work; work += es.work_stride, ++it) {
         const int t = work / p.num_splits;
         const int split = work - t * p.num_splits;
         const int n_tile = t % p.num_n_tiles;
@@ -145,12 +177,21 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
 
 #pragma unroll 1
         for (int sub = 0; sub < SUB; ++sub) {
-        int m = (m_group * SUB + sub) * BLOCK_M + row_in_tile;
+        int m_tile = (m_group * SUB + sub) * es.tile_mul + es.tile_add;
+        bool tile_ok = m_tile < p.num_m_tiles;
+        int pq = 0, pib = 0;
+        if (es.pix_ibp > 0) {
+            pq = m_group / es.pix_ibp;
+            pib = 2 * (m_group - pq * es.pix_ibp) + es.tile_add;
+            tile_ok = pib < p.pix_iblocks;
+            m_tile = pq * p.pix_iblocks + pib;
+        }
+        int m = m_tile * BLOCK_M + row_in_tile;
         int n_img = 0, h = 0, w = 0, r_local = 0;
         bool valid = m < p.M;
         int cls = 0;
         if (flags & EPI_PIXMAJOR) {              // row = image (img0 + row_in_tile) at the tile's pixel
-            const PixTile pt = pix_tile(p, m_group);
+            const PixTile pt = (es.pix_ibp > 0) ? pix_tile_qi(p, pq, pib) : pix_tile(p, m_tile);
             n_img = pt.img0 + row_in_tile;
             r_local = pt.ho * p.Wp + pt.wo;
             m = n_img * p.rows_per_img + r_local;
@@ -340,9 +381,11 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
                 const float s1 = warp_colsum32(xs, lane);
                 const float s2 = warp_colsum32(sq, lane);
                 if (p.stats_part != nullptr) {     // one plain store per (M tile, quadrant, channel): deterministic
-                    float* o = p.stats_part + ((long long)((m_group * SUB + sub) * 4 + quad) * 2) * p.Cout + nc0 + c0 + lane;
-                    o[0] = s1;
-                    o[p.Cout] = s2;
+                    if (tile_ok) {
+                        float* o = p.stats_part + ((long long)(m_tile * 4 + quad) * 2) * p.Cout + nc0 + c0 + lane;
+                        o[0] = s1;
+                        o[p.Cout] = s2;
+                    }
                 } else {
                     atomicAdd(p.stats + nc0 + c0 + lane, s1);
                     atomicAdd(p.stats + p.Cout + nc0 + c0 + lane, s2);
@@ -356,13 +399,13 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
                 }
             } else if (flags & EPI_POOL) {    // x is already zero on invalid rows
                 // deterministic: one plain store per (32-row block, image slot, channel); else atomics into pool
-                float* part = (p.pool_part != nullptr)
-                    ? p.pool_part + ((long long)((m_group * SUB + sub) * 4 + quad) * 2) * p.Cout + nc0 + c0 + lane : nullptr;
+                float* part = (p.pool_part != nullptr && tile_ok)
+                    ? p.pool_part + ((long long)(m_tile * 4 + quad) * 2) * p.Cout + nc0 + c0 + lane : nullptr;
                 if (n_lo == n_hi) {
                     const float s = warp_colsum32(x, lane);
                     if (n_lo < p.n_img) {
                         if (part) part[0] = s;
-                        else atomicAdd(p.pool + (long long)n_lo * p.Cout + nc0 + c0 + lane, s);
+                        else if (p.pool_part == nullptr) atomicAdd(p.pool + (long long)n_lo * p.Cout + nc0 + c0 + lane, s);
                     }
                 } else {               // the warp's 32 rows straddle two images
                     float xb[32];
@@ -375,11 +418,11 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
                     const float sb = warp_colsum32(xb, lane);
                     if (n_lo < p.n_img) {
                         if (part) part[0] = sa;
-                        else atomicAdd(p.pool + (long long)n_lo * p.Cout + nc0 + c0 + lane, sa);
+                        else if (p.pool_part == nullptr) atomicAdd(p.pool + (long long)n_lo * p.Cout + nc0 + c0 + lane, sa);
                     }
                     if (n_hi < p.n_img) {
                         if (part) part[p.Cout] = sb;
-                        else atomicAdd(p.pool + (long long)n_hi * p.Cout + nc0 + c0 + lane, sb);
+                        else if (p.pool_part == nullptr) atomicAdd(p.pool + (long long)n_hi * p.Cout + nc0 + c0 + lane, sb);
                     }
                 }
             }
@@ -397,7 +440,8 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
         }
         }   // sub
         tc_fence_before();
-        mbar_arrive(&tempty_bar[acc]);
+        if (es.tempty_remote) mbar_arrive_cluster(es.tempty_remote + acc * 8);
+        else mbar_arrive(&tempty_bar[acc]);
     }
     if (timed && threadIdx.x == 0) {
         atomicAdd(p.dbg + DBG_EPI_WAIT, (unsigned long long)w_e);
@@ -405,27 +449,37 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
     }
 }
 
-template <int BN>
+// PAIR: CTA pairs (cluster of 2, tcgen05 cta_group::2). A work item is two M tiles x one N tile: CTA rank r loads the A
+// tile of ITS M tile and rows [r * BN/2, (r+1) * BN/2) of the weight tile; the leader issues M = 256 MMAs that read both
+// CTAs' shared memory. Per SM the weight bytes halve: the tile-per-tap kernel streams 16 KB (A) + 32 KB (B) per 512 MMA
+// cycles at BN = 256 = 96 B/cycle/SM with single CTAs — more than twice what the L2 delivers when all SMs read
+// (~43 B/cycle/SM) — and 64 B/cycle/SM in pairs. Pixel-major tiles pair two image blocks of the SAME pixel (same
+// tap mask); with batched B both tiles must share a batch (b_mtile_div even).
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const ConvGemmParams p) {
     using Cfg = GemmCfg<BN>;
-    constexpr int STAGES = Cfg::STAGES;
+    constexpr int B_BYTES = PAIR ? Cfg::B_STAGE_BYTES / 2 : Cfg::B_STAGE_BYTES;     // this CTA's part of a weight tile
+    constexpr int STAGE_BYTES = A_STAGE_BYTES + B_BYTES;
+    constexpr int STAGES = PAIR ? Cfg::STAGES_PAIR : Cfg::STAGES;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-    uint64_t* full_bar = bars;                   // [STAGES]  TMA -> MMA
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full_bar = bars;                   // [STAGES]  TMA -> MMA   (pairs: the leader's copy is used)
     uint64_t* empty_bar = bars + STAGES;         // [STAGES]  MMA -> TMA
     uint64_t* tfull_bar = bars + 2 * STAGES;     // [2]       MMA -> epilogue
-    uint64_t* tempty_bar = bars + 2 * STAGES + 2;// [2]       epilogue -> MMA
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2;// [2]       epilogue -> MMA (pairs: the leader's copy is used)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-    float* sparam = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
+    float* sparam = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int rank = PAIR ? (int)cluster_ctarank() : 0;
+    const bool leader = rank == 0;
 
     if (warp == WARP_TMA && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -438,32 +492,51 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], EPI_THREADS);
+            mbar_init(&tempty_bar[a], PAIR ? 2 * EPI_THREADS : EPI_THREADS);
         }
         fence_mbar_init();
     }
-    if (warp == WARP_ALLOC) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    if (warp == WARP_ALLOC) {
+        if constexpr (PAIR) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
+        else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int num_work = p.num_m_tiles * p.num_n_tiles * p.num_splits;
+    // work items: single CTAs walk M tiles; pairs walk PAIRS of M tiles (pixel-major: pairs of image blocks per pixel)
+    const int pix_ibp = (PAIR && (p.flags & EPI_PIXMAJOR)) ? (p.pix_iblocks + 1) / 2 : 0;
+    const int m_items = !PAIR ? p.num_m_tiles
+                              : (pix_ibp > 0 ? (p.num_m_tiles / p.pix_iblocks) * pix_ibp : (p.num_m_tiles + 1) / 2);
+    const int num_work = m_items * p.num_n_tiles * p.num_splits;
+    const int work0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int work_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int kb_total = p.ntaps * p.kpt_a;
+    const int ibp_div = pix_ibp > 0 ? pix_ibp : 1;
 
     if (warp == WARP_TMA) {
         // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
         int stage = 0;
         uint32_t phase = 0;
-        for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+        const uint32_t full0 = PAIR ? mapa_shared(smem_u32(&full_bar[0]), 0) : 0u;   // the leader's full barriers
+        for (int work = work0; work < num_work; work += work_stride) {
             const int split = work % p.num_splits;
             const int t = work / p.num_splits;
             const int n_tile = t % p.num_n_tiles;
-            const int m_tile = t / p.num_n_tiles;
+            const int m_item = t / p.num_n_tiles;
+            const int m_tile = PAIR ? 2 * m_item + rank : m_item;       // (not used by pixel-major pairs)
             const int m0 = m_tile * BLOCK_M;
-            const int b_row = n_tile * BN + (m_tile / p.b_mtile_div) * p.b_rows_per_mtile;
+            const int b_row = n_tile * BN + (m_tile / p.b_mtile_div) * p.b_rows_per_mtile + (PAIR ? rank * (BN / 2) : 0);
             if (p.flags & EPI_PIXMAJOR) {        // A tile = 128 images at the tap's source pixel; taps outside are skipped
-                const PixTile pt = pix_tile(p, m_tile);
+                PixTile pt;
+                if (pix_ibp > 0) {
+                    const int q = m_item / ibp_div;
+                    pt = pix_tile_qi(p, q, 2 * (m_item - q * ibp_div) + rank);
+                } else {
+                    pt = pix_tile(p, m_item);
+                }
                 for (int tap = 0; tap < p.ntaps; ++tap) {
                     if (!((pt.tapmask >> tap) & 1u)) continue;
                     const int r = (p.ntaps == 9) ? tap / 3 : 1, s = (p.ntaps == 9) ? tap % 3 : 1;
@@ -472,11 +545,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const int cb = (c < p.kb_per_tap) ? c : c - p.kb_per_tap;
                         const int a_col = p.tap_ch_off[tap] + cb * BLOCK_K + ((c < p.kb_per_tap) ? 0 : p.a_lo_off);
                         if (elect_one_sync()) {
-                            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                            tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], a_col,
-                                        pt.wo + s - 1, pt.ho + r - 1, pt.img0);
-                            tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage],
-                                        (tap * p.kb_per_tap + cb) * BLOCK_K, b_row);
+                            if constexpr (PAIR) {
+                                if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+                                tma_load_4d_pair(sA + stage * A_STAGE_BYTES, &tmA, full0 + stage * 8, a_col,
+                                                 pt.wo + s - 1, pt.ho + r - 1, pt.img0);
+                                tma_load_2d_pair(sB + stage * B_BYTES, &tmB, full0 + stage * 8,
+                                                 (tap * p.kb_per_tap + cb) * BLOCK_K, b_row);
+                            } else {
+                                mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                                tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], a_col,
+                                            pt.wo + s - 1, pt.ho + r - 1, pt.img0);
+                                tma_load_2d(sB + stage * B_BYTES, &tmB, &full_bar[stage],
+                                            (tap * p.kb_per_tap + cb) * BLOCK_K, b_row);
+                            }
                         }
                         __syncwarp();
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -494,29 +575,38 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int a_col = p.tap_ch_off[tap] + cb * BLOCK_K + ((c < p.kb_per_tap) ? 0 : p.a_lo_off);
                 const int a_row = m0 + p.tap_row_shift[tap];
                 if (elect_one_sync()) {
-                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                    tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], a_col, a_row);
-                    tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage],
-                                (tap * p.kb_per_tap + cb) * BLOCK_K, b_row);
+                    if constexpr (PAIR) {
+                        if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+                        tma_load_2d_pair(sA + stage * A_STAGE_BYTES, &tmA, full0 + stage * 8, a_col, a_row);
+                        tma_load_2d_pair(sB + stage * B_BYTES, &tmB, full0 + stage * 8,
+                                         (tap * p.kb_per_tap + cb) * BLOCK_K, b_row);
+                    } else {
+                        mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                        tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], a_col, a_row);
+                        tma_load_2d(sB + stage * B_BYTES, &tmB, &full_bar[stage],
+                                    (tap * p.kb_per_tap + cb) * BLOCK_K, b_row);
+                    }
                 }
                 __syncwarp();
                 if (++c == p.kpt_a) { c = 0; ++tap; }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == WARP_MMA) {
+    } else if (warp == WARP_MMA && leader) {
         // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
-        const uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN) ^ p.idesc_xor;
+        const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, BN) ^ p.idesc_xor;
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
-        for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++it) {
+        for (int work = work0; work < num_work; work += work_stride, ++it) {
             const int split = work % p.num_splits;
             int kb0 = split * p.kb_per_split;
             int kb1 = min(kb0 + p.kb_per_split, kb_total);
             if (p.flags & EPI_PIXMAJOR) {        // the producer streams only the taps whose source pixel exists
+                const int m_item = (work / p.num_splits) / p.num_n_tiles;
+                const int q = (pix_ibp > 0) ? m_item / ibp_div : m_item / p.pix_iblocks;
                 kb0 = 0;
-                kb1 = __popc(pix_tile(p, (work / p.num_splits) / p.num_n_tiles).tapmask) * p.kpt_a;
+                kb1 = __popc(pix_tile_qi(p, q, 0).tapmask) * p.kpt_a;
             }
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
@@ -524,7 +614,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BN;
             if (kb1 <= kb0) {                    // pixel-major pad point: nothing to accumulate, the epilogue stores zeros
-                if (elect_one_sync()) umma_commit(&tfull_bar[acc]);
+                if (elect_one_sync()) {
+                    if constexpr (PAIR) umma_commit_pair(&tfull_bar[acc]);
+                    else umma_commit(&tfull_bar[acc]);
+                }
                 __syncwarp();
                 continue;
             }
@@ -532,28 +625,45 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 const uint64_t a_desc = umma_smem_desc_sw128(smem_u32(sA + stage * A_STAGE_BYTES));
-                const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(sB + stage * Cfg::B_STAGE_BYTES));
+                const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(sB + stage * B_BYTES));
                 const uint32_t first = (kb > kb0) ? 1u : 0u;
                 if (elect_one_sync()) {
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / 16; ++k)   // +32 B per K step == +2 in the (addr >> 4) field
-                        umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (k > 0) ? 1u : first);
-                    umma_commit(&empty_bar[stage]);          // frees the smem slot once these MMAs retire
-                    if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
+                    for (int k = 0; k < BLOCK_K / 16; ++k) {  // +32 B per K step == +2 in the (addr >> 4) field
+                        if constexpr (PAIR) umma_bf16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (k > 0) ? 1u : first);
+                        else umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (k > 0) ? 1u : first);
+                    }
+                    if constexpr (PAIR) {
+                        umma_commit_pair(&empty_bar[stage]);
+                        if (kb == kb1 - 1) umma_commit_pair(&tfull_bar[acc]);
+                    } else {
+                        umma_commit(&empty_bar[stage]);          // frees the smem slot once these MMAs retire
+                        if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
+                    }
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp < 8) {
-        epilogue_loop<BN, 1>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane);
+        EpiSched es;
+        es.work0 = work0;
+        es.work_stride = work_stride;
+        es.num_work = num_work;
+        es.tile_mul = PAIR ? 2 : 1;
+        es.tile_add = rank;
+        es.pix_ibp = pix_ibp;
+        es.tempty_remote = (PAIR && !leader) ? mapa_shared(smem_u32(&tempty_bar[0]), 0) : 0u;
+        epilogue_loop<BN, 1>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es);
     }
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();       // no CTA leaves (or frees TMEM) while its peer may still touch it
     if (warp == WARP_ALLOC) {
         tc_fence_after();
-        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+        if constexpr (PAIR) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+        else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
     }
 }
 
@@ -733,7 +843,7 @@ conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             atomicAdd(p.dbg + DBG_CTAS, 1ull);
         }
     } else if (warp < 8) {
-        epilogue_loop<BN, SUB>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane);
+        epilogue_loop<BN, SUB>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, epi_sched_single<BN, SUB>(p));
     }
 
     tc_fence_before();
@@ -742,6 +852,188 @@ conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tc_fence_after();
         tmem_dealloc<TMEM_COLS>(tmem_base);
     }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// CTA-pair variant of the sliding-window kernel (cluster of 2, tcgen05 cta_group::2), N = 256 layers.
+// With one CTA per tile every SM streams the WHOLE weight matrix through shared memory for each of its tiles: at
+// 256 -> 256 that is 1.15 MB of weights + 80 KB of windows per 18.4 k MMA cycles = 67 B/cycle/SM, 9.9 KB/cycle over the
+// chip — above what the L2 delivers to 148 SMs reading at once (~6.3 KB/cycle, B300_MICROARCH.md "LTS throughput cap"),
+// so the single-CTA kernel is L2-feed bound, not tensor bound. A pair computes 256 rows x 256 channels per work item:
+// each CTA loads the window of ITS 128 rows and HALF of every weight tile (128 of the 256 output channels); the
+// leader issues one M = 256 MMA that reads both halves. Weight bytes per SM halve (36 B/cycle/SM).
+// Barriers: full barriers live in the leader (both CTAs' TMA bytes are credited there), empty / tfull barriers are
+// per CTA and signalled by multicast commits, tempty lives in the leader and counts the epilogue threads of both CTAs.
+// ----------------------------------------------------------------------------------------------------------
+template <int BN, int TB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+conv_win2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const ConvGemmParams p, const WinCfg wc) {
+    constexpr int B_HALF_BYTES = (BN / 2) * BLOCK_K * 2;          // this CTA's half of a weight tile
+    constexpr uint32_t TMEM_COLS = 2 * BN;
+    static_assert(TMEM_COLS <= 512, "accumulators do not fit TMEM");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int win_bytes = wc.box_rows * wc.nbox * 128;            // multiple of 1024
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + wc.a_stages * win_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + wc.b_stages * B_HALF_BYTES);
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = bars + WIN_MAX_A_STAGES;
+    uint64_t* b_full = bars + 2 * WIN_MAX_A_STAGES;
+    uint64_t* b_empty = b_full + WIN_MAX_B_STAGES;
+    uint64_t* tfull_bar = b_empty + WIN_MAX_B_STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* sparam = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    if (warp == WARP_TMA && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == WARP_MMA && lane == 0) {
+        for (int s = 0; s < wc.a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < wc.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 2 * EPI_THREADS); }
+        fence_mbar_init();
+    }
+    if (warp == WARP_ALLOC) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                   // the peer's barriers are initialised before anything is signalled there
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+    const int num_work = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+    const int chunks = p.kb_per_tap;
+
+    if (warp == WARP_TMA) {
+        int sa = 0, sb = 0;
+        uint32_t pa = 0, pb = 0;
+        const uint32_t a_full0 = mapa_shared(smem_u32(&a_full[0]), 0);     // the leader's full barriers
+        const uint32_t b_full0 = mapa_shared(smem_u32(&b_full[0]), 0);
+        for (int work = cluster_id; work < num_work; work += num_clusters) {
+            const int n_tile = work % p.num_n_tiles;
+            const int m_pair = work / p.num_n_tiles;
+            const int row0 = (m_pair * 2 + (int)rank) * BLOCK_M - wc.G - 1;
+            const int n0 = n_tile * BN + (int)rank * (BN / 2);
+            for (int c = 0; c < chunks; ++c) {
+                mbar_wait(&a_empty[sa], pa ^ 1);
+                uint8_t* dst = sA + sa * win_bytes;
+                if (elect_one_sync()) {
+                    if (leader) mbar_arrive_expect_tx(&a_full[sa], 2 * win_bytes);
+                    tma_load_2d_pair(dst, &tmA, a_full0 + sa * 8, c * BLOCK_K, row0);
+                    if (wc.nbox == 2)
+                        tma_load_2d_pair(dst + wc.box_rows * 128, &tmA, a_full0 + sa * 8, c * BLOCK_K, row0 + wc.box_rows);
+                }
+                __syncwarp();
+                if (++sa == wc.a_stages) { sa = 0; pa ^= 1; }
+#pragma unroll 1
+                for (int t = 0; t < 9; ++t) {
+                    mbar_wait(&b_empty[sb], pb ^ 1);
+                    if (elect_one_sync()) {
+                        if (leader) mbar_arrive_expect_tx(&b_full[sb], 2 * B_HALF_BYTES);
+                        tma_load_2d_pair(sB + sb * B_HALF_BYTES, &tmB, b_full0 + sb * 8, (t * chunks + c) * BLOCK_K, n0);
+                    }
+                    __syncwarp();
+                    if (++sb == wc.b_stages) { sb = 0; pb ^= 1; }
+                }
+            }
+        }
+    } else if (warp == WARP_MMA && leader) {
+        const uint32_t idesc = umma_idesc_bf16(2 * BLOCK_M, BN) ^ p.idesc_xor;
+        int sa = 0, sb = 0;
+        uint32_t pa = 0, pb = 0;
+        int it = 0;
+        const bool timed = p.dbg != nullptr;
+        long long w_t = 0, w_a = 0, w_b = 0;
+        const long long t_begin = clock64();
+        for (int work = cluster_id; work < num_work; work += num_clusters, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait_timed(&tempty_bar[acc], acc_phase ^ 1, timed, w_t);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int c = 0; c < chunks; ++c) {
+                mbar_wait_timed(&a_full[sa], pa, timed, w_a);
+                tc_fence_after();
+                const uint32_t win_lo = static_cast<uint32_t>(umma_smem_desc_sw128(smem_u32(sA + sa * win_bytes)));
+#pragma unroll 1
+                for (int tb = 0; tb < 9 / TB; ++tb) {
+#pragma unroll
+                    for (int j = 0; j < TB; ++j) mbar_wait_timed(&b_full[sb + j], pb, timed, w_b);
+                    tc_fence_after();
+                    const uint32_t b_lo = static_cast<uint32_t>(umma_smem_desc_sw128(smem_u32(sB + sb * B_HALF_BYTES)));
+                    const uint32_t a_lo =
+                        win_lo + static_cast<uint32_t>((TB == 9 ? 0 : (TB == 3 ? tb * wc.G : (tb / 3) * wc.G + tb % 3)) * 8);
+                    const uint32_t g8 = static_cast<uint32_t>(wc.G * 8);
+                    const uint32_t first = (c > 0 || tb > 0) ? 1u : 0u;
+                    if (elect_one_sync()) {
+#pragma unroll
+                        for (int j = 0; j < TB; ++j) {
+                            const uint32_t a_tap = (TB == 9) ? a_lo + (j / 3) * g8 + (j % 3) * 8 : a_lo + j * 8;
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 16; ++k)
+                                umma_bf16_pair(d_tmem, UMMA_DESC_HI | (a_tap + 2 * k),
+                                               UMMA_DESC_HI | (b_lo + j * (B_HALF_BYTES >> 4) + 2 * k), idesc,
+                                               (j > 0 || k > 0) ? 1u : first);
+                            umma_commit_pair(&b_empty[sb + j]);
+                        }
+                        if (tb == 9 / TB - 1) {
+                            umma_commit_pair(&a_empty[sa]);
+                            if (c == chunks - 1) umma_commit_pair(&tfull_bar[acc]);
+                        }
+                    }
+                    __syncwarp();
+                    sb += TB;
+                    if (sb == wc.b_stages) { sb = 0; pb ^= 1; }
+                }
+                if (++sa == wc.a_stages) { sa = 0; pa ^= 1; }
+            }
+        }
+        if (timed && lane == 0) {
+            atomicAdd(p.dbg + DBG_MMA_WAIT_TMEM, (unsigned long long)w_t);
+            atomicAdd(p.dbg + DBG_MMA_WAIT_A, (unsigned long long)w_a);
+            atomicAdd(p.dbg + DBG_MMA_WAIT_B, (unsigned long long)w_b);
+            atomicAdd(p.dbg + DBG_MMA_TOTAL, (unsigned long long)(clock64() - t_begin));
+            atomicAdd(p.dbg + DBG_CTAS, 1ull);
+        }
+    } else if (warp < 8) {
+        EpiSched es;
+        es.work0 = cluster_id;
+        es.work_stride = num_clusters;
+        es.num_work = num_work;
+        es.tile_mul = 2;
+        es.tile_add = (int)rank;
+        es.tempty_remote = leader ? 0u : mapa_shared(smem_u32(&tempty_bar[0]), 0);
+        epilogue_loop<BN, 1>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                   // no CTA leaves (or frees TMEM) while its peer may still touch it
+    if (warp == WARP_ALLOC) {
+        tc_fence_after();
+        tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+    }
+}
+
+template <int BN, int TB>
+static int launch_win2(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, const WinCfg& wc,
+                       int smem_bytes, int grid, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        FFR_CUDA(cudaFuncSetAttribute(conv_win2_kernel<BN, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        attr_set = true;
+    }
+    conv_win2_kernel<BN, TB><<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, p, wc);
+    return launch_status("conv_win2_kernel");
 }
 
 template <int BN, int SUB, int TB>
@@ -759,6 +1051,9 @@ static int launch_win(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
 
 static bool g_use_window = true;
 void set_use_window(bool on) { g_use_window = on; }
+// CTA pairs (conv_win2_kernel) for the N = 256 sliding-window layers: -1 / 1 = on (default), 0 = off (tests, A/B runs)
+static int g_pair_mode = -1;
+void set_pair_mode(int mode) { g_pair_mode = mode; }
 static unsigned long long* g_dbg = nullptr;
 void set_debug_counters(unsigned long long* dptr) { g_dbg = dptr; }
 
@@ -780,12 +1075,39 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
     using Cfg = GemmCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        FFR_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        FFR_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    conv_gemm_kernel<BN><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+    conv_gemm_kernel<BN, false><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
     return launch_status("conv_gemm_kernel");
+}
+
+// CTA pairs: `grid` = 2 x (number of pairs), launched as clusters of 2
+template <int BN>
+static int launch_cfg_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int grid,
+                           cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FFR_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Cfg::SMEM_BYTES_PAIR));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES_PAIR;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    FFR_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, true>, tmA, tmB, p));
+    return launch_status("conv_gemm_kernel<pair>");
 }
 
 // Host entry used by every C-ABI wrapper. `a`: activation matrix [a_rows, a_ld]; `wp`: packed weights
@@ -887,13 +1209,57 @@ int conv_gemm_launch(const void* a, long long a_rows, int a_cols, int a_ld, cons
     if (rc) return rc;
 
     int G = 0;
+    // CTA pairs for the tile-per-tap kernel: two M tiles per work item, half of every weight tile per CTA
+    const bool pair_ok = g_pair_mode != 0 && p.num_m_tiles >= 2 && (p.b_rows_per_mtile == 0 || p.b_mtile_div % 2 == 0);
+    long long pair_items = pix ? (long long)(p.num_m_tiles / p.pix_iblocks) * ((p.pix_iblocks + 1) / 2)
+                               : (long long)(p.num_m_tiles + 1) / 2;
+    pair_items *= (long long)p.num_n_tiles * p.num_splits;
+    const int max_pairs = num_sms() / 2;
+    const int pair_grid = 2 * (int)((pair_items < max_pairs) ? pair_items : max_pairs);
     if (pix) {
         rc = make_tmap_pixel_bf16(&tmA, a, (uint64_t)p.n_img, (uint32_t)p.Wp, (uint64_t)a_cols, (uint64_t)a_ld, BLOCK_M);
         if (rc) return rc;
+        if (pair_ok) {
+            rc = make_tmap_2d_bf16(&tmB, wp, b_rows, (uint64_t)p.ntaps * Cin, (uint64_t)p.ntaps * Cin, BN / 2);
+            if (rc) return rc;
+            switch (BN) {
+                case 256: return launch_cfg_pair<256>(tmA, tmB, p, pair_grid, stream);
+                case 128: return launch_cfg_pair<128>(tmA, tmB, p, pair_grid, stream);
+                default:  return launch_cfg_pair<64>(tmA, tmB, p, pair_grid, stream);
+            }
+        }
         switch (BN) {
             case 256: return launch_cfg<256>(tmA, tmB, p, grid, stream);
             case 128: return launch_cfg<128>(tmA, tmB, p, grid, stream);
             default:  return launch_cfg<64>(tmA, tmB, p, grid, stream);
+        }
+    }
+    if (window_eligible(p, &G) && BN == 256 && g_pair_mode != 0 && p.num_m_tiles >= 2) {
+        // CTA pairs: two windows of 128 rows + halves of the weight tiles per CTA
+        WinCfg wc;
+        wc.G = G;
+        wc.b_resident = 0;
+        const int need = BLOCK_M + 2 * G + 2;
+        if (need <= 256) { wc.nbox = 1; wc.box_rows = (need + 7) & ~7; }
+        else             { wc.nbox = 2; wc.box_rows = (((need + 1) / 2) + 7) & ~7; }
+        const int win_bytes = wc.box_rows * wc.nbox * 128;
+        const int b_half = (BN / 2) * BLOCK_K * 2;
+        const int fixed = 1024 + 512 + 10 * BN * 4;
+        const int budget = 226 * 1024 - fixed;
+        constexpr int TB2 = 3;
+        wc.b_stages = 9;
+        wc.a_stages = (budget - wc.b_stages * b_half) / win_bytes;
+        if (wc.a_stages > WIN_MAX_A_STAGES) wc.a_stages = WIN_MAX_A_STAGES;
+        if (wc.a_stages >= 2 && wc.box_rows <= 256) {
+            rc = make_tmap_2d_bf16(&tmA, a, (uint64_t)a_rows, (uint64_t)a_cols, (uint64_t)a_ld, wc.box_rows);
+            if (rc) return rc;
+            rc = make_tmap_2d_bf16(&tmB, wp, b_rows, (uint64_t)p.ntaps * Cin, (uint64_t)p.ntaps * Cin, BN / 2);
+            if (rc) return rc;
+            const int smem_bytes = fixed + wc.a_stages * win_bytes + wc.b_stages * b_half;
+            const long long work = (long long)((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+            const int max_pairs = num_sms() / 2;
+            const int wgrid = 2 * (int)((work < max_pairs) ? work : max_pairs);
+            return launch_win2<256, TB2>(tmA, tmB, p, wc, smem_bytes, wgrid, stream);
         }
     }
     if (window_eligible(p, &G)) {
@@ -937,6 +1303,15 @@ int conv_gemm_launch(const void* a, long long a_rows, int a_cols, int a_ld, cons
     }
     rc = make_tmap_2d_bf16(&tmA, a, (uint64_t)a_rows, (uint64_t)a_cols, (uint64_t)a_ld, BLOCK_M);
     if (rc) return rc;
+    if (pair_ok) {
+        rc = make_tmap_2d_bf16(&tmB, wp, b_rows, (uint64_t)p.ntaps * Cin, (uint64_t)p.ntaps * Cin, BN / 2);
+        if (rc) return rc;
+        switch (BN) {
+            case 256: return launch_cfg_pair<256>(tmA, tmB, p, pair_grid, stream);
+            case 128: return launch_cfg_pair<128>(tmA, tmB, p, pair_grid, stream);
+            default:  return launch_cfg_pair<64>(tmA, tmB, p, pair_grid, stream);
+        }
+    }
     switch (BN) {
         case 256: return launch_cfg<256>(tmA, tmB, p, grid, stream);
         case 128: return launch_cfg<128>(tmA, tmB, p, grid, stream);

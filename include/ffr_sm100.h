@@ -417,6 +417,10 @@ FFR_API int ffr_threshold_sweep(const float* score, const int* label, const doub
  * tile-per-tap kernel (the two must agree; tests run both). */
 FFR_API int ffr_debug_set_window(int enable);
 
+/* Debug/tuning: CTA pairs (cluster of 2, tcgen05 cta_group::2, half of every weight tile per CTA) for the sliding-window
+ * layers with 256-wide N tiles: -1 / 1 = on (default), 0 = off (single-CTA kernel; the two must agree, tests run both). */
+FFR_API void ffr_debug_set_pair(int mode);
+
 /* Debug/tuning: device buffer of 16 uint64 that the sliding-window kernel fills with per-role barrier-wait cycle
  * counts (summed over CTAs; slots in csrc/conv_gemm.cuh DbgSlot); NULL (default) disables the counters. */
 FFR_API int ffr_debug_set_counters(void* counters);

@@ -22,12 +22,15 @@ def _stream():
     return _lib.stream_ptr()
 
 
-@pytest.fixture(params=["window", "tiles"], autouse=True)
+@pytest.fixture(params=["window", "window1", "tiles"], autouse=True)
 def conv_variant(request, lib):
-    """Every test runs with the sliding-window kernel enabled and with the tile-per-tap kernel forced."""
-    lib.ffr_debug_set_window(1 if request.param == "window" else 0)
+    """Every test runs with the sliding-window kernels enabled (CTA pairs on the 256-wide N tiles), with the
+    single-CTA window kernel everywhere ("window1"), and with the tile-per-tap kernel forced."""
+    lib.ffr_debug_set_window(0 if request.param == "tiles" else 1)
+    lib.ffr_debug_set_pair(0 if request.param == "window1" else -1)
     yield request.param
     lib.ffr_debug_set_window(1)
+    lib.ffr_debug_set_pair(-1)
 
 
 def _gemm(lib, a, wp, cin, cout, taps, M, flags=0, bias=None, slope=None, out=None, ldo=0, geom=(64, 1, 1, 0, 1),

@@ -14,8 +14,10 @@ N = 512
 res = []
 names = ["mma_wait_tmem", "mma_wait_a", "mma_wait_b", "mma_total", "tma_wait_a", "tma_wait_b", "tma_total", "-",
          "epi_wait", "epi_total", "ctas"]
-for (S, cin, cout) in [(112, 64, 64), (56, 64, 64), (56, 64, 128), (28, 128, 128), (28, 128, 256), (14, 256, 256),
-                       (14, 256, 512), (7, 512, 512)]:
+SHAPES = [(112, 64, 64), (56, 64, 64), (56, 64, 128), (28, 128, 128), (28, 128, 256), (14, 256, 256), (14, 256, 512),
+          (7, 512, 512)]
+for (S, cin, cout, pair) in [(S, ci, co, pr) for (S, ci, co) in SHAPES for pr in ((0, 1) if co >= 256 else (0,))]:
+    lib.ffr_debug_set_pair(pair)
     g = torch.Generator(device="cuda").manual_seed(0)
     rows = N * (S + 1) * (S + 1)
     x = (torch.randn(rows, cin, generator=g, device="cuda") * 0.5).to(torch.bfloat16)
@@ -43,7 +45,7 @@ for (S, cin, cout) in [(112, 64, 64), (56, 64, 64), (56, 64, 128), (28, 128, 128
     d = dbg.tolist()
     ctas = max(1, d[10])
     flop = 2.0 * N * S * S * cout * cin * 9
-    row = dict(S=S, cin=cin, cout=cout, ms=ms, tflops=flop / ms / 1e9, **{n: d[i] / ctas for i, n in enumerate(names) if n != "-"})
+    row = dict(S=S, cin=cin, cout=cout, pair=pair, ms=ms, tflops=flop / ms / 1e9, **{n: d[i] / ctas for i, n in enumerate(names) if n != "-"})
     res.append(row)
     print(json.dumps(row))
 os.makedirs("gpurun_out", exist_ok=True)
