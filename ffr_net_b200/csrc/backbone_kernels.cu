@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(128, 4) stem_kernel(const void* __restrict__ x
                                                    int swap_rb, const float* __restrict__ w,
                                                    const float* __restrict__ b, const float* __restrict__ a,
                                                    __nv_bfloat16* __restrict__ out, int n_img, int S) {
+    pdl_sync();
     __shared__ __align__(16) uint32_t stage[4][16 * 32];   // per warp: 16 rows x 64 bf16
     __shared__ float lut[U8 ? 256 : 1];
     const float* x = reinterpret_cast<const float*>(xin);
@@ -220,7 +221,7 @@ int stem_launch(const float* x, const float* w, const float* b, const float* a, 
     long long grid = (tiles + 3) / 4;
     const long long cap = (long long)num_sms() * 16;
     if (grid > cap) grid = cap;
-    stem_kernel<false><<<(int)grid, 128, 0, stream>>>(x, nullptr, 0, w, b, a, reinterpret_cast<__nv_bfloat16*>(out), n_img, S);
+    launch_ex(stem_kernel<false>, dim3((int)grid), dim3(128), 0, stream, 1, x, nullptr, 0, w, b, a, reinterpret_cast<__nv_bfloat16*>(out), n_img, S);
     return launch_status("stem_kernel");
 }
 
@@ -231,7 +232,7 @@ int stem_u8_launch(const unsigned char* img, const unsigned char* flip, int swap
     long long grid = (tiles + 3) / 4;
     const long long cap = (long long)num_sms() * 16;
     if (grid > cap) grid = cap;
-    stem_kernel<true><<<(int)grid, 128, 0, stream>>>(img, flip, swap_rb, w, b, a, reinterpret_cast<__nv_bfloat16*>(out), n_img, S);
+    launch_ex(stem_kernel<true>, dim3((int)grid), dim3(128), 0, stream, 1, img, flip, swap_rb, w, b, a, reinterpret_cast<__nv_bfloat16*>(out), n_img, S);
     return launch_status("stem_kernel<u8>");
 }
 
@@ -247,6 +248,7 @@ template <int C>
 __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ pool_part, int dense,
                                                       const float* __restrict__ w1, const float* __restrict__ w2,
                                                       float* __restrict__ gate, float* __restrict__ sums, int rpi, float inv) {
+    pdl_sync();
     constexpr int R = C / 16;
     constexpr int PARTS = (C >= 256) ? 1 : 256 / C;      // threads (c, part): part strides over the blocks
     __shared__ float s_part[PARTS][C];
@@ -300,10 +302,10 @@ int se_gate_launch(const float* pool_part, int dense, const float* w1, const flo
     const float inv = 1.0f / (float)(S * S);
     FFR_CHECK_ARG(rpi >= 64, "se_gate: map %dx%d too small for the 32-row block scheme", S, S);
     switch (C) {
-        case 64:  se_gate_kernel<64><<<n_img, 256, 0, stream>>>(pool_part, dense, w1, w2, gate, sums, rpi, inv); break;
-        case 128: se_gate_kernel<128><<<n_img, 256, 0, stream>>>(pool_part, dense, w1, w2, gate, sums, rpi, inv); break;
-        case 256: se_gate_kernel<256><<<n_img, 256, 0, stream>>>(pool_part, dense, w1, w2, gate, sums, rpi, inv); break;
-        case 512: se_gate_kernel<512><<<n_img, 256, 0, stream>>>(pool_part, dense, w1, w2, gate, sums, rpi, inv); break;
+        case 64:  launch_ex(se_gate_kernel<64>, dim3(n_img), dim3(256), 0, stream, 1, pool_part, dense, w1, w2, gate, sums, rpi, inv); break;
+        case 128: launch_ex(se_gate_kernel<128>, dim3(n_img), dim3(256), 0, stream, 1, pool_part, dense, w1, w2, gate, sums, rpi, inv); break;
+        case 256: launch_ex(se_gate_kernel<256>, dim3(n_img), dim3(256), 0, stream, 1, pool_part, dense, w1, w2, gate, sums, rpi, inv); break;
+        case 512: launch_ex(se_gate_kernel<512>, dim3(n_img), dim3(256), 0, stream, 1, pool_part, dense, w1, w2, gate, sums, rpi, inv); break;
         default: return set_error(-1, "se_gate: unsupported C=%d", C);
     }
     return launch_status("se_gate_kernel");
@@ -320,6 +322,7 @@ __global__ void __launch_bounds__(256) se_residual_kernel(const __nv_bfloat16* _
                                                           const float* __restrict__ gate,
                                                           const __nv_bfloat16* __restrict__ sc, int shortcut_mode,
                                                           __nv_bfloat16* __restrict__ y, int S, long long total_rows) {
+    pdl_sync();
     constexpr int TPR = C / 8;          // threads per row
     constexpr int RPB = 256 / TPR;      // rows per CTA pass
     constexpr int UNR = 4;
@@ -375,10 +378,10 @@ int se_residual_launch(const void* u, const float* gate, const void* sc, int sho
     const __nv_bfloat16* sp = reinterpret_cast<const __nv_bfloat16*>(sc);
     __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
     switch (C) {
-        case 64:  se_residual_kernel<64><<<(int)grid, 256, 0, stream>>>(up, gate, sp, shortcut_mode, yp, S, total_rows); break;
-        case 128: se_residual_kernel<128><<<(int)grid, 256, 0, stream>>>(up, gate, sp, shortcut_mode, yp, S, total_rows); break;
-        case 256: se_residual_kernel<256><<<(int)grid, 256, 0, stream>>>(up, gate, sp, shortcut_mode, yp, S, total_rows); break;
-        case 512: se_residual_kernel<512><<<(int)grid, 256, 0, stream>>>(up, gate, sp, shortcut_mode, yp, S, total_rows); break;
+        case 64:  launch_ex(se_residual_kernel<64>, dim3((int)grid), dim3(256), 0, stream, 1, up, gate, sp, shortcut_mode, yp, S, total_rows); break;
+        case 128: launch_ex(se_residual_kernel<128>, dim3((int)grid), dim3(256), 0, stream, 1, up, gate, sp, shortcut_mode, yp, S, total_rows); break;
+        case 256: launch_ex(se_residual_kernel<256>, dim3((int)grid), dim3(256), 0, stream, 1, up, gate, sp, shortcut_mode, yp, S, total_rows); break;
+        case 512: launch_ex(se_residual_kernel<512>, dim3((int)grid), dim3(256), 0, stream, 1, up, gate, sp, shortcut_mode, yp, S, total_rows); break;
         default: return set_error(-1, "se_residual: unsupported C=%d", C);
     }
     return launch_status("se_residual_kernel");
@@ -390,6 +393,7 @@ int se_residual_launch(const void* u, const float* gate, const void* sc, int sho
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) subsample2_kernel(const uint4* __restrict__ x, uint4* __restrict__ out,
                                                          int n_img, int So, int C8) {
+    pdl_sync();
     const int G = So + 1, G2 = 2 * So + 1;
     const long long total = (long long)n_img * G * G * C8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -407,7 +411,7 @@ int subsample2_launch(const void* x, void* out, int n_img, int So, int C, cudaSt
     const long long total = (long long)n_img * (So + 1) * (So + 1) * (C / 8);
     int grid = (int)((total + 255) / 256);
     if (grid > num_sms() * 16) grid = num_sms() * 16;
-    subsample2_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), n_img,
+    launch_ex(subsample2_kernel, dim3(grid), dim3(256), 0, stream, 1, reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), n_img,
                                                 So, C / 8);
     return launch_status("subsample2_kernel");
 }
@@ -420,6 +424,7 @@ __global__ void __launch_bounds__(256) export_nchw_kernel(const __nv_bfloat16* _
                                                           const float* __restrict__ scale,
                                                           const float* __restrict__ shift, float* __restrict__ y,
                                                           int S, int C) {
+    pdl_sync();
     extern __shared__ float tile[];  // [S*S][65]
     const int n = blockIdx.y, c0 = blockIdx.x * 64;
     const int G = S + 1, P = S * S;
@@ -442,7 +447,7 @@ int export_nchw_launch(const void* h, const float* scale, const float* shift, fl
     dim3 grid(C / 64, n_img);
     const size_t smem = (size_t)S * S * 65 * sizeof(float);
     FFR_CHECK_ARG(smem <= 48 * 1024, "export_nchw: map %dx%d too large", S, S);
-    export_nchw_kernel<<<grid, 256, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(h), scale, shift, y, S, C);
+    launch_ex(export_nchw_kernel, dim3(grid), dim3(256), smem, stream, 1, reinterpret_cast<const __nv_bfloat16*>(h), scale, shift, y, S, C);
     return launch_status("export_nchw_kernel");
 }
 
@@ -453,6 +458,7 @@ int export_nchw_launch(const void* h, const float* scale, const float* shift, fl
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bias_l2norm_kernel(const float* __restrict__ acc, int splits, long long split_stride,
                                                           const float* __restrict__ bias, float* __restrict__ f, int rows) {
+    pdl_sync();
     constexpr int D = 512;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -476,7 +482,7 @@ __global__ void __launch_bounds__(256) bias_l2norm_kernel(const float* __restric
 int bias_l2norm_launch(const float* acc, int splits, long long split_stride, const float* bias, float* f, int rows, int D,
                        cudaStream_t stream) {
     FFR_CHECK_ARG(D == 512, "bias_l2norm: D=%d", D);
-    bias_l2norm_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(acc, splits, split_stride, bias, f, rows);
+    launch_ex(bias_l2norm_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, 1, acc, splits, split_stride, bias, f, rows);
     return launch_status("bias_l2norm_kernel");
 }
 

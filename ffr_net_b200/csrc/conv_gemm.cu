@@ -30,6 +30,12 @@ struct GemmCfg {
     static constexpr int SMEM_BYTES_PAIR = 1024 + STAGES_PAIR * (A_STAGE_BYTES + B_STAGE_BYTES / 2) + 256 + PARAM_FLOATS * 4;
 };
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // mbarrier wait that adds the time spent to a counter when profiling counters are enabled
 __device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, bool timed, long long& acc) {
     if (!timed) { mbar_wait(bar, parity); return; }
@@ -505,6 +511,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if constexpr (PAIR) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();        // everything above touched no global memory; the predecessor's outputs are visible from here on
 
     // work items: single CTAs walk M tiles; pairs walk PAIRS of M tiles (pixel-major: pairs of image blocks per pixel)
     const int pix_ibp = (PAIR && (p.flags & EPI_PIXMAJOR)) ? (p.pix_iblocks + 1) / 2 : 0;
@@ -732,6 +739,7 @@ conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();
 
     const int num_work = ((p.num_m_tiles + SUB - 1) / SUB) * p.num_n_tiles;
     const int chunks = p.kb_per_tap;
@@ -889,6 +897,7 @@ conv_win2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    if (p.dbg != nullptr && threadIdx.x == 0) atomicMin(p.dbg + DBG_T_ENTRY, globaltimer_ns());
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     if (warp == WARP_TMA && lane == 0) {
@@ -907,6 +916,7 @@ conv_win2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     cluster_sync_all();                   // the peer's barriers are initialised before anything is signalled there
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();
 
     const int cluster_id = blockIdx.x >> 1;
     const int num_clusters = gridDim.x >> 1;
@@ -954,6 +964,7 @@ conv_win2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool timed = p.dbg != nullptr;
         long long w_t = 0, w_a = 0, w_b = 0;
         const long long t_begin = clock64();
+        if (timed && lane == 0) atomicMin(p.dbg + DBG_T_MMA_BEGIN, globaltimer_ns());
         for (int work = cluster_id; work < num_work; work += num_clusters, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
@@ -1003,6 +1014,8 @@ conv_win2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             atomicAdd(p.dbg + DBG_MMA_WAIT_B, (unsigned long long)w_b);
             atomicAdd(p.dbg + DBG_MMA_TOTAL, (unsigned long long)(clock64() - t_begin));
             atomicAdd(p.dbg + DBG_CTAS, 1ull);
+            atomicMax(p.dbg + DBG_T_MMA_END, globaltimer_ns());
+            atomicMax(p.dbg + DBG_MMA_TOTAL_MAX, (unsigned long long)(clock64() - t_begin));
         }
     } else if (warp < 8) {
         EpiSched es;
@@ -1022,6 +1035,7 @@ conv_win2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         tmem_dealloc_pair<TMEM_COLS>(tmem_base);
     }
+    if (p.dbg != nullptr && threadIdx.x == 0) atomicMax(p.dbg + DBG_T_EXIT, globaltimer_ns());
 }
 
 template <int BN, int TB>
@@ -1032,7 +1046,7 @@ static int launch_win2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
         FFR_CUDA(cudaFuncSetAttribute(conv_win2_kernel<BN, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         attr_set = true;
     }
-    conv_win2_kernel<BN, TB><<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, p, wc);
+    FFR_CUDA(launch_ex(conv_win2_kernel<BN, TB>, dim3(grid), dim3(NUM_THREADS), smem_bytes, stream, 1, tmA, tmB, p, wc));
     return launch_status("conv_win2_kernel");
 }
 
@@ -1045,7 +1059,7 @@ static int launch_win(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
                                       232448));
         attr_set = true;
     }
-    conv_win_kernel<BN, SUB, TB><<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, p, wc);
+    FFR_CUDA(launch_ex(conv_win_kernel<BN, SUB, TB>, dim3(grid), dim3(NUM_THREADS), smem_bytes, stream, 1, tmA, tmB, p, wc));
     return launch_status("conv_win_kernel");
 }
 
@@ -1079,7 +1093,7 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
                                       Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    conv_gemm_kernel<BN, false><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+    FFR_CUDA(launch_ex(conv_gemm_kernel<BN, false>, dim3(grid), dim3(NUM_THREADS), Cfg::SMEM_BYTES, stream, 1, tmA, tmB, p));
     return launch_status("conv_gemm_kernel");
 }
 
@@ -1094,19 +1108,7 @@ static int launch_cfg_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const
                                       Cfg::SMEM_BYTES_PAIR));
         attr_set = true;
     }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES_PAIR;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    FFR_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, true>, tmA, tmB, p));
+    FFR_CUDA(launch_ex(conv_gemm_kernel<BN, true>, dim3(grid), dim3(NUM_THREADS), Cfg::SMEM_BYTES_PAIR, stream, 2, tmA, tmB, p));
     return launch_status("conv_gemm_kernel<pair>");
 }
 

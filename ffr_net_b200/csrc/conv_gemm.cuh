@@ -105,6 +105,9 @@ struct ConvGemmParams {
 // dbg slots (cycles summed over CTAs): MMA warp waits, producer waits, epilogue waits, totals
 enum DbgSlot { DBG_MMA_WAIT_TMEM = 0, DBG_MMA_WAIT_A = 1, DBG_MMA_WAIT_B = 2, DBG_MMA_TOTAL = 3,
                DBG_TMA_WAIT_A = 4, DBG_TMA_WAIT_B = 5, DBG_TMA_TOTAL = 6, DBG_EPI_WAIT = 8, DBG_EPI_TOTAL = 9,
-               DBG_CTAS = 10 };
+               DBG_CTAS = 10,
+               // conv_win2_kernel only, %globaltimer ns: earliest CTA entry (slot must be preset to ~0), earliest start
+               // and latest end of an MMA issue loop, latest CTA exit; longest MMA issue loop in cycles
+               DBG_T_ENTRY = 11, DBG_T_MMA_BEGIN = 12, DBG_T_MMA_END = 13, DBG_T_EXIT = 14, DBG_MMA_TOTAL_MAX = 15 };
 
 }  // namespace ffr

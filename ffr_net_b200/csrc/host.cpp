@@ -101,6 +101,10 @@ int launch_status(const char* what) {
 
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
+static std::atomic<bool> g_pdl{true};
+bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed); }
+void set_pdl_enabled(bool on) { g_pdl.store(on, std::memory_order_relaxed); }
+
 int num_sms() {
     static int n = 0;
     if (n == 0) {

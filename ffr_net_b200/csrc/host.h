@@ -39,4 +39,38 @@ int make_tmap_pixel_bf16(CUtensorMap* out, const void* base, uint64_t n_img, uin
 
 int num_sms();
 
+// Programmatic dependent launch (ptx.cuh: pdl_wait / pdl_launch_dependents) for kernels that call pdl_sync(): on by
+// default, ffr_debug_set_pdl(0) turns the launch attribute off (plain stream order; A/B runs and tests).
+bool pdl_enabled();
+void set_pdl_enabled(bool on);
+
+// Kernel launch with optional cluster size and the programmatic-stream-serialization attribute. ONLY for kernels that
+// execute pdl_wait() before their first access to global memory another kernel may write (or still read).
+template <typename... P, typename... A>
+inline cudaError_t launch_ex(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                             A... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    unsigned n = 0;
+    if (cluster_x > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = (unsigned)cluster_x;
+        at[n].val.clusterDim.y = 1;
+        at[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl_enabled()) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+
 }  // namespace ffr

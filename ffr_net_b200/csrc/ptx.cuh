@@ -29,6 +29,18 @@ __device__ __forceinline__ bool elect_one_sync() {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL). A kernel launched with the programmatic-stream-serialization attribute
+// (host.h: launch_ex) may be scheduled while its predecessor in the stream is still running; pdl_wait() blocks until
+// the predecessor grid has COMPLETED and its memory operations are visible. Everything before the wait must not touch
+// global memory that any earlier kernel writes or reads (barrier init, TMEM allocation, descriptor prefetch only).
+// pdl_launch_dependents() lets the NEXT kernel in the stream be scheduled once every CTA of this grid has executed it
+// (or exited). Both are no-ops for a kernel launched without the attribute.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_launch_dependents(); }
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -421,6 +421,12 @@ FFR_API int ffr_debug_set_window(int enable);
  * layers with 256-wide N tiles: -1 / 1 = on (default), 0 = off (single-CTA kernel; the two must agree, tests run both). */
 FFR_API void ffr_debug_set_pair(int mode);
 
+/* Debug/tuning: programmatic dependent launch. 1 (default): the kernels of the forward chain are launched with the
+ * programmatic-stream-serialization attribute, so a kernel's CTAs are scheduled, and its prologue runs, while the
+ * previous kernel drains; every such kernel executes griddepcontrol.wait before touching global memory. 0: plain
+ * stream order (results are identical; A/B timing and tests). */
+FFR_API void ffr_debug_set_pdl(int enable);
+
 /* Debug/tuning: device buffer of 16 uint64 that the sliding-window kernel fills with per-role barrier-wait cycle
  * counts (summed over CTAs; slots in csrc/conv_gemm.cuh DbgSlot); NULL (default) disables the counters. */
 FFR_API int ffr_debug_set_counters(void* counters);

@@ -204,3 +204,29 @@ def test_backbone_forward_u8_matches_fp32_input(models):
     assert (f2 - f3).abs().max().item() <= 2e-3 and (y2 - y3).abs().max().item() <= 2e-2 * y3.abs().max().item()
     assert (f2[1] - f0[1]).abs().max().item() <= 2e-3          # image 1 is not flipped
     assert (f2[0] - f0[0]).abs().max().item() > 1e-2            # image 0 is
+
+
+def test_launch_modes_bit_identical(models, lib):
+    """Programmatic dependent launch (a kernel's CTAs are scheduled while its predecessor drains) and CTA pairs
+    (cta_group::2) change scheduling, not arithmetic: the forward is bit-identical with either switched off, and
+    repeated back-to-back forwards (no host sync in between: the dependent-launch race window) stay identical."""
+    _, m = models
+    x = ob.synth_faces(16, seed=21).repeat(4, 1, 1, 1).cuda()      # 64 images: several tiles per layer
+    with torch.no_grad():
+        y0, f0 = m(x)
+        outs = [m(x) for _ in range(4)]                                # back to back, same workspace
+        torch.cuda.synchronize()
+        for y, f in outs:
+            assert torch.equal(y, y0) and torch.equal(f, f0)
+        try:
+            lib.ffr_debug_set_pdl(0)
+            y1, f1 = m(x)
+            lib.ffr_debug_set_pdl(1)
+            lib.ffr_debug_set_pair(0)
+            y2, f2 = m(x)
+        finally:
+            lib.ffr_debug_set_pdl(1)
+            lib.ffr_debug_set_pair(-1)
+        torch.cuda.synchronize()
+    assert torch.equal(y1, y0) and torch.equal(f1, f0)
+    assert torch.equal(y2, y0) and torch.equal(f2, f0)

@@ -1,0 +1,52 @@
+"""A/B timing of the eval step (IR-SE50 + RecNet, batch 512) under the launch-mode switches, interleaved in one process
+on one box (box-to-box clocks differ by a few %): programmatic dependent launch on/off x CTA pairs on/off."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ffr_net_b200 import _lib, synth
+from ffr_net_b200.backbone import Backbone
+from ffr_net_b200.recnet import RecNet
+
+lib = _lib.load()
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+enc = Backbone(50, 0.6, "ir_se")
+enc.load_state_dict(synth.synth_backbone_state_dict(0))
+enc = enc.cuda().eval()
+rec = RecNet()
+rec.load_state_dict(synth.synth_recnet_state_dict(0))
+rec = rec.cuda().eval()
+x = synth.synth_faces(64, seed=0).repeat((n + 63) // 64, 1, 1, 1)[:n].cuda()
+
+
+def run(iters):
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        s.record()
+        for _ in range(iters):
+            rec.embed_from_images(enc, x)
+        e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+res = {}
+with torch.no_grad():
+    for _ in range(5):
+        rec.embed_from_images(enc, x)
+for rnd in range(3):
+    for pdl in (1, 0):
+        for pair in (-1, 0):
+            lib.ffr_debug_set_pdl(pdl)
+            lib.ffr_debug_set_pair(pair)
+            run(2)
+            res.setdefault("pdl=%d pair=%d" % (pdl, 1 if pair else 0), []).append(run(10))
+lib.ffr_debug_set_pdl(1)
+lib.ffr_debug_set_pair(-1)
+out = {k: {"ms": [round(v, 3) for v in vs], "best_ms": round(min(vs), 3), "img_s": round(n / min(vs) * 1e3)} for k, vs in res.items()}
+print(json.dumps(out, indent=1))
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(out, open("gpurun_out/ab_bench_%d.json" % n, "w"), indent=1)

@@ -27,6 +27,7 @@ for (S, cin, cout, pair) in [(S, ci, co, pr) for (S, ci, co) in SHAPES for pr in
     slope = torch.full((cout,), 0.25, device="cuda")
     out = torch.empty(rows, cout, dtype=torch.bfloat16, device="cuda")
     dbg = torch.zeros(16, dtype=torch.int64, device="cuda")
+    dbg[11] = dbg[12] = 2 ** 62
     st = _lib.stream_ptr()
     for _ in range(3):
         _lib.check(lib.ffr_conv3x3_bnpre_prelu_fwd(P(x), N, S, cin, P(wp), cout, P(bias9), P(slope), P(out), 0, st))
@@ -46,6 +47,8 @@ for (S, cin, cout, pair) in [(S, ci, co, pr) for (S, ci, co) in SHAPES for pr in
     ctas = max(1, d[10])
     flop = 2.0 * N * S * S * cout * cin * 9
     row = dict(S=S, cin=cin, cout=cout, pair=pair, ms=ms, tflops=flop / ms / 1e9, **{n: d[i] / ctas for i, n in enumerate(names) if n != "-"})
+    if pair and d[14] > 0:      # wall-clock phases of the pair kernel (ns since the earliest CTA entry)
+        row.update(t_mma_begin_ns=d[12] - d[11], t_mma_end_ns=d[13] - d[11], t_exit_ns=d[14] - d[11], mma_total_max_cycles=d[15])
     res.append(row)
     print(json.dumps(row))
 os.makedirs("gpurun_out", exist_ok=True)
