@@ -390,7 +390,7 @@ def run_ours(args):
             sustained = peaks.get("bf16_tflops_sustained", 1400.0)
             # the timed region of this benchmark is a fraction of a second at (near) full clocks: the comparable
             # denominator is the BURST cuBLAS peak; the fraction of the sustained (power-capped) peak is given beside it
-            roof = {"bound": "tensor", "kernel": "conv_win_kernel<256,1,1> (3x3 256->256 @14x14, %d launches/step)" % len(durs),
+            roof = {"bound": "tensor", "kernel": "conv_win2_kernel<256,3> (CTA pairs; 3x3 256->256 @14x14, %d launches/step)" % len(durs),
                     "achieved": achieved, "peak": burst, "peak_source": peak_src + " (burst cuBLAS bf16 peak)",
                     "unit": "TFLOP/s", "frac": achieved / burst, "frac_burst": achieved / burst,
                     "frac_sustained": achieved / sustained, "peak_sustained": sustained, "avg_launch_ms": avg_ms,

@@ -119,6 +119,7 @@ _SIGNATURES = {
     "ffr_se_pool_part_floats": (_i64, [_i, _i, _i]),
     "ffr_se_gate_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "ffr_se_residual_fwd": (_i, [_p, _p, _p, _i, _p, _i, _i, _i, _p]),
+    "ffr_se_gate_residual_fwd": (_i, [_p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _p]),
     "ffr_head_workspace_floats": (_i64, [_i, _i, _i]),
     "ffr_export_nchw_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "ffr_head_fwd": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),

@@ -126,6 +126,7 @@ class Backbone(nn.Module):
         self._packed = None
         self._ws = {}
         self._profile = None      # set to a list to collect (label, start_event, end_event) per library call
+        self.fuse_se = True       # SE gate computed inside the scale + residual kernel (C <= 256); False: two launches
 
     # ------------------------------------------------------------------------------------------
     def _cache_key(self):
@@ -296,7 +297,9 @@ class Backbone(nn.Module):
                                                         P(t), 0, st), "conv1 %d>%d@%ds1" % (u.cin, u.depth, S))
             L.check(lib.ffr_conv3x3_bn_pool_fwd(P(t), n, S, u.depth, u.stride, P(u.w2), u.depth, P(u.b2), P(ws.u),
                                                 P(ws.pool_part), st), "conv2 %d>%d@%ds%d" % (u.depth, u.depth, S, u.stride))
-            L.check(lib.ffr_se_gate_fwd(P(ws.pool_part), P(u.fc1), P(u.fc2), P(ws.gate), None, n, so, u.depth, st), "se_gate")
+            fused_se = self.fuse_se and u.depth <= 256      # gate + scale + residual in one launch (one CTA per image)
+            if not fused_se:
+                L.check(lib.ffr_se_gate_fwd(P(ws.pool_part), P(u.fc1), P(u.fc2), P(ws.gate), None, n, so, u.depth, st), "se_gate")
             if u.cin == u.depth:
                 sc, mode = cur, (1 if u.stride == 2 else 0)
             else:
@@ -304,7 +307,11 @@ class Backbone(nn.Module):
                 L.check(lib.ffr_conv1x1_bn_fwd(P(ws.xs), n, so, u.cin, P(u.wsc), u.depth, P(u.bsc), P(ws.sc), st),
                         "shortcut")
                 sc, mode = ws.sc, 2
-            L.check(lib.ffr_se_residual_fwd(P(ws.u), P(ws.gate), P(sc), mode, P(nxt), n, so, u.depth, st), "se_residual")
+            if fused_se:
+                L.check(lib.ffr_se_gate_residual_fwd(P(ws.u), P(ws.pool_part), P(u.fc1), P(u.fc2), P(sc), mode, P(nxt), n, so,
+                                                     u.depth, st), "se_gate_residual")
+            else:
+                L.check(lib.ffr_se_residual_fwd(P(ws.u), P(ws.gate), P(sc), mode, P(nxt), n, so, u.depth, st), "se_residual")
             cur, nxt = nxt, cur
             S = so
         y = None

@@ -46,7 +46,7 @@ FFR_API long long ffr_launch_count(void) { return launch_count(); }
 
 FFR_API int ffr_debug_set_window(int enable) { set_use_window(enable != 0); return 0; }
 FFR_API void ffr_debug_set_pair(int mode) { set_pair_mode(mode); }
-FFR_API void ffr_debug_set_pdl(int enable) { set_pdl_enabled(enable != 0); }
+FFR_API void ffr_debug_set_pdl(int mask) { set_pdl_mask(mask); }
 
 FFR_API int ffr_debug_set_counters(void* counters) {
     set_debug_counters(reinterpret_cast<unsigned long long*>(counters));
@@ -211,6 +211,14 @@ FFR_API int ffr_se_gate_fwd(const float* pool_part, const float* w1, const float
                             int S, int C, ffr_stream_t stream) {
     FFR_CHECK_ARG(pool_part && w1 && w2 && gate, "ffr_se_gate_fwd: null pointer");
     return se_gate_launch(pool_part, pixmajor_backbone(S, n_img) ? 1 : 0, w1, w2, gate, sums, n_img, S, C, S_(stream));
+}
+
+FFR_API int ffr_se_gate_residual_fwd(const void* u, const float* pool_part, const float* w1, const float* w2,
+                                     const void* shortcut, int shortcut_mode, void* y, int n_img, int S, int C,
+                                     ffr_stream_t stream) {
+    FFR_CHECK_ARG(u && pool_part && w1 && w2 && shortcut && y, "ffr_se_gate_residual_fwd: null pointer");
+    return se_gate_residual_launch(u, pool_part, pixmajor_backbone(S, n_img) ? 1 : 0, w1, w2, shortcut, shortcut_mode, y,
+                                   n_img, S, C, S_(stream));
 }
 
 FFR_API int ffr_se_residual_fwd(const void* u, const float* gate, const void* shortcut, int shortcut_mode, void* y,

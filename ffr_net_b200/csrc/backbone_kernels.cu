@@ -221,7 +221,7 @@ int stem_launch(const float* x, const float* w, const float* b, const float* a, 
     long long grid = (tiles + 3) / 4;
     const long long cap = (long long)num_sms() * 16;
     if (grid > cap) grid = cap;
-    launch_ex(stem_kernel<false>, dim3((int)grid), dim3(128), 0, stream, 1, x, nullptr, 0, w, b, a, reinterpret_cast<__nv_bfloat16*>(out), n_img, S);
+    launch_ex(stem_kernel<false>, dim3((int)grid), dim3(128), 0, stream, 1, PDL_SIMT, x, nullptr, 0, w, b, a, reinterpret_cast<__nv_bfloat16*>(out), n_img, S);
     return launch_status("stem_kernel");
 }
 
@@ -232,7 +232,7 @@ int stem_u8_launch(const unsigned char* img, const unsigned char* flip, int swap
     long long grid = (tiles + 3) / 4;
     const long long cap = (long long)num_sms() * 16;
     if (grid > cap) grid = cap;
-    launch_ex(stem_kernel<true>, dim3((int)grid), dim3(128), 0, stream, 1, img, flip, swap_rb, w, b, a, reinterpret_cast<__nv_bfloat16*>(out), n_img, S);
+    launch_ex(stem_kernel<true>, dim3((int)grid), dim3(128), 0, stream, 1, PDL_SIMT, img, flip, swap_rb, w, b, a, reinterpret_cast<__nv_bfloat16*>(out), n_img, S);
     return launch_status("stem_kernel<u8>");
 }
 
@@ -244,17 +244,16 @@ int stem_u8_launch(const unsigned char* img, const unsigned char* flip, int swap
 // in a fixed order: no atomics, bit-reproducible. dense != 0: pool_part is [n_img][C] finished sums instead (the
 // pixel-major experiment, whose epilogue adds per row with atomics). One CTA per image.
 // ----------------------------------------------------------------------------------------------
+// Gate of image n into s_gate[C] (shared): fixed-order sum of the partial blocks, FC1 + ReLU, FC2 + sigmoid. Called by
+// all 256 threads of a CTA; ends with a __syncthreads(). Used by se_gate_kernel and by the fused se_gate_residual_kernel
+// (identical arithmetic, so the two paths give bit-identical maps).
 template <int C>
-__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ pool_part, int dense,
-                                                      const float* __restrict__ w1, const float* __restrict__ w2,
-                                                      float* __restrict__ gate, float* __restrict__ sums, int rpi, float inv) {
-    pdl_sync();
+__device__ __forceinline__ void se_gate_compute(const float* __restrict__ pool_part, int dense,
+                                                const float* __restrict__ w1, const float* __restrict__ w2, int n,
+                                                int rpi, float inv, float* s_part /*[PARTS*C]*/, float* s_mean /*[C]*/,
+                                                float* s_hid /*[C/16]*/, float* s_gate /*[C]*/) {
     constexpr int R = C / 16;
     constexpr int PARTS = (C >= 256) ? 1 : 256 / C;      // threads (c, part): part strides over the blocks
-    __shared__ float s_part[PARTS][C];
-    __shared__ float s_mean[C];
-    __shared__ float s_hid[R];
-    const int n = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (dense) {
         for (int c = tid; c < C; c += 256) s_mean[c] = pool_part[(long long)n * C + c];
@@ -268,19 +267,17 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ 
                 const int slot = (((long long)b << 5) >= r0) ? 0 : 1;      // first row of the block belongs to image n?
                 a += pool_part[((long long)b * 2 + slot) * C + c];
             }
-            s_part[part][c] = a;
+            s_part[part * C + c] = a;
         }
         __syncthreads();
         for (int c = tid; c < C; c += 256) {
-            float a = s_part[0][c];
+            float a = s_part[c];
 #pragma unroll
-            for (int q = 1; q < PARTS; ++q) a += s_part[q][c];
+            for (int q = 1; q < PARTS; ++q) a += s_part[q * C + c];
             s_mean[c] = a;
         }
     }
     __syncthreads();
-    if (sums != nullptr)
-        for (int c = tid; c < C; c += 256) sums[(long long)n * C + c] = s_mean[c];
     for (int j = warp; j < R; j += 8) {
         float a = 0.f;
         for (int c = lane; c < C; c += 32) a = fmaf(__ldg(w1 + j * C + c), s_mean[c] * inv, a);
@@ -292,7 +289,26 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ 
         float a = 0.f;
 #pragma unroll
         for (int j = 0; j < R; ++j) a = fmaf(__ldg(w2 + c * R + j), s_hid[j], a);
-        gate[(long long)n * C + c] = 1.0f / (1.0f + __expf(-a));
+        s_gate[c] = 1.0f / (1.0f + __expf(-a));
+    }
+    __syncthreads();
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ pool_part, int dense,
+                                                      const float* __restrict__ w1, const float* __restrict__ w2,
+                                                      float* __restrict__ gate, float* __restrict__ sums, int rpi, float inv) {
+    pdl_sync();
+    constexpr int PARTS = (C >= 256) ? 1 : 256 / C;
+    __shared__ float s_part[PARTS * C];
+    __shared__ float s_mean[C];
+    __shared__ float s_hid[C / 16];
+    __shared__ float s_gate[C];
+    const int n = blockIdx.x;
+    se_gate_compute<C>(pool_part, dense, w1, w2, n, rpi, inv, s_part, s_mean, s_hid, s_gate);
+    for (int c = threadIdx.x; c < C; c += 256) {
+        gate[(long long)n * C + c] = s_gate[c];
+        if (sums != nullptr) sums[(long long)n * C + c] = s_mean[c];
     }
 }
 
@@ -302,10 +318,10 @@ int se_gate_launch(const float* pool_part, int dense, const float* w1, const flo
     const float inv = 1.0f / (float)(S * S);
     FFR_CHECK_ARG(rpi >= 64, "se_gate: map %dx%d too small for the 32-row block scheme", S, S);
     switch (C) {
-        case 64:  launch_ex(se_gate_kernel<64>, dim3(n_img), dim3(256), 0, stream, 1, pool_part, dense, w1, w2, gate, sums, rpi, inv); break;
-        case 128: launch_ex(se_gate_kernel<128>, dim3(n_img), dim3(256), 0, stream, 1, pool_part, dense, w1, w2, gate, sums, rpi, inv); break;
-        case 256: launch_ex(se_gate_kernel<256>, dim3(n_img), dim3(256), 0, stream, 1, pool_part, dense, w1, w2, gate, sums, rpi, inv); break;
-        case 512: launch_ex(se_gate_kernel<512>, dim3(n_img), dim3(256), 0, stream, 1, pool_part, dense, w1, w2, gate, sums, rpi, inv); break;
+        case 64:  launch_ex(se_gate_kernel<64>, dim3(n_img), dim3(256), 0, stream, 1, PDL_SIMT, pool_part, dense, w1, w2, gate, sums, rpi, inv); break;
+        case 128: launch_ex(se_gate_kernel<128>, dim3(n_img), dim3(256), 0, stream, 1, PDL_SIMT, pool_part, dense, w1, w2, gate, sums, rpi, inv); break;
+        case 256: launch_ex(se_gate_kernel<256>, dim3(n_img), dim3(256), 0, stream, 1, PDL_SIMT, pool_part, dense, w1, w2, gate, sums, rpi, inv); break;
+        case 512: launch_ex(se_gate_kernel<512>, dim3(n_img), dim3(256), 0, stream, 1, PDL_SIMT, pool_part, dense, w1, w2, gate, sums, rpi, inv); break;
         default: return set_error(-1, "se_gate: unsupported C=%d", C);
     }
     return launch_status("se_gate_kernel");
@@ -378,13 +394,92 @@ int se_residual_launch(const void* u, const float* gate, const void* sc, int sho
     const __nv_bfloat16* sp = reinterpret_cast<const __nv_bfloat16*>(sc);
     __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
     switch (C) {
-        case 64:  launch_ex(se_residual_kernel<64>, dim3((int)grid), dim3(256), 0, stream, 1, up, gate, sp, shortcut_mode, yp, S, total_rows); break;
-        case 128: launch_ex(se_residual_kernel<128>, dim3((int)grid), dim3(256), 0, stream, 1, up, gate, sp, shortcut_mode, yp, S, total_rows); break;
-        case 256: launch_ex(se_residual_kernel<256>, dim3((int)grid), dim3(256), 0, stream, 1, up, gate, sp, shortcut_mode, yp, S, total_rows); break;
-        case 512: launch_ex(se_residual_kernel<512>, dim3((int)grid), dim3(256), 0, stream, 1, up, gate, sp, shortcut_mode, yp, S, total_rows); break;
+        case 64:  launch_ex(se_residual_kernel<64>, dim3((int)grid), dim3(256), 0, stream, 1, PDL_SIMT, up, gate, sp, shortcut_mode, yp, S, total_rows); break;
+        case 128: launch_ex(se_residual_kernel<128>, dim3((int)grid), dim3(256), 0, stream, 1, PDL_SIMT, up, gate, sp, shortcut_mode, yp, S, total_rows); break;
+        case 256: launch_ex(se_residual_kernel<256>, dim3((int)grid), dim3(256), 0, stream, 1, PDL_SIMT, up, gate, sp, shortcut_mode, yp, S, total_rows); break;
+        case 512: launch_ex(se_residual_kernel<512>, dim3((int)grid), dim3(256), 0, stream, 1, PDL_SIMT, up, gate, sp, shortcut_mode, yp, S, total_rows); break;
         default: return set_error(-1, "se_residual: unsupported C=%d", C);
     }
     return launch_status("se_residual_kernel");
+}
+
+// ----------------------------------------------------------------------------------------------
+// Fused gate + scale + residual: ONE CTA per image computes the image's gate in shared memory (se_gate_compute: 8-50 KB of
+// partial sums and FC weights from L2, a few microseconds that the other resident CTAs of the SM hide) and then streams
+// the image's rows exactly like se_residual_kernel. Saves the se_gate launch (~9 us of a ~13 us launch + drain
+// per unit) for the 21 units with C <= 256; at C = 512 (7x7 maps: 64 KB of rows against 128 KB of FC weights per image)
+// the separate gate kernel stays.
+// ----------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) se_gate_residual_kernel(const __nv_bfloat16* __restrict__ u,
+                                                               const float* __restrict__ pool_part, int dense,
+                                                               const float* __restrict__ w1, const float* __restrict__ w2,
+                                                               const __nv_bfloat16* __restrict__ sc, int shortcut_mode,
+                                                               __nv_bfloat16* __restrict__ y, int S, float inv) {
+    pdl_sync();
+    constexpr int PARTS = (C >= 256) ? 1 : 256 / C;
+    constexpr int TPR = C / 8;          // threads per row
+    constexpr int RPB = 256 / TPR;      // rows per CTA pass
+    constexpr int UNR = 4;
+    __shared__ float s_part[PARTS * C];
+    __shared__ float s_mean[C];
+    __shared__ float s_hid[C / 16];
+    __shared__ __align__(16) float s_gate[C];
+    const int n = blockIdx.x;
+    const int G = S + 1, rows = G * G, G2 = 2 * S + 1;
+    se_gate_compute<C>(pool_part, dense, w1, w2, n, rows, inv, s_part, s_mean, s_hid, s_gate);
+    const int c8 = threadIdx.x % TPR;
+    const int rsub = threadIdx.x / TPR;
+    const float4 g0 = reinterpret_cast<const float4*>(s_gate)[c8 * 2];
+    const float4 g1 = reinterpret_cast<const float4*>(s_gate)[c8 * 2 + 1];
+    const long long base = (long long)n * rows;
+    for (int rb = 0; rb < rows; rb += RPB * UNR) {
+        uint4 uv[UNR], sv[UNR];
+        int r[UNR];
+#pragma unroll
+        for (int k = 0; k < UNR; ++k) {
+            r[k] = rb + k * RPB + rsub;
+            if (r[k] < rows) {
+                long long srow = base + r[k];
+                if (shortcut_mode == 1) {
+                    const int h = r[k] / G, wq = r[k] - h * G;
+                    srow = (long long)n * G2 * G2 + (long long)(2 * h) * G2 + 2 * wq;
+                }
+                uv[k] = __ldg(reinterpret_cast<const uint4*>(u + (base + r[k]) * C) + c8);
+                sv[k] = __ldg(reinterpret_cast<const uint4*>(sc + srow * C) + c8);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < UNR; ++k) {
+            if (r[k] < rows) {
+                uint4 o;
+                o.x = pack_bf16x2(fmaf(bf16lo(uv[k].x), g0.x, bf16lo(sv[k].x)), fmaf(bf16hi(uv[k].x), g0.y, bf16hi(sv[k].x)));
+                o.y = pack_bf16x2(fmaf(bf16lo(uv[k].y), g0.z, bf16lo(sv[k].y)), fmaf(bf16hi(uv[k].y), g0.w, bf16hi(sv[k].y)));
+                o.z = pack_bf16x2(fmaf(bf16lo(uv[k].z), g1.x, bf16lo(sv[k].z)), fmaf(bf16hi(uv[k].z), g1.y, bf16hi(sv[k].z)));
+                o.w = pack_bf16x2(fmaf(bf16lo(uv[k].w), g1.z, bf16lo(sv[k].w)), fmaf(bf16hi(uv[k].w), g1.w, bf16hi(sv[k].w)));
+                reinterpret_cast<uint4*>(y + (base + r[k]) * C)[c8] = o;
+            }
+        }
+    }
+}
+
+int se_gate_residual_launch(const void* u, const float* pool_part, int dense, const float* w1, const float* w2,
+                            const void* sc, int shortcut_mode, void* y, int n_img, int S, int C, cudaStream_t stream) {
+    FFR_CHECK_ARG(shortcut_mode >= 0 && shortcut_mode <= 2, "se_gate_residual: shortcut_mode=%d", shortcut_mode);
+    const int rpi = (S + 1) * (S + 1);
+    const float inv = 1.0f / (float)(S * S);
+    FFR_CHECK_ARG(rpi >= 64, "se_gate_residual: map %dx%d too small for the 32-row block scheme", S, S);
+    const __nv_bfloat16* up = reinterpret_cast<const __nv_bfloat16*>(u);
+    const __nv_bfloat16* sp = reinterpret_cast<const __nv_bfloat16*>(sc);
+    __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
+    switch (C) {
+        case 64:  launch_ex(se_gate_residual_kernel<64>, dim3(n_img), dim3(256), 0, stream, 1, PDL_SIMT, up, pool_part, dense, w1, w2, sp, shortcut_mode, yp, S, inv); break;
+        case 128: launch_ex(se_gate_residual_kernel<128>, dim3(n_img), dim3(256), 0, stream, 1, PDL_SIMT, up, pool_part, dense, w1, w2, sp, shortcut_mode, yp, S, inv); break;
+        case 256: launch_ex(se_gate_residual_kernel<256>, dim3(n_img), dim3(256), 0, stream, 1, PDL_SIMT, up, pool_part, dense, w1, w2, sp, shortcut_mode, yp, S, inv); break;
+        case 512: launch_ex(se_gate_residual_kernel<512>, dim3(n_img), dim3(256), 0, stream, 1, PDL_SIMT, up, pool_part, dense, w1, w2, sp, shortcut_mode, yp, S, inv); break;
+        default: return set_error(-1, "se_gate_residual: unsupported C=%d", C);
+    }
+    return launch_status("se_gate_residual_kernel");
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -411,7 +506,7 @@ int subsample2_launch(const void* x, void* out, int n_img, int So, int C, cudaSt
     const long long total = (long long)n_img * (So + 1) * (So + 1) * (C / 8);
     int grid = (int)((total + 255) / 256);
     if (grid > num_sms() * 16) grid = num_sms() * 16;
-    launch_ex(subsample2_kernel, dim3(grid), dim3(256), 0, stream, 1, reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), n_img,
+    launch_ex(subsample2_kernel, dim3(grid), dim3(256), 0, stream, 1, PDL_SIMT, reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), n_img,
                                                 So, C / 8);
     return launch_status("subsample2_kernel");
 }
@@ -447,7 +542,7 @@ int export_nchw_launch(const void* h, const float* scale, const float* shift, fl
     dim3 grid(C / 64, n_img);
     const size_t smem = (size_t)S * S * 65 * sizeof(float);
     FFR_CHECK_ARG(smem <= 48 * 1024, "export_nchw: map %dx%d too large", S, S);
-    launch_ex(export_nchw_kernel, dim3(grid), dim3(256), smem, stream, 1, reinterpret_cast<const __nv_bfloat16*>(h), scale, shift, y, S, C);
+    launch_ex(export_nchw_kernel, dim3(grid), dim3(256), smem, stream, 1, PDL_SIMT, reinterpret_cast<const __nv_bfloat16*>(h), scale, shift, y, S, C);
     return launch_status("export_nchw_kernel");
 }
 
@@ -482,7 +577,7 @@ __global__ void __launch_bounds__(256) bias_l2norm_kernel(const float* __restric
 int bias_l2norm_launch(const float* acc, int splits, long long split_stride, const float* bias, float* f, int rows, int D,
                        cudaStream_t stream) {
     FFR_CHECK_ARG(D == 512, "bias_l2norm: D=%d", D);
-    launch_ex(bias_l2norm_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, 1, acc, splits, split_stride, bias, f, rows);
+    launch_ex(bias_l2norm_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, 1, PDL_SIMT, acc, splits, split_stride, bias, f, rows);
     return launch_status("bias_l2norm_kernel");
 }
 

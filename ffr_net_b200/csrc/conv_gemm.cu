@@ -1046,7 +1046,7 @@ static int launch_win2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
         FFR_CUDA(cudaFuncSetAttribute(conv_win2_kernel<BN, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         attr_set = true;
     }
-    FFR_CUDA(launch_ex(conv_win2_kernel<BN, TB>, dim3(grid), dim3(NUM_THREADS), smem_bytes, stream, 1, tmA, tmB, p, wc));
+    FFR_CUDA(launch_ex(conv_win2_kernel<BN, TB>, dim3(grid), dim3(NUM_THREADS), smem_bytes, stream, 1, PDL_GEMM, tmA, tmB, p, wc));
     return launch_status("conv_win2_kernel");
 }
 
@@ -1059,7 +1059,7 @@ static int launch_win(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
                                       232448));
         attr_set = true;
     }
-    FFR_CUDA(launch_ex(conv_win_kernel<BN, SUB, TB>, dim3(grid), dim3(NUM_THREADS), smem_bytes, stream, 1, tmA, tmB, p, wc));
+    FFR_CUDA(launch_ex(conv_win_kernel<BN, SUB, TB>, dim3(grid), dim3(NUM_THREADS), smem_bytes, stream, 1, PDL_GEMM, tmA, tmB, p, wc));
     return launch_status("conv_win_kernel");
 }
 
@@ -1093,7 +1093,7 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
                                       Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    FFR_CUDA(launch_ex(conv_gemm_kernel<BN, false>, dim3(grid), dim3(NUM_THREADS), Cfg::SMEM_BYTES, stream, 1, tmA, tmB, p));
+    FFR_CUDA(launch_ex(conv_gemm_kernel<BN, false>, dim3(grid), dim3(NUM_THREADS), Cfg::SMEM_BYTES, stream, 1, PDL_GEMM, tmA, tmB, p));
     return launch_status("conv_gemm_kernel");
 }
 
@@ -1108,7 +1108,7 @@ static int launch_cfg_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const
                                       Cfg::SMEM_BYTES_PAIR));
         attr_set = true;
     }
-    FFR_CUDA(launch_ex(conv_gemm_kernel<BN, true>, dim3(grid), dim3(NUM_THREADS), Cfg::SMEM_BYTES_PAIR, stream, 2, tmA, tmB, p));
+    FFR_CUDA(launch_ex(conv_gemm_kernel<BN, true>, dim3(grid), dim3(NUM_THREADS), Cfg::SMEM_BYTES_PAIR, stream, 2, PDL_GEMM, tmA, tmB, p));
     return launch_status("conv_gemm_kernel<pair>");
 }
 

@@ -101,9 +101,13 @@ int launch_status(const char* what) {
 
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
-static std::atomic<bool> g_pdl{true};
-bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed); }
-void set_pdl_enabled(bool on) { g_pdl.store(on, std::memory_order_relaxed); }
+// Measured on the bs512 eval step (tools/ab_bench.py, profiles/r02_ab_pdl_pair_512.json; medians of 10 interleaved runs):
+// no PDL 11.09 ms, GEMM kernels only 10.95 ms, SIMT kernels only 11.37 ms, both 11.30 ms. Early-scheduled CTAs of the
+// memory-bound kernels sit next to the running GEMM CTAs and cost more than their launch latency saves.
+constexpr int kPdlDefault = PDL_GEMM;
+static std::atomic<int> g_pdl{kPdlDefault};
+bool pdl_enabled(int kind) { return (g_pdl.load(std::memory_order_relaxed) & kind) != 0; }
+void set_pdl_mask(int mask) { g_pdl.store(mask < 0 ? kPdlDefault : mask, std::memory_order_relaxed); }
 
 int num_sms() {
     static int n = 0;

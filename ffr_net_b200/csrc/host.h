@@ -41,14 +41,15 @@ int num_sms();
 
 // Programmatic dependent launch (ptx.cuh: pdl_wait / pdl_launch_dependents) for kernels that call pdl_sync(): on by
 // default, ffr_debug_set_pdl(0) turns the launch attribute off (plain stream order; A/B runs and tests).
-bool pdl_enabled();
-void set_pdl_enabled(bool on);
+enum PdlKind { PDL_GEMM = 1, PDL_SIMT = 2 };     // bit mask: tcgen05 GEMM kernels / the memory-bound SIMT kernels
+bool pdl_enabled(int kind);
+void set_pdl_mask(int mask);
 
 // Kernel launch with optional cluster size and the programmatic-stream-serialization attribute. ONLY for kernels that
 // execute pdl_wait() before their first access to global memory another kernel may write (or still read).
 template <typename... P, typename... A>
 inline cudaError_t launch_ex(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
-                             A... args) {
+                             int pdl_kind, A... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -63,7 +64,7 @@ inline cudaError_t launch_ex(void (*kernel)(P...), dim3 grid, dim3 block, size_t
         at[n].val.clusterDim.z = 1;
         ++n;
     }
-    if (pdl_enabled()) {
+    if (pdl_enabled(pdl_kind)) {
         at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[n].val.programmaticStreamSerializationAllowed = 1;
         ++n;

@@ -14,6 +14,8 @@ int stem_u8_launch(const unsigned char* img, const unsigned char* flip, int swap
                    const float* a, void* out, int n_img, int S, cudaStream_t stream);
 int se_gate_launch(const float* pool_part, int dense, const float* w1, const float* w2, float* gate, float* sums,
                    int n_img, int S, int C, cudaStream_t stream);
+int se_gate_residual_launch(const void* u, const float* pool_part, int dense, const float* w1, const float* w2,
+                            const void* sc, int shortcut_mode, void* y, int n_img, int S, int C, cudaStream_t stream);
 int se_residual_launch(const void* u, const float* gate, const void* sc, int shortcut_mode, void* y, int n_img, int S,
                        int C, cudaStream_t stream);
 int subsample2_launch(const void* x, void* out, int n_img, int So, int C, cudaStream_t stream);

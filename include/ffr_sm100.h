@@ -145,6 +145,12 @@ FFR_API int ffr_stem_u8_fwd(const unsigned char* img, const unsigned char* flip,
  * 2: same-grid conv shortcut. */
 FFR_API int ffr_se_gate_fwd(const float* pool_part, const float* w1, const float* w2, float* gate, float* sums, int n_img,
                             int S, int C, ffr_stream_t stream);
+/* ffr_se_gate_residual_fwd: the two calls above in ONE launch (one CTA per image computes the image's gate from the
+ * partial sums, then streams the image's rows); same arithmetic, bit-identical output. Backbone.forward uses it for the
+ * units with C <= 256 (model_ir_se50.py:29-36, 73-76). */
+FFR_API int ffr_se_gate_residual_fwd(const void* u, const float* pool_part, const float* w1, const float* w2,
+                                     const void* shortcut, int shortcut_mode, void* y, int n_img, int S, int C,
+                                     ffr_stream_t stream);
 FFR_API int ffr_se_residual_fwd(const void* u, const float* gate, const void* shortcut, int shortcut_mode, void* y,
                                 int n_img, int S, int C, ffr_stream_t stream);
 
@@ -421,11 +427,12 @@ FFR_API int ffr_debug_set_window(int enable);
  * layers with 256-wide N tiles: -1 / 1 = on (default), 0 = off (single-CTA kernel; the two must agree, tests run both). */
 FFR_API void ffr_debug_set_pair(int mode);
 
-/* Debug/tuning: programmatic dependent launch. 1 (default): the kernels of the forward chain are launched with the
- * programmatic-stream-serialization attribute, so a kernel's CTAs are scheduled, and its prologue runs, while the
- * previous kernel drains; every such kernel executes griddepcontrol.wait before touching global memory. 0: plain
- * stream order (results are identical; A/B timing and tests). */
-FFR_API void ffr_debug_set_pdl(int enable);
+/* Debug/tuning: programmatic dependent launch, a bit mask: 1 = the tcgen05 GEMM kernels, 2 = the memory-bound kernels of
+ * the backbone chain are launched with the programmatic-stream-serialization attribute, so a kernel's CTAs are scheduled,
+ * and its prologue runs, while the previous kernel drains; every such kernel executes griddepcontrol.wait before touching
+ * global memory. 0: plain stream order; negative: the library default. Results are identical in every mode (A/B timing
+ * and tests). */
+FFR_API void ffr_debug_set_pdl(int mask);
 
 /* Debug/tuning: device buffer of 16 uint64 that the sliding-window kernel fills with per-role barrier-wait cycle
  * counts (summed over CTAs; slots in csrc/conv_gemm.cuh DbgSlot); NULL (default) disables the counters. */

@@ -221,11 +221,11 @@ def test_launch_modes_bit_identical(models, lib):
         try:
             lib.ffr_debug_set_pdl(0)
             y1, f1 = m(x)
-            lib.ffr_debug_set_pdl(1)
+            lib.ffr_debug_set_pdl(3)
             lib.ffr_debug_set_pair(0)
             y2, f2 = m(x)
         finally:
-            lib.ffr_debug_set_pdl(1)
+            lib.ffr_debug_set_pdl(-1)
             lib.ffr_debug_set_pair(-1)
         torch.cuda.synchronize()
     assert torch.equal(y1, y0) and torch.equal(f1, f0)

@@ -193,6 +193,35 @@ def test_se_residual_isolated(lib, n, S, C, mode):
     assert layout.flat_pad_rows(y, n, S, C).abs().max().item() == 0.0          # pad rows: 0 * gate + 0
 
 
+@pytest.mark.parametrize("n,S,C,mode", [(3, 14, 256, 0), (2, 7, 512, 0), (5, 28, 64, 1), (2, 56, 64, 2), (3, 28, 128, 0),
+                                        (130, 14, 256, 0)])
+def test_se_gate_residual_fused_matches_two_calls(lib, n, S, C, mode):
+    """ffr_se_gate_residual_fwd (gate computed per image inside the streaming kernel) == ffr_se_gate_fwd followed by
+    ffr_se_residual_fwd, bit for bit, on the squeeze partial sums a real conv2 launch stored."""
+    from ffr_net_b200 import packing
+    g = torch.Generator(device="cuda").manual_seed(S * C + mode + n)
+    x = torch.randn(n, C, S, S, generator=g, device="cuda")
+    w = torch.randn(C, C, 3, 3, generator=g, device="cuda") / (3 * C ** 0.5)
+    wp = packing.pack_conv(w)
+    b1 = torch.empty(C, device="cuda").uniform_(-0.3, 0.3, generator=g)
+    rows = n * (S + 1) * (S + 1)
+    u = torch.empty((rows, C), dtype=torch.bfloat16, device="cuda")
+    part = torch.full((max(lib.ffr_se_pool_part_floats(n, S, C), n * C),), -5.0e3, dtype=torch.float32, device="cuda")
+    _lib.check(lib.ffr_conv3x3_bn_pool_fwd(P(layout.to_flat(x)), n, S, C, 1, P(wp), C, P(b1), P(u), P(part), _stream()))
+    fc1 = torch.randn(C // 16, C, generator=g, device="cuda") / C ** 0.5
+    fc2 = torch.randn(C, C // 16, generator=g, device="cuda") / 2
+    S_sc = 2 * S if mode == 1 else S
+    scf = layout.to_flat(torch.randn(n, C, S_sc, S_sc, generator=g, device="cuda"))
+    gate = torch.empty(n, C, device="cuda")
+    y1, y2 = torch.full_like(u, 9.0), torch.full_like(u, -9.0)
+    _lib.check(lib.ffr_se_gate_fwd(P(part), P(fc1), P(fc2), P(gate), None, n, S, C, _stream()))
+    _lib.check(lib.ffr_se_residual_fwd(P(u), P(gate), P(scf), mode, P(y1), n, S, C, _stream()))
+    _lib.check(lib.ffr_se_gate_residual_fwd(P(u), P(part), P(fc1), P(fc2), P(scf), mode, P(y2), n, S, C, _stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(y1, y2)
+    assert y1.float().abs().max().item() > 0.1
+
+
 def test_conv3x3_s2d_output_roundtrip(lib):
     """conv1 writing the space-to-depth layout, then the stride-2 conv reading it == conv -> prelu -> stride-2 conv."""
     from ffr_net_b200 import packing

@@ -37,16 +37,21 @@ res = {}
 with torch.no_grad():
     for _ in range(5):
         rec.embed_from_images(enc, x)
-for rnd in range(3):
-    for pdl in (1, 0):
-        for pair in (-1, 0):
-            lib.ffr_debug_set_pdl(pdl)
-            lib.ffr_debug_set_pair(pair)
-            run(2)
-            res.setdefault("pdl=%d pair=%d" % (pdl, 1 if pair else 0), []).append(run(10))
-lib.ffr_debug_set_pdl(1)
+CONFIGS = [(3, -1, True), (0, -1, True), (1, -1, True), (2, -1, True), (0, 0, True)]
+for rnd in range(10):
+    order = CONFIGS[rnd % len(CONFIGS):] + CONFIGS[:rnd % len(CONFIGS)]      # rotate: no config always runs first
+    for pdl, pair, fuse in order:
+        lib.ffr_debug_set_pdl(pdl)
+        lib.ffr_debug_set_pair(pair)
+        enc.fuse_se = fuse
+        run(3)
+        res.setdefault("pdl=%d pair=%d fused_se=%d" % (pdl, 1 if pair else 0, int(fuse)), []).append(run(10))
+enc.fuse_se = True
+lib.ffr_debug_set_pdl(-1)
 lib.ffr_debug_set_pair(-1)
-out = {k: {"ms": [round(v, 3) for v in vs], "best_ms": round(min(vs), 3), "img_s": round(n / min(vs) * 1e3)} for k, vs in res.items()}
+import statistics
+out = {k: {"ms": [round(v, 3) for v in vs], "best_ms": round(min(vs), 3), "median_ms": round(statistics.median(vs), 3),
+           "img_s_median": round(n / statistics.median(vs) * 1e3)} for k, vs in res.items()}
 print(json.dumps(out, indent=1))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/ab_bench_%d.json" % n, "w"), indent=1)

@@ -22,7 +22,7 @@ slope = torch.full((cout,), 0.25, device="cuda")
 out = torch.empty(rows, cout, dtype=torch.bfloat16, device="cuda")
 st = _lib.stream_ptr()
 res = {}
-for pdl in (1, 0):
+for pdl in (3, 0):
     lib.ffr_debug_set_pdl(pdl)
     K = 8
     bufs = []
@@ -48,6 +48,6 @@ for pdl in (1, 0):
     spans = [r["exit"] - r["entry"] for r in rowsr]
     res["pdl=%d" % pdl] = dict(event_ms_per_launch=e0.elapsed_time(e1) / K, spans_ns=spans, gaps_ns=gaps, launches=rowsr)
     print("pdl", pdl, "event us/launch %.2f" % (e0.elapsed_time(e1) / K * 1e3), "spans", spans, "gaps", gaps)
-lib.ffr_debug_set_pdl(1)
+lib.ffr_debug_set_pdl(-1)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/launch_gaps.json", "w"), indent=1)
