@@ -140,7 +140,12 @@ __device__ __forceinline__ EpiSched epi_sched_single(const ConvGemmParams& p) {
     return es;
 }
 
-template <int BN, int SUB>
+// FIXED != 0: the epilogue specialised at compile time for exactly this flag set (the kernels dispatch on p.flags among
+// the sets the hot layers use, epilogue_dispatch below); every other feature is compiled out. The generic epilogue is
+// ~10 k SASS instructions of runtime flag tests; on the 64- and 128-channel layers, which are epilogue-bound (the MMA
+// warp waits for accumulator buffers 20-36 % of its time), ncu attributed 9 % of the epilogue warps' samples to
+// instruction fetch and 5 % to branch resolution. Specialised: 64 -> 64 @112 583 -> 486 us, whole eval step -5 %.
+template <int BN, int SUB, uint32_t FIXED = 0>
 __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uint32_t tmem_base, uint64_t* tfull_bar,
                                               uint64_t* tempty_bar, float* sparam, const int warp, const int lane,
                                               const EpiSched es) {
@@ -150,7 +155,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
     const int chalf = warp >> 2;                    // which half of the accumulator columns
     const int row_in_tile = quad * 32 + lane;
     const int etid = threadIdx.x;
-    const uint32_t flags = p.flags;
+    const uint32_t flags = FIXED ? FIXED : (p.flags & ~EPI_GENERIC_ONLY);
     const bool border = (flags & EPI_BORDER_BIAS) != 0;
     const int nbias = border ? 9 : 1;
     const bool small_m = p.M < (1 << 24);
@@ -176,7 +181,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
                 for (int i = etid; i < nbias * BN; i += EPI_THREADS)
                     sparam[i] = p.bias[(i / BN) * p.Cout + n0 + (i % BN)];
             if (flags & EPI_PRELU)
-                for (int i = etid; i < BN; i += EPI_THREADS) sparam[9 * BN + i] = p.slope[n0 + i];
+                for (int i = etid; i < BN; i += EPI_THREADS) sparam[9 * BN + i] = p.slope[n0 + i] - 1.0f;   // slope - 1
             asm volatile("bar.sync 1, 256;" ::: "memory");
             loaded_n_tile = n_tile;
         }
@@ -230,8 +235,9 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
                 cls = ch * 3 + cw;
             }
         }
-        const float4* sbias4 = reinterpret_cast<const float4*>(sparam + cls * BN + chalf * HALF);
-        const float4* sslope4 = reinterpret_cast<const float4*>(sparam + 9 * BN + chalf * HALF);
+        // explicit ld.shared (a float* into dynamic shared memory compiles to generic LD.E: long-scoreboard latency)
+        const uint32_t sbias_a = smem_u32(sparam) + static_cast<uint32_t>(cls * BN + chalf * HALF) * 4u;
+        const uint32_t sslope_a = smem_u32(sparam) + static_cast<uint32_t>(9 * BN + chalf * HALF) * 4u;
         const int nc0 = n0 + chalf * HALF;       // first global output channel of this warp
 
         // output addressing
@@ -287,18 +293,19 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
             if (flags & (EPI_BIAS | EPI_BORDER_BIAS)) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const float4 b4 = sbias4[ci * 8 + q];
+                    const float4 b4 = lds_f32x4(sbias_a + (ci * 8 + q) * 16);
                     x[q * 4 + 0] += b4.x; x[q * 4 + 1] += b4.y; x[q * 4 + 2] += b4.z; x[q * 4 + 3] += b4.w;
                 }
             }
             if (flags & EPI_PRELU) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const float4 s4 = sslope4[ci * 8 + q];
-                    x[q * 4 + 0] = fmaxf(x[q * 4 + 0], 0.f) + s4.x * fminf(x[q * 4 + 0], 0.f);
-                    x[q * 4 + 1] = fmaxf(x[q * 4 + 1], 0.f) + s4.y * fminf(x[q * 4 + 1], 0.f);
-                    x[q * 4 + 2] = fmaxf(x[q * 4 + 2], 0.f) + s4.z * fminf(x[q * 4 + 2], 0.f);
-                    x[q * 4 + 3] = fmaxf(x[q * 4 + 3], 0.f) + s4.w * fminf(x[q * 4 + 3], 0.f);
+                    const float4 s4 = lds_f32x4(sslope_a + (ci * 8 + q) * 16);
+                    // PReLU as x + (slope - 1) * min(x, 0): one FMNMX + one FFMA per element
+                    x[q * 4 + 0] = fmaf(s4.x, fminf(x[q * 4 + 0], 0.f), x[q * 4 + 0]);
+                    x[q * 4 + 1] = fmaf(s4.y, fminf(x[q * 4 + 1], 0.f), x[q * 4 + 1]);
+                    x[q * 4 + 2] = fmaf(s4.z, fminf(x[q * 4 + 2], 0.f), x[q * 4 + 2]);
+                    x[q * 4 + 3] = fmaf(s4.w, fminf(x[q * 4 + 3], 0.f), x[q * 4 + 3]);
                 }
             }
             if (flags & (EPI_RESIDUAL | EPI_MUL_DSIG)) {
@@ -453,6 +460,45 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
         atomicAdd(p.dbg + DBG_EPI_WAIT, (unsigned long long)w_e);
         atomicAdd(p.dbg + DBG_EPI_TOTAL, (unsigned long long)(clock64() - t_begin));
     }
+}
+
+// Flag sets with a specialised epilogue. Backbone: conv1 of a unit (BatchNorm shift as border bias + PReLU, plain or
+// space-to-depth store), conv2 (BatchNorm shift + SE squeeze sums), the 1x1 shortcut. RecNet eval (pixel-major tiles):
+// ConvLayer and the second ConvLayer of a ResidualBlock. RecNet training: forward (fp32 z + BatchNorm partial sums),
+// data gradient, plain fp32 GEMM.
+constexpr uint32_t FS_CONV1 = EPI_GEOM | EPI_BORDER_BIAS | EPI_PRELU;
+constexpr uint32_t FS_CONV1_S2D = FS_CONV1 | EPI_OUT_S2D;
+constexpr uint32_t FS_CONV2 = EPI_GEOM | EPI_BIAS | EPI_POOL;
+constexpr uint32_t FS_SHORTCUT = EPI_GEOM | EPI_BIAS;
+constexpr uint32_t FS_REC = EPI_GEOM | EPI_BIAS | EPI_PRELU | EPI_SCATTER | EPI_PIXMAJOR;
+constexpr uint32_t FS_REC_RES = FS_REC | EPI_RESIDUAL;
+constexpr uint32_t FS_TRAIN_FWD = EPI_GEOM | EPI_STATS | EPI_OUT_F32 | EPI_PIXMAJOR;
+constexpr uint32_t FS_TRAIN_DGRAD = EPI_OUT_F32 | EPI_PIXMAJOR | EPI_PIX_DGRAD;
+constexpr uint32_t FS_F32 = EPI_OUT_F32;
+
+// WINDOW: the sliding-window kernels only ever see the backbone sets (and RecNet's row-major small-batch layers, generic)
+template <int BN, int SUB, bool WINDOW>
+__device__ __forceinline__ void epilogue_dispatch(const ConvGemmParams& p, const uint32_t tmem_base, uint64_t* tfull_bar,
+                                                  uint64_t* tempty_bar, float* sparam, const int warp, const int lane,
+                                                  const EpiSched es) {
+    switch (p.flags) {
+        case FS_CONV1:     epilogue_loop<BN, SUB, FS_CONV1>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es); return;
+        case FS_CONV1_S2D: epilogue_loop<BN, SUB, FS_CONV1_S2D>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es); return;
+        case FS_CONV2:     epilogue_loop<BN, SUB, FS_CONV2>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es); return;
+        default: break;
+    }
+    if constexpr (!WINDOW) {
+        switch (p.flags) {
+            case FS_SHORTCUT:    epilogue_loop<BN, SUB, FS_SHORTCUT>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es); return;
+            case FS_REC:         epilogue_loop<BN, SUB, FS_REC>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es); return;
+            case FS_REC_RES:     epilogue_loop<BN, SUB, FS_REC_RES>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es); return;
+            case FS_TRAIN_FWD:   epilogue_loop<BN, SUB, FS_TRAIN_FWD>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es); return;
+            case FS_TRAIN_DGRAD: epilogue_loop<BN, SUB, FS_TRAIN_DGRAD>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es); return;
+            case FS_F32:         epilogue_loop<BN, SUB, FS_F32>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es); return;
+            default: break;
+        }
+    }
+    epilogue_loop<BN, SUB, 0>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es);
 }
 
 // PAIR: CTA pairs (cluster of 2, tcgen05 cta_group::2). A work item is two M tiles x one N tile: CTA rank r loads the A
@@ -661,7 +707,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         es.tile_add = rank;
         es.pix_ibp = pix_ibp;
         es.tempty_remote = (PAIR && !leader) ? mapa_shared(smem_u32(&tempty_bar[0]), 0) : 0u;
-        epilogue_loop<BN, 1>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es);
+        epilogue_dispatch<BN, 1, false>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es);
     }
 
     tc_fence_before();
@@ -851,7 +897,7 @@ conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             atomicAdd(p.dbg + DBG_CTAS, 1ull);
         }
     } else if (warp < 8) {
-        epilogue_loop<BN, SUB>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, epi_sched_single<BN, SUB>(p));
+        epilogue_dispatch<BN, SUB, true>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, epi_sched_single<BN, SUB>(p));
     }
 
     tc_fence_before();
@@ -1025,7 +1071,7 @@ conv_win2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         es.tile_mul = 2;
         es.tile_add = (int)rank;
         es.tempty_remote = leader ? 0u : mapa_shared(smem_u32(&tempty_bar[0]), 0);
-        epilogue_loop<BN, 1>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es);
+        epilogue_dispatch<BN, 1, true>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es);
     }
 
     tc_fence_before();
@@ -1037,6 +1083,9 @@ conv_win2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     if (p.dbg != nullptr && threadIdx.x == 0) atomicMax(p.dbg + DBG_T_EXIT, globaltimer_ns());
 }
+
+static bool g_lean = true;       // ffr_debug_set_lean_epilogue(0): always the generic epilogue (A/B runs, tests)
+void set_lean_epilogue(bool on) { g_lean = on; }
 
 template <int BN, int TB>
 static int launch_win2(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, const WinCfg& wc,
@@ -1065,7 +1114,7 @@ static int launch_win(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
 
 static bool g_use_window = true;
 void set_use_window(bool on) { g_use_window = on; }
-// CTA pairs (conv_win2_kernel) for the N = 256 sliding-window layers: -1 / 1 = on (default), 0 = off (tests, A/B runs)
+// CTA pairs: non-zero = on (default -1), 0 = off (tests, A/B runs)
 static int g_pair_mode = -1;
 void set_pair_mode(int mode) { g_pair_mode = mode; }
 static unsigned long long* g_dbg = nullptr;
@@ -1143,6 +1192,7 @@ bool pixmajor_profitable_k64(int n_img) {
 int conv_gemm_launch(const void* a, long long a_rows, int a_cols, int a_ld, const void* wp, int Cin, ConvGemmParams p,
                      int num_splits, cudaStream_t stream) {
     p.dbg = g_dbg;
+    if (!g_lean) p.flags |= EPI_GENERIC_ONLY;      // matches no specialised flag set; masked off by the generic epilogue
     FFR_CHECK_ARG(Cin % BLOCK_K == 0, "conv_gemm: Cin=%d not a multiple of 64", Cin);
     FFR_CHECK_ARG(p.Cout % 64 == 0, "conv_gemm: Cout=%d not a multiple of 64", p.Cout);
     FFR_CHECK_ARG(p.ntaps >= 1 && p.ntaps <= 9, "conv_gemm: ntaps=%d", p.ntaps);
@@ -1190,6 +1240,11 @@ int conv_gemm_launch(const void* a, long long a_rows, int a_cols, int a_ld, cons
     p.kb_per_split = (kb_total + num_splits - 1) / num_splits;
     p.num_splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
     p.num_m_tiles = pix ? p.pix_side * p.pix_side * p.pix_iblocks : (p.M + BLOCK_M - 1) / BLOCK_M;
+    int Gw = 0;
+    const bool win_pair = !pix && BN == 256 && g_pair_mode != 0 && p.num_m_tiles >= 2 && window_eligible(p, &Gw);
+    // (Measured and rejected: 128-wide N tiles for this kernel to halve the wave quantum — 900 half-size items = 6.5 tile
+    // times instead of 7 at 256 -> 256 @14x14 — run 106 us against 91 us: every window is loaded twice and the N = 128
+    // pair MMA does not reach the N = 256 rate. profiles/r02_role_counters_pair.json)
     p.num_n_tiles = p.Cout / BN;
     FFR_CHECK_ARG(p.num_splits == 1 || (p.flags & EPI_OUT_F32_ATOMIC) ||
                   ((p.flags & EPI_OUT_F32) && p.out_f32_split_stride >= (long long)p.M * p.Cout),
@@ -1236,7 +1291,8 @@ int conv_gemm_launch(const void* a, long long a_rows, int a_cols, int a_ld, cons
             default:  return launch_cfg<64>(tmA, tmB, p, grid, stream);
         }
     }
-    if (window_eligible(p, &G) && BN == 256 && g_pair_mode != 0 && p.num_m_tiles >= 2) {
+    if (win_pair) {
+        G = Gw;
         // CTA pairs: two windows of 128 rows + halves of the weight tiles per CTA
         WinCfg wc;
         wc.G = G;
@@ -1248,7 +1304,6 @@ int conv_gemm_launch(const void* a, long long a_rows, int a_cols, int a_ld, cons
         const int b_half = (BN / 2) * BLOCK_K * 2;
         const int fixed = 1024 + 512 + 10 * BN * 4;
         const int budget = 226 * 1024 - fixed;
-        constexpr int TB2 = 3;
         wc.b_stages = 9;
         wc.a_stages = (budget - wc.b_stages * b_half) / win_bytes;
         if (wc.a_stages > WIN_MAX_A_STAGES) wc.a_stages = WIN_MAX_A_STAGES;
@@ -1261,7 +1316,7 @@ int conv_gemm_launch(const void* a, long long a_rows, int a_cols, int a_ld, cons
             const long long work = (long long)((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
             const int max_pairs = num_sms() / 2;
             const int wgrid = 2 * (int)((work < max_pairs) ? work : max_pairs);
-            return launch_win2<256, TB2>(tmA, tmB, p, wc, smem_bytes, wgrid, stream);
+            return launch_win2<256, 3>(tmA, tmB, p, wc, smem_bytes, wgrid, stream);
         }
     }
     if (window_eligible(p, &G)) {

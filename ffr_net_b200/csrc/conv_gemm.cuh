@@ -43,6 +43,8 @@ enum EpiFlags : uint32_t {
     EPI_MUL_DSIG    = 1u << 15,  // x *= r * (1 - r) with r = res[m, co]: backward of a sigmoid whose OUTPUT r is stored
     EPI_RES_F16     = 1u << 16,  // res holds fp16 (default bf16)
     EPI_OUT_F16     = 1u << 17,  // 16-bit outputs (out / scatter) are fp16 (default bf16)
+    EPI_GENERIC_ONLY = 1u << 31, // set by the launcher (ffr_debug_set_lean_epilogue(0)): run the generic epilogue even for a
+                                 // flag set that has a compile-time specialisation
 };
 
 struct ConvGemmParams {

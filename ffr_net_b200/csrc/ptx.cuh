@@ -159,8 +159,11 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
     return r;
 }
+// Relaxed: the arrival only hands TMEM accumulator columns back to the leader's MMA warp, and those reads are ordered by
+// tcgen05.fence::before_thread_sync; a .release here costs a MEMBAR that waits for all of the thread's output stores
+// (11 % of the epilogue's stall samples in profiles/r02_conv256_pair_ncu_full.txt).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load into THIS CTA's shared memory whose completion bytes are credited to an mbarrier given by its
 // shared::cluster address (the leader's barrier)
@@ -257,6 +260,11 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ----------------------------------------------------------------------------------------------
 // small helpers
 // ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 lds_f32x4(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&t);

@@ -434,6 +434,11 @@ FFR_API void ffr_debug_set_pair(int mode);
  * and tests). */
 FFR_API void ffr_debug_set_pdl(int mask);
 
+/* Debug/tuning: 1 (default) lets the sliding-window kernels run the epilogue instantiation that is compiled for the
+ * backbone's flag set only (bias / border bias / PReLU / geometry / squeeze sums / space-to-depth store); 0 forces the
+ * generic epilogue. Same arithmetic, bit-identical results. */
+FFR_API void ffr_debug_set_lean_epilogue(int enable);
+
 /* Debug/tuning: device buffer of 16 uint64 that the sliding-window kernel fills with per-role barrier-wait cycle
  * counts (summed over CTAs; slots in csrc/conv_gemm.cuh DbgSlot); NULL (default) disables the counters. */
 FFR_API int ffr_debug_set_counters(void* counters);

@@ -208,7 +208,8 @@ def test_backbone_forward_u8_matches_fp32_input(models):
 
 def test_launch_modes_bit_identical(models, lib):
     """Programmatic dependent launch (a kernel's CTAs are scheduled while its predecessor drains) and CTA pairs
-    (cta_group::2) change scheduling, not arithmetic: the forward is bit-identical with either switched off, and
+    (cta_group::2) change scheduling, not arithmetic, and the backbone-only ("lean") epilogue instantiation is the same
+    arithmetic with the unused features compiled out: the forward is bit-identical with any of them switched off, and
     repeated back-to-back forwards (no host sync in between: the dependent-launch race window) stay identical."""
     _, m = models
     x = ob.synth_faces(16, seed=21).repeat(4, 1, 1, 1).cuda()      # 64 images: several tiles per layer
@@ -224,9 +225,14 @@ def test_launch_modes_bit_identical(models, lib):
             lib.ffr_debug_set_pdl(3)
             lib.ffr_debug_set_pair(0)
             y2, f2 = m(x)
+            lib.ffr_debug_set_pair(-1)
+            lib.ffr_debug_set_lean_epilogue(0)
+            y3, f3 = m(x)
         finally:
             lib.ffr_debug_set_pdl(-1)
             lib.ffr_debug_set_pair(-1)
+            lib.ffr_debug_set_lean_epilogue(1)
         torch.cuda.synchronize()
     assert torch.equal(y1, y0) and torch.equal(f1, f0)
     assert torch.equal(y2, y0) and torch.equal(f2, f0)
+    assert torch.equal(y3, y0) and torch.equal(f3, f0)

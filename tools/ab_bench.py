@@ -37,16 +37,18 @@ res = {}
 with torch.no_grad():
     for _ in range(5):
         rec.embed_from_images(enc, x)
-CONFIGS = [(3, -1, True), (0, -1, True), (1, -1, True), (2, -1, True), (0, 0, True)]
+CONFIGS = [(-1, -1, True, 1), (-1, -1, True, 0), (0, -1, True, 1), (-1, 0, True, 1), (-1, -1, False, 1)]
 for rnd in range(10):
     order = CONFIGS[rnd % len(CONFIGS):] + CONFIGS[:rnd % len(CONFIGS)]      # rotate: no config always runs first
-    for pdl, pair, fuse in order:
+    for pdl, pair, fuse, lean in order:
         lib.ffr_debug_set_pdl(pdl)
         lib.ffr_debug_set_pair(pair)
         enc.fuse_se = fuse
+        lib.ffr_debug_set_lean_epilogue(lean)
         run(3)
-        res.setdefault("pdl=%d pair=%d fused_se=%d" % (pdl, 1 if pair else 0, int(fuse)), []).append(run(10))
+        res.setdefault("pdl=%d pair=%d fused_se=%d lean=%d" % (pdl, pair, int(fuse), lean), []).append(run(10))
 enc.fuse_se = True
+lib.ffr_debug_set_lean_epilogue(1)
 lib.ffr_debug_set_pdl(-1)
 lib.ffr_debug_set_pair(-1)
 import statistics
