@@ -65,16 +65,22 @@ def test_lfw_600_pairs_decisions_match_oracle(lib):
             assert ref.max() - ref.min() > 0.1                                     # the embeddings spread
         # decisions at the oracle-chosen threshold of each fold, on that fold's held-out pairs
         per = N_PAIRS // 10
-        flips = ambiguous = 0
+        flips = flips_all = ambiguous = 0
         for f, thr in enumerate(sweep_ref["best_thr"]):
             sl = slice(f * per, (f + 1) * per)
             d_ref, d_got = ref[sl].astype(np.float64) > thr, got[sl].astype(np.float64) > thr
             near = np.abs(ref[sl].astype(np.float64) - thr) <= tol
             ambiguous += int(near.sum())
             flips += int(((d_ref != d_got) & ~near).sum())
-        print("%s: %d pairs within %.0e of their threshold, %d decision flips outside that band" % (name, ambiguous, tol, flips))
-        assert flips == 0
-        assert ambiguous <= N_PAIRS // 3
+            flips_all += int((d_ref != d_got).sum())
+        print("%s: %d pairs within %.0e of their threshold, %d decision flips outside that band, %d flips in all"
+              % (name, ambiguous, tol, flips, flips_all))
+        assert flips == 0                          # every disagreement is explained by the cosine tolerance
+        # ... and the statement is not vacuous: most pairs lie outside the band, and the decisions agree on >= 97 % of
+        # ALL pairs (the band's population depends on the briefly fitted weights: 150-240 of 600 on the rectified set)
+        assert ambiguous <= N_PAIRS // 2
+        assert flips_all <= 0.03 * N_PAIRS
+        assert abs(sweep_got["avg_acc"] - sweep_ref["avg_acc"]) <= 0.02
     # the device sweep itself (ffr_threshold_sweep) reproduces the oracle sweep on the device's own scores bit for bit
     for key, got in (("sweep_rectified", res["scores_rectified"]), ("sweep_raw", res["scores_raw"])):
         ref = osc.sweep(got.cpu().numpy(), labels, 10)
