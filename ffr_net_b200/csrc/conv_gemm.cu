@@ -159,6 +159,8 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
     const bool border = (flags & EPI_BORDER_BIAS) != 0;
     const int nbias = border ? 9 : 1;
     const bool small_m = p.M < (1 << 24);
+    // 32-byte aligned output rows (the S2D / plain addressing adds multiples of 64 channels): 256-bit stores
+    const bool out32 = ((reinterpret_cast<uintptr_t>(p.out) | static_cast<uintptr_t>(p.ldo * 2)) & 31) == 0;
     const float inv_rpi = 1.0f / (float)max(p.rows_per_img, 1);
     const float inv_wp = 1.0f / (float)max(p.Wp, 1);
     int loaded_n_tile = -1;
@@ -372,9 +374,14 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
                     pk[q].w = pack16x2(x[q * 8 + 6], x[q * 8 + 7], of16);
                 }
                 if (do_store) {
-                    uint4* o = reinterpret_cast<uint4*>(orow + c0);
+                    if (out32) {         // two 32-byte stores: each fills a whole sector of the thread's row
+                        st_global_256(orow + c0, pk[0], pk[1]);
+                        st_global_256(orow + c0 + 16, pk[2], pk[3]);
+                    } else {
+                        uint4* o = reinterpret_cast<uint4*>(orow + c0);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) o[q] = pk[q];
+                        for (int q = 0; q < 4; ++q) o[q] = pk[q];
+                    }
                 }
                 if (flags & EPI_SCATTER) {
 #pragma unroll
@@ -475,6 +482,8 @@ constexpr uint32_t FS_REC_RES = FS_REC | EPI_RESIDUAL;
 constexpr uint32_t FS_TRAIN_FWD = EPI_GEOM | EPI_STATS | EPI_OUT_F32 | EPI_PIXMAJOR;
 constexpr uint32_t FS_TRAIN_DGRAD = EPI_OUT_F32 | EPI_PIXMAJOR | EPI_PIX_DGRAD;
 constexpr uint32_t FS_F32 = EPI_OUT_F32;
+constexpr uint32_t FS_MCHANNEL = EPI_BIAS | EPI_SIGMOID;        // M_channel = sigmoid(h W^T + b): a K = 64 GEMM, all epilogue
+constexpr uint32_t FS_FEAT_CHANNEL = EPI_GEOM | EPI_SCATTER;    // M_channel @ X into the flip / cat slots
 
 // WINDOW: the sliding-window kernels only ever see the backbone sets (and RecNet's row-major small-batch layers, generic)
 template <int BN, int SUB, bool WINDOW>
@@ -495,6 +504,8 @@ __device__ __forceinline__ void epilogue_dispatch(const ConvGemmParams& p, const
             case FS_TRAIN_FWD:   epilogue_loop<BN, SUB, FS_TRAIN_FWD>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es); return;
             case FS_TRAIN_DGRAD: epilogue_loop<BN, SUB, FS_TRAIN_DGRAD>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es); return;
             case FS_F32:         epilogue_loop<BN, SUB, FS_F32>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es); return;
+            case FS_MCHANNEL:    epilogue_loop<BN, SUB, FS_MCHANNEL>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es); return;
+            case FS_FEAT_CHANNEL: epilogue_loop<BN, SUB, FS_FEAT_CHANNEL>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es); return;
             default: break;
         }
     }

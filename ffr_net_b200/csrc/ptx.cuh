@@ -260,6 +260,12 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ----------------------------------------------------------------------------------------------
 // small helpers
 // ----------------------------------------------------------------------------------------------
+// 256-bit global store (sm_100: STG.E.ENL2.256); `p` must be 32-byte aligned
+__device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z),
+                 "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
 __device__ __forceinline__ float4 lds_f32x4(uint32_t saddr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
