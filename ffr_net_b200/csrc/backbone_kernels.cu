@@ -278,17 +278,31 @@ __device__ __forceinline__ void se_gate_compute(const float* __restrict__ pool_p
         }
     }
     __syncthreads();
-    for (int j = warp; j < R; j += 8) {
+    for (int j = warp; j < R; j += 8) {          // FC1: 16-byte loads of a weight row, 4 channels per lane and step
         float a = 0.f;
-        for (int c = lane; c < C; c += 32) a = fmaf(__ldg(w1 + j * C + c), s_mean[c] * inv, a);
+        const float4* wr = reinterpret_cast<const float4*>(w1 + j * C);
+        for (int i = lane; i < C / 4; i += 32) {
+            const float4 wv = __ldg(wr + i);
+            a = fmaf(wv.x, s_mean[4 * i] * inv, a);
+            a = fmaf(wv.y, s_mean[4 * i + 1] * inv, a);
+            a = fmaf(wv.z, s_mean[4 * i + 2] * inv, a);
+            a = fmaf(wv.w, s_mean[4 * i + 3] * inv, a);
+        }
         a = warp_sum(a);
         if (lane == 0) s_hid[j] = fmaxf(a, 0.f);
     }
     __syncthreads();
-    for (int c = tid; c < C; c += 256) {
+    for (int c = tid; c < C; c += 256) {           // FC2: the R = C/16 weights of channel c are contiguous
         float a = 0.f;
+        const float4* wr = reinterpret_cast<const float4*>(w2 + c * R);
 #pragma unroll
-        for (int j = 0; j < R; ++j) a = fmaf(__ldg(w2 + c * R + j), s_hid[j], a);
+        for (int j = 0; j < R / 4; ++j) {
+            const float4 wv = __ldg(wr + j);
+            a = fmaf(wv.x, s_hid[4 * j], a);
+            a = fmaf(wv.y, s_hid[4 * j + 1], a);
+            a = fmaf(wv.z, s_hid[4 * j + 2], a);
+            a = fmaf(wv.w, s_hid[4 * j + 3], a);
+        }
         s_gate[c] = 1.0f / (1.0f + __expf(-a));
     }
     __syncthreads();
@@ -551,33 +565,35 @@ int export_nchw_launch(const void* h, const float* scale, const float* shift, fl
 // `acc` holds the per-split fp32 partial products of the folded head GEMM (BN2d, Linear, BN1d folded into W', b'),
 // [splits][rows][D], added here in split order (deterministic split-K).
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bias_l2norm_kernel(const float* __restrict__ acc, int splits, long long split_stride,
+// One CTA of 128 threads per row: thread t owns columns 4t .. 4t+3 (float4 loads of every split's partial product, added
+// in split order: deterministic), sum of squares by a fixed-order block reduction.
+__global__ void __launch_bounds__(128) bias_l2norm_kernel(const float* __restrict__ acc, int splits, long long split_stride,
                                                           const float* __restrict__ bias, float* __restrict__ f, int rows) {
     pdl_sync();
     constexpr int D = 512;
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= rows) return;
-    float v[D / 32];
-    float ss = 0.f;
-#pragma unroll
-    for (int i = 0; i < D / 32; ++i) {
-        const int c = lane + 32 * i;
-        float a = acc[(long long)row * D + c];
-        for (int s = 1; s < splits; ++s) a += acc[(long long)s * split_stride + (long long)row * D + c];
-        v[i] = a + bias[c];
-        ss = fmaf(v[i], v[i], ss);
+    __shared__ float s_ss[4];
+    const int row = blockIdx.x;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const float4* src = reinterpret_cast<const float4*>(acc + (long long)row * D) + t;
+    float4 a = __ldg(src);
+    for (int s = 1; s < splits; ++s) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(acc + (long long)s * split_stride + (long long)row * D) + t);
+        a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
     }
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + t);
+    a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+    float ss = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, a.w * a.w)));
     ss = warp_sum(ss);
-    const float inv = 1.0f / sqrtf(ss);
-#pragma unroll
-    for (int i = 0; i < D / 32; ++i) f[(long long)row * D + lane + 32 * i] = v[i] * inv;
+    if (lane == 0) s_ss[warp] = ss;
+    __syncthreads();
+    const float inv = 1.0f / sqrtf((s_ss[0] + s_ss[1]) + (s_ss[2] + s_ss[3]));
+    reinterpret_cast<float4*>(f + (long long)row * D)[t] = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
 }
 
 int bias_l2norm_launch(const float* acc, int splits, long long split_stride, const float* bias, float* f, int rows, int D,
                        cudaStream_t stream) {
     FFR_CHECK_ARG(D == 512, "bias_l2norm: D=%d", D);
-    launch_ex(bias_l2norm_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, 1, PDL_SIMT, acc, splits, split_stride, bias, f, rows);
+    launch_ex(bias_l2norm_kernel, dim3(rows), dim3(128), 0, stream, 1, PDL_SIMT, acc, splits, split_stride, bias, f, rows);
     return launch_status("bias_l2norm_kernel");
 }
 
