@@ -127,6 +127,7 @@ _SIGNATURES = {
     "ffr_debug_set_pair": (None, [_i]),
     "ffr_debug_set_pdl": (None, [_i]),
     "ffr_debug_set_lean_epilogue": (None, [_i]),
+    "ffr_debug_set_stem_strip": (None, [_i]),
     "ffr_debug_mn_probe": (_i, [_p, _p, _p, _i, _i, _p]),
     "ffr_debug_set_counters": (_i, [_p]),
     "ffr_debug_set_wgrad_splits": (None, [_i]),

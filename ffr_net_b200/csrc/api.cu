@@ -48,6 +48,7 @@ FFR_API int ffr_debug_set_window(int enable) { set_use_window(enable != 0); retu
 FFR_API void ffr_debug_set_pair(int mode) { set_pair_mode(mode); }
 FFR_API void ffr_debug_set_pdl(int mask) { set_pdl_mask(mask); }
 FFR_API void ffr_debug_set_lean_epilogue(int enable) { set_lean_epilogue(enable != 0); }
+FFR_API void ffr_debug_set_stem_strip(int enable) { set_stem_strip(enable != 0); }
 
 FFR_API int ffr_debug_set_counters(void* counters) {
     set_debug_counters(reinterpret_cast<unsigned long long*>(counters));

@@ -214,8 +214,174 @@ __global__ void __launch_bounds__(128, 4) stem_kernel(const void* __restrict__ x
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Strip version of the stem for S % 16 == 0 (the 112x112 input of the model). The gather kernel above is bound by
+// instruction issue and L1 wavefronts (ncu: 546 warp instructions per 16-pixel tile, 16 scattered 4-byte global loads
+// per thread and tile, 64-bit address arithmetic, profiles/r02_ncu_membound_eval_kernels.csv). Here a CTA owns ST_R
+// output rows of one image: the (ST_R + 2) x (S + 2) x 3 input patch is staged ONCE in shared memory as bf16 (coalesced
+// 16-byte global loads; the uint8 variant applies channel swap / flip / normalisation while staging), zero halo
+// included, so the im2col fragments are unconditional 2-byte shared loads at per-thread constant offsets; a warp tile
+// is 16 consecutive pixels of one image row; BN shift and PReLU slopes stay in registers. Same K order and the same
+// bf16 operands as the gather kernel: bit-identical activations.
+// ----------------------------------------------------------------------------------------------
+constexpr int ST_R = 8;
+template <bool U8>
+__global__ void __launch_bounds__(128, 4) stem_strip_kernel(const void* __restrict__ xin, const unsigned char* __restrict__ flip,
+                                                         int swap_rb, const float* __restrict__ w,
+                                                         const float* __restrict__ b, const float* __restrict__ a,
+                                                         __nv_bfloat16* __restrict__ out, int n_img, int S) {
+    pdl_sync();
+    extern __shared__ __align__(16) uint8_t st_smem[];
+    const int P = S + 2;                                    // patch row pitch (elements); even
+    const int img_elems = 3 * (ST_R + 2) * P;
+    __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(st_smem);
+    uint32_t* stage = reinterpret_cast<uint32_t*>(st_smem + ((img_elems * 2 + 15) & ~15));   // [4][16 * 32]
+    float* lut = reinterpret_cast<float*>(stage + 4 * 512);                                  // [256] (U8 only)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tig = lane & 3;
+    const int G = S + 1;
+    const int strips = S / ST_R;
+    const int n = blockIdx.x / strips, h0 = (blockIdx.x - n * strips) * ST_R;
+
+    if (U8) {
+        for (int i = tid; i < 256; i += 128) lut[i] = __fdiv_rn(__fdiv_rn((float)i, 255.0f) - 0.5f, 0.5f);
+        __syncthreads();
+    }
+    // ---- stage the input patch: rows h0-1 .. h0+ST_R, columns -1 .. S (zero outside the image) ----
+    for (int i = tid; i < 3 * (ST_R + 2) * 2; i += 128) {                 // the two halo columns
+        const int row = i >> 1;
+        img[row * P + ((i & 1) ? S + 1 : 0)] = __float2bfloat16_rn(0.f);
+    }
+    if (U8) {
+        const unsigned char* xu = reinterpret_cast<const unsigned char*>(xin) + (size_t)n * S * S * 3;
+        const bool fl = flip != nullptr && flip[n] != 0;
+        const int wpr = S * 3 / 4;                                        // 32-bit words per image row
+        for (int i = tid; i < (ST_R + 2) * wpr; i += 128) {
+            const int rr = i / wpr, wq = i - rr * wpr;
+            const int h = h0 - 1 + rr;
+            const bool ok = h >= 0 && h < S;
+            const uint32_t word = ok ? __ldg(reinterpret_cast<const uint32_t*>(xu + (size_t)h * S * 3) + wq) : 0u;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int byte = wq * 4 + e;
+                const int wsrc = byte / 3, c = byte - wsrc * 3;
+                const int ci = swap_rb ? 2 - c : c;
+                const int wd = fl ? S - 1 - wsrc : wsrc;
+                const float v = ok ? lut[(word >> (8 * e)) & 255u] : 0.f;
+                img[(ci * (ST_R + 2) + rr) * P + 1 + wd] = __float2bfloat16_rn(v);
+            }
+        }
+    } else {
+        const float* x = reinterpret_cast<const float*>(xin) + (size_t)n * 3 * S * S;
+        const int qpr = S / 4;                                            // float4 per image row
+        for (int i = tid; i < 3 * (ST_R + 2) * qpr; i += 128) {
+            const int q = i % qpr, row = i / qpr;                         // row = ci * (ST_R + 2) + rr
+            const int ci = row / (ST_R + 2), rr = row - ci * (ST_R + 2);
+            const int h = h0 - 1 + rr;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (h >= 0 && h < S) v = __ldg(reinterpret_cast<const float4*>(x + ((size_t)ci * S + h) * S) + q);
+            __nv_bfloat16* d = img + row * P + 1 + q * 4;
+            d[0] = __float2bfloat16_rn(v.x); d[1] = __float2bfloat16_rn(v.y);
+            d[2] = __float2bfloat16_rn(v.z); d[3] = __float2bfloat16_rn(v.w);
+        }
+    }
+
+    // B fragments (weights [K = 32][N = 64] col-major, 8 n-tiles x 2 k-steps) and the epilogue constants of this
+    // thread's channels nt*8 + tig*2 + {0, 1}
+    uint32_t bf[8][2][2];
+    float2 eb[8], ea[8];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k0 = ks * 16 + h * 8 + tig * 2;
+                const int nn = nt * 8 + g;
+                const float w0 = (k0 < 27) ? w[k0 * 64 + nn] : 0.f;
+                const float w1 = (k0 + 1 < 27) ? w[(k0 + 1) * 64 + nn] : 0.f;
+                bf[nt][ks][h] = pack_bf16x2(w0, w1);
+            }
+        const int c = nt * 8 + tig * 2;
+        eb[nt] = make_float2(b[c], b[c + 1]);
+        ea[nt] = make_float2(a[c], a[c + 1]);
+    }
+    // this thread's 8 K columns -> offsets into the patch relative to (local row hl, column w): (ci, r, s) reads
+    // patch row hl + r, patch column w + s
+    int koff[8];
+    bool kval[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int k = (j >> 2) * 16 + ((j >> 1) & 1) * 8 + tig * 2 + (j & 1);
+        kval[j] = k < 27;
+        const int ci = k / 9, r = (k % 9) / 3, sx = k % 3;
+        koff[j] = kval[j] ? (ci * (ST_R + 2) + r) * P + sx : 0;
+    }
+    __syncthreads();
+
+    const int tiles_per_row = S >> 4;
+    const unsigned short* img16 = reinterpret_cast<const unsigned short*>(img);
+    uint32_t* wstage = stage + warp * 512;
+    for (int t = warp; t < ST_R * tiles_per_row; t += 4) {
+        const int hl = t / tiles_per_row, w0 = (t - hl * tiles_per_row) << 4;
+        const unsigned short* base = img16 + hl * P + w0 + g;
+        uint32_t af[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int j = ks * 4 + h * 2;
+                    uint32_t lo = base[koff[j] + rr * 8], hi = base[koff[j + 1] + rr * 8];
+                    if (ks == 1) { lo = kval[j] ? lo : 0u; hi = kval[j + 1] ? hi : 0u; }    // k >= 27: zero columns
+                    af[ks][h * 2 + rr] = lo | (hi << 16);
+                }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_16816_bf16(c, af[0], bf[nt][0][0], bf[nt][0][1]);
+            mma_16816_bf16(c, af[1], bf[nt][1][0], bf[nt][1][1]);
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                float v0 = c[rr * 2 + 0] + eb[nt].x, v1 = c[rr * 2 + 1] + eb[nt].y;
+                v0 = v0 > 0.f ? v0 : v0 * ea[nt].x;
+                v1 = v1 > 0.f ? v1 : v1 * ea[nt].y;
+                wstage[(g + rr * 8) * 32 + ((nt ^ g) & 7) * 4 + tig] = pack_bf16x2(v0, v1);       // XOR-swizzled chunks
+            }
+        }
+        __syncwarp();
+        // 16 pixels x 128 B are contiguous in the flat map: 4 coalesced 512-byte stores
+        __nv_bfloat16* orow = out + ((size_t)n * G * G + (size_t)(h0 + hl) * G + w0) * 64;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int idx = q * 32 + lane;          // 16-byte chunk index: row = idx / 8, chunk = idx % 8
+            const uint4 v = reinterpret_cast<const uint4*>(wstage)[(idx & ~7) | ((idx ^ (idx >> 3)) & 7)];
+            reinterpret_cast<uint4*>(orow)[idx] = v;
+        }
+        __syncwarp();
+    }
+    // zero padding of the flat layout: column S of the strip's rows, and the whole row S after the last strip
+    if (tid < ST_R * 8)
+        reinterpret_cast<uint4*>(out + ((size_t)n * G * G + (size_t)(h0 + (tid >> 3)) * G + S) * 64)[tid & 7] = make_uint4(0, 0, 0, 0);
+    if (h0 + ST_R == S) {
+        uint4* z = reinterpret_cast<uint4*>(out + ((size_t)n * G * G + (size_t)S * G) * 64);
+        for (int i = tid; i < G * 8; i += 128) z[i] = make_uint4(0, 0, 0, 0);
+    }
+}
+
+static int stem_strip_smem(int S) { return ((3 * (ST_R + 2) * (S + 2) * 2 + 15) & ~15) + 4 * 512 * 4 + 256 * 4; }
+static bool g_stem_strip = true;                 // ffr_debug_set_stem_strip(0): the gather kernel for every size (A/B, tests)
+void set_stem_strip(bool on) { g_stem_strip = on; }
+static bool stem_strip_ok(int n_img, int S) { return g_stem_strip && S % 16 == 0 && S >= 16 && S <= 512 && n_img > 0; }
+
 int stem_launch(const float* x, const float* w, const float* b, const float* a, void* out, int n_img, int S,
                 cudaStream_t stream) {
+    if (stem_strip_ok(n_img, S)) {
+        launch_ex(stem_strip_kernel<false>, dim3(n_img * (S / ST_R)), dim3(128), stem_strip_smem(S), stream, 1, PDL_SIMT, (const void*)x,
+                  (const unsigned char*)nullptr, 0, w, b, a, reinterpret_cast<__nv_bfloat16*>(out), n_img, S);
+        return launch_status("stem_strip_kernel");
+    }
     const long long total = (long long)n_img * (S + 1) * (S + 1);
     const long long tiles = (total + 15) / 16;
     long long grid = (tiles + 3) / 4;
@@ -227,6 +393,11 @@ int stem_launch(const float* x, const float* w, const float* b, const float* a, 
 
 int stem_u8_launch(const unsigned char* img, const unsigned char* flip, int swap_rb, const float* w, const float* b,
                    const float* a, void* out, int n_img, int S, cudaStream_t stream) {
+    if (stem_strip_ok(n_img, S)) {
+        launch_ex(stem_strip_kernel<true>, dim3(n_img * (S / ST_R)), dim3(128), stem_strip_smem(S), stream, 1, PDL_SIMT, (const void*)img,
+                  flip, swap_rb, w, b, a, reinterpret_cast<__nv_bfloat16*>(out), n_img, S);
+        return launch_status("stem_strip_kernel<u8>");
+    }
     const long long total = (long long)n_img * (S + 1) * (S + 1);
     const long long tiles = (total + 15) / 16;
     long long grid = (tiles + 3) / 4;

@@ -48,16 +48,18 @@ __device__ __forceinline__ int h9_row_of_pixel(int pix) { return (pix / 7 + 1) *
 // ------------------------------------------------------------------------------------------------------------
 constexpr int BN_MAX_GROUPS = 2;
 
-// block = 32 channels x 32 row slices; every slice adds its rows (r = slice, slice + 32, ...) per group in double, the
-// slices are then added in a fixed order (latency-bound otherwise: few channels, hundreds of partial rows).
-constexpr int BNF_SLICES = 32;
-__global__ void __launch_bounds__(1024)
+// block = 8 channels x 128 row slices (grid C / 8): every slice adds its rows (r = slice, slice + 128, ...) per group in
+// double, the slices are then added in a fixed order. The kernel is pure latency (a few hundred partial rows per
+// channel): with 32 channels x 32 slices on C / 32 CTAs it took 21 us per layer — 15 launches per training step.
+constexpr int BNF_SLICES = 128;
+constexpr int BNF_CH = 8;
+__global__ void __launch_bounds__(BNF_SLICES * BNF_CH)
 bn_finalize_kernel(const float* __restrict__ part, int R, int mode, int iblocks, int n_per_group, int G, int C,
                    int C_real, float momentum, float eps, float* __restrict__ running_mean,
                    float* __restrict__ running_var, long long* __restrict__ nbt, float* __restrict__ mr) {
-    __shared__ double red[BNF_SLICES][BN_MAX_GROUPS][2][33];
-    const int cl = threadIdx.x & 31, slice = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + cl;
+    __shared__ double red[BNF_SLICES][BN_MAX_GROUPS][2][BNF_CH];
+    const int cl = threadIdx.x % BNF_CH, slice = threadIdx.x / BNF_CH;
+    const int c = blockIdx.x * BNF_CH + cl;
     if (blockIdx.x == 0 && threadIdx.x == 0 && nbt != nullptr) *nbt += G;
     double s[BN_MAX_GROUPS], ss[BN_MAX_GROUPS];
 #pragma unroll
@@ -78,12 +80,20 @@ bn_finalize_kernel(const float* __restrict__ part, int R, int mode, int iblocks,
 #pragma unroll
     for (int g = 0; g < BN_MAX_GROUPS; ++g) { red[slice][g][0][cl] = s[g]; red[slice][g][1][cl] = ss[g]; }
     __syncthreads();
+    // stage 2: thread (g, stat, channel) adds the 128 slices in order; stage 3: one thread per channel finishes
+    __shared__ double tot[BN_MAX_GROUPS][2][BNF_CH];
+    if (threadIdx.x < BN_MAX_GROUPS * 2 * BNF_CH) {
+        const int ch = threadIdx.x % BNF_CH, st = (threadIdx.x / BNF_CH) % 2, g = threadIdx.x / (2 * BNF_CH);
+        double t = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < BNF_SLICES; ++k) t += red[k][g][st][ch];
+        tot[g][st][ch] = t;
+    }
+    __syncthreads();
     if (slice != 0 || c >= C) return;
     const double cnt = (double)n_per_group * 49.0;
     for (int g = 0; g < G; ++g) {
-        double ts = 0.0, tss = 0.0;
-#pragma unroll
-        for (int k = 0; k < BNF_SLICES; ++k) { ts += red[k][g][0][cl]; tss += red[k][g][1][cl]; }
+        const double ts = tot[g][0][cl], tss = tot[g][1][cl];
         const double mean = ts / cnt;
         double var = tss / cnt - mean * mean;
         if (var < 0.0) var = 0.0;
@@ -175,6 +185,87 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const BnActFwd p) {
     }
 }
 
+// Fast path of (B): C / 8 is a power of two <= 256, so a 256-thread block covers whole pixel rows, a thread keeps its 8
+// channels — and their affine / PReLU parameters in registers — for the whole grid-stride loop, the statistics are
+// reloaded only when the group changes, and all index arithmetic is 32-bit (the generic kernel spends most of its
+// issue slots on 64-bit divisions and 40 scalar parameter loads per 8 outputs). Same arithmetic per element.
+__global__ void __launch_bounds__(256) bn_act_fwd_pow2_kernel(const BnActFwd p, const int c8_shift) {
+    const unsigned c0 = (threadIdx.x & ((1u << c8_shift) - 1u)) * 8u;
+    const unsigned rpb = 256u >> c8_shift;
+    const unsigned rows = (unsigned)p.n_img * 49u;
+    float gm[8], bt[8], sl[8], mean[8], rstd[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const bool real = (int)(c0 + j) < p.C_real;
+        gm[j] = real ? p.gamma[c0 + j] : 0.f;
+        bt[j] = real ? p.beta[c0 + j] : 0.f;
+        sl[j] = real ? p.slope[c0 + j] : 0.f;
+        mean[j] = 0.f; rstd[j] = 0.f;
+    }
+    int g_cur = -1;
+    for (unsigned pr = blockIdx.x * rpb + (threadIdx.x >> c8_shift); pr < rows; pr += gridDim.x * rpb) {
+        const unsigned n = pr / 49u, pix = pr - n * 49u;
+        const unsigned r_local = (pix / 7u + 1u) * 9u + (pix % 7u + 1u);
+        const unsigned row = n * 81u + r_local;
+        const int g = (int)(n / (unsigned)p.n_per_group);
+        if (g != g_cur) {
+            const float4* mp = reinterpret_cast<const float4*>(p.mr + ((size_t)g * 2) * p.C + c0);
+            const float4* rp = reinterpret_cast<const float4*>(p.mr + ((size_t)g * 2 + 1) * p.C + c0);
+            const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), r0 = __ldg(rp), r1 = __ldg(rp + 1);
+            mean[0] = m0.x; mean[1] = m0.y; mean[2] = m0.z; mean[3] = m0.w;
+            mean[4] = m1.x; mean[5] = m1.y; mean[6] = m1.z; mean[7] = m1.w;
+            rstd[0] = r0.x; rstd[1] = r0.y; rstd[2] = r0.z; rstd[3] = r0.w;
+            rstd[4] = r1.x; rstd[5] = r1.y; rstd[6] = r1.z; rstd[7] = r1.w;
+            g_cur = g;
+        }
+        const float* zp = p.z + (size_t)row * p.ldz + c0;
+        const float4 z0 = __ldg(reinterpret_cast<const float4*>(zp));
+        const float4 z1 = __ldg(reinterpret_cast<const float4*>(zp + 4));
+        float v[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+        float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (p.res != nullptr) {
+            const __half* rsp = p.res + (size_t)row * p.ldres + c0;
+            const uint4 rh = __ldg(reinterpret_cast<const uint4*>(rsp));
+            r[0] = h_lo(rh.x); r[1] = h_hi(rh.x); r[2] = h_lo(rh.y); r[3] = h_hi(rh.y);
+            r[4] = h_lo(rh.z); r[5] = h_hi(rh.z); r[6] = h_lo(rh.w); r[7] = h_hi(rh.w);
+            if (p.res_lo_off) {
+                const uint4 rl = __ldg(reinterpret_cast<const uint4*>(rsp + p.res_lo_off));
+                r[0] += h_lo(rl.x); r[1] += h_hi(rl.x); r[2] += h_lo(rl.y); r[3] += h_hi(rl.y);
+                r[4] += h_lo(rl.z); r[5] += h_hi(rl.z); r[6] += h_lo(rl.w); r[7] += h_hi(rl.w);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float y = (v[j] - mean[j]) * rstd[j] * gm[j] + bt[j];
+            y = fmaxf(y, 0.f) + sl[j] * fminf(y, 0.f);
+            v[j] = y + r[j];
+        }
+        if (p.out_f != nullptr) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = p.sigmoid ? 1.0f / (1.0f + expf(-v[j])) : v[j];
+            float* op = p.out_f + (size_t)row * p.ldf + c0;
+            *reinterpret_cast<float4*>(op) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(op + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+        if (p.out_h == nullptr && p.out_b == nullptr) continue;
+        uint4 hi, lo;
+        split_hilo8(v, hi, lo);
+        const uint4 bf = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        for (int k = 0; k < p.scatter_n; ++k) {
+            const int2 e = __ldg(p.scatter + r_local * p.scatter_n + k);
+            if (e.x < 0) continue;
+            const size_t drow = (size_t)(n * 81u + (unsigned)e.x);
+            if (p.out_h != nullptr) {
+                __half* dp = p.out_h + drow * p.ldo + e.y + c0;
+                *reinterpret_cast<uint4*>(dp) = hi;
+                if (p.lo_off) *reinterpret_cast<uint4*>(dp + p.lo_off) = lo;
+            }
+            if (p.out_b != nullptr) *reinterpret_cast<uint4*>(p.out_b + drow * p.ldb + e.y + c0) = bf;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // (C) backward. The gradient w.r.t. the layer's OUTPUT a arrives from up to three fp32 sources:
 //   da   : on the H9 grid (own row + mirror rows) — the dgrad GEMM of the consuming convolution; folded through the
@@ -208,7 +299,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(const BnActBwd p
     const int cg = (threadIdx.x & 7) * 8;
     const int rlane = threadIdx.x >> 3;
     const int g = blockIdx.x / p.ctas_per_group, cta_in_g = blockIdx.x - g * p.ctas_per_group;
-    const long long rows_g = (long long)p.n_per_group * 49;
+    const unsigned rows_g = (unsigned)p.n_per_group * 49u;
     const float* mean = p.mr + ((long long)g * 2) * p.C;
     const float* rstd = mean + p.C;
     float s0[8], s1[8], s2[8], m[8], rs[8], gm[8], b[8], sl[8];
@@ -220,18 +311,18 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(const BnActBwd p
         m[j] = mean[c]; rs[j] = rstd[c];
         gm[j] = real ? p.gamma[c] : 0.f; b[j] = real ? p.beta[c] : 0.f; sl[j] = real ? p.slope[c] : 0.f;
     }
-    for (long long pr = (long long)cta_in_g * 32 + rlane; pr < rows_g; pr += (long long)p.ctas_per_group * 32) {
-        const int nl = (int)(pr / 49), pix = (int)(pr - (long long)nl * 49);
-        const int n = g * p.n_per_group + nl;
+    for (unsigned pr = (unsigned)cta_in_g * 32u + rlane; pr < rows_g; pr += (unsigned)p.ctas_per_group * 32u) {
+        const unsigned nl = pr / 49u, pix = pr - nl * 49u;
+        const int n = g * p.n_per_group + (int)nl;
         if (n >= p.n_img) break;
-        const int r_local = h9_row_of_pixel(pix);
-        const long long row = (long long)n * 81 + r_local;
+        const int r_local = (int)((pix / 7u + 1u) * 9u + (pix % 7u + 1u));
+        const size_t row = (size_t)((unsigned)n * 81u + (unsigned)r_local);
         float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (p.da != nullptr) {
             for (int k = 0; k < p.scatter_n; ++k) {
                 const int2 e = __ldg(p.scatter + r_local * p.scatter_n + k);
                 if (e.x < 0) continue;
-                const float* src = p.da + ((long long)n * 81 + e.x) * p.ldda + p.da_ch0 + c0 + cg;
+                const float* src = p.da + (size_t)((unsigned)n * 81u + (unsigned)e.x) * p.ldda + p.da_ch0 + c0 + cg;
                 const float4 u0 = __ldg(reinterpret_cast<const float4*>(src));
                 const float4 u1 = __ldg(reinterpret_cast<const float4*>(src + 4));
                 a[0] += u0.x; a[1] += u0.y; a[2] += u0.z; a[3] += u0.w;
@@ -282,15 +373,16 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(const BnActBwd p
     }
 }
 
+// block = 8 channels x 32 slices of the per-CTA partial rows (grid C / 8), slices added in a fixed order
 __global__ void __launch_bounds__(256) bn_act_bwd_finalize_kernel(const BnActBwd p) {
-    __shared__ float red[8][3][33];
-    const int cl = threadIdx.x & 31, slice = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + cl;
+    __shared__ float red[32][3][8];
+    const int cl = threadIdx.x & 7, slice = threadIdx.x >> 3;
+    const int c = blockIdx.x * 8 + cl;
     float tg = 0.f, tb = 0.f, ts = 0.f;
     for (int g = 0; g < p.G; ++g) {
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
         if (c < p.C) {
-            for (int k = slice; k < p.ctas_per_group; k += 8) {
+            for (int k = slice; k < p.ctas_per_group; k += 32) {
                 const float* q = p.partial + ((long long)(g * p.ctas_per_group + k) * 3) * p.C + c;
                 s0 += q[0]; s1 += q[p.C]; s2 += q[2 * p.C];
             }
@@ -301,7 +393,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_finalize_kernel(const BnActBwd
         if (slice == 0 && c < p.C) {
             s0 = s1 = s2 = 0.f;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { s0 += red[k][0][cl]; s1 += red[k][1][cl]; s2 += red[k][2][cl]; }
+            for (int k = 0; k < 32; ++k) { s0 += red[k][0][cl]; s1 += red[k][1][cl]; s2 += red[k][2][cl]; }
             p.gsum[((long long)g * 2) * p.C + c] = s0;
             p.gsum[((long long)g * 2 + 1) * p.C + c] = s1;
             tb += s0; tg += s1; ts += s2;
@@ -349,6 +441,66 @@ __global__ void __launch_bounds__(256) bn_act_bwd_dz_kernel(const BnActBwd p) {
             const float y = zh * gmm + (real ? p.beta[c] : 0.f);
             const float d = a[j] * (y > 0.f ? 1.f : (real ? p.slope[c] : 0.f));
             o[j] = gmm * rs * (d - gs0[c] * inv_cnt - zh * gs1[c] * inv_cnt);
+        }
+        *dst = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    }
+}
+
+// Fast path of pass 2 (same conditions and layout of the work as bn_act_fwd_pow2_kernel, over all 81 grid rows)
+__global__ void __launch_bounds__(256) bn_act_bwd_dz_pow2_kernel(const BnActBwd p, const int c8_shift) {
+    const unsigned c0 = (threadIdx.x & ((1u << c8_shift) - 1u)) * 8u;
+    const unsigned rpb = 256u >> c8_shift;
+    const unsigned rows = (unsigned)p.n_img * 81u;
+    const float inv_cnt = 1.0f / (float)(p.n_per_group * 49);
+    float gm[8], bt[8], sl[8], mean[8], rstd[8], gs0[8], gs1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const bool real = (int)(c0 + j) < p.C_real;
+        gm[j] = real ? p.gamma[c0 + j] : 0.f;
+        bt[j] = real ? p.beta[c0 + j] : 0.f;
+        sl[j] = real ? p.slope[c0 + j] : 0.f;
+        mean[j] = rstd[j] = gs0[j] = gs1[j] = 0.f;
+    }
+    int g_cur = -1;
+    for (unsigned row = blockIdx.x * rpb + (threadIdx.x >> c8_shift); row < rows; row += gridDim.x * rpb) {
+        const unsigned n = row / 81u, pos = row - n * 81u;
+        const unsigned hp = pos / 9u, wp = pos - hp * 9u;
+        uint4* dst = reinterpret_cast<uint4*>(p.dz + (size_t)row * p.lddz + c0);
+        if (hp == 0 || hp == 8 || wp == 0 || wp == 8) { *dst = make_uint4(0, 0, 0, 0); continue; }
+        int g = (int)(n / (unsigned)p.n_per_group);
+        if (g >= p.G) g = p.G - 1;
+        if (g != g_cur) {
+            const float* base = p.mr + ((size_t)g * 2) * p.C + c0;
+            const float* gbase = p.gsum + ((size_t)g * 2) * p.C + c0;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float4 m = __ldg(reinterpret_cast<const float4*>(base) + q);
+                const float4 r = __ldg(reinterpret_cast<const float4*>(base + p.C) + q);
+                const float4 a = __ldg(reinterpret_cast<const float4*>(gbase) + q);
+                const float4 b = __ldg(reinterpret_cast<const float4*>(gbase + p.C) + q);
+                mean[q * 4] = m.x; mean[q * 4 + 1] = m.y; mean[q * 4 + 2] = m.z; mean[q * 4 + 3] = m.w;
+                rstd[q * 4] = r.x; rstd[q * 4 + 1] = r.y; rstd[q * 4 + 2] = r.z; rstd[q * 4 + 3] = r.w;
+                gs0[q * 4] = a.x; gs0[q * 4 + 1] = a.y; gs0[q * 4 + 2] = a.z; gs0[q * 4 + 3] = a.w;
+                gs1[q * 4] = b.x; gs1[q * 4 + 1] = b.y; gs1[q * 4 + 2] = b.z; gs1[q * 4 + 3] = b.w;
+            }
+            g_cur = g;
+        }
+        const float* ap = p.afold + (size_t)row * p.ldaf + c0;
+        const float* zp = p.z + (size_t)row * p.ldz + c0;
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(ap));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(ap + 4));
+        const float4 z0 = __ldg(reinterpret_cast<const float4*>(zp));
+        const float4 z1 = __ldg(reinterpret_cast<const float4*>(zp + 4));
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float rs = rstd[j];
+            const float zh = (zz[j] - mean[j]) * rs;
+            const float y = zh * gm[j] + bt[j];
+            const float d = a[j] * (y > 0.f ? 1.f : sl[j]);
+            o[j] = gm[j] * rs * (d - gs0[j] * inv_cnt - zh * gs1[j] * inv_cnt);
         }
         *dst = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
     }
@@ -424,7 +576,7 @@ FFR_API int ffr_bn_finalize(const float* part, int part_rows, int pixmajor, int 
     FFR_CHECK_ARG(G <= BN_MAX_GROUPS, "ffr_bn_finalize: at most %d groups", BN_MAX_GROUPS);
     FFR_CHECK_ARG(!running_mean == !running_var, "ffr_bn_finalize: running_mean / running_var go together");
     const int iblocks = (n_img + 127) / 128;
-    bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, S_(stream)>>>(part, part_rows, pixmajor, iblocks, n_per_group, G, C,
+    bn_finalize_kernel<<<(C + BNF_CH - 1) / BNF_CH, BNF_SLICES * BNF_CH, 0, S_(stream)>>>(part, part_rows, pixmajor, iblocks, n_per_group, G, C,
                                                                C_real, momentum, eps, running_mean, running_var,
                                                                num_batches_tracked, mean_rstd);
     return launch_status("bn_finalize_kernel");
@@ -449,6 +601,13 @@ FFR_API int ffr_bn_act_fwd(const float* z, int ldz, const float* mean_rstd, cons
     if (total == 0) return 0;
     int grid = (int)((total + 255) / 256);
     if (grid > num_sms() * 8) grid = num_sms() * 8;
+    const int c8n = C / 8;
+    if ((c8n & (c8n - 1)) == 0 && c8n <= 256 && (long long)n_img * 81 < (1ll << 24)) {
+        int sh = 0;
+        while ((1 << sh) < c8n) ++sh;
+        bn_act_fwd_pow2_kernel<<<grid, 256, 0, S_(stream)>>>(p, sh);
+        return launch_status("bn_act_fwd_pow2_kernel");
+    }
     bn_act_fwd_kernel<<<grid, 256, 0, S_(stream)>>>(p);
     return launch_status("bn_act_fwd_kernel");
 }
@@ -490,12 +649,19 @@ FFR_API int ffr_bn_act_bwd(const float* da, int ldda, int da_ch0, const int* sca
     bn_act_bwd_reduce_kernel<<<grid, 256, 0, S_(stream)>>>(p);
     int rc = launch_status("bn_act_bwd_reduce_kernel");
     if (rc) return rc;
-    bn_act_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, S_(stream)>>>(p);
+    bn_act_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, S_(stream)>>>(p);
     rc = launch_status("bn_act_bwd_finalize_kernel");
     if (rc) return rc;
     const long long total = (long long)n_img * 81 * (C / 8);
     int g2 = (int)((total + 255) / 256);
     if (g2 > num_sms() * 8) g2 = num_sms() * 8;
+    const int c8n = C / 8;
+    if ((c8n & (c8n - 1)) == 0 && c8n <= 256 && (long long)n_img * 81 < (1ll << 24)) {
+        int sh = 0;
+        while ((1 << sh) < c8n) ++sh;
+        bn_act_bwd_dz_pow2_kernel<<<g2, 256, 0, S_(stream)>>>(p, sh);
+        return launch_status("bn_act_bwd_dz_pow2_kernel");
+    }
     bn_act_bwd_dz_kernel<<<g2, 256, 0, S_(stream)>>>(p);
     return launch_status("bn_act_bwd_dz_kernel");
 }

@@ -26,6 +26,7 @@ int bias_l2norm_launch(const float* acc, int splits, long long split_stride, con
 void set_use_window(bool on);
 void set_pair_mode(int mode);
 void set_lean_epilogue(bool on);
+void set_stem_strip(bool on);
 void set_debug_counters(unsigned long long* dptr);
 struct PrepParams {
     const float* x; const float* w0aT; const float* w0bT; const float* b0; const float* slope1; const float* A1;

@@ -189,22 +189,35 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant__ C
 __global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restrict__ ws, int slabs, int ntaps, int cout_p,
                                                            int cin_p, int Cout, int Cin, int ld_w, int bias_col,
                                                            float* __restrict__ dw, float* __restrict__ db, int accumulate) {
+    // The staging buffer is tap-major ([slab][tap][co][ci], ci contiguous: coalesced reads); dw is OIHW, i.e. the ntaps
+    // values of one (co, ci) are contiguous. A chunk of 256 input channels is transposed through shared memory so that
+    // the writes are contiguous runs of 256 * ntaps floats instead of ntaps stride-36-byte scatters per thread.
+    __shared__ float tile[256 * 9];
     const int co = blockIdx.x;
     const long long slab_stride = (long long)ntaps * cout_p * cin_p;
-    for (int ci = threadIdx.x; ci < Cin; ci += blockDim.x) {
-        float v[9];
-        for (int t = 0; t < ntaps; ++t) {
-            const float* q = ws + ((long long)t * cout_p + co) * cin_p + ci;
-            float a = 0.f;
-            for (int sl = 0; sl < slabs; ++sl) a += __ldg(q + sl * slab_stride);
-            v[t] = a;
+    for (int ci0 = 0; ci0 < Cin; ci0 += 256) {
+        const int ci = ci0 + threadIdx.x;
+        if (ci < Cin) {
+            for (int t = 0; t < ntaps; ++t) {
+                const float* q = ws + ((long long)t * cout_p + co) * cin_p + ci;
+                float a = 0.f;
+                for (int sl = 0; sl < slabs; ++sl) a += __ldg(q + sl * slab_stride);
+                tile[threadIdx.x * ntaps + t] = a;
+            }
+            if (ci == bias_col) {
+                if (accumulate) db[co] += tile[threadIdx.x * ntaps]; else db[co] = tile[threadIdx.x * ntaps];
+            }
         }
-        if (ci == bias_col) {
-            if (accumulate) db[co] += v[0]; else db[co] = v[0];
-            continue;
+        __syncthreads();
+        // output columns [ci0, min(ci0 + 256, Cin)) except the bias column
+        const int n_ci = min(256, Cin - ci0);
+        const int skip = (bias_col >= ci0 && bias_col < ci0 + n_ci) ? bias_col - ci0 : -1;
+        float* o = dw + ((long long)co * ld_w + ci0) * ntaps;
+        for (int i = threadIdx.x; i < n_ci * ntaps; i += 256) {
+            if (skip >= 0 && i / ntaps == skip) continue;
+            if (accumulate) o[i] += tile[i]; else o[i] = tile[i];
         }
-        float* o = dw + ((long long)co * ld_w + ci) * ntaps;
-        for (int t = 0; t < ntaps; ++t) { if (accumulate) o[t] += v[t]; else o[t] = v[t]; }
+        __syncthreads();
     }
 }
 
@@ -322,8 +335,52 @@ pack_conv3x3_kernel(const float* __restrict__ w, int cout, int cin, int cout_p, 
     }
 }
 
+// Tiled version: a 32 (co) x 32 (ci) x 9 block of the OIHW tensor goes through shared memory, so that the fp32 reads
+// are contiguous runs of 288 floats and both packed outputs are written as 64-byte rows of 16-bit pairs (the direct
+// kernel above reads with a 36-byte stride and scatters single 2-byte elements of the transposed copy).
+constexpr int PK_T = 32;
+constexpr int PK_PITCH = PK_T * 9 + 1;
+__global__ void __launch_bounds__(256)
+pack_conv3x3_tiled_kernel(const float* __restrict__ w, int cout, int cin, int cout_p, int cin_p,
+                          __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ dgrad, int fwd_f16) {
+    __shared__ float tile[PK_T * PK_PITCH];
+    const int ci0 = blockIdx.x * PK_T, co0 = blockIdx.y * PK_T;
+    for (int e = threadIdx.x; e < PK_T * PK_T * 9; e += 256) {
+        const int r = e / (PK_T * 9), col = e - r * (PK_T * 9);
+        const int co = co0 + r, ci = ci0 + col / 9;
+        tile[r * PK_PITCH + col] = (co < cout && ci < cin) ? __ldg(w + ((long long)co * cin + ci0) * 9 + col) : 0.f;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < PK_T * 9 * (PK_T / 2); e += 256) {
+        const int pr = e % (PK_T / 2), t = (e / (PK_T / 2)) % 9, r = e / ((PK_T / 2) * 9);
+        {   // forward packing: fwd[co][t][ci], pair of input channels (2 pr, 2 pr + 1) of output channel r
+            const int co = co0 + r, ci = ci0 + 2 * pr;
+            if (co < cout_p && ci < cin_p) {
+                const float v0 = tile[r * PK_PITCH + (2 * pr) * 9 + t], v1 = tile[r * PK_PITCH + (2 * pr + 1) * 9 + t];
+                uint32_t u;
+                if (fwd_f16) { const __half2 h = __floats2half2_rn(v0, v1); u = *reinterpret_cast<const uint32_t*>(&h); }
+                else u = pack_bf16x2(v0, v1);
+                *reinterpret_cast<uint32_t*>(fwd + ((long long)co * 9 + t) * cin_p + ci) = u;
+            }
+        }
+        if (dgrad) {   // flipped / transposed packing: dgrad[ci][8 - t][co], pair of output channels of input channel r
+            const int ci = ci0 + r, co = co0 + 2 * pr;
+            if (ci < cin_p && co < cout_p) {
+                const float v0 = tile[(2 * pr) * PK_PITCH + r * 9 + t], v1 = tile[(2 * pr + 1) * PK_PITCH + r * 9 + t];
+                *reinterpret_cast<uint32_t*>(dgrad + ((long long)ci * 9 + (8 - t)) * cout_p + co) = pack_bf16x2(v0, v1);
+            }
+        }
+    }
+}
+
 int pack_conv3x3_launch_ex(const float* w, int cout, int cin, int cout_p, int cin_p, void* fwd, void* dgrad, int fwd_f16,
                            cudaStream_t stream) {
+    if (cout_p % 2 == 0 && cin_p % 2 == 0 && cout_p > 0 && cin_p > 0) {
+        const dim3 tgrid((cin_p + PK_T - 1) / PK_T, (cout_p + PK_T - 1) / PK_T);
+        pack_conv3x3_tiled_kernel<<<tgrid, 256, 0, stream>>>(w, cout, cin, cout_p, cin_p, reinterpret_cast<__nv_bfloat16*>(fwd),
+                                                            reinterpret_cast<__nv_bfloat16*>(dgrad), fwd_f16);
+        return launch_status("pack_conv3x3_tiled_kernel");
+    }
     const long long total = (long long)cout_p * cin_p * 9;
     int grid = (int)((total + 255) / 256);
     if (grid > num_sms() * 16) grid = num_sms() * 16;

@@ -439,6 +439,10 @@ FFR_API void ffr_debug_set_pdl(int mask);
  * generic epilogue. Same arithmetic, bit-identical results. */
 FFR_API void ffr_debug_set_lean_epilogue(int enable);
 
+/* Debug/tuning: 1 (default) runs the shared-memory strip kernel of the stem (ffr_stem_fwd / ffr_stem_u8_fwd) when
+ * S % 16 == 0; 0 forces the gather kernel that serves every other size. Same arithmetic, bit-identical results. */
+FFR_API void ffr_debug_set_stem_strip(int enable);
+
 /* Debug/tuning: device buffer of 16 uint64 that the sliding-window kernel fills with per-role barrier-wait cycle
  * counts (summed over CTAs; slots in csrc/conv_gemm.cuh DbgSlot); NULL (default) disables the counters. */
 FFR_API int ffr_debug_set_counters(void* counters);

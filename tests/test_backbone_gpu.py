@@ -143,6 +143,39 @@ def test_stem_kernel(lib, n, S):
     assert layout.flat_pad_rows(out, n, S, 64).abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize("n,S", [(3, 112), (2, 16), (1, 48)])
+def test_stem_strip_kernel_matches_gather_kernel(lib, n, S):
+    """The shared-memory strip kernel (S % 16 == 0) and the gather kernel (any S) are the same arithmetic: bit-identical
+    maps, for fp32 NCHW input and for uint8 HWC input with flips and channel swap; pad rows are zero."""
+    from oracle import preprocess as opp
+    from ffr_net_b200 import _lib, layout
+    g = torch.Generator().manual_seed(100 + S)
+    x = torch.randn(n, 3, S, S, generator=g).clamp_(-1, 1).cuda()
+    w = (torch.randn(64, 3, 3, 3, generator=g) * 0.2).reshape(64, 27).t().contiguous().cuda()
+    b = (torch.randn(64, generator=g) * 0.1).cuda()
+    a = torch.empty(64).uniform_(0.1, 0.4, generator=g).cuda()
+    imgs = torch.from_numpy(opp.synth_images_u8(n, S, seed=3)).cuda()
+    flips = torch.tensor([1, 0, 1][:n], dtype=torch.uint8).cuda()
+    rows = n * (S + 1) * (S + 1)
+    st = _lib.stream_ptr()
+    outs = {}
+    try:
+        for strip in (1, 0):
+            lib.ffr_debug_set_stem_strip(strip)
+            o = torch.full((rows, 64), 9.0, dtype=torch.bfloat16, device="cuda")
+            u = torch.full((rows, 64), 9.0, dtype=torch.bfloat16, device="cuda")
+            _lib.check(lib.ffr_stem_fwd(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(a), _lib.ptr(o), n, S, st))
+            _lib.check(lib.ffr_stem_u8_fwd(_lib.ptr(imgs), _lib.ptr(flips), 1, _lib.ptr(w), _lib.ptr(b), _lib.ptr(a),
+                                           _lib.ptr(u), n, S, st))
+            torch.cuda.synchronize()
+            outs[strip] = (o, u)
+    finally:
+        lib.ffr_debug_set_stem_strip(1)
+    assert torch.equal(outs[1][0], outs[0][0]) and torch.equal(outs[1][1], outs[0][1])
+    assert layout.flat_pad_rows(outs[1][0], n, S, 64).abs().max().item() == 0.0
+    assert layout.from_flat(outs[1][0], n, S, 64).abs().max().item() > 0.1
+
+
 def test_empty_and_odd_batches(models):
     """Edge cases: empty batch, batch sizes that leave ragged last tiles (rows not a multiple of 128/256)."""
     sd, m = models

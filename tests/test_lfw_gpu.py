@@ -76,9 +76,18 @@ def test_lfw_600_pairs_decisions_match_oracle(lib):
         print("%s: %d pairs within %.0e of their threshold, %d decision flips outside that band, %d flips in all"
               % (name, ambiguous, tol, flips, flips_all))
         assert flips == 0                          # every disagreement is explained by the cosine tolerance
-        # ... and the statement is not vacuous: most pairs lie outside the band, and the decisions agree on >= 97 % of
-        # ALL pairs (the band's population depends on the briefly fitted weights: 150-240 of 600 on the rectified set)
-        assert ambiguous <= N_PAIRS // 2
+        # ... and the statement is not vacuous. The brief fit is chaotic: depending on rounding details of the training
+        # kernels the fitted rectifier spreads the cosines over 0.4..1.0 (worst |dcos| 3e-2) or only over ~0.1 (worst
+        # |dcos| 3e-3), so the fixed 5e-2 band can cover most pairs. Scale-aware form: at least half of the pairs are
+        # decided with a margin of more than 1.5x the WORST cosine error of this run, and the decisions agree on
+        # >= 97 % of ALL pairs.
+        margin = 1.5 * float(err)
+        decided = 0
+        for f, thr in enumerate(sweep_ref["best_thr"]):
+            sl = slice(f * per, (f + 1) * per)
+            decided += int((np.abs(ref[sl].astype(np.float64) - thr) > margin).sum())
+        print("%s: %d of %d pairs farther than 1.5 x max |dcos| = %.1e from their threshold" % (name, decided, N_PAIRS, margin))
+        assert decided >= N_PAIRS // 2
         assert flips_all <= 0.03 * N_PAIRS
         assert abs(sweep_got["avg_acc"] - sweep_ref["avg_acc"]) <= 0.02
     # the device sweep itself (ffr_threshold_sweep) reproduces the oracle sweep on the device's own scores bit for bit
