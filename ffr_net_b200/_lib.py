@@ -128,6 +128,10 @@ _SIGNATURES = {
     "ffr_debug_set_pdl": (None, [_i]),
     "ffr_debug_set_lean_epilogue": (None, [_i]),
     "ffr_debug_set_stem_strip": (None, [_i]),
+    "ffr_debug_set_streamk": (None, [_i]),
+    "ffr_debug_last_streamk": (_i, []),
+    "ffr_conv_scratch_bytes": (ctypes.c_longlong, []),
+    "ffr_set_conv_scratch": (_i, [_p, ctypes.c_longlong]),
     "ffr_debug_mn_probe": (_i, [_p, _p, _p, _i, _i, _p]),
     "ffr_debug_set_counters": (_i, [_p]),
     "ffr_debug_set_wgrad_splits": (None, [_i]),

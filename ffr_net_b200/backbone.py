@@ -205,6 +205,8 @@ class Backbone(nn.Module):
         ws.pool_part = torch.empty(part, dtype=torch.float32, device=device)
         ws.gate = torch.empty(n * 512, dtype=torch.float32, device=device)
         ws.acc = torch.empty(lib.ffr_head_workspace_floats(n, res, 512), dtype=torch.float32, device=device)
+        # stream-K scratch of the 256-wide 3x3 convolutions (flag words first: must start out zero)
+        ws.sk = torch.zeros(lib.ffr_conv_scratch_bytes(), dtype=torch.uint8, device=device)
         self._ws[slot] = (key, ws)                            # keep one batch size resident per stream slot
         return ws
 
@@ -285,35 +287,41 @@ class Backbone(nn.Module):
         else:
             L.check(lib.ffr_stem_fwd(P(x), P(pk.stem_w), P(pk.stem_b), P(pk.stem_a), P(ws.a), n, S, st), "stem")
         cur, nxt = ws.a, ws.b
-        for i, u in enumerate(pk.units):
-            so = S // u.stride
-            if u.stride == 2:
-                t = ws.s2d[i]
-                L.check(lib.ffr_conv3x3_bnpre_prelu_fwd(P(cur), n, S, u.cin, P(u.w1), u.depth, P(u.bias9), P(u.slope),
-                                                        P(t), 1, st), "conv1 %d>%d@%ds1" % (u.cin, u.depth, S))
-            else:
-                t = ws.t
-                L.check(lib.ffr_conv3x3_bnpre_prelu_fwd(P(cur), n, S, u.cin, P(u.w1), u.depth, P(u.bias9), P(u.slope),
-                                                        P(t), 0, st), "conv1 %d>%d@%ds1" % (u.cin, u.depth, S))
-            L.check(lib.ffr_conv3x3_bn_pool_fwd(P(t), n, S, u.depth, u.stride, P(u.w2), u.depth, P(u.b2), P(ws.u),
-                                                P(ws.pool_part), st), "conv2 %d>%d@%ds%d" % (u.depth, u.depth, S, u.stride))
-            fused_se = self.fuse_se and u.depth <= 256      # gate + scale + residual in one launch (one CTA per image)
-            if not fused_se:
-                L.check(lib.ffr_se_gate_fwd(P(ws.pool_part), P(u.fc1), P(u.fc2), P(ws.gate), None, n, so, u.depth, st), "se_gate")
-            if u.cin == u.depth:
-                sc, mode = cur, (1 if u.stride == 2 else 0)
-            else:
-                L.check(lib.ffr_subsample2(P(cur), P(ws.xs), n, so, u.cin, st), "subsample")
-                L.check(lib.ffr_conv1x1_bn_fwd(P(ws.xs), n, so, u.cin, P(u.wsc), u.depth, P(u.bsc), P(ws.sc), st),
-                        "shortcut")
-                sc, mode = ws.sc, 2
-            if fused_se:
-                L.check(lib.ffr_se_gate_residual_fwd(P(ws.u), P(ws.pool_part), P(u.fc1), P(u.fc2), P(sc), mode, P(nxt), n, so,
-                                                     u.depth, st), "se_gate_residual")
-            else:
-                L.check(lib.ffr_se_residual_fwd(P(ws.u), P(ws.gate), P(sc), mode, P(nxt), n, so, u.depth, st), "se_residual")
-            cur, nxt = nxt, cur
-            S = so
+        # stream-K scratch of this workspace slot for the convolution launches below (unregistered afterwards: the library
+        # keeps only the pointer)
+        _lib.check(lib.ffr_set_conv_scratch(P(ws.sk), ws.sk.numel()), "set_conv_scratch")
+        try:
+            for i, u in enumerate(pk.units):
+                so = S // u.stride
+                if u.stride == 2:
+                    t = ws.s2d[i]
+                    L.check(lib.ffr_conv3x3_bnpre_prelu_fwd(P(cur), n, S, u.cin, P(u.w1), u.depth, P(u.bias9), P(u.slope),
+                                                            P(t), 1, st), "conv1 %d>%d@%ds1" % (u.cin, u.depth, S))
+                else:
+                    t = ws.t
+                    L.check(lib.ffr_conv3x3_bnpre_prelu_fwd(P(cur), n, S, u.cin, P(u.w1), u.depth, P(u.bias9), P(u.slope),
+                                                            P(t), 0, st), "conv1 %d>%d@%ds1" % (u.cin, u.depth, S))
+                L.check(lib.ffr_conv3x3_bn_pool_fwd(P(t), n, S, u.depth, u.stride, P(u.w2), u.depth, P(u.b2), P(ws.u),
+                                                    P(ws.pool_part), st), "conv2 %d>%d@%ds%d" % (u.depth, u.depth, S, u.stride))
+                fused_se = self.fuse_se and u.depth <= 256      # gate + scale + residual in one launch (one CTA per image)
+                if not fused_se:
+                    L.check(lib.ffr_se_gate_fwd(P(ws.pool_part), P(u.fc1), P(u.fc2), P(ws.gate), None, n, so, u.depth, st), "se_gate")
+                if u.cin == u.depth:
+                    sc, mode = cur, (1 if u.stride == 2 else 0)
+                else:
+                    L.check(lib.ffr_subsample2(P(cur), P(ws.xs), n, so, u.cin, st), "subsample")
+                    L.check(lib.ffr_conv1x1_bn_fwd(P(ws.xs), n, so, u.cin, P(u.wsc), u.depth, P(u.bsc), P(ws.sc), st),
+                            "shortcut")
+                    sc, mode = ws.sc, 2
+                if fused_se:
+                    L.check(lib.ffr_se_gate_residual_fwd(P(ws.u), P(ws.pool_part), P(u.fc1), P(u.fc2), P(sc), mode, P(nxt), n, so,
+                                                         u.depth, st), "se_gate_residual")
+                else:
+                    L.check(lib.ffr_se_residual_fwd(P(ws.u), P(ws.gate), P(sc), mode, P(nxt), n, so, u.depth, st), "se_residual")
+                cur, nxt = nxt, cur
+                S = so
+        finally:
+            lib.ffr_set_conv_scratch(None, 0)
         y = None
         if want_y:
             y = out_y if out_y is not None else torch.empty(n, 512, S, S, dtype=torch.float32, device=dev)

@@ -49,6 +49,15 @@ FFR_API void ffr_debug_set_pair(int mode) { set_pair_mode(mode); }
 FFR_API void ffr_debug_set_pdl(int mask) { set_pdl_mask(mask); }
 FFR_API void ffr_debug_set_lean_epilogue(int enable) { set_lean_epilogue(enable != 0); }
 FFR_API void ffr_debug_set_stem_strip(int enable) { set_stem_strip(enable != 0); }
+FFR_API void ffr_debug_set_streamk(int enable) { set_streamk(enable); }
+FFR_API int ffr_debug_last_streamk(void) { return last_streamk(); }
+FFR_API long long ffr_conv_scratch_bytes(void) { return conv_scratch_bytes(); }
+FFR_API int ffr_set_conv_scratch(void* scratch, long long bytes) {
+    FFR_CHECK_ARG(scratch == nullptr || (bytes >= 1024 && (reinterpret_cast<uintptr_t>(scratch) & 15) == 0),
+                  "ffr_set_conv_scratch: scratch must be 16-byte aligned and hold the flag words");
+    set_conv_scratch(scratch, scratch ? bytes : 0);
+    return 0;
+}
 
 FFR_API int ffr_debug_set_counters(void* counters) {
     set_debug_counters(reinterpret_cast<unsigned long long*>(counters));

@@ -125,6 +125,16 @@ struct EpiSched {
     int pix_ibp;                 // > 0 (pixel-major CTA pairs): image-block PAIRS per pixel; m_group = q * pix_ibp + pair,
                                  // this CTA owns image block 2 * pair + tile_add of pixel q
     uint32_t tempty_remote;      // 0, or the shared::cluster address of the leader's tempty_bar[0]
+    // stream-K (conv_win2_kernel): work item whose accumulator is only DUMPED to this CTA's slot (-1: none), work item
+    // that first adds the PEER pair's dumped partial (-1: none); see ConvGemmParams::sk_enable
+    int sk_dump_work, sk_add_work;
+    int n_pre, pre_work[4];      // work items walked BEFORE the arithmetic sequence work0, work0 + stride, ... (stream-K: the
+                                 // partial items of the pair's step range go early, so that the fix-up of the item
+                                 // shared with the next pair overlaps the MMAs of the whole items)
+    float* sk_my_ws;             // this CTA's slot   [128][BN] fp32
+    const float* sk_peer_ws;     // the slot of the same-rank CTA of the next pair
+    int* sk_my_flag;
+    int* sk_peer_flag;
 };
 
 template <int BN, int SUB>
@@ -137,6 +147,8 @@ __device__ __forceinline__ EpiSched epi_sched_single(const ConvGemmParams& p) {
     es.tile_add = 0;
     es.pix_ibp = 0;
     es.tempty_remote = 0;
+    es.sk_dump_work = es.sk_add_work = -1;
+    es.n_pre = 0;
     return es;
 }
 
@@ -145,7 +157,7 @@ __device__ __forceinline__ EpiSched epi_sched_single(const ConvGemmParams& p) {
 // ~10 k SASS instructions of runtime flag tests; on the 64- and 128-channel layers, which are epilogue-bound (the MMA
 // warp waits for accumulator buffers 20-36 % of its time), ncu attributed 9 % of the epilogue warps' samples to
 // instruction fetch and 5 % to branch resolution. Specialised: 64 -> 64 @112 583 -> 486 us, whole eval step -5 %.
-template <int BN, int SUB, uint32_t FIXED = 0>
+template <int BN, int SUB, uint32_t FIXED = 0, bool SK = false>
 __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uint32_t tmem_base, uint64_t* tfull_bar,
                                               uint64_t* tempty_bar, float* sparam, const int warp, const int lane,
                                               const EpiSched es) {
@@ -168,7 +180,14 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
     const bool timed = p.dbg != nullptr;
     long long w_e = 0;
     const long long t_begin = clock64();
-    for (int work = es.work0; work < num_work; work += es.work_stride, ++it) {
+    for (int widx = 0;; ++widx, ++it) {
+        int work;
+        if (SK && widx < es.n_pre) {
+            work = (widx == 0) ? es.pre_work[0] : (widx == 1 ? es.pre_work[1] : (widx == 2 ? es.pre_work[2] : es.pre_work[3]));
+        } else {
+            work = es.work0 + (widx - (SK ? es.n_pre : 0)) * es.work_stride;
+            if (work >= num_work) break;
+        }
         const int t = work / p.num_splits;
         const int split = work - t * p.num_splits;
         const int n_tile = t % p.num_n_tiles;
@@ -176,6 +195,15 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
         const int n0 = n_tile * BN;
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
+        const bool sk_dump = SK && work == es.sk_dump_work;
+        const bool sk_add = SK && work == es.sk_add_work;
+        if (sk_add) {                            // the peer dumped its part of this item at the START of its run
+            if (etid == 0) {
+                while (ld_acquire_gpu(es.sk_peer_flag) == 0) __nanosleep(64);
+                *es.sk_peer_flag = 0;            // idle again for the next launch (stream order)
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
 
         if (n_tile != loaded_n_tile) {           // stage per-channel epilogue parameters in smem
             asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -292,6 +320,23 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
             float x[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(vbuf[ci & 1][j]);
+            if (SK && sk_dump) {                 // raw partial accumulator -> this CTA's stream-K slot, nothing else
+                // slot layout [column / 4][row][4]: the 32 lanes (rows) of a warp store 512 contiguous bytes per instruction
+                float4* o = reinterpret_cast<float4*>(es.sk_my_ws) + ((chalf * HALF + c0) / 4) * BLOCK_M + row_in_tile;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) o[q * BLOCK_M] = make_float4(x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
+                continue;
+            }
+            if (SK && sk_add) {                  // all eight loads in flight before the first add (L2 round trips)
+                const float* q0 = es.sk_peer_ws + ((long long)((chalf * HALF + c0) / 4) * BLOCK_M + row_in_tile) * 4;
+                float4 t[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) t[q] = ld_cg_f32x4(q0 + q * (BLOCK_M * 4));
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    x[q * 4 + 0] += t[q].x; x[q * 4 + 1] += t[q].y; x[q * 4 + 2] += t[q].z; x[q * 4 + 3] += t[q].w;
+                }
+            }
             if (flags & (EPI_BIAS | EPI_BORDER_BIAS)) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -462,6 +507,11 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const uin
         tc_fence_before();
         if (es.tempty_remote) mbar_arrive_cluster(es.tempty_remote + acc * 8);
         else mbar_arrive(&tempty_bar[acc]);
+        if (SK && sk_dump) {                     // every epilogue thread's stores are visible before the flag goes up
+            __threadfence();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (etid == 0) st_release_gpu(es.sk_my_flag, 1);
+        }
     }
     if (timed && threadIdx.x == 0) {
         atomicAdd(p.dbg + DBG_EPI_WAIT, (unsigned long long)w_e);
@@ -486,14 +536,14 @@ constexpr uint32_t FS_MCHANNEL = EPI_BIAS | EPI_SIGMOID;        // M_channel = s
 constexpr uint32_t FS_FEAT_CHANNEL = EPI_GEOM | EPI_SCATTER;    // M_channel @ X into the flip / cat slots
 
 // WINDOW: the sliding-window kernels only ever see the backbone sets (and RecNet's row-major small-batch layers, generic)
-template <int BN, int SUB, bool WINDOW>
+template <int BN, int SUB, bool WINDOW, bool SK = false>
 __device__ __forceinline__ void epilogue_dispatch(const ConvGemmParams& p, const uint32_t tmem_base, uint64_t* tfull_bar,
                                                   uint64_t* tempty_bar, float* sparam, const int warp, const int lane,
                                                   const EpiSched es) {
     switch (p.flags) {
-        case FS_CONV1:     epilogue_loop<BN, SUB, FS_CONV1>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es); return;
-        case FS_CONV1_S2D: epilogue_loop<BN, SUB, FS_CONV1_S2D>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es); return;
-        case FS_CONV2:     epilogue_loop<BN, SUB, FS_CONV2>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es); return;
+        case FS_CONV1:     epilogue_loop<BN, SUB, FS_CONV1, SK>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es); return;
+        case FS_CONV1_S2D: epilogue_loop<BN, SUB, FS_CONV1_S2D, SK>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es); return;
+        case FS_CONV2:     epilogue_loop<BN, SUB, FS_CONV2, SK>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es); return;
         default: break;
     }
     if constexpr (!WINDOW) {
@@ -509,7 +559,7 @@ __device__ __forceinline__ void epilogue_dispatch(const ConvGemmParams& p, const
             default: break;
         }
     }
-    epilogue_loop<BN, SUB, 0>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es);
+    epilogue_loop<BN, SUB, 0, SK>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es);
 }
 
 // PAIR: CTA pairs (cluster of 2, tcgen05 cta_group::2). A work item is two M tiles x one N tile: CTA rank r loads the A
@@ -718,6 +768,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         es.tile_add = rank;
         es.pix_ibp = pix_ibp;
         es.tempty_remote = (PAIR && !leader) ? mapa_shared(smem_u32(&tempty_bar[0]), 0) : 0u;
+        es.sk_dump_work = es.sk_add_work = -1;
+        es.n_pre = 0;
         epilogue_dispatch<BN, 1, false>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es);
     }
 
@@ -979,18 +1031,36 @@ conv_win2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int num_clusters = gridDim.x >> 1;
     const int num_work = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
     const int chunks = p.kb_per_tap;
+    // Work = (item, chunk) steps. Without stream-K pair c walks whole items c, c + num_clusters, ...; with it the pair
+    // owns the contiguous step range [s0, s1) of the item-major order, which may begin and end inside an item. Its steps
+    // run as four ranges: [s0, hb) = the last chunks of an item the previous pair began (dumped to the scratch); up to
+    // two whole items [hb, mb); [tb, s1) = the first chunks of an item the next pair finishes (this pair adds the
+    // peer's part and runs the fused epilogue - the peer dumped that part as ITS first range, two items ago, and the
+    // fix-up runs under the MMAs of what follows); then the remaining whole items [mb, tb).
+    const bool sk = p.sk_enable != 0;
+    const int steps_total = num_work * chunks;
+    const int s0 = sk ? (int)((long long)cluster_id * steps_total / num_clusters) : 0;
+    const int s1 = sk ? (int)((long long)(cluster_id + 1) * steps_total / num_clusters) : 0;
+    const int hb = ((s0 + chunks - 1) / chunks) * chunks;
+    const int tb = (s1 / chunks) * chunks;
+    const int mb = min(hb + 2 * chunks, tb);
+    const int n_rng = sk ? 4 : 1;
 
     if (warp == WARP_TMA) {
         int sa = 0, sb = 0;
         uint32_t pa = 0, pb = 0;
         const uint32_t a_full0 = mapa_shared(smem_u32(&a_full[0]), 0);     // the leader's full barriers
         const uint32_t b_full0 = mapa_shared(smem_u32(&b_full[0]), 0);
-        for (int work = cluster_id; work < num_work; work += num_clusters) {
-            const int n_tile = work % p.num_n_tiles;
-            const int m_pair = work / p.num_n_tiles;
-            const int row0 = (m_pair * 2 + (int)rank) * BLOCK_M - wc.G - 1;
-            const int n0 = n_tile * BN + (int)rank * (BN / 2);
-            for (int c = 0; c < chunks; ++c) {
+        for (int rg = 0; rg < n_rng; ++rg) {
+            int step = !sk ? 0 : (rg == 0 ? s0 : (rg == 1 ? hb : (rg == 2 ? tb : mb)));
+            const int step_end = !sk ? 0 : (rg == 0 ? hb : (rg == 1 ? mb : (rg == 2 ? s1 : tb)));
+            int work = sk ? step / chunks : cluster_id;
+            int c = sk ? step - work * chunks : 0;
+            while (sk ? (step < step_end) : (work < num_work)) {
+                const int n_tile = work % p.num_n_tiles;
+                const int m_pair = work / p.num_n_tiles;
+                const int row0 = (m_pair * 2 + (int)rank) * BLOCK_M - wc.G - 1;
+                const int n0 = n_tile * BN + (int)rank * (BN / 2);
                 mbar_wait(&a_empty[sa], pa ^ 1);
                 uint8_t* dst = sA + sa * win_bytes;
                 if (elect_one_sync()) {
@@ -1011,6 +1081,8 @@ conv_win2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     __syncwarp();
                     if (++sb == wc.b_stages) { sb = 0; pb ^= 1; }
                 }
+                ++step;
+                if (++c == chunks) { c = 0; work += sk ? 1 : num_clusters; }
             }
         }
     } else if (warp == WARP_MMA && leader) {
@@ -1022,26 +1094,34 @@ conv_win2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         long long w_t = 0, w_a = 0, w_b = 0;
         const long long t_begin = clock64();
         if (timed && lane == 0) atomicMin(p.dbg + DBG_T_MMA_BEGIN, globaltimer_ns());
-        for (int work = cluster_id; work < num_work; work += num_clusters, ++it) {
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
-            mbar_wait_timed(&tempty_bar[acc], acc_phase ^ 1, timed, w_t);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * BN;
-            for (int c = 0; c < chunks; ++c) {
+        for (int rg = 0; rg < n_rng; ++rg) {
+            int step = !sk ? 0 : (rg == 0 ? s0 : (rg == 1 ? hb : (rg == 2 ? tb : mb)));
+            const int step_end = !sk ? 0 : (rg == 0 ? hb : (rg == 1 ? mb : (rg == 2 ? s1 : tb)));
+            int work = sk ? step / chunks : cluster_id;
+            int c = sk ? step - work * chunks : 0;
+            bool seg_first = true;               // first chunk of an accumulator segment (an item, or its part in range)
+            while (sk ? (step < step_end) : (work < num_work)) {
+                const bool seg_last = (c == chunks - 1) || (sk && step == step_end - 1);
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                if (seg_first) {
+                    mbar_wait_timed(&tempty_bar[acc], acc_phase ^ 1, timed, w_t);
+                    tc_fence_after();
+                }
+                const uint32_t d_tmem = tmem_base + acc * BN;
                 mbar_wait_timed(&a_full[sa], pa, timed, w_a);
                 tc_fence_after();
                 const uint32_t win_lo = static_cast<uint32_t>(umma_smem_desc_sw128(smem_u32(sA + sa * win_bytes)));
 #pragma unroll 1
-                for (int tb = 0; tb < 9 / TB; ++tb) {
+                for (int tb_ = 0; tb_ < 9 / TB; ++tb_) {
 #pragma unroll
                     for (int j = 0; j < TB; ++j) mbar_wait_timed(&b_full[sb + j], pb, timed, w_b);
                     tc_fence_after();
                     const uint32_t b_lo = static_cast<uint32_t>(umma_smem_desc_sw128(smem_u32(sB + sb * B_HALF_BYTES)));
                     const uint32_t a_lo =
-                        win_lo + static_cast<uint32_t>((TB == 9 ? 0 : (TB == 3 ? tb * wc.G : (tb / 3) * wc.G + tb % 3)) * 8);
+                        win_lo + static_cast<uint32_t>((TB == 9 ? 0 : (TB == 3 ? tb_ * wc.G : (tb_ / 3) * wc.G + tb_ % 3)) * 8);
                     const uint32_t g8 = static_cast<uint32_t>(wc.G * 8);
-                    const uint32_t first = (c > 0 || tb > 0) ? 1u : 0u;
+                    const uint32_t first = (!seg_first || tb_ > 0) ? 1u : 0u;
                     if (elect_one_sync()) {
 #pragma unroll
                         for (int j = 0; j < TB; ++j) {
@@ -1053,9 +1133,9 @@ conv_win2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                                (j > 0 || k > 0) ? 1u : first);
                             umma_commit_pair(&b_empty[sb + j]);
                         }
-                        if (tb == 9 / TB - 1) {
+                        if (tb_ == 9 / TB - 1) {
                             umma_commit_pair(&a_empty[sa]);
-                            if (c == chunks - 1) umma_commit_pair(&tfull_bar[acc]);
+                            if (seg_last) umma_commit_pair(&tfull_bar[acc]);
                         }
                     }
                     __syncwarp();
@@ -1063,6 +1143,10 @@ conv_win2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (sb == wc.b_stages) { sb = 0; pb ^= 1; }
                 }
                 if (++sa == wc.a_stages) { sa = 0; pa ^= 1; }
+                seg_first = seg_last;
+                if (seg_last) ++it;
+                ++step;
+                if (++c == chunks) { c = 0; work += sk ? 1 : num_clusters; }
             }
         }
         if (timed && lane == 0) {
@@ -1076,13 +1160,36 @@ conv_win2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp < 8) {
         EpiSched es;
-        es.work0 = cluster_id;
-        es.work_stride = num_clusters;
-        es.num_work = num_work;
         es.tile_mul = 2;
         es.tile_add = (int)rank;
+        es.pix_ibp = 0;
         es.tempty_remote = leader ? 0u : mapa_shared(smem_u32(&tempty_bar[0]), 0);
-        epilogue_dispatch<BN, 1, true>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es);
+        es.sk_dump_work = es.sk_add_work = -1;
+        es.n_pre = 0;
+        if (!sk) {
+            es.work0 = cluster_id;
+            es.work_stride = num_clusters;
+            es.num_work = num_work;
+            epilogue_dispatch<BN, 1, true, false>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es);
+        } else {
+            if (hb > s0) es.sk_dump_work = s0 / chunks;   // the item's first chunks belong to the previous pair: dump
+            if (s1 > tb) es.sk_add_work = tb / chunks;    // ... its last chunks to the next pair: add the peer's part
+            int pre[4] = {-1, -1, -1, -1}, np = 0;
+            if (hb > s0) pre[np++] = es.sk_dump_work;
+            for (int w = hb / chunks; w < mb / chunks; ++w) pre[np++] = w;
+            if (s1 > tb) pre[np++] = es.sk_add_work;
+            es.pre_work[0] = pre[0]; es.pre_work[1] = pre[1]; es.pre_work[2] = pre[2]; es.pre_work[3] = pre[3];
+            es.n_pre = np;
+            es.work0 = mb / chunks;               // the remaining whole items
+            es.work_stride = 1;
+            es.num_work = tb / chunks;
+            const long long slot = (long long)BLOCK_M * BN;
+            es.sk_my_ws = p.sk_ws + ((long long)cluster_id * 2 + rank) * slot;
+            es.sk_peer_ws = p.sk_ws + ((long long)(cluster_id + 1) * 2 + rank) * slot;
+            es.sk_my_flag = p.sk_flags + cluster_id * 2 + rank;
+            es.sk_peer_flag = p.sk_flags + (cluster_id + 1) * 2 + rank;
+            epilogue_dispatch<BN, 1, true, true>(p, tmem_base, tfull_bar, tempty_bar, sparam, warp, lane, es);
+        }
     }
 
     tc_fence_before();
@@ -1130,6 +1237,17 @@ static int g_pair_mode = -1;
 void set_pair_mode(int mode) { g_pair_mode = mode; }
 static unsigned long long* g_dbg = nullptr;
 void set_debug_counters(unsigned long long* dptr) { g_dbg = dptr; }
+// stream-K scratch of the CTA-pair window kernel (ConvGemmParams::sk_enable): registered by the caller for the launches
+// that follow on this host thread (the library never allocates); layout [flags: 1024 B][pairs][2][128][256] fp32.
+// The flag words must be zero when registered; every launch leaves them zero again.
+static void* g_sk_scratch = nullptr;
+static long long g_sk_bytes = 0;
+static int g_streamk = 0;       // measured neutral inside a step (see DESIGN.md section 3 finding 10): opt-in
+void set_conv_scratch(void* ptr, long long bytes) { g_sk_scratch = ptr; g_sk_bytes = bytes; }
+long long conv_scratch_bytes() { return 1024 + (long long)(num_sms() / 2) * 2 * BLOCK_M * 256 * (long long)sizeof(float); }
+void set_streamk(int on) { g_streamk = on; }
+static int g_last_streamk = 0;          // did the most recent CTA-pair window launch run stream-K? (tests)
+int last_streamk() { return g_last_streamk; }
 
 // Is this launch a plain 3x3/stride-1 flat convolution (taps (r-1)*G + (s-1), no channel offsets)?
 static bool window_eligible(const ConvGemmParams& p, int* G_out) {
@@ -1327,6 +1445,21 @@ int conv_gemm_launch(const void* a, long long a_rows, int a_cols, int a_ld, cons
             const long long work = (long long)((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
             const int max_pairs = num_sms() / 2;
             const int wgrid = 2 * (int)((work < max_pairs) ? work : max_pairs);
+            // stream-K when whole items leave the last wave mostly empty: e.g. 450 items on 74 pairs are 7 waves of
+            // items but 6.25 waves of (item, chunk) steps
+            p.sk_enable = 0;
+            if (g_streamk && g_sk_scratch != nullptr && g_sk_bytes >= conv_scratch_bytes() && work > max_pairs &&
+                work % max_pairs != 0) {
+                const long long steps = work * p.kb_per_tap;
+                const double waves_items = (double)((work + max_pairs - 1) / max_pairs);
+                const double waves_steps = (double)((steps + max_pairs - 1) / max_pairs) / p.kb_per_tap;
+                if (waves_steps + 0.15 < waves_items) {
+                    p.sk_enable = 1;
+                    p.sk_flags = reinterpret_cast<int*>(g_sk_scratch);
+                    p.sk_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(g_sk_scratch) + 1024);
+                }
+            }
+            g_last_streamk = p.sk_enable;
             return launch_win2<256, 3>(tmA, tmB, p, wc, smem_bytes, wgrid, stream);
         }
     }

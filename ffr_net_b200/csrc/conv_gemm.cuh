@@ -101,6 +101,13 @@ struct ConvGemmParams {
     unsigned long long* ce_argkey;  // [M], zeroed by the caller: (orderable cos bits << 32) | (0xFFFFFFFF - class)
     int ce_classes;                 // real class count (columns >= ce_classes are padding)
     float ce_s, ce_m;
+    // stream-K (conv_win2_kernel, filled in by conv_gemm_launch): the (work item, k-chunk) steps are split EVENLY over
+    // the CTA pairs instead of whole work items, so the last wave is as full as the others. A pair whose range starts
+    // inside a work item stores that partial accumulator (fp32) in its slot of sk_ws and raises its flag; the pair that
+    // computed the item's first chunks adds it (fixed order: own + peer) and runs the fused epilogue.
+    int sk_enable;
+    float* sk_ws;             // [pairs][2 CTAs][128 rows][BN] fp32
+    int* sk_flags;            // [pairs][2], zero when idle
     unsigned long long* dbg;  // optional: per-role wait-cycle counters (ffr_debug_set_counters), else nullptr
 };
 

@@ -27,6 +27,10 @@ void set_use_window(bool on);
 void set_pair_mode(int mode);
 void set_lean_epilogue(bool on);
 void set_stem_strip(bool on);
+void set_conv_scratch(void* ptr, long long bytes);
+long long conv_scratch_bytes();
+void set_streamk(int on);
+int last_streamk();
 void set_debug_counters(unsigned long long* dptr);
 struct PrepParams {
     const float* x; const float* w0aT; const float* w0bT; const float* b0; const float* slope1; const float* A1;

@@ -443,6 +443,24 @@ FFR_API void ffr_debug_set_lean_epilogue(int enable);
  * S % 16 == 0; 0 forces the gather kernel that serves every other size. Same arithmetic, bit-identical results. */
 FFR_API void ffr_debug_set_stem_strip(int enable);
 
+/* Stream-K scratch of the 3x3 / stride-1 convolutions with 256-wide N tiles (ffr_conv3x3_bnpre_prelu_fwd,
+ * ffr_conv3x3_bn_pool_fwd at Cout % 256 == 0): when whole (256-row, 256-channel) work items would leave the last wave of
+ * the 74 CTA pairs mostly empty (e.g. 450 items = 7 waves at 14x14 x 512 images), the (item, 64-channel k-chunk) steps are
+ * split evenly over the pairs instead (6.25 waves); a pair that starts inside an item parks its fp32 partial
+ * accumulator in this scratch and the pair that began the item adds it before the fused epilogue (own + peer, a fixed
+ * order: bit-reproducible). The library never allocates: register ffr_conv_scratch_bytes() bytes of ZEROED device memory
+ * (the first 1024 bytes are flag words that every launch leaves zero again) before the launches that should use it, on
+ * the launching host thread; one scratch per stream that runs such convolutions concurrently. NULL unregisters (whole
+ * items, as without scratch). The schedule is OPT-IN: ffr_debug_set_streamk(1) enables it for launches with a scratch
+ * registered (default 0). Measured on B200 (tools/streamk_ab.py, tools/ab_bench.py): the last MMA of the 256->256@14x14
+ * layer retires 7 % earlier, but the whole eval step does not get faster — with whole items the 68 of 74 pairs that
+ * finish early already run the NEXT kernel's prologue under programmatic dependent launch, and the step is power-capped.
+ * Replaces nothing in the reference: scheduling of model_ir_se50.py:67,69 on 148 SMs. */
+FFR_API long long ffr_conv_scratch_bytes(void);
+FFR_API int ffr_set_conv_scratch(void* scratch, long long bytes);
+FFR_API void ffr_debug_set_streamk(int enable);
+FFR_API int ffr_debug_last_streamk(void);   /* 1 if the most recent such launch was scheduled stream-K */
+
 /* Debug/tuning: device buffer of 16 uint64 that the sliding-window kernel fills with per-role barrier-wait cycle
  * counts (summed over CTAs; slots in csrc/conv_gemm.cuh DbgSlot); NULL (default) disables the counters. */
 FFR_API int ffr_debug_set_counters(void* counters);

@@ -256,16 +256,25 @@ def test_launch_modes_bit_identical(models, lib):
             lib.ffr_debug_set_pdl(0)
             y1, f1 = m(x)
             lib.ffr_debug_set_pdl(3)
+            lib.ffr_debug_set_lean_epilogue(0)
+            y3, f3 = m(x)
+            lib.ffr_debug_set_lean_epilogue(1)
             lib.ffr_debug_set_pair(0)
             y2, f2 = m(x)
             lib.ffr_debug_set_pair(-1)
-            lib.ffr_debug_set_lean_epilogue(0)
-            y3, f3 = m(x)
+            # opt-in stream-K schedule: split work items are finished as (own + peer) partial sums, i.e. another fp32
+            # summation order than whole items: equal within the bf16 noise, and bit-reproducible in itself
+            lib.ffr_debug_set_streamk(1)
+            y4, f4 = m(x)
+            y5, f5 = m(x)
         finally:
             lib.ffr_debug_set_pdl(-1)
             lib.ffr_debug_set_pair(-1)
             lib.ffr_debug_set_lean_epilogue(1)
+            lib.ffr_debug_set_streamk(0)
         torch.cuda.synchronize()
     assert torch.equal(y1, y0) and torch.equal(f1, f0)
-    assert torch.equal(y2, y0) and torch.equal(f2, f0)
     assert torch.equal(y3, y0) and torch.equal(f3, f0)
+    assert torch.equal(y2, y0) and torch.equal(f2, f0)
+    assert torch.equal(y5, y4) and torch.equal(f5, f4)
+    assert (f4 - f0).abs().max().item() <= 2e-3 and (y4 - y0).abs().max().item() <= 2e-2 * y0.abs().max().item()

@@ -169,6 +169,57 @@ def test_conv3x3_bn_pool(lib, n, S, c, cout, stride, backbone_tiles):
         assert torch.equal(out, out2) and torch.equal(pool, pool2) and torch.equal(gate, gate2)
 
 
+@pytest.mark.parametrize("n,S,c,cout", [(345, 14, 256, 256), (330, 7, 512, 512), (512, 14, 256, 256)])
+def test_conv3x3_stream_k(lib, n, S, c, cout, conv_variant):
+    """Stream-K scheduling of the CTA-pair window kernel (ffr_set_conv_scratch): the (item, k-chunk) steps are split evenly
+    over the pairs and split items are finished as own + peer partial. Against F.conv2d within the usual tolerance,
+    within one bf16 rounding of the whole-item schedule, bit-reproducible, flag words left zero, squeeze sums right."""
+    if conv_variant != "window":
+        pytest.skip("CTA-pair window kernel only")
+    from ffr_net_b200 import packing
+    g = torch.Generator(device="cuda").manual_seed(S + c + n)
+    x = torch.randn(n, c, S, S, generator=g, device="cuda")
+    w = torch.randn(cout, c, 3, 3, generator=g, device="cuda") / (3 * c ** 0.5)
+    s1 = torch.empty(cout, device="cuda").uniform_(0.8, 1.2, generator=g)
+    b1 = torch.empty(cout, device="cuda").uniform_(-0.3, 0.3, generator=g)
+    wp = packing.pack_conv(w, out_scale=s1)
+    xin = layout.to_flat(x)
+    rows = n * (S + 1) * (S + 1)
+    scratch = torch.zeros(lib.ffr_conv_scratch_bytes(), dtype=torch.uint8, device="cuda")
+    fc1 = torch.randn(cout // 16, cout, generator=g, device="cuda") / cout ** 0.5
+    fc2 = torch.randn(cout, cout // 16, generator=g, device="cuda") / 2
+
+    def run(use_scratch):
+        out = torch.full((rows, cout), 3.0, dtype=torch.bfloat16, device="cuda")
+        part = torch.full((max(lib.ffr_se_pool_part_floats(n, S, cout), n * cout),), 7.0e3, dtype=torch.float32, device="cuda")
+        pool, gate = torch.empty(n, cout, device="cuda"), torch.empty(n, cout, device="cuda")
+        _lib.check(lib.ffr_set_conv_scratch(P(scratch) if use_scratch else None, scratch.numel() if use_scratch else 0))
+        lib.ffr_debug_set_streamk(1)              # opt-in schedule (default off)
+        try:
+            _lib.check(lib.ffr_conv3x3_bn_pool_fwd(P(xin), n, S, c, 1, P(wp), cout, P(b1), P(out), P(part), _stream()))
+        finally:
+            lib.ffr_set_conv_scratch(None, 0)
+            lib.ffr_debug_set_streamk(0)
+        assert lib.ffr_debug_last_streamk() == (1 if use_scratch else 0)      # the schedule under test really ran
+        _lib.check(lib.ffr_se_gate_fwd(P(part), P(fc1), P(fc2), P(gate), P(pool), n, S, cout, _stream()))
+        torch.cuda.synchronize()
+        return out, pool
+
+    o_sk, p_sk = run(True)
+    assert int(scratch[:1024].max()) == 0                       # every flag consumed
+    o_sk2, p_sk2 = run(True)
+    o_it, p_it = run(False)
+    assert torch.equal(o_sk, o_sk2) and torch.equal(p_sk, p_sk2)
+    xb = x.to(torch.bfloat16).float()
+    wb = wp.float().reshape(cout, 3, 3, c).permute(0, 3, 1, 2)
+    ref = F.conv2d(xb, wb, padding=1) + b1.view(1, -1, 1, 1)
+    scale = ref.abs().max().item()
+    assert (layout.from_flat(o_sk, n, S, cout) - ref).abs().max().item() <= (2e-3 + 2 ** -8) * scale
+    assert layout.flat_pad_rows(o_sk, n, S, cout).abs().max().item() == 0.0
+    assert (o_sk.float() - o_it.float()).abs().max().item() <= 2 ** -7 * scale
+    assert (p_sk - ref.sum(dim=(2, 3))).abs().max().item() <= 2e-3 * scale * S * S ** 0.5 + 1e-3
+
+
 @pytest.mark.parametrize("n,S,C,mode", [(3, 14, 256, 0), (2, 7, 512, 0), (5, 28, 64, 1), (2, 56, 64, 2), (1, 7, 128, 2)])
 def test_se_residual_isolated(lib, n, S, C, mode):
     """ffr_se_residual_fwd alone: y = u * gate[n] + shortcut on the flat map (model_ir_se50.py:36,73-76), against torch on
