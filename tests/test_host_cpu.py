@@ -89,10 +89,15 @@ def test_argument_errors_are_reported_without_a_gpu():
         (lambda: lib.ffr_wgrad(one, 60, one, 64, 0, 81, 64, 64, 9, 0, 1, 0, 64, -1, one, None, one, None), b"pitches"),
         (lambda: lib.ffr_self_similarity(one, 1, None, None, None), b"no output"),
         (lambda: lib.ffr_stem_u8_fwd(None, None, 1, one, one, one, one, 1, 112, None), b"null pointer"),
+        (lambda: lib.ffr_set_conv_scratch(ctypes.c_void_p(24), 1 << 20), b"16-byte aligned"),
+        (lambda: lib.ffr_set_conv_scratch(one, 512), b"flag words"),
     ]
     for call, needle in cases:
         rc = call()
         assert rc < 0 and needle in lib.ffr_last_error(), (rc, needle, lib.ffr_last_error())
+    # the stream-K scratch: registering and unregistering is host-only bookkeeping; its size covers 74 CTA pairs
+    assert lib.ffr_set_conv_scratch(one, lib.ffr_conv_scratch_bytes()) == 0 and lib.ffr_set_conv_scratch(None, 0) == 0
+    assert lib.ffr_conv_scratch_bytes() == 0 or lib.ffr_conv_scratch_bytes() >= 1024
     assert lib.ffr_pixmajor_profitable(4) == 0 and lib.ffr_pixmajor_profitable(512) == 1
     assert lib.ffr_pixmajor_profitable(130) == 0                  # a second, nearly empty image block does not pay
 
