@@ -9,6 +9,7 @@ expressed as scatter tables) and for the two per-sample GEMMs of the channel rec
 The torch sub-modules only hold parameters under the reference's names. There is no CPU / PyTorch fallback.
 """
 import ctypes
+import os
 import math
 
 import torch
@@ -198,6 +199,10 @@ class RecNet(nn.Module):
         self._packed = None
         self._ws = {}
         self._profile = None
+        # eval forward: spatial branch on a side stream (see _forward_eval). Opt-in (FFR_RECNET_BRANCH_STREAMS=1): measured
+        # at batch 512 it changes nothing (9.528 vs 9.528 ms per step, tools/ab_bench.py 512 branch) - every kernel is a
+        # persistent grid that fills the SMs, so the branches time-slice instead of overlapping
+        self.branch_streams = os.environ.get("FFR_RECNET_BRANCH_STREAMS", "0") == "1"
 
     # ------------------------------------------------------------------------------------------
     def conv_layers(self):
@@ -382,49 +387,61 @@ class RecNet(nn.Module):
             chk(lib.ffr_recnet_convlayer_fwd(P(src), n, c.cin_p, P(c.wp), c.cout_p, P(c.bias), P(c.slope),
                                              P(res), (res.shape[1] if res is not None else 0), 1 if sigmoid else 0,
                                              P(dst), (dst.shape[1] if dst is not None else 0), P(tab), 4, 81,
-                                             P(out_f32), P(pool), st), name)
+                                             P(out_f32), P(pool), _lib.stream_ptr()), name)
 
-        # ---- spatial rectifier (recnet.py:362-371, 404-405) ----
-        conv("Conv4Space.0", ws.s0, ws.b256[0])
-        conv("Conv4Space.1.conv1", ws.b256[0], ws.b256[1])
-        conv("Conv4Space.1.conv2", ws.b256[1], ws.b256[2], res=ws.b256[0])
-        conv("Conv4Space.2", ws.b256[2], ws.b128[0])
-        conv("Conv4Space.3.conv1", ws.b128[0], ws.b128[1])
-        conv("Conv4Space.3.conv2", ws.b128[1], ws.b128[2], res=ws.b128[0])
-        conv("Conv4Space.4", ws.b128[2], ws.b64[0])
-        conv("Conv4Space.5.conv1", ws.b64[0], ws.b64[1])
-        conv("Conv4Space.5.conv2", ws.b64[1], None, res=ws.b64[0], sigmoid=True, out_f32=ws.mspace)
-        fs_nchw = None
-        if aux is not None:
-            fs_nchw = torch.empty(n, 512, 7, 7, dtype=torch.float32, device=dev)
-            aux["feat_space"] = fs_nchw
-        chk(lib.ffr_feat_space(P(x), P(ws.mspace), P(ws.cm), P(fs_nchw), n, st), "feat_space")
+        # The spatial branch (nine small convolutions, latency- / feed-bound, + feat_space) and the channel branch
+        # (M_channel, feat_channel, three 512-wide convolutions) are independent until Conv4Merge (recnet.py:404-420) and
+        # write disjoint channel slots of the Conv4Merge input; with `branch_streams` the spatial branch runs on a side
+        # stream so that its CTAs fill the SMs the channel branch's tail waves leave idle (same kernels, same bits).
+        def spatial_branch():
+            # ---- spatial rectifier (recnet.py:362-371, 404-405) ----
+            conv("Conv4Space.0", ws.s0, ws.b256[0])
+            conv("Conv4Space.1.conv1", ws.b256[0], ws.b256[1])
+            conv("Conv4Space.1.conv2", ws.b256[1], ws.b256[2], res=ws.b256[0])
+            conv("Conv4Space.2", ws.b256[2], ws.b128[0])
+            conv("Conv4Space.3.conv1", ws.b128[0], ws.b128[1])
+            conv("Conv4Space.3.conv2", ws.b128[1], ws.b128[2], res=ws.b128[0])
+            conv("Conv4Space.4", ws.b128[2], ws.b64[0])
+            conv("Conv4Space.5.conv1", ws.b64[0], ws.b64[1])
+            conv("Conv4Space.5.conv2", ws.b64[1], None, res=ws.b64[0], sigmoid=True, out_f32=ws.mspace)
+            fs_nchw = None
+            if aux is not None:
+                fs_nchw = torch.empty(n, 512, 7, 7, dtype=torch.float32, device=dev)
+                aux["feat_space"] = fs_nchw
+            chk(lib.ffr_feat_space(P(x), P(ws.mspace), P(ws.cm), P(fs_nchw), n, _lib.stream_ptr()), "feat_space")
 
-        # ---- channel rectifier (recnet.py:372-386, 406, 410): M_channel = sigmoid(h5 W8^T + b8); M_channel @ X ----
-        EPI = _lib.EPI
-        d = _lib.ConvGemmDesc()                      # M_channel rows (sample, c) = sigmoid(h5 W8^T + b8), K = 64 (32 valid)
-        d.a, d.a_rows, d.a_cols, d.a_ld = P(ws.h5), n * 512, 64, 64
-        d.wp, d.Cin, d.Cout, d.ntaps = P(pk.w8), 64, 512, 1
-        d.M, d.n_img = n * 512, n
-        d.flags = EPI.BIAS | EPI.SIGMOID
-        d.bias = P(pk.b8)
-        d.out, d.ldo = P(ws.mch), 512
-        d.num_splits = 1
-        chk(lib.ffr_conv_gemm_ex(ctypes.byref(d), st), "M_channel")
-        d = _lib.ConvGemmDesc()                      # feat_channel = M_channel @ X per sample: batched weight operand
-        d.a, d.a_rows, d.a_cols, d.a_ld = P(ws.xt), n * 128, 512, 512
-        d.wp, d.Cin, d.Cout, d.ntaps = P(ws.mch), 512, 512, 1
-        d.M, d.rows_per_img, d.Wp, d.n_img = n * 128, 128, 128, n
-        d.flags = EPI.GEOM | EPI.SCATTER             # rows (h*7+w) -> flip / cat slots + reflection mirrors (t_flip)
-        d.out, d.ldo = P(ws.fm), 1024
-        d.scatter, d.scatter_n, d.out_rows_per_img = P(pk.t_flip), 8, 81
-        d.num_splits, d.b_rows_per_mtile, d.b_mtile_div = 1, 512, 1
-        chk(lib.ffr_conv_gemm_ex(ctypes.byref(d), st), "feat_channel")
+        def channel_branch():
+            # ---- channel rectifier (recnet.py:372-386, 406, 410): M_channel = sigmoid(h5 W8^T + b8); M_channel @ X ----
+            EPI = _lib.EPI
+            d = _lib.ConvGemmDesc()                      # M_channel rows (sample, c) = sigmoid(h5 W8^T + b8), K = 64 (32 valid)
+            d.a, d.a_rows, d.a_cols, d.a_ld = P(ws.h5), n * 512, 64, 64
+            d.wp, d.Cin, d.Cout, d.ntaps = P(pk.w8), 64, 512, 1
+            d.M, d.n_img = n * 512, n
+            d.flags = EPI.BIAS | EPI.SIGMOID
+            d.bias = P(pk.b8)
+            d.out, d.ldo = P(ws.mch), 512
+            d.num_splits = 1
+            chk(lib.ffr_conv_gemm_ex(ctypes.byref(d), _lib.stream_ptr()), "M_channel")
+            d = _lib.ConvGemmDesc()                      # feat_channel = M_channel @ X per sample: batched weight operand
+            d.a, d.a_rows, d.a_cols, d.a_ld = P(ws.xt), n * 128, 512, 512
+            d.wp, d.Cin, d.Cout, d.ntaps = P(ws.mch), 512, 512, 1
+            d.M, d.rows_per_img, d.Wp, d.n_img = n * 128, 128, 128, n
+            d.flags = EPI.GEOM | EPI.SCATTER             # rows (h*7+w) -> flip / cat slots + reflection mirrors (t_flip)
+            d.out, d.ldo = P(ws.fm), 1024
+            d.scatter, d.scatter_n, d.out_rows_per_img = P(pk.t_flip), 8, 81
+            d.num_splits, d.b_rows_per_mtile, d.b_mtile_div = 1, 512, 1
+            chk(lib.ffr_conv_gemm_ex(ctypes.byref(d), _lib.stream_ptr()), "feat_channel")
 
-        # ---- flip merge (recnet.py:415-418) and final merge (:420-423) ----
-        conv("ChannelFlipMerge.0", ws.fm, ws.c512[0])
-        conv("ChannelFlipMerge.1.conv1", ws.c512[0], ws.c512[1])
-        conv("ChannelFlipMerge.1.conv2", ws.c512[1], ws.cm, res=ws.c512[0], scatter=pk.t_h9[512])
+            # ---- flip merge (recnet.py:415-418) and final merge (:420-423) ----
+            conv("ChannelFlipMerge.0", ws.fm, ws.c512[0])
+            conv("ChannelFlipMerge.1.conv1", ws.c512[0], ws.c512[1])
+            conv("ChannelFlipMerge.1.conv2", ws.c512[1], ws.cm, res=ws.c512[0], scatter=pk.t_h9[512])
+
+        if self.branch_streams:
+            streams.fork_join([(0, 0), (1, 1)], dev, lambda i, lo, hi: (channel_branch if i == 0 else spatial_branch)())
+        else:
+            spatial_branch()
+            channel_branch()
         conv("Conv4Merge.0", ws.cm, ws.d512[0])
         conv("Conv4Merge.1.conv1", ws.d512[0], ws.d512[1])
         conv("Conv4Merge.1.conv2", ws.d512[1], ws.d512[2], res=ws.d512[0])

@@ -37,21 +37,27 @@ res = {}
 with torch.no_grad():
     for _ in range(5):
         rec.embed_from_images(enc, x)
-# (pdl, pair, fused SE, lean epilogue, stream-K, strip stem)
-CONFIGS = [(-1, -1, True, 1, 1, 1), (-1, -1, True, 1, 0, 1), (-1, -1, True, 1, 1, 0), (0, -1, True, 1, 1, 1), (-1, 0, True, 1, 1, 1)]
+# (pdl, pair, fused SE, lean epilogue, stream-K, strip stem, RecNet branches on two streams)
+CONFIGS = [(-1, -1, True, 1, 0, 1, 1), (-1, -1, True, 1, 0, 1, 0), (-1, -1, True, 1, 1, 1, 1), (-1, -1, True, 1, 0, 0, 1),
+           (0, -1, True, 1, 0, 1, 1), (-1, 0, True, 1, 0, 1, 1)]
 if len(sys.argv) > 2 and sys.argv[2] == "sk":
+    CONFIGS = [CONFIGS[0], CONFIGS[2]]
+if len(sys.argv) > 2 and sys.argv[2] == "branch":
     CONFIGS = CONFIGS[:2]
 for rnd in range(10):
     order = CONFIGS[rnd % len(CONFIGS):] + CONFIGS[:rnd % len(CONFIGS)]      # rotate: no config always runs first
-    for pdl, pair, fuse, lean, sk, strip in order:
+    for pdl, pair, fuse, lean, sk, strip, br in order:
         lib.ffr_debug_set_pdl(pdl)
         lib.ffr_debug_set_pair(pair)
         enc.fuse_se = fuse
         lib.ffr_debug_set_lean_epilogue(lean)
         lib.ffr_debug_set_streamk(sk)
         lib.ffr_debug_set_stem_strip(strip)
+        rec.branch_streams = bool(br)
         run(3)
-        res.setdefault("pdl=%d pair=%d fused_se=%d lean=%d streamk=%d strip_stem=%d" % (pdl, pair, int(fuse), lean, sk, strip), []).append(run(10))
+        res.setdefault("pdl=%d pair=%d fused_se=%d lean=%d streamk=%d strip_stem=%d branch_streams=%d" %
+                       (pdl, pair, int(fuse), lean, sk, strip, br), []).append(run(10))
+rec.branch_streams = False
 enc.fuse_se = True
 lib.ffr_debug_set_lean_epilogue(1)
 lib.ffr_debug_set_streamk(0)
