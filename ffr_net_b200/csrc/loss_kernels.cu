@@ -140,9 +140,15 @@ __global__ void __launch_bounds__(256) sumsq_reduce_kernel(const float* __restri
     const int rows_per_chunk = (rows_per_group + SUMSQ_CHUNKS - 1) / SUMSQ_CHUNKS;
     const int r0 = chunk * rows_per_chunk, r1 = min(r0 + rows_per_chunk, rows_per_group);
     float acc = 0.f;
-    for (int r = r0; r < r1; ++r) {
+    for (int r = r0; r < r1; r += 8) {           // eight rows of loads in flight per thread (a fixed order all the same)
         const float* q = part + (((long long)g * rows_per_group + r) * 2 + 1) * C;
-        for (int c = threadIdx.x; c < C; c += blockDim.x) acc += q[c];
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (r + u < r1) ? __ldg(q + (long long)u * 2 * C + c) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += v[u];
+        }
     }
     const float t = block_sum(acc, scratch);
     if (threadIdx.x == 0) out[g * SUMSQ_CHUNKS + chunk] = t;

@@ -361,29 +361,36 @@ __global__ void __launch_bounds__(256) fc_scatter_kernel(const float* __restrict
 // ----------------------------------------------------------------------------------------------------------
 // Composed maps of the channel rectifier: A = W_b W_a (32x32), cvec = W_b b_a + b_b for (a,b) = (2,3) and (5,6).
 //   wa [512][32], ba [512], wb [32][512], bb [32]  ->  A [32][32] (A[i][k] = sum_j wb[i][j] wa[j][k]), cvec [32]
-// grid = 2 (one composition per CTA), 1024 threads = one output each (+ the first 32 also cvec).
 // ----------------------------------------------------------------------------------------------------------
 struct ComposeArgs { const float* wa[2]; const float* ba[2]; const float* wb[2]; const float* bb[2]; float* A[2]; float* cv[2];
                      const float* w8; __nv_bfloat16* w8t; };   // optional: W8 [512][32] -> bf16 W8^T [64][512] (rows >= 32 zero)
 
-__global__ void __launch_bounds__(1024) chan_compose_kernel(const ComposeArgs p) {
-    if (blockIdx.x == 2) {           // K-major operand of dh7 = dM_pre @ W8 (backward)
-        for (int o = threadIdx.x; o < 64 * 512; o += 1024) {
+// grid = 64 composition CTAs (composition q = block / 32, output row i = block % 32) + 16 CTAs for W8^T; a composition
+// CTA has 33 columns (32 of A + cvec) x 8 slices of the 512-long contraction, added in a fixed order. (One CTA per
+// composition with a serial 512-step dot product per thread took 62 us of pure load latency.)
+__global__ void __launch_bounds__(264) chan_compose_kernel(const ComposeArgs p) {
+    if (blockIdx.x >= 64) {          // K-major operand of dh7 = dM_pre @ W8 (backward)
+        const int part = blockIdx.x - 64;                    // 16 parts of 2048 elements
+        for (int o = part * 2048 + threadIdx.x; o < (part + 1) * 2048; o += 264) {
             const int k = o >> 9, j = o & 511;
             p.w8t[o] = __float2bfloat16_rn(k < 32 ? p.w8[j * 32 + k] : 0.f);
         }
         return;
     }
-    const int q = blockIdx.x, i = threadIdx.x >> 5, k = threadIdx.x & 31;
-    const float* wa = p.wa[q]; const float* wb = p.wb[q];
+    __shared__ float red[8][33];
+    const int q = blockIdx.x >> 5, i = blockIdx.x & 31;
+    const int k = threadIdx.x % 33, slice = threadIdx.x / 33;        // k == 32: the cvec column
+    const float* wa = p.wa[q]; const float* wb = p.wb[q] + i * 512; const float* ba = p.ba[q];
     float a = 0.f;
-    for (int j = 0; j < 512; ++j) a = fmaf(wb[i * 512 + j], wa[j * 32 + k], a);
-    p.A[q][i * 32 + k] = a;
-    if (threadIdx.x < 32) {
-        const int r = threadIdx.x;
-        float s = p.bb[q][r];
-        for (int j = 0; j < 512; ++j) s = fmaf(wb[r * 512 + j], p.ba[q][j], s);
-        p.cv[q][r] = s;
+#pragma unroll 8
+    for (int j = slice * 64; j < slice * 64 + 64; ++j) a = fmaf(wb[j], (k < 32) ? wa[j * 32 + k] : ba[j], a);
+    red[slice][k] = a;
+    __syncthreads();
+    if (slice == 0) {
+        float t = (k < 32) ? 0.f : p.bb[q][i];
+#pragma unroll
+        for (int s2 = 0; s2 < 8; ++s2) t += red[s2][k];
+        if (k < 32) p.A[q][i * 32 + k] = t; else p.cv[q][i] = t;
     }
 }
 
@@ -830,7 +837,7 @@ FFR_API int ffr_chan_compose(const float* w2, const float* b2, const float* w3, 
     p.w8 = w8; p.w8t = reinterpret_cast<__nv_bfloat16*>(w8t);
     p.wa[0] = w2; p.ba[0] = b2; p.wb[0] = w3; p.bb[0] = b3; p.A[0] = A1; p.cv[0] = c1;
     p.wa[1] = w5; p.ba[1] = b5; p.wb[1] = w6; p.bb[1] = b6; p.A[1] = A2; p.cv[1] = c2;
-    chan_compose_kernel<<<w8t ? 3 : 2, 1024, 0, S_(stream)>>>(p);
+    chan_compose_kernel<<<w8t ? 80 : 64, 264, 0, S_(stream)>>>(p);
     return launch_status("chan_compose_kernel");
 }
 

@@ -198,12 +198,26 @@ __global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restri
     for (int ci0 = 0; ci0 < Cin; ci0 += 256) {
         const int ci = ci0 + threadIdx.x;
         if (ci < Cin) {
-            for (int t = 0; t < ntaps; ++t) {
-                const float* q = ws + ((long long)t * cout_p + co) * cin_p + ci;
-                float a = 0.f;
-                for (int sl = 0; sl < slabs; ++sl) a += __ldg(q + sl * slab_stride);
-                tile[threadIdx.x * ntaps + t] = a;
+            // slabs outermost with the taps unrolled: nine independent loads in flight per thread (the tap-outer order had
+            // one); every tap still adds its slabs in ascending order: same bits
+            float a[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const float* q = ws + (long long)co * cin_p + ci;
+            const long long tap_stride = (long long)cout_p * cin_p;
+            if (ntaps == 9) {
+                for (int sl = 0; sl < slabs; ++sl) {
+                    float v[9];
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) v[t] = __ldg(q + sl * slab_stride + t * tap_stride);
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) a[t] += v[t];
+                }
+            } else {
+                for (int t = 0; t < ntaps; ++t)
+                    for (int sl = 0; sl < slabs; ++sl) a[t] += __ldg(q + sl * slab_stride + t * tap_stride);
             }
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+                if (t < ntaps) tile[threadIdx.x * ntaps + t] = a[t];
             if (ci == bias_col) {
                 if (accumulate) db[co] += tile[threadIdx.x * ntaps]; else db[co] = tile[threadIdx.x * ntaps];
             }
@@ -416,6 +430,41 @@ clip_adam_kernel(const AdamTensor* __restrict__ tab, const int2* __restrict__ ch
     const float lr_over_bc1 = lr / (1.f - powf(b1, step));
     const float inv_sqrt_bc2 = rsqrtf(1.f - powf(b2, step));
     const long long base = (long long)ch.y * ADAM_CHUNK;
+    // full chunks of 16-byte aligned tensors: 128-bit accesses, the four loads of a group issued together (the tensors
+    // are views of flat buffers at arbitrary element offsets, hence the run-time alignment test); same arithmetic
+    if (base + ADAM_CHUNK <= t.n &&
+        ((reinterpret_cast<uintptr_t>(t.p + base) | reinterpret_cast<uintptr_t>(t.g + base) |
+          reinterpret_cast<uintptr_t>(t.m + base) | reinterpret_cast<uintptr_t>(t.v + base)) & 15) == 0) {
+        float4* p4 = reinterpret_cast<float4*>(t.p + base);
+        float4* g4 = reinterpret_cast<float4*>(t.g + base);
+        float4* m4 = reinterpret_cast<float4*>(t.m + base);
+        float4* v4 = reinterpret_cast<float4*>(t.v + base);
+#pragma unroll 2
+        for (int k = 0; k < ADAM_CHUNK / 1024; ++k) {
+            const int i = k * 256 + threadIdx.x;
+            const float4 gi = g4[i], pi = p4[i], mi = m4[i], vi = v4[i];
+            float gg[4] = {gi.x, gi.y, gi.z, gi.w}, pp[4] = {pi.x, pi.y, pi.z, pi.w};
+            float mm[4] = {mi.x, mi.y, mi.z, mi.w}, vv[4] = {vi.x, vi.y, vi.z, vi.w};
+            float gc[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float g = fminf(fmaxf(gg[e], -clip), clip);
+                gc[e] = g;
+                const float p = pp[e];
+                g = fmaf(wd, p, g);
+                const float m = fmaf(b1, mm[e], (1.f - b1) * g);
+                const float v = fmaf(b2, vv[e], (1.f - b2) * g * g);
+                mm[e] = m;
+                vv[e] = v;
+                pp[e] = p - lr_over_bc1 * m / (sqrtf(v) * inv_sqrt_bc2 + eps);
+            }
+            g4[i] = make_float4(gc[0], gc[1], gc[2], gc[3]);
+            m4[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+            v4[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+            p4[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+        }
+        return;
+    }
     for (int k = 0; k < ADAM_CHUNK / 256; ++k) {
         const long long i = base + k * 256 + threadIdx.x;
         if (i >= t.n) break;
