@@ -494,12 +494,49 @@ feat_space_bwd_kernel(const float* __restrict__ x, const float* __restrict__ msp
         const int cb = half * 256;
         __syncthreads();
         for (int i = tid; i < 256 * 49; i += 448) xs[i] = x[((long long)n * 512 + cb) * 49 + i];
-        for (int i = tid; i < 49 * 256; i += 448) {
-            const int j = i >> 8, c = i & 255;
-            const int h = j / 7, w = j - h * 7;
-            float v = dfs ? dfs[((long long)n * 81 + (h + 1) * 9 + (w + 1)) * lddfs + cb + c] : 0.f;
-            if (dcm) for_each_mirror(n, h, w, [&](long long row) { v += dcm[row * lddcm + cb + c]; });
-            ds[j * 257 + c] = v;
+        // four elements per step, all of their (up to five) loads issued before the first add: the fold is a chain of
+        // dependent adds and with one element per step the kernel spent most of its time on one load latency after the
+        // other. Same order of additions per element (own row, row mirror, column mirror, corner mirror).
+        for (int i0 = tid; i0 < 49 * 256; i0 += 4 * 448) {
+            float t[4][5];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * 448;
+#pragma unroll
+                for (int e = 0; e < 5; ++e) t[u][e] = 0.f;
+                if (i < 49 * 256) {
+                    const int j = i >> 8, c = i & 255;
+                    const int h = j / 7, w = j - h * 7;
+                    const int mh = (h == 1) ? -2 : ((h == 5) ? 2 : 0);
+                    const int mw = (w == 1) ? -2 : ((w == 5) ? 2 : 0);
+                    const long long base = (long long)n * 81 + (h + 1) * 9 + (w + 1);
+                    if (dfs) t[u][0] = __ldg(dfs + base * lddfs + cb + c);
+                    if (dcm) {
+                        const float* q = dcm + cb + c;
+                        t[u][1] = __ldg(q + base * lddcm);
+                        if (mh) t[u][2] = __ldg(q + (base + mh * 9) * lddcm);
+                        if (mw) t[u][3] = __ldg(q + (base + mw) * lddcm);
+                        if (mh && mw) t[u][4] = __ldg(q + (base + mh * 9 + mw) * lddcm);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * 448;
+                if (i < 49 * 256) {
+                    const int j = i >> 8, c = i & 255;
+                    const int h = j / 7, w = j - h * 7;
+                    const bool mh = (h == 1) || (h == 5), mw = (w == 1) || (w == 5);
+                    float v = t[u][0];
+                    if (dcm) {
+                        v += t[u][1];
+                        if (mh) v += t[u][2];
+                        if (mw) v += t[u][3];
+                        if (mh && mw) v += t[u][4];
+                    }
+                    ds[j * 257 + c] = v;
+                }
+            }
         }
         __syncthreads();
         if (split < 8) {
@@ -551,9 +588,31 @@ __global__ void __launch_bounds__(256) fc_bwd_gather_kernel(const float* __restr
     for (int i = threadIdx.x; i < 49 * 64; i += 256) {
         const int pix = i >> 6, c = i & 63;
         const int h = pix / 7, w = pix - h * 7;
+        // the (up to eight) loads of both folds first, then the adds in the order own row, row mirror, column mirror,
+        // corner mirror (a chain of load-dependent adds costs one memory latency per term)
+        float t[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        bool mhs[2], mws[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int we = e == 0 ? w : 6 - w;
+            const int mh = (h == 1) ? -2 : ((h == 5) ? 2 : 0);
+            const int mw = (we == 1) ? -2 : ((we == 5) ? 2 : 0);
+            mhs[e] = mh != 0; mws[e] = mw != 0;
+            const long long base = (long long)n * 81 + (h + 1) * 9 + (we + 1);
+            const float* q = dfm + (e == 0 ? 512 : 0) + c0 + c;
+            t[e][0] = __ldg(q + base * lddfm);
+            if (mh) t[e][1] = __ldg(q + (base + mh * 9) * lddfm);
+            if (mw) t[e][2] = __ldg(q + (base + mw) * lddfm);
+            if (mh && mw) t[e][3] = __ldg(q + (base + mh * 9 + mw) * lddfm);
+        }
         float v = 0.f;
-        for_each_mirror(n, h, w, [&](long long row) { v += dfm[row * lddfm + 512 + c0 + c]; });
-        for_each_mirror(n, h, 6 - w, [&](long long row) { v += dfm[row * lddfm + c0 + c]; });
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            v += t[e][0];
+            if (mhs[e]) v += t[e][1];
+            if (mws[e]) v += t[e][2];
+            if (mhs[e] && mws[e]) v += t[e][3];
+        }
         tile[pix][c] = v;
     }
     __syncthreads();
