@@ -232,18 +232,25 @@ int recnet_prep_launch(const PrepParams& p, int n, cudaStream_t stream) {
 __global__ void __launch_bounds__(256) feat_space_kernel(const float* __restrict__ x, const float* __restrict__ mspace,
                                                          __nv_bfloat16* __restrict__ cm, float* __restrict__ out_nchw) {
     __shared__ float Ms[49 * 49];     // Ms[i*49 + j] = M_space[n,i,j]
+    extern __shared__ __align__(16) float fs_xs[];   // [512][49]: the sample's X, staged with coalesced 16-byte loads
     const int n = blockIdx.x, tid = threadIdx.x;
     for (int o = tid; o < 49 * 49; o += 256) {
         const int j = o / 49, i = o - j * 49;
         const int pos = (j / 7 + 1) * 9 + (j % 7 + 1);
         Ms[i * 49 + j] = mspace[((long long)n * 81 + pos) * 64 + i];
     }
+    {   // (a thread's two rows are 196 bytes apart from its neighbour's: read straight from global memory every one of
+        // the 98 loads of a warp touched 32 lines)
+        const float4* src = reinterpret_cast<const float4*>(x + (long long)n * 512 * 49);
+        float4* dst = reinterpret_cast<float4*>(fs_xs);
+        for (int o = tid; o < 512 * 49 / 4; o += 256) dst[o] = __ldg(src + o);
+    }
     __syncthreads();
     const int c2 = tid * 2;
     float xa[49], xb[49];
-    const float* xr = x + ((long long)n * 512 + c2) * 49;
+    const float* xr = fs_xs + c2 * 49;
 #pragma unroll
-    for (int i = 0; i < 49; ++i) { xa[i] = __ldg(xr + i); xb[i] = __ldg(xr + 49 + i); }
+    for (int i = 0; i < 49; ++i) { xa[i] = xr[i]; xb[i] = xr[49 + i]; }
     for (int j = 0; j < 49; ++j) {
         float a = 0.f, b = 0.f;
 #pragma unroll
@@ -269,7 +276,13 @@ __global__ void __launch_bounds__(256) feat_space_kernel(const float* __restrict
 }
 
 int feat_space_launch(const float* x, const float* mspace, void* cm, float* out_nchw, int n, cudaStream_t stream) {
-    feat_space_kernel<<<n, 256, 0, stream>>>(x, mspace, reinterpret_cast<__nv_bfloat16*>(cm), out_nchw);
+    const int smem = 512 * 49 * (int)sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        FFR_CUDA(cudaFuncSetAttribute(feat_space_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    feat_space_kernel<<<n, 256, smem, stream>>>(x, mspace, reinterpret_cast<__nv_bfloat16*>(cm), out_nchw);
     return launch_status("feat_space_kernel");
 }
 

@@ -442,17 +442,23 @@ __global__ void __launch_bounds__(512) chan_compose_bwd_kernel(const ComposeBwdA
 __global__ void __launch_bounds__(256) feat_space_train_kernel(const float* __restrict__ x, const float* __restrict__ mspace,
                                                                const ActDst cm, float* __restrict__ fs_f32, int ldfs) {
     __shared__ float Ms[49 * 49];     // Ms[i*49 + j] = M_space[n,i,j]
+    extern __shared__ __align__(16) float fst_xs[];  // [512][49]: the sample's X, staged with coalesced 16-byte loads
     const int n = blockIdx.x, tid = threadIdx.x;
     for (int o = tid; o < 49 * 49; o += 256) {
         const int j = o / 49, i = o - j * 49;
         Ms[i * 49 + j] = mspace[((long long)n * 81 + h9_row(j)) * 64 + i];
     }
+    {
+        const float4* src = reinterpret_cast<const float4*>(x + (long long)n * 512 * 49);
+        float4* dst = reinterpret_cast<float4*>(fst_xs);
+        for (int o = tid; o < 512 * 49 / 4; o += 256) dst[o] = __ldg(src + o);
+    }
     __syncthreads();
     const int c2 = tid * 2;
     float xa[49], xb[49];
-    const float* xr = x + ((long long)n * 512 + c2) * 49;
+    const float* xr = fst_xs + c2 * 49;
 #pragma unroll
-    for (int i = 0; i < 49; ++i) { xa[i] = __ldg(xr + i); xb[i] = __ldg(xr + 49 + i); }
+    for (int i = 0; i < 49; ++i) { xa[i] = xr[i]; xb[i] = xr[49 + i]; }
     for (int j = 0; j < 49; ++j) {
         float a = 0.f, b = 0.f;
 #pragma unroll
@@ -920,7 +926,13 @@ FFR_API int ffr_feat_space_train(const float* x, const float* mspace, void* cm_h
                                  int cm_ldb, float* fs_f32, int ldfs, int n, ffr_stream_t stream) {
     FFR_CHECK_ARG(x && mspace && cm_h, "ffr_feat_space_train: null pointer");
     if (n == 0) return 0;
-    feat_space_train_kernel<<<n, 256, 0, S_(stream)>>>(x, mspace, mk_dst(cm_h, cm_ld, cm_lo, cm_b, cm_ldb), fs_f32, ldfs);
+    const int smem = 512 * 49 * (int)sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        FFR_CUDA(cudaFuncSetAttribute(feat_space_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    feat_space_train_kernel<<<n, 256, smem, S_(stream)>>>(x, mspace, mk_dst(cm_h, cm_ld, cm_lo, cm_b, cm_ldb), fs_f32, ldfs);
     return launch_status("feat_space_train_kernel");
 }
 
