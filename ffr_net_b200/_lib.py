@@ -129,6 +129,7 @@ _SIGNATURES = {
     "ffr_debug_set_lean_epilogue": (None, [_i]),
     "ffr_debug_set_stem_strip": (None, [_i]),
     "ffr_debug_set_streamk": (None, [_i]),
+    "ffr_debug_set_prep_mma": (None, [_i]),
     "ffr_debug_last_streamk": (_i, []),
     "ffr_conv_scratch_bytes": (ctypes.c_longlong, []),
     "ffr_set_conv_scratch": (_i, [_p, ctypes.c_longlong]),

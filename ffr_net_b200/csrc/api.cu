@@ -50,6 +50,7 @@ FFR_API void ffr_debug_set_pdl(int mask) { set_pdl_mask(mask); }
 FFR_API void ffr_debug_set_lean_epilogue(int enable) { set_lean_epilogue(enable != 0); }
 FFR_API void ffr_debug_set_stem_strip(int enable) { set_stem_strip(enable != 0); }
 FFR_API void ffr_debug_set_streamk(int enable) { set_streamk(enable); }
+FFR_API void ffr_debug_set_prep_mma(int enable) { set_prep_mma(enable); }
 FFR_API int ffr_debug_last_streamk(void) { return last_streamk(); }
 FFR_API long long ffr_conv_scratch_bytes(void) { return conv_scratch_bytes(); }
 FFR_API int ffr_set_conv_scratch(void* scratch, long long bytes) {

@@ -30,6 +30,7 @@ void set_stem_strip(bool on);
 void set_conv_scratch(void* ptr, long long bytes);
 long long conv_scratch_bytes();
 void set_streamk(int on);
+void set_prep_mma(int on);
 int last_streamk();
 void set_debug_counters(unsigned long long* dptr);
 struct PrepParams {

@@ -213,12 +213,311 @@ __global__ void __launch_bounds__(512, 1) recnet_prep_kernel(const PrepParams p)
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Warp-MMA version of recnet_prep_kernel (same inputs, outputs and algebra). The SIMT kernel above executes ~300 k warp
+// instructions per sample (49x49x512 Gram, 49x32x512 T, 512x49x64 first chain layer, two 32x32 maps per row: every FMA
+// with a shared-memory operand) at 40 % issue efficiency: 320-360 us for 512 samples, the largest non-GEMM kernel of the
+// eval step. Here X is staged ONCE as bf16 in the pixel-major layout XT [64 pixels][512 channels] — the precision every
+// other consumer of X in the eval path has (s0 / cm / xt ARE this matrix) — and
+//   Gram  G = XT XT^T          (M 64 x N 56 x K 512)   m16n8k16 bf16, fp32 accumulate        warps 0-7
+//   T     = XT (W0b^T / |x_c|) (M 64 x N 32 x K 512)   m16n8k16 bf16                          warps 8-15
+//   H     = X [W0a | T]        (M 512 x N 64 x K 64)   m16n8k16 bf16, 32 rows per warp
+//   the two composed 32x32 maps                        m16n8k8 tf32, A straight from the previous accumulators
+// run on the tensor cores through ldmatrix fragments; row / column norms come from the staged values (so the Gram of
+// the staged matrix has a unit diagonal), the fan-out copies 4-byte channel pairs from XT without conversions.
+// The pad rows 49..63 of XT are zero: they are the zero K / M / N padding of all four contractions.
+// ----------------------------------------------------------------------------------------------
+constexpr int PM_XP = 520;     // XT pitch (bf16): 1040 B = 260 words = 4 mod 32 -> ldmatrix rows hit disjoint bank groups
+constexpr int PM_BP = 40;      // W0b^T / |x_c| pitch (bf16), [512][32]
+constexpr int PM_WP = 72;      // [W0a | T] pitch (bf16), [64][64]
+constexpr int PM_AP = 36;      // composed 32x32 maps pitch (fp32)
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void mma_bf16_k16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_tf32_k8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+
+// One composed 32x32 map + PReLU on the accumulator fragments of a warp's two 16-row tiles: out = prelu(in A^T + cvec).
+// The tf32 A fragment of k-step s is the C fragment of n-tile s with the K slots permuted (slot t <-> column 2t,
+// slot t + 4 <-> column 2t + 1); the B fragment reads the map with the same permutation, so no data moves between lanes.
+__device__ __forceinline__ void chain_map_tf32(float (&h)[2][4][4], const float* As, const float* cvec, const float (&slope)[2][2],
+                                               int g, int t) {
+    float o[2][4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float c0 = cvec[8 * q + 2 * t], c1 = cvec[8 * q + 2 * t + 1];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) { o[m][q][0] = c0; o[m][q][1] = c1; o[m][q][2] = c0; o[m][q][3] = c1; }
+    }
+#pragma unroll
+    for (int s2 = 0; s2 < 4; ++s2) {
+        uint32_t a[2][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            a[m][0] = to_tf32(h[m][s2][0]); a[m][1] = to_tf32(h[m][s2][2]);
+            a[m][2] = to_tf32(h[m][s2][1]); a[m][3] = to_tf32(h[m][s2][3]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float2 bv = *reinterpret_cast<const float2*>(As + (8 * q + g) * PM_AP + 8 * s2 + 2 * t);
+            const uint32_t b0 = to_tf32(bv.x), b1 = to_tf32(bv.y);
+            mma_tf32_k8(o[0][q], a[0], b0, b1);
+            mma_tf32_k8(o[1][q], a[1], b0, b1);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float v = o[m][q][e];
+                h[m][q][e] = v > 0.f ? v : v * slope[m][e >> 1];
+            }
+}
+
+__global__ void __launch_bounds__(512, 1) recnet_prep_mma_kernel(const PrepParams p) {
+    extern __shared__ __align__(16) uint8_t pm_smem[];
+    __nv_bfloat16* xt = reinterpret_cast<__nv_bfloat16*>(pm_smem);                  // [64][PM_XP]
+    __nv_bfloat16* Bs = xt + 64 * PM_XP;                                            // [512][PM_BP]
+    __nv_bfloat16* Wc = Bs + 512 * PM_BP;                                           // [64][PM_WP]
+    float* Gs = reinterpret_cast<float*>(Wc + 64 * PM_WP);                          // [49][49] (+3)
+    float* A1s = Gs + 2404;                                                         // [32][PM_AP]
+    float* A2s = A1s + 32 * PM_AP;
+    float* inv_c = A2s + 32 * PM_AP;                                                // [512]
+    float* inv_s = inv_c + 512;                                                     // [64]
+    float* misc = inv_s + 64;                                                       // b0, c1, c2 [3][32]
+    const int n = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const float* x = p.x + (long long)n * 512 * 49;
+
+    // ---- stage X as bf16 XT[hw][c] (coalesced reads), zero pad rows, small operands ----
+    for (int i = tid; i < 512 * 49; i += 512) {
+        const int c = i / 49, hw = i - c * 49;
+        xt[hw * PM_XP + c] = __float2bfloat16_rn(__ldg(x + i));
+    }
+    for (int i = tid; i < 15 * (PM_XP / 2); i += 512) reinterpret_cast<uint32_t*>(xt + 49 * PM_XP)[i] = 0u;   // rows 49..63
+    for (int i = tid; i < 64 * 32; i += 512) {           // W0a half of [W0a | T]; rows >= 49 zero
+        const int hw = i >> 5, j = i & 31;
+        Wc[hw * PM_WP + j] = __float2bfloat16_rn(hw < 49 ? p.w0aT[hw * 32 + j] : 0.f);
+    }
+    for (int i = tid; i < 1024; i += 512) {
+        A1s[(i >> 5) * PM_AP + (i & 31)] = p.A1[i];
+        A2s[(i >> 5) * PM_AP + (i & 31)] = p.A2[i];
+    }
+    if (tid < 32) { misc[tid] = p.b0[tid]; misc[32 + tid] = p.c1[tid]; misc[64 + tid] = p.c2[tid]; }
+    __syncthreads();
+
+    // ---- norms of the staged matrix: rows of X (over hw, F.normalize(dim=2) of (N,C,HW)) and pixel columns (over C) ----
+    {
+        float ss = 0.f;
+        for (int hw = 0; hw < 49; ++hw) { const float v = __bfloat162float(xt[hw * PM_XP + tid]); ss = fmaf(v, v, ss); }
+        inv_c[tid] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    }
+    for (int hw = warp; hw < 64; hw += 16) {
+        float ss = 0.f;
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(xt + hw * PM_XP);
+        for (int k = lane; k < 256; k += 32) { const uint32_t u = row[k]; const float a = bf16lo(u), b = bf16hi(u); ss = fmaf(a, a, fmaf(b, b, ss)); }
+        ss = warp_sum_r(ss);
+        if (lane == 0) inv_s[hw] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    }
+    __syncthreads();
+    for (int i = tid; i < 512 * 32; i += 512) {           // B operand of T: W0b^T[c][j] / |x_c|
+        const int c = i >> 5, j = i & 31;
+        Bs[c * PM_BP + j] = __float2bfloat16_rn(__ldg(p.w0bT + i) * inv_c[c]);
+    }
+    __syncthreads();
+
+    const uint32_t xt_s = smem_u32(xt), bs_s = smem_u32(Bs), wc_s = smem_u32(Wc);
+    if (warp < 8) {
+        // ---- spatial Gram: rows i = 16 mt .. +15, columns j = 32 ng .. +31 (n-tiles 4 ng .. 4 ng + 3) ----
+        const int mt = warp >> 1, ng = warp & 1;
+        float acc[4][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[q][e] = 0.f;
+        // A[m = hw][k = c] = XT[hw][c]: non-transposed; B[k = c][n = hw'] = XT[hw'][c]: memory [n][k], non-transposed
+        const uint32_t a_addr = xt_s + (uint32_t)(((16 * mt + (lane & 7) + ((lane >> 3) & 1) * 8) * PM_XP + (lane >> 4) * 8) * 2);
+        const uint32_t b_addr = xt_s + (uint32_t)(((32 * ng + (lane & 7) + (lane >> 4) * 8) * PM_XP + ((lane >> 3) & 1) * 8) * 2);
+#pragma unroll 4
+        for (int ks = 0; ks < 32; ++ks) {
+            uint32_t a[4], b01[4], b23[4];
+            ldsm_x4(a, a_addr + ks * 32);
+            ldsm_x4(b01, b_addr + ks * 32);
+            ldsm_x4(b23, b_addr + 16 * PM_XP * 2 + ks * 32);
+            mma_bf16_k16(acc[0], a, b01[0], b01[1]);
+            mma_bf16_k16(acc[1], a, b01[2], b01[3]);
+            mma_bf16_k16(acc[2], a, b23[0], b23[1]);
+            mma_bf16_k16(acc[3], a, b23[2], b23[3]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = 16 * mt + g + (e >> 1) * 8, j = 32 * ng + 8 * q + 2 * t + (e & 1);
+                if (i < 49 && j < 49) Gs[i * 49 + j] = acc[q][e] * inv_s[i] * inv_s[j];
+            }
+    } else {
+        // ---- T[hw][j] = sum_c XT[hw][c] * Bs[c][j]: rows 16 mt .. +15, columns 16 nh .. +15 ----
+        const int w8 = warp - 8, mt = w8 >> 1, nh = w8 & 1;
+        float acc[2][4];
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[q][e] = 0.f;
+        const uint32_t a_addr = xt_s + (uint32_t)(((16 * mt + (lane & 7) + ((lane >> 3) & 1) * 8) * PM_XP + (lane >> 4) * 8) * 2);
+        // B[k = c][n = j] = Bs[c][j]: memory [k][n] -> transposed load; matrices (k 0-7, n 0-7), (k 8-15, n 0-7), (k 0-7, n 8-15), (k 8-15, n 8-15)
+        const uint32_t b_addr = bs_s + (uint32_t)((((lane & 7) + ((lane >> 3) & 1) * 8) * PM_BP + 16 * nh + (lane >> 4) * 8) * 2);
+#pragma unroll 4
+        for (int ks = 0; ks < 32; ++ks) {
+            uint32_t a[4], b[4];
+            ldsm_x4(a, a_addr + ks * 32);
+            ldsm_x4_t(b, b_addr + ks * 16 * PM_BP * 2);
+            mma_bf16_k16(acc[0], a, b[0], b[1]);
+            mma_bf16_k16(acc[1], a, b[2], b[3]);
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int e = 0; e < 4; e += 2) {
+                const int hw = 16 * mt + g + (e >> 1) * 8, j = 16 * nh + 8 * q + 2 * t;
+                // rows >= 49 are exact zeros (zero rows of XT)
+                *reinterpret_cast<uint32_t*>(Wc + hw * PM_WP + 32 + j) = pack_bf16x2(acc[q][e], acc[q][e + 1]);
+            }
+    }
+    __syncthreads();
+
+    // ---- layout fan-out of X: 4-byte channel pairs straight from XT ----
+    {
+        const int cp = tid & 255;                  // channel pair (2 cp, 2 cp + 1)
+        const int half = tid >> 8;                 // two row streams
+        for (int hw = half; hw < 49; hw += 2) {
+            const uint32_t v = reinterpret_cast<const uint32_t*>(xt + hw * PM_XP)[cp];
+            *reinterpret_cast<uint32_t*>(p.xt + ((long long)n * 128 + hw) * 512 + 2 * cp) = v;
+        }
+        for (int pos = half; pos < 81; pos += 2) {
+            const int hp = pos / 9, wp = pos - hp * 9;
+            const int hw = reflect_src(hp) * 7 + reflect_src(wp);
+            const uint32_t v = reinterpret_cast<const uint32_t*>(xt + hw * PM_XP)[cp];
+            *reinterpret_cast<uint32_t*>(p.s0 + ((long long)n * 81 + pos) * 576 + 2 * cp) = v;
+            *reinterpret_cast<uint32_t*>(p.cm + ((long long)n * 81 + pos) * 1536 + 1024 + 2 * cp) = v;
+        }
+    }
+    // ss_space as 49 extra channels of the Conv4Space input: channel i at pixel j holds Gram[i][j]
+    for (int o = tid; o < 81 * 49; o += 512) {
+        const int pos = o / 49, i = o - pos * 49;
+        const int hp = pos / 9, wp = pos - hp * 9;
+        const int j = reflect_src(hp) * 7 + reflect_src(wp);
+        p.s0[((long long)n * 81 + pos) * 576 + 512 + i] = __float2bfloat16(Gs[i * 49 + j]);
+    }
+    if (p.ss_space)
+        for (int o = tid; o < 49 * 49; o += 512) p.ss_space[(long long)n * 2401 + o] = Gs[o];
+
+    // ---- channel-rectifier chain on the warp's 32 channel rows: H = X [W0a | T] (K = 64 pixels, 49 real) ----
+    {
+        const int m_base = 32 * warp;
+        float acc[2][8][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[m][q][e] = 0.f;
+        // A[m = c][k = hw] = XT[hw][c]: memory [k][m] -> transposed load; matrices (m 0-7, k 0-7), (m 8-15, k 0-7), (m 0-7, k 8-15), (m 8-15, k 8-15)
+        const uint32_t a_addr = xt_s + (uint32_t)((((lane & 7) + (lane >> 4) * 8) * PM_XP + m_base + ((lane >> 3) & 1) * 8) * 2);
+        // B[k = hw][n = j] = Wc[hw][j]: memory [k][n] -> transposed load, two n-tiles per instruction
+        const uint32_t b_addr = wc_s + (uint32_t)((((lane & 7) + ((lane >> 3) & 1) * 8) * PM_WP + (lane >> 4) * 8) * 2);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            uint32_t a0[4], a1[4];
+            ldsm_x4_t(a0, a_addr + ks * 16 * PM_XP * 2);
+            ldsm_x4_t(a1, a_addr + ks * 16 * PM_XP * 2 + 32);
+#pragma unroll
+            for (int pq = 0; pq < 4; ++pq) {
+                uint32_t b[4];
+                ldsm_x4_t(b, b_addr + ks * 16 * PM_WP * 2 + pq * 32);
+                mma_bf16_k16(acc[0][2 * pq], a0, b[0], b[1]);
+                mma_bf16_k16(acc[0][2 * pq + 1], a0, b[2], b[3]);
+                mma_bf16_k16(acc[1][2 * pq], a1, b[0], b[1]);
+                mma_bf16_k16(acc[1][2 * pq + 1], a1, b[2], b[3]);
+            }
+        }
+        // h = X W0a^T + b0 + (X T) / |x_c|, PReLU over the channel rows (recnet.py:373-374)
+        float h[2][4][4];
+        float sl1[2][2], sl4[2][2], sl7[2][2];
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int c = m_base + 16 * m + g + 8 * r;
+                sl1[m][r] = p.slope1[c]; sl4[m][r] = p.slope4[c]; sl7[m][r] = p.slope7[c];
+                const float ic = inv_c[c];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int e2 = 0; e2 < 2; ++e2) {
+                        const int e = 2 * r + e2;
+                        const float v = fmaf(ic, acc[m][q + 4][e], acc[m][q][e] + misc[8 * q + 2 * t + e2]);
+                        h[m][q][e] = v > 0.f ? v : v * sl1[m][r];
+                    }
+            }
+        chain_map_tf32(h, A1s, misc + 32, sl4, g, t);
+        chain_map_tf32(h, A2s, misc + 64, sl7, g, t);
+        // H5 rows: 32 real columns as bf16 pairs, columns 32..63 zero
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int c = m_base + 16 * m + g + 8 * r;
+                __nv_bfloat16* o = p.h5 + ((long long)n * 512 + c) * 64;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<uint32_t*>(o + 8 * q + 2 * t) = pack_bf16x2(h[m][q][2 * r], h[m][q][2 * r + 1]);
+                *reinterpret_cast<uint4*>(o + 32 + 8 * t) = make_uint4(0, 0, 0, 0);
+            }
+    }
+}
+
+static int g_prep_mma = 1;      // ffr_debug_set_prep_mma(0): the SIMT kernel (A/B runs, tests)
+void set_prep_mma(int on) { g_prep_mma = on; }
+
 int recnet_prep_launch(const PrepParams& p, int n, cudaStream_t stream) {
     const int smem = (512 * 49 + 512 + 64 + 49 * 49 + 3 + 49 * 32 * 2 + 2048 + 96 + 8 * 2401) * (int)sizeof(float);
     static bool attr = false;
     if (!attr) {
         FFR_CUDA(cudaFuncSetAttribute(recnet_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr = true;
+    }
+    if (g_prep_mma) {
+        const int smem2 = (64 * PM_XP + 512 * PM_BP + 64 * PM_WP) * 2 + (2404 + 2 * 32 * PM_AP + 512 + 64 + 96) * (int)sizeof(float);
+        static bool attr2 = false;
+        if (!attr2) {
+            FFR_CUDA(cudaFuncSetAttribute(recnet_prep_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+            attr2 = true;
+        }
+        recnet_prep_mma_kernel<<<n, 512, smem2, stream>>>(p);
+        return launch_status("recnet_prep_mma_kernel");
     }
     recnet_prep_kernel<<<n, 512, smem, stream>>>(p);
     return launch_status("recnet_prep_kernel");

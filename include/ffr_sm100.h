@@ -461,6 +461,10 @@ FFR_API int ffr_set_conv_scratch(void* scratch, long long bytes);
 FFR_API void ffr_debug_set_streamk(int enable);
 FFR_API int ffr_debug_last_streamk(void);   /* 1 if the most recent such launch was scheduled stream-K */
 
+/* Debug/tuning: 1 (default) runs ffr_recnet_prep on the warp-MMA kernel (bf16 / tf32 tensor-core contractions of the
+ * staged bf16 X); 0 forces the fp32 SIMT kernel. Same algebra; the results agree within the bf16 noise of the eval path. */
+FFR_API void ffr_debug_set_prep_mma(int enable);
+
 /* Debug/tuning: device buffer of 16 uint64 that the sliding-window kernel fills with per-role barrier-wait cycle
  * counts (summed over CTAs; slots in csrc/conv_gemm.cuh DbgSlot); NULL (default) disables the counters. */
 FFR_API int ffr_debug_set_counters(void* counters);
