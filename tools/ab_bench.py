@@ -44,9 +44,13 @@ if len(sys.argv) > 2 and sys.argv[2] == "sk":
     CONFIGS = [CONFIGS[0], CONFIGS[2]]
 if len(sys.argv) > 2 and sys.argv[2] == "branch":
     CONFIGS = CONFIGS[:2]
+PREP = [1]
+if len(sys.argv) > 2 and sys.argv[2] == "prep":      # warp-MMA vs SIMT recnet_prep, everything else at its default
+    CONFIGS, PREP = CONFIGS[:1], [1, 0]
 for rnd in range(10):
     order = CONFIGS[rnd % len(CONFIGS):] + CONFIGS[:rnd % len(CONFIGS)]      # rotate: no config always runs first
-    for pdl, pair, fuse, lean, sk, strip, br in order:
+    for (pdl, pair, fuse, lean, sk, strip, br), prep in [(c, q) for c in order for q in (PREP if rnd % 2 == 0 else PREP[::-1])]:
+        lib.ffr_debug_set_prep_mma(prep)
         lib.ffr_debug_set_pdl(pdl)
         lib.ffr_debug_set_pair(pair)
         enc.fuse_se = fuse
@@ -55,9 +59,10 @@ for rnd in range(10):
         lib.ffr_debug_set_stem_strip(strip)
         rec.branch_streams = bool(br)
         run(3)
-        res.setdefault("pdl=%d pair=%d fused_se=%d lean=%d streamk=%d strip_stem=%d branch_streams=%d" %
-                       (pdl, pair, int(fuse), lean, sk, strip, br), []).append(run(10))
+        res.setdefault("pdl=%d pair=%d fused_se=%d lean=%d streamk=%d strip_stem=%d branch_streams=%d prep_mma=%d" %
+                       (pdl, pair, int(fuse), lean, sk, strip, br, prep), []).append(run(10))
 rec.branch_streams = False
+lib.ffr_debug_set_prep_mma(1)
 enc.fuse_se = True
 lib.ffr_debug_set_lean_epilogue(1)
 lib.ffr_debug_set_streamk(0)
