@@ -96,6 +96,7 @@ _SIGNATURES = {
     "ffr_recnet_convlayer_fwd": (_i, [_p, _i, _i, _p, _i, _p, _p, _p, _i, _i, _p, _i, _p, _i, _i, _p, _p, _p]),
     "ffr_self_similarity": (_i, [_p, _i, _p, _p, _p]),
     "ffr_feat_space": (_i, [_p, _p, _p, _p, _i, _p]),
+    "ffr_feat_space_xt": (_i, [_p, _p, _p, _p, _i, _p]),
     "ffr_rows_to_nchw": (_i, [_p, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "ffr_pack_conv3x3": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
     "ffr_gallery_cosine": (_i, [_p, _i, _p, _i, _i, _p, _p, _p]),

@@ -333,6 +333,12 @@ FFR_API int ffr_feat_space(const float* x, const float* mspace, void* cm, float*
     return feat_space_launch(x, mspace, cm, out_nchw, n, S_(stream));
 }
 
+FFR_API int ffr_feat_space_xt(const void* xt, const float* mspace, void* cm, float* out_nchw, int n, ffr_stream_t stream) {
+    FFR_CHECK_ARG(xt && mspace && cm, "ffr_feat_space_xt: null pointer");
+    if (n == 0) return 0;
+    return feat_space_xt_launch(xt, mspace, cm, out_nchw, n, S_(stream));
+}
+
 FFR_API int ffr_rows_to_nchw(const void* rows, int is_f32, int ld, int ch0, const float* scale, const float* shift,
                              float* y, int n, int S, int G, int off, int rows_per_img, int C, ffr_stream_t stream) {
     FFR_CHECK_ARG(rows && y, "ffr_rows_to_nchw: null pointer");

@@ -40,6 +40,7 @@ struct PrepParams {
 };
 int recnet_prep_launch(const PrepParams& p, int n, cudaStream_t stream);
 int feat_space_launch(const float* x, const float* mspace, void* cm, float* out_nchw, int n, cudaStream_t stream);
+int feat_space_xt_launch(const void* xt, const float* mspace, void* cm, float* out_nchw, int n, cudaStream_t stream);
 int rows_to_nchw_launch(const void* rows, int is_f32, int ld, int ch0, const float* scale, const float* shift, float* y,
                         int n, int S, int G, int off, int rows_per_img, int C, cudaStream_t stream);
 int cosface_pack_launch(const float* x, int rows, int rows_pad, int mode, void* packed, void* transposed, int t_ld,

@@ -585,6 +585,103 @@ int feat_space_launch(const float* x, const float* mspace, void* cm, float* out_
     return launch_status("feat_space_kernel");
 }
 
+// Warp-MMA version of feat_space_kernel, fed by the XT matrix recnet_prep already wrote (bf16 [n*128][512], rows = pixels):
+//   FS^T[j][c] = sum_i M_space[i][j] * XT[i][c]      (M 64 x N 512 x K 64; 49 real pixels, pad rows / columns zero)
+// m16n8k16 bf16 MMAs through ldmatrix (both operands are stored k-major: transposed loads); a thread's accumulators are
+// channel PAIRS of one pixel, exactly the 4-byte stores of the H9 fan-out. 8 warps x 64 channels, two passes of two
+// 16-pixel tiles. M_space is rounded to bf16 for the contraction (its output is stored as bf16).
+constexpr int FS_MP = 72;      // M_space pitch (bf16), [64][64]
+__global__ void __launch_bounds__(256) feat_space_mma_kernel(const __nv_bfloat16* __restrict__ xt_g, const float* __restrict__ mspace,
+                                                             __nv_bfloat16* __restrict__ cm, float* __restrict__ out_nchw) {
+    extern __shared__ __align__(16) uint8_t fsm_smem[];
+    __nv_bfloat16* xts = reinterpret_cast<__nv_bfloat16*>(fsm_smem);      // [64][PM_XP]
+    __nv_bfloat16* Ms = xts + 64 * PM_XP;                                  // [64][FS_MP]: Ms[i][j] = M_space[n, i, j]
+    const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(xt_g + (long long)n * 128 * 512);
+        for (int o = tid; o < 49 * 64; o += 256) {
+            const int hw = o >> 6, q = o & 63;
+            reinterpret_cast<uint4*>(xts + hw * PM_XP)[q] = __ldg(src + hw * 64 + q);
+        }
+        for (int o = tid; o < 15 * (PM_XP / 2); o += 256) reinterpret_cast<uint32_t*>(xts + 49 * PM_XP)[o] = 0u;
+        for (int o = tid; o < 64 * 64; o += 256) {
+            const int j = o >> 6, i = o & 63;
+            float v = 0.f;
+            if (i < 49 && j < 49) v = mspace[((long long)n * 81 + (j / 7 + 1) * 9 + (j % 7 + 1)) * 64 + i];
+            Ms[i * FS_MP + j] = __float2bfloat16_rn(v);
+        }
+    }
+    __syncthreads();
+    const uint32_t xt_s = smem_u32(xts), ms_s = smem_u32(Ms);
+    const int n_base = 64 * warp;
+    // A[m = j][k = i] = Ms[i][j]: memory [k][m] -> transposed; B[k = i][n = c] = XT[i][c]: memory [k][n] -> transposed
+    const uint32_t a_addr = ms_s + (uint32_t)((((lane & 7) + (lane >> 4) * 8) * FS_MP + ((lane >> 3) & 1) * 8) * 2);
+    const uint32_t b_addr = xt_s + (uint32_t)((((lane & 7) + ((lane >> 3) & 1) * 8) * PM_XP + n_base + (lane >> 4) * 8) * 2);
+#pragma unroll 1
+    for (int mp = 0; mp < 2; ++mp) {
+        float acc[2][8][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[m][q][e] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            uint32_t a0[4], a1[4];
+            ldsm_x4_t(a0, a_addr + (ks * 16 * FS_MP + 32 * mp) * 2);
+            ldsm_x4_t(a1, a_addr + (ks * 16 * FS_MP + 32 * mp + 16) * 2);
+#pragma unroll
+            for (int pq = 0; pq < 4; ++pq) {
+                uint32_t b[4];
+                ldsm_x4_t(b, b_addr + (ks * 16 * PM_XP + 16 * pq) * 2);
+                mma_bf16_k16(acc[0][2 * pq], a0, b[0], b[1]);
+                mma_bf16_k16(acc[0][2 * pq + 1], a0, b[2], b[3]);
+                mma_bf16_k16(acc[1][2 * pq], a1, b[0], b[1]);
+                mma_bf16_k16(acc[1][2 * pq + 1], a1, b[2], b[3]);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int j = 16 * (2 * mp + m) + g + 8 * r;
+                if (j >= 49) continue;
+                const int h = j / 7, w = j - h * 7;
+                const int mh = (h == 1) ? -2 : ((h == 5) ? 2 : 0);
+                const int mw = (w == 1) ? -2 : ((w == 5) ? 2 : 0);
+                const long long base = (long long)n * 81 + (h + 1) * 9 + (w + 1);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int c = n_base + 8 * q + 2 * t;
+                    const float a = acc[m][q][2 * r], b = acc[m][q][2 * r + 1];
+                    if (out_nchw) {
+                        out_nchw[((long long)n * 512 + c) * 49 + j] = a;
+                        out_nchw[((long long)n * 512 + c + 1) * 49 + j] = b;
+                    }
+                    const uint32_t v = pack_bf16x2(a, b);
+                    *reinterpret_cast<uint32_t*>(cm + base * 1536 + c) = v;
+                    if (mh) *reinterpret_cast<uint32_t*>(cm + (base + mh * 9) * 1536 + c) = v;
+                    if (mw) *reinterpret_cast<uint32_t*>(cm + (base + mw) * 1536 + c) = v;
+                    if (mh && mw) *reinterpret_cast<uint32_t*>(cm + (base + mh * 9 + mw) * 1536 + c) = v;
+                }
+            }
+    }
+}
+
+int feat_space_xt_launch(const void* xt, const float* mspace, void* cm, float* out_nchw, int n, cudaStream_t stream) {
+    const int smem = (64 * PM_XP + 64 * FS_MP) * 2;
+    static bool attr = false;
+    if (!attr) {
+        FFR_CUDA(cudaFuncSetAttribute(feat_space_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    feat_space_mma_kernel<<<n, 256, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(xt), mspace,
+                                                    reinterpret_cast<__nv_bfloat16*>(cm), out_nchw);
+    return launch_status("feat_space_mma_kernel");
+}
+
 // ----------------------------------------------------------------------------------------------
 // Rows of a haloed/flat grid -> fp32 NCHW (S x S valid pixels at row (h+off)*G + (w+off)), from bf16 or fp32 rows,
 // optional per-channel affine. grid = (C/64, n).

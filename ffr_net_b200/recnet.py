@@ -203,6 +203,7 @@ class RecNet(nn.Module):
         # at batch 512 it changes nothing (9.528 vs 9.528 ms per step, tools/ab_bench.py 512 branch) - every kernel is a
         # persistent grid that fills the SMs, so the branches time-slice instead of overlapping
         self.branch_streams = os.environ.get("FFR_RECNET_BRANCH_STREAMS", "0") == "1"
+        self.feat_space_mma = os.environ.get("FFR_FEAT_SPACE_MMA", "1") != "0"      # 0: the fp32 SIMT kernel
 
     # ------------------------------------------------------------------------------------------
     def conv_layers(self):
@@ -408,7 +409,10 @@ class RecNet(nn.Module):
             if aux is not None:
                 fs_nchw = torch.empty(n, 512, 7, 7, dtype=torch.float32, device=dev)
                 aux["feat_space"] = fs_nchw
-            chk(lib.ffr_feat_space(P(x), P(ws.mspace), P(ws.cm), P(fs_nchw), n, _lib.stream_ptr()), "feat_space")
+            if self.feat_space_mma:           # warp-MMA kernel on the X^T matrix recnet_prep wrote (same stream, earlier)
+                chk(lib.ffr_feat_space_xt(P(ws.xt), P(ws.mspace), P(ws.cm), P(fs_nchw), n, _lib.stream_ptr()), "feat_space")
+            else:
+                chk(lib.ffr_feat_space(P(x), P(ws.mspace), P(ws.cm), P(fs_nchw), n, _lib.stream_ptr()), "feat_space")
 
         def channel_branch():
             # ---- channel rectifier (recnet.py:372-386, 406, 410): M_channel = sigmoid(h5 W8^T + b8); M_channel @ X ----

@@ -193,6 +193,9 @@ FFR_API int ffr_self_similarity(const float* x, int n, float* ss_space, float* s
 
 /* feat_space = X @ M_space (recnet.py:409) -> slot [0,512) of cm (H9 + mirrors); optional fp32 NCHW copy. */
 FFR_API int ffr_feat_space(const float* x, const float* mspace, void* cm, float* out_nchw, int n, ffr_stream_t stream);
+/* The same product (recnet.py:409) on warp-level tensor cores, fed by the bf16 X^T matrix ffr_recnet_prep wrote
+ * (xt: [n*128][512], rows = pixels) instead of the fp32 map; M_space is rounded to bf16 for the contraction. */
+FFR_API int ffr_feat_space_xt(const void* xt, const float* mspace, void* cm, float* out_nchw, int n, ffr_stream_t stream);
 
 /* Rows of a haloed/flat grid -> fp32 NCHW (S x S valid pixels at row (h+off)*G + (w+off)), optional affine. */
 FFR_API int ffr_rows_to_nchw(const void* rows, int is_f32, int ld, int ch0, const float* scale, const float* shift,
